@@ -1,0 +1,979 @@
+// tess.cu — K1 (stroke subdivision / hull emission) and K2 (fill fan + Loop-Blinn classification) for sm_100a,
+// plus the scans that size the output and the per-shape convex hull.
+//
+// Replaces, on the device: src/curve.rs (all), src/stroke.rs (all), src/fill.rs (all), src/convex_hull.rs,
+// src/vertex.rs and the buffer concatenation of Shape::from_paths (src/renderer.rs:184-209).
+//
+// Structure: one thread walks one Path exactly like StrokeBuilder::add_path / FillBuilder::add_path do (the
+// sequential state — arc length, previous tangent, strip cuts, the five per-type cursors — lives in registers),
+// first with a counting sink, then, after an exclusive scan over paths, with an emitting sink that writes
+// every vertex / index / proto-hull point to its final address. The per-sample root solving of
+// interpolate_normal! (src/curve.rs:228-252) only runs in the emit pass.
+//
+// Output layout in HBM: one array per vertex category for the WHOLE batch (all shapes), categories in
+// concat_buffers! order; a shape's slice of category c is [cat_begin[c][s], cat_begin[c][s+1]). Index buffers are
+// 32-bit: (vertex index within the shape's category << 1) | strip parity, CR_RESTART between strips.
+#include "device_common.cuh"
+#include "tess.h"
+#include "prims.h"
+
+using namespace crd;
+
+namespace {
+
+// ================================================================================================ curve.rs
+__device__ __forceinline__ Pt mvt1(const Pt* pb, float a0) { return pb[0] * a0; }
+__device__ __forceinline__ Pt mvt2(const Pt* pb, float a0, float a1) { return pb[0] * a0 + pb[1] * a1; }
+__device__ __forceinline__ Pt mvt3(const Pt* pb, float a0, float a1, float a2) { return pb[0] * a0 + (pb[1] * a1 + pb[2] * a2); }
+__device__ __forceinline__ Pt mvt4(const Pt* pb, float a0, float a1, float a2, float a3) {
+    return pb[0] * a0 + (pb[1] * a1 + (pb[2] * a2 + pb[3] * a3));
+}
+// src/curve.rs:26-42
+__device__ __forceinline__ void quad_power_basis(const Pt* cp, Pt* pb) {
+    pb[0] = mvt1(cp, 1.0f);
+    pb[1] = mvt2(cp, -2.0f, 2.0f);
+    pb[2] = mvt3(cp, 1.0f, -2.0f, 1.0f);
+}
+__device__ __forceinline__ void cubic_power_basis(const Pt* cp, Pt* pb) {
+    pb[0] = mvt1(cp, 1.0f);
+    pb[1] = mvt2(cp, -3.0f, 3.0f);
+    pb[2] = mvt3(cp, 3.0f, -6.0f, 3.0f);
+    pb[3] = mvt4(cp, -1.0f, 3.0f, -3.0f, 1.0f);
+}
+// src/curve.rs:58-83
+__device__ void reparametrize_cubic(const Pt* pb, float a, float b, Pt* out) {
+    const float a2 = a * a, a3 = a * a * a, b2 = b * b, b3 = b * b * b;
+    const float amb = a - b;
+    out[0] = mvt4(pb, 1.0f, a, a2, a3);
+    out[1] = mvt4(pb, 0.0f, b - a, -2.0f * a2 + 2.0f * a * b, 3.0f * a2 * b - 3.0f * a3);
+    out[2] = mvt4(pb, 0.0f, 0.0f, amb * amb, -6.0f * a2 * b + 3.0f * a * b2 + 3.0f * a3);
+    out[3] = mvt4(pb, 0.0f, 0.0f, 0.0f, 3.0f * a2 * b - 3.0f * a * b2 - a3 + b3);
+}
+// src/curve.rs:86-114
+__device__ __forceinline__ Pt quad_point(const Pt* pb, float t) { return mvt3(pb, 1.0f, t, t * t); }
+__device__ __forceinline__ Ln quad_d1(const Pt* pb, float t) { return join(mvt3(pb, 1.0f, t, t * t), mvt3(pb, 0.0f, 1.0f, 2.0f * t)); }
+__device__ __forceinline__ Pt cubic_point(const Pt* pb, float t) { return mvt4(pb, 1.0f, t, t * t, t * t * t); }
+__device__ __forceinline__ Ln cubic_d1(const Pt* pb, float t) {
+    return join(mvt4(pb, 1.0f, t, t * t, t * t * t), mvt4(pb, 0.0f, 1.0f, 2.0f * t, 3.0f * (t * t)));
+}
+// src/curve.rs:133-144
+__device__ void ippc_of(const Pt* pb, bool integral, float* ippc) {
+    ippc[0] = 0.0f;
+    if (!integral) ippc[0] = triple(pb[1], pb[2], pb[3]) * -1.0f;
+    ippc[1] = triple(pb[0], pb[2], pb[3]) * 1.0f;
+    ippc[2] = triple(pb[0], pb[1], pb[3]) * -1.0f;
+    ippc[3] = triple(pb[0], pb[1], pb[2]) * 1.0f;
+    const float m = cr::sqrt_f(ippc[0] * ippc[0] + ippc[1] * ippc[1] + ippc[2] * ippc[2] + ippc[3] * ippc[3]);
+    const float inv = 1.0f / m;
+    ippc[0] = ippc[0] * inv; ippc[1] = ippc[1] * inv; ippc[2] = ippc[2] * inv; ippc[3] = ippc[3] * inv;
+}
+struct Inflections { float disc; cr::Root r[3]; };
+// src/curve.rs:151-190
+__device__ Inflections integral_inflections(const float* ippc, bool loop_self_intersection) {
+    Inflections o;
+    o.r[1] = cr::no_root(); o.r[2] = cr::no_root();
+    const float disc = 3.0f * (ippc[2] * ippc[2]) - 4.0f * ippc[1] * ippc[3];
+    if (cr::fabs_f(ippc[1]) <= CR_ERROR_MARGIN) {
+        if (cr::fabs_f(ippc[2]) <= CR_ERROR_MARGIN) { o.disc = -1.0f; o.r[0] = cr::make_root(-1.0f, 0.0f, 1.0f); }
+        else { o.disc = 1.0f; o.r[0] = cr::make_root(ippc[3], 0.0f, 3.0f * ippc[2]); }
+        return o;
+    }
+    const float d = cr::sqrt_f(disc * (disc < 0.0f ? (loop_self_intersection ? -1.0f : 0.0f) : 1.0f / 3.0f));
+    o.disc = disc;
+    o.r[0] = cr::make_root(ippc[2] + d, 0.0f, 2.0f * ippc[1]);
+    o.r[1] = cr::make_root(ippc[2] - d, 0.0f, 2.0f * ippc[1]);
+    return o;
+}
+// src/curve.rs:197-226
+__device__ Inflections rational_inflections(const float* ippc, bool loop_self_intersection) {
+    if (cr::fabs_f(ippc[0]) <= CR_ERROR_MARGIN) return integral_inflections(ippc, loop_self_intersection);
+    const cr::Roots cubic = cr::solve_cubic(ippc[3] * -1.0f, ippc[2] * 3.0f, ippc[1] * -3.0f, ippc[0], CR_ERROR_MARGIN);
+    Inflections o;
+    o.r[0] = cubic.r[0]; o.r[1] = cubic.r[1]; o.r[2] = cubic.r[2];
+    if (!loop_self_intersection) { o.disc = cubic.discriminant; return o; }
+    const cr::Roots hess = cr::solve_quadratic(ippc[1] * ippc[3] - ippc[2] * ippc[2], ippc[1] * ippc[2] - ippc[0] * ippc[3],
+                                               ippc[0] * ippc[2] - ippc[1] * ippc[1], CR_ERROR_MARGIN);
+    if (hess.discriminant > 0.0f) {
+        o.r[2] = cubic.real_root == 0 ? cubic.r[0] : (cubic.real_root == 1 ? cubic.r[1] : cubic.r[2]);
+        if (hess.count == 2) { o.r[0] = hess.r[0]; o.r[1] = hess.r[1]; }
+        else if (hess.count == 1) { o.r[0] = hess.r[0]; o.r[1] = cr::no_root(); }
+    }
+    o.disc = -hess.discriminant;
+    return o;
+}
+
+// Which polynomial interpolate_normal! solves for one curve kind (src/curve.rs:318,342,368,405).
+enum { K_IQ = 0, K_IC = 1, K_RQ = 2, K_RC = 3 };
+struct SolvePlanes { Ln p[5]; };
+template <int KIND>
+__device__ __forceinline__ float first_root_in_unit(const SolvePlanes& sp, Ln normal) {
+    cr::Roots r;
+    if (KIND == K_IQ) r = cr::solve_linear(dot(normal, sp.p[0]), dot(normal, sp.p[1]), CR_ERROR_MARGIN);
+    else if (KIND == K_IC) r = cr::solve_quadratic(dot(normal, sp.p[0]), dot(normal, sp.p[1]), dot(normal, sp.p[2]), CR_ERROR_MARGIN);
+    else if (KIND == K_RQ) {
+        const Ln n = rot90cw(normal);
+        r = cr::solve_quadratic(dot(n, sp.p[0]), dot(n, sp.p[1]), dot(n, sp.p[2]), CR_ERROR_MARGIN);
+    } else {
+        const Ln n = rot90cw(normal);
+        r = cr::solve_quartic(dot(n, sp.p[0]), dot(n, sp.p[1]), dot(n, sp.p[2]), dot(n, sp.p[3]), dot(n, sp.p[4]), CR_ERROR_MARGIN);
+    }
+    for (int k = 0; k < r.count; ++k) {
+        if (r.r[k].denominator == 0.0f) continue;
+        const float parameter = r.r[k].numerator.re / r.r[k].denominator;
+        if (parameter >= 0.0f && parameter <= 1.0f) return parameter;
+    }
+    return 0.0f;
+}
+// The polar interpolation set-up of interpolate_normal! (src/curve.rs:230-234).
+struct Polar { cr::Complex start, step; uint32_t steps; };
+__device__ __forceinline__ uint32_t polar_steps(Ln st, Ln et, float angle_step, cr::Complex* range_out, cr::Complex* start_out) {
+    const cr::Complex ps = cr::cplx(st.g1, st.g2), pe = cr::cplx(et.g1, et.g2);
+    const cr::Complex range = cr::cdiv(pe, ps);
+    *range_out = range;
+    *start_out = ps;
+    return cr::f32_to_usize_sat(cr::fabs_f(cr::carg(range) / angle_step) + 0.5f);
+}
+
+// ============================================================================================== output sinks
+struct PathOffsets { uint32_t v[CNT_COUNT]; };   // absolute begin of this path's slice in every counter's array
+
+template <bool EMIT>
+struct Sink {
+    uint32_t n[CNT_COUNT];
+    uint32_t strip_start;
+    // emit-only state
+    TessOutput out;
+    PathOffsets base;
+    uint32_t shape_base[3];    // the shape's first vertex in CAT_LINE / CAT_JOINT / CAT_SOLID (index values are shape-relative)
+    uint32_t solid_total;      // S.len() of this path (known from the count pass) for the fan->strip scatter
+    uint32_t err;
+
+    __device__ void init() {
+#pragma unroll
+        for (int i = 0; i < CNT_COUNT; ++i) n[i] = 0;
+        strip_start = 0;
+        err = 0;
+    }
+    __device__ __forceinline__ void proto(float2 p) {
+        if (EMIT) {
+            if (!cr::is_finite(p.x) || !cr::is_finite(p.y)) err |= CR_DEVERR_NON_FINITE;
+            out.proto[base.v[CNT_PROTO] + n[CNT_PROTO]] = make_float2(cr::canon_zero(p.x), cr::canon_zero(p.y));
+        }
+        n[CNT_PROTO] += 1;
+    }
+    // Vertex2f1i + its proto_hull entry (pushed at the next cut_stroke_polygon, src/stroke.rs:125)
+    __device__ __forceinline__ void line_vertex(float2 p, float side, float along, uint32_t flags) {
+        if (EMIT) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(out.vtx[CAT_LINE]) + (size_t)(base.v[CAT_LINE] + n[CAT_LINE]) * 5;
+            w[0] = __float_as_uint(p.x); w[1] = __float_as_uint(p.y); w[2] = __float_as_uint(side); w[3] = __float_as_uint(along); w[4] = flags;
+        }
+        n[CAT_LINE] += 1;
+        proto(p);
+    }
+    // cut_stroke_polygon (src/stroke.rs:123-132)
+    __device__ void cut() {
+        const uint32_t count = n[CAT_LINE] - strip_start;
+        if (count == 0) return;
+        if (EMIT) {
+            uint32_t* idx = out.idx[0] + base.v[CNT_LINE_IDX] + n[CNT_LINE_IDX];
+            const uint32_t rel = base.v[CAT_LINE] + strip_start - shape_base[0];
+            for (uint32_t i = 0; i < count; ++i) idx[i] = ((rel + i) << 1) | (i & 1u);
+            idx[count] = CR_RESTART;
+        }
+        n[CNT_LINE_IDX] += count + 1;
+        strip_start = n[CAT_LINE];
+    }
+    __device__ __forceinline__ void joint_vertex(float2 p, float t0, float t1, float t2, uint32_t flags) {
+        if (EMIT) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(out.vtx[CAT_JOINT]) + (size_t)(base.v[CAT_JOINT] + n[CAT_JOINT]) * 6;
+            w[0] = __float_as_uint(p.x); w[1] = __float_as_uint(p.y); w[2] = __float_as_uint(t0); w[3] = __float_as_uint(t1);
+            w[4] = __float_as_uint(t2); w[5] = flags;
+        }
+        n[CAT_JOINT] += 1;
+    }
+    __device__ void joint_indices() {  // the five vertices just written
+        if (EMIT) {
+            uint32_t* idx = out.idx[1] + base.v[CNT_JOINT_IDX] + n[CNT_JOINT_IDX];
+            const uint32_t rel = base.v[CAT_JOINT] + n[CAT_JOINT] - 5 - shape_base[1];
+            for (uint32_t i = 0; i < 5; ++i) idx[i] = ((rel + i) << 1) | (i & 1u);
+            idx[5] = CR_RESTART;
+        }
+        n[CNT_JOINT_IDX] += 6;
+    }
+    // path_solid_vertices.push(..): written straight to its triangle_fan_to_strip position (src/vertex.rs:28-35)
+    __device__ __forceinline__ void solid(float2 p) {
+        if (EMIT) {
+            const uint32_t j = n[CAT_SOLID], total = solid_total;
+            const uint32_t i = (j < (total + 1) / 2) ? 2 * j : 2 * (total - 1 - j) + 1;
+            reinterpret_cast<float2*>(out.vtx[CAT_SOLID])[base.v[CAT_SOLID] + i] = p;
+        }
+        n[CAT_SOLID] += 1;
+    }
+    __device__ void solid_indices() {
+        const uint32_t count = n[CAT_SOLID];
+        if (EMIT) {
+            uint32_t* idx = out.idx[2] + base.v[CNT_SOLID_IDX];
+            const uint32_t rel = base.v[CAT_SOLID] - shape_base[2];
+            for (uint32_t i = 0; i < count; ++i) idx[i] = ((rel + i) << 1) | (i & 1u);
+            idx[count] = CR_RESTART;
+        }
+        n[CNT_SOLID_IDX] += count + 1;
+    }
+    template <int CAT, int NW>
+    __device__ __forceinline__ void curve_vertex(float2 p, const float* w) {
+        if (EMIT) {
+            float* dst = reinterpret_cast<float*>(out.vtx[CAT]) + (size_t)(base.v[CAT] + n[CAT]) * (2 + NW);
+            dst[0] = p.x; dst[1] = p.y;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) dst[2 + k] = w[k];
+        }
+        n[CAT] += 1;
+    }
+};
+
+// ================================================================================================ stroke.rs
+struct StrokeCtx {
+    float width, offset, miter_clip;
+    uint32_t group;
+    float length;   // length_accumulator
+};
+// src/stroke.rs:18-22
+__device__ __forceinline__ Pt offset_cp(Pt cp, Ln tangent, float offset) { return cp + mk_pt(0.0f, tangent.g1, tangent.g2) * offset; }
+// emit_stroke_vertices (src/stroke.rs:28-51)
+template <bool EMIT>
+__device__ __forceinline__ void emit_stroke_vertices(Sink<EMIT>& s, const StrokeCtx& c, uint32_t flags, float length, Pt pt, Ln tangent) {
+    if (EMIT) {
+        const float along = length / c.width;
+        s.line_vertex(to_vec(offset_cp(pt, tangent, (c.offset - 0.5f) * c.width)), -0.5f, along, flags);
+        s.line_vertex(to_vec(offset_cp(pt, tangent, (c.offset + 0.5f) * c.width)), 0.5f, along, flags);
+    } else {
+        s.n[CAT_LINE] += 2;
+        s.n[CNT_PROTO] += 2;
+    }
+}
+// emit_stroke_join (src/stroke.rs:53-121)
+template <bool EMIT>
+__device__ void emit_stroke_join(Sink<EMIT>& s, StrokeCtx& c, Pt cp, Ln prev, Ln next) {
+    const float d = dot(prev, next);
+    if (cr::fabs_f(d - 1.0f) <= CR_ERROR_MARGIN) return;
+    const float side_sign = cr::rust_signum(meet(prev, next).g0);
+    const float miter_clip = c.width * c.miter_clip;
+    const float side_offset = (c.offset - side_sign * 0.5f) * c.width;
+    const Pt pe = offset_cp(cp, prev, side_offset);
+    const Pt ne = offset_cp(cp, next, side_offset);
+    const Ln pl = parallel_through(prev, pe);
+    const Ln nl = parallel_through(next, ne);
+    const Pt x = intersect(pl, nl);
+    Pt v3 = x, v4 = x;
+    const bool anti = cr::fabs_f(d + 1.0f) <= CR_ERROR_MARGIN;
+    if (anti || mag(join(cp, x)) > miter_clip) {
+        const Ln mid = anti ? neg(rot90cw(prev)) : unit(prev + next);
+        const Pt cv = offset_cp(cp, mid, -side_sign * miter_clip);
+        const Ln cl = parallel_through(mid, cv);
+        v3 = intersect(pl, cl);
+        v4 = intersect(cl, nl);
+        s.proto(to_vec(v3));
+        s.proto(to_vec(v4));
+    } else {
+        s.proto(to_vec(v3));
+    }
+    if (EMIT) {
+        const Ln st = prev * (1.0f / -c.width);
+        const float along = c.length / c.width;
+        const Pt vs[5] = {cp, pe, ne, v3, v4};
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            s.joint_vertex(to_vec(vs[k]), side_sign * incidence(vs[k], st), dot(join(vs[k], cp), st), along, c.group);
+    } else {
+        s.n[CAT_JOINT] += 5;
+    }
+    s.joint_indices();
+    c.length += cr::acos_f(d) / (3.14159274101257324219f * 2.0f) * c.width;
+    s.cut();
+    emit_stroke_vertices(s, c, c.group, c.length, cp, next);
+}
+// get_quadratic_tangents / get_cubic_tangents (src/stroke.rs:179-202)
+__device__ __forceinline__ void quad_tangents(Pt a, Pt b, Pt c, Ln& s, Ln& e) {
+    s = unit(join(a, b));
+    e = unit(join(b, c));
+    if (cr::is_nan(s.g0) || cr::is_nan(e.g0)) { s = unit(join(a, c)); e = s; }
+}
+__device__ __forceinline__ void cubic_tangents(Pt a, Pt b, Pt c, Pt d, Ln& s, Ln& e) {
+    s = unit(join(a, b));
+    if (cr::is_nan(s.g0)) s = unit(join(a, c));
+    e = unit(join(c, d));
+    if (cr::is_nan(e.g0)) e = unit(join(b, d));
+    if (cr::is_nan(s.g0) || cr::is_nan(e.g0)) e = unit(join(a, d));
+}
+
+// One sample of emit_curve_stroke! (src/stroke.rs:143-166).
+template <bool CUBIC>
+__device__ __forceinline__ void stroke_sample(Sink<true>& s, StrokeCtx& c, const Pt* pb, float t, Pt& previous_point) {  // emit pass only
+    Ln tangent = CUBIC ? cubic_d1(pb, t) : quad_d1(pb, t);
+    if (sqmag(tangent) == 0.0f) {
+        if (t < 0.5f) t += CR_F32_EPSILON; else t -= CR_F32_EPSILON;
+        tangent = CUBIC ? cubic_d1(pb, t) : quad_d1(pb, t);
+    }
+    tangent = unit(tangent);
+    Pt pt = CUBIC ? cubic_point(pb, t) : quad_point(pb, t);
+    pt = pt * (1.0f / pt.g0);
+    c.length += mag(join(previous_point, pt));
+    emit_stroke_vertices(s, c, c.group, c.length, pt, tangent);
+    previous_point = pt;
+}
+__device__ __forceinline__ uint32_t clamp_steps(uint32_t steps, uint32_t& err) {
+    if (steps > CR_MAX_STEPS_PER_INTERVAL) { err |= CR_DEVERR_STEPS; return CR_MAX_STEPS_PER_INTERVAL; }
+    return steps;
+}
+
+// Quadratic curve body: *_quadratic_uniform_tangent_angle (src/curve.rs:306-322,355-380) + emit_curve_stroke!.
+template <bool EMIT, int KIND>
+__device__ void stroke_quadratic(Sink<EMIT>& s, StrokeCtx& c, const Pt* pb, Ln st, Ln et, bool uta, float angle_step, uint32_t usp_steps, Pt start) {
+    if (!uta) {
+        if constexpr (EMIT) {
+            Pt prev = start;
+            for (uint32_t i = 1; i < usp_steps + 1; ++i) stroke_sample<false>(s, c, pb, (float)i / (float)usp_steps, prev);
+        } else { s.n[CAT_LINE] += 2 * usp_steps; s.n[CNT_PROTO] += 2 * usp_steps; }
+        return;
+    }
+    cr::Complex range, pstart;
+    const uint32_t steps = clamp_steps(polar_steps(st, et, angle_step, &range, &pstart), s.err);
+    const uint32_t n_params = (steps >= 2 ? steps - 1 : 0) + 1;
+    if constexpr (!EMIT) { s.n[CAT_LINE] += 2 * n_params; s.n[CNT_PROTO] += 2 * n_params; return; } else {
+    SolvePlanes sp;
+    if (KIND == K_IQ) { sp.p[0] = dual(pb[1]); sp.p[1] = dual(pb[2]) * 2.0f; }
+    else { sp.p[0] = join(pb[1], pb[0]); sp.p[1] = join(pb[2], pb[0]) * 2.0f; sp.p[2] = join(pb[2], pb[1]); }
+    Pt prev = start;
+    if (steps >= 2) {
+        const cr::Complex pstep = cr::cpowf(range, 1.0f / (float)steps);
+        for (uint32_t i = 1; i < steps; ++i) {
+            const cr::Complex ip = cr::cmul(pstart, cr::cpowi(pstep, i));
+            const float t = first_root_in_unit<KIND>(sp, mk_ln(0.0f, ip.re, ip.im));
+            stroke_sample<false>(s, c, pb, t, prev);
+        }
+    }
+    stroke_sample<false>(s, c, pb, 1.0f, prev);
+    }
+}
+
+// Cubic curve body: cubic_uniform_tangent_angle! (src/curve.rs:254-303) + emit_curve_stroke!.
+template <bool EMIT, int KIND>
+__device__ void stroke_cubic(Sink<EMIT>& s, StrokeCtx& c, const Pt* pb, bool uta, float angle_step, uint32_t usp_steps, Pt start) {
+    if (!uta) {
+        if constexpr (EMIT) {
+            Pt prev = start;
+            for (uint32_t i = 1; i < usp_steps + 1; ++i) stroke_sample<true>(s, c, pb, (float)i / (float)usp_steps, prev);
+        } else { s.n[CAT_LINE] += 2 * usp_steps; s.n[CNT_PROTO] += 2 * usp_steps; }
+        return;
+    }
+    float ippc[4];
+    ippc_of(pb, KIND == K_IC, ippc);
+    const Inflections inf = (KIND == K_IC) ? integral_inflections(ippc, false) : rational_inflections(ippc, false);
+    // split parameters: roots in [0,1], sorted, near-duplicates (< ERROR_MARGIN apart) removed
+    float split[3];
+    int n_split = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (inf.r[k].denominator == 0.0f) continue;
+        const float p = inf.r[k].numerator.re / inf.r[k].denominator;
+        if (p >= 0.0f && p <= 1.0f) {
+            int j = n_split++;
+            while (j > 0 && split[j - 1] > p) { split[j] = split[j - 1]; --j; }
+            split[j] = p;
+        }
+    }
+    {
+        int i = 1;
+        while (i < n_split) {
+            if (split[i] - split[i - 1] < CR_ERROR_MARGIN) { for (int j = i; j + 1 < n_split; ++j) split[j] = split[j + 1]; --n_split; }
+            else ++i;
+        }
+    }
+    const bool cusp = cr::fabs_f(inf.disc) < CR_ERROR_MARGIN;
+    float previous_split = 0.0f;
+    Pt prev = start;
+    float params[EMIT ? CR_MAX_STEPS_PER_INTERVAL : 1];
+    (void)params;
+    for (int iv = 0; iv <= n_split; ++iv) {
+        float a = previous_split, b = 1.0f;
+        if (iv < n_split) {
+            if (cusp) { b = split[iv] - CR_F32_EPSILON; previous_split = split[iv] + CR_F32_EPSILON; }
+            else { b = split[iv]; previous_split = split[iv]; }
+        }
+        const Ln st = unit(cubic_d1(pb, a));
+        const Ln et = unit(cubic_d1(pb, b));
+        cr::Complex range, pstart;
+        const uint32_t steps = clamp_steps(polar_steps(st, et, angle_step, &range, &pstart), s.err);
+        const uint32_t n_params = (steps >= 2 ? steps - 1 : 0) + 1;
+        if constexpr (!EMIT) { s.n[CAT_LINE] += 2 * n_params; s.n[CNT_PROTO] += 2 * n_params; continue; } else {
+        uint32_t np = 0;
+        if (steps >= 2) {
+            Pt tr[4];
+            reparametrize_cubic(pb, a, b, tr);
+            SolvePlanes sp;
+            if (KIND == K_IC) { sp.p[0] = dual(tr[1]); sp.p[1] = dual(tr[2]) * 2.0f; sp.p[2] = dual(tr[3]) * 3.0f; }
+            else {
+                sp.p[0] = join(tr[1], tr[0]);
+                sp.p[1] = join(tr[2], tr[0]) * 2.0f;
+                sp.p[2] = join(tr[2], tr[1]) + join(tr[3], tr[0]) * 3.0f;
+                sp.p[3] = join(tr[3], tr[1]) * 2.0f;
+                sp.p[4] = join(tr[3], tr[2]);
+            }
+            const cr::Complex pstep = cr::cpowf(range, 1.0f / (float)steps);
+            for (uint32_t i = 1; i < steps; ++i) {
+                const cr::Complex ip = cr::cmul(pstart, cr::cpowi(pstep, i));
+                const float t = first_root_in_unit<KIND>(sp, mk_ln(0.0f, ip.re, ip.im));
+                const float mapped = a + (b - a) * t;
+                uint32_t j = np++;   // stable insertion sort (src/curve.rs:297)
+                while (j > 0 && params[j - 1] > mapped) { params[j] = params[j - 1]; --j; }
+                params[j] = mapped;
+            }
+        }
+        for (uint32_t i = 0; i < np; ++i) stroke_sample<true>(s, c, pb, params[i], prev);
+        stroke_sample<true>(s, c, pb, b, prev);
+        }
+    }
+}
+
+struct PathView {
+    float2 start;
+    const uint8_t* seg_types;
+    uint32_t n_segments;
+    const float* seg[5];   // per-type arrays positioned at this path's first segment of that type
+    cr_stroke_options so;
+};
+
+// StrokeBuilder::add_path (src/stroke.rs:205-465)
+template <bool EMIT>
+__device__ void stroke_path(Sink<EMIT>& s, const PathView& pv) {
+    StrokeCtx c;
+    c.width = pv.so.width; c.offset = pv.so.offset; c.miter_clip = pv.so.miter_clip;
+    c.group = pv.so.dynamic_stroke_options_group;
+    c.length = 0.0f;
+    const bool closed = (pv.so.flags & CR_STROKE_FLAG_CLOSED) != 0;
+    const bool uta = (pv.so.flags & CR_STROKE_FLAG_UNIFORM_TANGENT_ANGLE) != 0;
+    const float angle_step = pv.so.approximation.angle_step;
+    const uint32_t usp = pv.so.approximation.steps;
+    Pt prev_cp = from_vec(pv.start.x, pv.start.y);
+    Ln first_tangent = mk_ln(0.0f, 0.0f, 0.0f), prev_tangent = mk_ln(0.0f, 0.0f, 0.0f);
+    uint32_t cur[5] = {0, 0, 0, 0, 0};
+    bool is_first = true;
+    for (uint32_t si = 0; si < pv.n_segments; ++si) {
+        const uint32_t type = pv.seg_types[si];
+        Pt next_cp;
+        Ln st, et;
+        const float* d = nullptr;
+        switch (type) {
+            case CR_SEG_LINE:
+                d = pv.seg[0] + 2 * (size_t)cur[0]++;
+                next_cp = from_vec(d[0], d[1]);
+                st = unit(join(prev_cp, next_cp));
+                et = st;
+                break;
+            case CR_SEG_INTEGRAL_QUADRATIC:
+                d = pv.seg[1] + 4 * (size_t)cur[1];
+                next_cp = from_vec(d[2], d[3]);
+                quad_tangents(prev_cp, from_vec(d[0], d[1]), next_cp, st, et);
+                break;
+            case CR_SEG_INTEGRAL_CUBIC:
+                d = pv.seg[2] + 6 * (size_t)cur[2];
+                next_cp = from_vec(d[4], d[5]);
+                cubic_tangents(prev_cp, from_vec(d[0], d[1]), from_vec(d[2], d[3]), next_cp, st, et);
+                break;
+            case CR_SEG_RATIONAL_QUADRATIC:
+                d = pv.seg[3] + 5 * (size_t)cur[3];
+                next_cp = from_vec(d[3], d[4]);
+                quad_tangents(prev_cp, from_vec(d[1], d[2]), next_cp, st, et);
+                break;
+            default:
+                d = pv.seg[4] + 10 * (size_t)cur[4];
+                next_cp = from_vec(d[8], d[9]);
+                cubic_tangents(prev_cp, from_vec(d[4], d[5]), from_vec(d[6], d[7]), next_cp, st, et);
+                break;
+        }
+        if (cr::is_nan(st.g0) || cr::is_nan(et.g0)) continue;  // cursors of curve types are NOT advanced (quirk C.3)
+        if (is_first) {
+            is_first = false;
+            first_tangent = st;
+            if (!closed) {
+                const Ln normal = rot90cw(st);
+                emit_stroke_vertices(s, c, c.group, c.length - 0.5f * c.width, offset_cp(prev_cp, normal, 0.5f * cr::fabs_f(c.width)), st);
+            }
+            if (closed || type != CR_SEG_LINE) emit_stroke_vertices(s, c, c.group, c.length, prev_cp, st);
+        } else {
+            emit_stroke_join(s, c, prev_cp, prev_tangent, st);
+        }
+        switch (type) {
+            case CR_SEG_LINE:
+                c.length += mag(join(prev_cp, next_cp));
+                emit_stroke_vertices(s, c, c.group, c.length, next_cp, et);
+                break;
+            case CR_SEG_INTEGRAL_QUADRATIC: {
+                cur[1]++;
+                const Pt cp[3] = {prev_cp, from_vec(d[0], d[1]), from_vec(d[2], d[3])};
+                Pt pb[3];
+                quad_power_basis(cp, pb);
+                stroke_quadratic<EMIT, K_IQ>(s, c, pb, st, et, uta, angle_step, usp, prev_cp);
+            } break;
+            case CR_SEG_INTEGRAL_CUBIC: {
+                cur[2]++;
+                const Pt cp[4] = {prev_cp, from_vec(d[0], d[1]), from_vec(d[2], d[3]), from_vec(d[4], d[5])};
+                Pt pb[4];
+                cubic_power_basis(cp, pb);
+                stroke_cubic<EMIT, K_IC>(s, c, pb, uta, angle_step, usp, prev_cp);
+            } break;
+            case CR_SEG_RATIONAL_QUADRATIC: {
+                cur[3]++;
+                const Pt cp[3] = {prev_cp, from_wvec(d[0], d[1], d[2]), from_vec(d[3], d[4])};
+                Pt pb[3];
+                quad_power_basis(cp, pb);
+                stroke_quadratic<EMIT, K_RQ>(s, c, pb, st, et, uta, angle_step, usp, prev_cp);
+            } break;
+            default: {
+                cur[4]++;
+                const float2 pv2 = to_vec(prev_cp);
+                const Pt cp[4] = {from_wvec(d[0], pv2.x, pv2.y), from_wvec(d[1], d[4], d[5]), from_wvec(d[2], d[6], d[7]), from_wvec(d[3], d[8], d[9])};
+                Pt pb[4];
+                cubic_power_basis(cp, pb);
+                stroke_cubic<EMIT, K_RC>(s, c, pb, uta, angle_step, usp, prev_cp);
+            } break;
+        }
+        prev_cp = next_cp;
+        prev_tangent = et;
+    }
+    if (closed) {
+        const Pt start = from_vec(pv.start.x, pv.start.y);
+        const Ln line = join(prev_cp, start);
+        const float length = mag(line);
+        if (length > 0.0f) {
+            const Ln tangent = line * (1.0f / length);
+            emit_stroke_join(s, c, prev_cp, prev_tangent, tangent);
+            c.length += length;
+            emit_stroke_vertices(s, c, c.group, c.length, start, tangent);
+            emit_stroke_join(s, c, start, tangent, first_tangent);
+        } else {
+            emit_stroke_join(s, c, start, prev_tangent, first_tangent);
+        }
+    } else {
+        s.cut();
+        emit_stroke_vertices(s, c, c.group | 0x10000u, c.length, prev_cp, prev_tangent);
+        const Ln normal = rot90cw(prev_tangent);
+        emit_stroke_vertices(s, c, c.group | 0x10000u, c.length + 0.5f * c.width, offset_cp(prev_cp, normal, -0.5f * cr::fabs_f(c.width)), prev_tangent);
+    }
+    s.cut();
+}
+
+// ================================================================================================== fill.rs
+struct W4 { float k, l, m, n; };
+__device__ __forceinline__ float implicit_value(W4 w) { return w.k * w.k * w.k - w.l * w.m * w.n; }
+// weight_derivatives (src/fill.rs:34-49) for one column; returns the four Bernstein-blossom weights.
+__device__ void weight_column(const cr::Root& r0, const cr::Root& r1, const cr::Root& r2, float* col) {
+    const float n0 = r0.numerator.re, n1 = r1.numerator.re, n2 = r2.numerator.re;
+    const float d0 = r0.denominator, d1 = r1.denominator, d2 = r2.denominator;
+    const float p0 = n0 * n1 * n2;
+    const float p1 = -d0 * n1 * n2 - n0 * d1 * n2 - n0 * n1 * d2;
+    const float p2 = n0 * d1 * d2 + d0 * n1 * d2 + d0 * d1 * n2;
+    const float p3 = -d0 * d1 * d2;
+    col[0] = p0;
+    col[1] = p0 + p1 * 1.0f / 3.0f;
+    col[2] = p0 + p1 * 2.0f / 3.0f + p2 * 1.0f / 3.0f;
+    col[3] = p0 + p1 + p2 + p3;
+}
+__device__ __forceinline__ float det3(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2) {
+    return a0 * (b1 * c2 - b2 * c1) - a1 * (b0 * c2 - b2 * c0) + a2 * (b0 * c1 - b1 * c0);
+}
+// weight_planes (src/fill.rs:70-85) for one weight column: plane through three (w, wx, wy, weight) points.
+__device__ Ln weight_plane(const Pt* cp, const float* col) {
+    float pl[4];
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int third = attempt == 0 ? 2 : 3;
+        const float P[4] = {cp[0].g0, cp[0].g1, cp[0].g2, col[0]};
+        const float Q[4] = {cp[1].g0, cp[1].g1, cp[1].g2, col[1]};
+        const float R[4] = {cp[third].g0, cp[third].g1, cp[third].g2, col[third]};
+        pl[0] = det3(P[1], P[2], P[3], Q[1], Q[2], Q[3], R[1], R[2], R[3]);
+        pl[1] = -det3(P[0], P[2], P[3], Q[0], Q[2], Q[3], R[0], R[2], R[3]);
+        pl[2] = det3(P[0], P[1], P[3], Q[0], Q[1], Q[3], R[0], R[1], R[3]);
+        pl[3] = -det3(P[0], P[1], P[2], Q[0], Q[1], Q[2], R[0], R[1], R[2]);
+        if (!(pl[1] * pl[1] + pl[2] * pl[2] + pl[3] * pl[3] < CR_ERROR_MARGIN)) break;
+    }
+    const float sc = 1.0f / -pl[3];
+    return mk_ln(pl[0] * sc, pl[1] * sc, pl[2] * sc);
+}
+
+// emit_cubic_curve_triangle! (src/fill.rs:116-132)
+template <bool EMIT, bool RATIONAL>
+__device__ void cubic_triangle(Sink<EMIT>& s, const float* areas, const Pt* cp, const W4* w, int skip) {
+    const float area = areas[skip];
+    if (!(cr::fabs_f(area) > CR_ERROR_MARGIN)) return;
+    int idx[3], n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i != skip) idx[n++] = i;
+    if (area < 0.0f) { const int t = idx[0]; idx[0] = idx[2]; idx[2] = t; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const W4 ww = w[idx[k]];
+        const float wv[4] = {ww.k, ww.l, ww.m, ww.n};
+        if (RATIONAL) s.template curve_vertex<CAT_RC, 4>(to_vec(cp[idx[k]]), wv);
+        else s.template curve_vertex<CAT_IC, 3>(to_vec(cp[idx[k]]), wv);
+    }
+}
+// triangulate_cubic_curve_quadrilateral! (src/fill.rs:134-204)
+template <bool EMIT, bool RATIONAL>
+__device__ void cubic_quadrilateral(Sink<EMIT>& s, const Pt* cp, W4* w) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float sc = 1.0f / cp[j].g0;
+        w[j].k *= sc; w[j].l *= sc; w[j].m *= sc; w[j].n *= sc;
+    }
+    float areas[4];
+    areas[0] = triple(cp[1], cp[2], cp[3]);
+    areas[1] = triple(cp[0], cp[2], cp[3]);
+    areas[2] = triple(cp[0], cp[1], cp[3]);
+    areas[3] = triple(cp[0], cp[1], cp[2]);
+    const float sum = cr::fabs_f(areas[0]) + cr::fabs_f(areas[1]) + cr::fabs_f(areas[2]) + cr::fabs_f(areas[3]);
+    int enclosing = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float equilibrium = 0.5f * sum;
+        if (cr::fabs_f(equilibrium - cr::fabs_f(areas[i])) <= CR_ERROR_MARGIN) enclosing = (enclosing == -1) ? i : -1;
+    }
+    if (enclosing >= 0) {
+        cubic_triangle<EMIT, RATIONAL>(s, areas, cp, w, enclosing);
+    } else {
+        int opposite = 0;
+        bool bad = false;
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            const float side_of_a = areas[j];
+            const float side_of_d = areas[0] * (j == 2 ? -1.0f : 1.0f);
+            if (side_of_a * side_of_d < 0.0f) { if (opposite != 0) bad = true; opposite = j; }
+        }
+        if (opposite == 0 || bad) { s.err |= CR_DEVERR_CUBIC; return; }   // the reference panics here (src/fill.rs:174,178)
+        cubic_triangle<EMIT, RATIONAL>(s, areas, cp, w, 0);
+        cubic_triangle<EMIT, RATIONAL>(s, areas, cp, w, opposite);
+    }
+    const bool add1 = enclosing != 1 && implicit_value(w[1]) < 0.0f;
+    const bool add2 = enclosing != 2 && implicit_value(w[2]) < 0.0f;
+    if (add1 && add2) {
+        if (areas[0] * areas[1] < 0.0f) { s.solid(to_vec(cp[2])); s.solid(to_vec(cp[1])); }
+        else { s.solid(to_vec(cp[1])); s.solid(to_vec(cp[2])); }
+    } else if (add1) s.solid(to_vec(cp[1]));
+    else if (add2) s.solid(to_vec(cp[2]));
+}
+__device__ __forceinline__ Pt lerp_pt(Pt a, Pt b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ W4 lerp_w(W4 a, W4 b, float t) {
+    W4 o;
+    o.k = a.k * (1.0f - t) + b.k * t; o.l = a.l * (1.0f - t) + b.l * t; o.m = a.m * (1.0f - t) + b.m * t; o.n = a.n * (1.0f - t) + b.n * t;
+    return o;
+}
+// emit_cubic_curve! (src/fill.rs:218-250)
+template <bool EMIT, bool RATIONAL>
+__device__ void fill_cubic(Sink<EMIT>& s, const Pt* cp) {
+    Pt pb[4];
+    cubic_power_basis(cp, pb);
+    float ippc[4];
+    ippc_of(pb, !RATIONAL, ippc);
+    const Inflections inf = RATIONAL ? rational_inflections(ippc, true) : integral_inflections(ippc, true);
+    // weights (src/fill.rs:51-68): columns k, l, m, n
+    float col[4][4];
+    if (inf.disc == 0.0f) {
+        weight_column(inf.r[0], inf.r[0], inf.r[2], col[0]);
+        weight_column(inf.r[0], inf.r[0], inf.r[0], col[1]);
+        weight_column(inf.r[0], inf.r[0], inf.r[0], col[2]);
+    } else if (inf.disc < 0.0f) {
+        weight_column(inf.r[0], inf.r[1], inf.r[2], col[0]);
+        weight_column(inf.r[0], inf.r[0], inf.r[1], col[1]);
+        weight_column(inf.r[1], inf.r[1], inf.r[0], col[2]);
+    } else {
+        weight_column(inf.r[0], inf.r[1], inf.r[2], col[0]);
+        weight_column(inf.r[0], inf.r[0], inf.r[0], col[1]);
+        weight_column(inf.r[1], inf.r[1], inf.r[1], col[2]);
+    }
+    weight_column(inf.r[2], inf.r[2], inf.r[2], col[3]);
+    // gradient of k^3 - l m n at control point 0 (src/fill.rs:91-96) and side normalisation (:98-114)
+    const Ln p0 = weight_plane(cp, col[0]), p1 = weight_plane(cp, col[1]), p2 = weight_plane(cp, col[2]), p3 = weight_plane(cp, col[3]);
+    const float wk = col[0][0], wl = col[1][0], wm = col[2][0], wn = col[3][0];
+    const Ln gradient = p0 * (3.0f * wk * wk) - p1 * (wm * wn) - p2 * (wl * wn) - p3 * (wl * wm);
+    const Ln tangent = cubic_d1(pb, 0.0f);
+    const float flip = dot(tangent, gradient) > 0.0f ? -1.0f : 1.0f;
+    W4 w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        w[j].k = col[0][j]; w[j].l = col[1][j]; w[j].m = col[2][j]; w[j].n = col[3][j];
+        if (flip < 0.0f) { w[j].k *= -1.0f; w[j].l *= -1.0f; }
+    }
+    // find_double_point_issue (src/fill.rs:14-32)
+    float param = -1.0f;
+    int inside = 0;
+    if (inf.disc < 0.0f) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (inf.r[k].denominator != 0.0f) {
+                const float p = inf.r[k].numerator.re / inf.r[k].denominator;
+                if (0.0f < p && p < 1.0f) { param = p; inside += 1; }
+            }
+        }
+    }
+    if (inside == 1) {
+        // split_curve_at! (src/fill.rs:206-216) on control points and on weights
+        const Pt p10 = lerp_pt(cp[0], cp[1], param), p11 = lerp_pt(cp[1], cp[2], param), p12 = lerp_pt(cp[2], cp[3], param);
+        const Pt p20 = lerp_pt(p10, p11, param), p21 = lerp_pt(p11, p12, param);
+        const Pt p30 = lerp_pt(p20, p21, param);
+        const W4 w10 = lerp_w(w[0], w[1], param), w11 = lerp_w(w[1], w[2], param), w12 = lerp_w(w[2], w[3], param);
+        const W4 w20 = lerp_w(w10, w11, param), w21 = lerp_w(w11, w12, param);
+        const W4 w30 = lerp_w(w20, w21, param);
+        const Pt cpa[4] = {cp[0], p10, p20, p30};
+        W4 wa[4] = {w[0], w10, w20, w30};
+        cubic_quadrilateral<EMIT, RATIONAL>(s, cpa, wa);
+        const Pt cpb[4] = {p30, p21, p12, cp[3]};
+        s.solid(to_vec(cpb[0]));
+        W4 wb[4] = {w30, w21, w12, w[3]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { wb[j].k *= -1.0f; wb[j].l *= -1.0f; }
+        cubic_quadrilateral<EMIT, RATIONAL>(s, cpb, wb);
+    } else {
+        cubic_quadrilateral<EMIT, RATIONAL>(s, cp, w);
+    }
+    s.proto(to_vec(cp[1]));
+    s.proto(to_vec(cp[2]));
+    s.proto(to_vec(cp[3]));
+    s.solid(to_vec(cp[3]));
+}
+
+// FillBuilder::add_path (src/fill.rs:263-367)
+template <bool EMIT>
+__device__ void fill_path(Sink<EMIT>& s, const PathView& pv) {
+    float2 last = pv.start;
+    s.solid(last);
+    s.proto(last);
+    uint32_t cur[5] = {0, 0, 0, 0, 0};
+    for (uint32_t si = 0; si < pv.n_segments; ++si) {
+        switch (pv.seg_types[si]) {
+            case CR_SEG_LINE: {
+                const float* d = pv.seg[0] + 2 * (size_t)cur[0]++;
+                last = make_float2(d[0], d[1]);
+                s.proto(last);
+                s.solid(last);
+            } break;
+            case CR_SEG_INTEGRAL_QUADRATIC: {
+                const float* d = pv.seg[1] + 4 * (size_t)cur[1]++;
+                const float w0[2] = {1.0f, 1.0f}, w1[2] = {0.5f, 0.0f}, w2[2] = {0.0f, 0.0f};
+                s.template curve_vertex<CAT_IQ, 2>(make_float2(d[2], d[3]), w0);
+                s.template curve_vertex<CAT_IQ, 2>(make_float2(d[0], d[1]), w1);
+                s.template curve_vertex<CAT_IQ, 2>(last, w2);
+                s.proto(make_float2(d[0], d[1]));
+                s.proto(make_float2(d[2], d[3]));
+                last = make_float2(d[2], d[3]);
+                s.solid(last);
+            } break;
+            case CR_SEG_INTEGRAL_CUBIC: {
+                const float* d = pv.seg[2] + 6 * (size_t)cur[2]++;
+                const Pt cp[4] = {from_vec(last.x, last.y), from_vec(d[0], d[1]), from_vec(d[2], d[3]), from_vec(d[4], d[5])};
+                fill_cubic<EMIT, false>(s, cp);
+                last = to_vec(cp[3]);
+            } break;
+            case CR_SEG_RATIONAL_QUADRATIC: {
+                const float* d = pv.seg[3] + 5 * (size_t)cur[3]++;
+                const float weight = 1.0f / d[0];
+                const float w0[3] = {1.0f, 1.0f, 1.0f}, w1[3] = {0.5f * weight, 0.0f, weight}, w2[3] = {0.0f, 0.0f, 1.0f};
+                s.template curve_vertex<CAT_RQ, 3>(make_float2(d[3], d[4]), w0);
+                s.template curve_vertex<CAT_RQ, 3>(make_float2(d[1], d[2]), w1);
+                s.template curve_vertex<CAT_RQ, 3>(last, w2);
+                s.proto(make_float2(d[1], d[2]));
+                s.proto(make_float2(d[3], d[4]));
+                last = make_float2(d[3], d[4]);
+                s.solid(last);
+            } break;
+            default: {
+                const float* d = pv.seg[4] + 10 * (size_t)cur[4]++;
+                const Pt cp[4] = {from_wvec(d[0], last.x, last.y), from_wvec(d[1], d[4], d[5]), from_wvec(d[2], d[6], d[7]), from_wvec(d[3], d[8], d[9])};
+                fill_cubic<EMIT, true>(s, cp);
+                last = to_vec(cp[3]);
+            } break;
+        }
+    }
+    s.solid_indices();
+}
+
+__device__ __forceinline__ PathView load_path(const DevicePaths& P, uint32_t p) {
+    PathView pv;
+    pv.start = make_float2(P.start[2 * (size_t)p], P.start[2 * (size_t)p + 1]);
+    const uint32_t sb = P.segment_begin[p];
+    pv.seg_types = P.segment_types + sb;
+    pv.n_segments = P.segment_begin[p + 1] - sb;
+    const size_t stride = (size_t)P.n_paths + 1;
+    pv.seg[0] = P.seg[0] + 2 * (size_t)P.type_begin[0 * stride + p];
+    pv.seg[1] = P.seg[1] + 4 * (size_t)P.type_begin[1 * stride + p];
+    pv.seg[2] = P.seg[2] + 6 * (size_t)P.type_begin[2 * stride + p];
+    pv.seg[3] = P.seg[3] + 5 * (size_t)P.type_begin[3 * stride + p];
+    pv.seg[4] = P.seg[4] + 10 * (size_t)P.type_begin[4 * stride + p];
+    pv.so = P.stroke_options[p];
+    return pv;
+}
+
+// ------------------------------------------------------------------------------------------------- kernels
+// Pass A: per-path output sizes. counts is [CNT_COUNT][n_paths + 1].
+__global__ void __launch_bounds__(128) tess_count_kernel(DevicePaths P, uint32_t n_groups, uint32_t* __restrict__ counts, uint32_t* __restrict__ err) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_paths) return;
+    const PathView pv = load_path(P, p);
+    Sink<false> s;
+    s.init();
+    if (pv.so.flags & CR_STROKE_FLAG_STROKED) {
+        if (pv.so.dynamic_stroke_options_group >= n_groups) s.err |= CR_DEVERR_GROUP_OOB;
+        else stroke_path<false>(s, pv);
+    } else {
+        fill_path<false>(s, pv);
+    }
+    const size_t stride = (size_t)P.n_paths + 1;
+#pragma unroll
+    for (int c = 0; c < CNT_COUNT; ++c) counts[c * stride + p] = s.n[c];
+    if (s.err) atomicOr(err, s.err);
+}
+
+// Pass B: write everything. offsets is the exclusive scan of counts ([CNT_COUNT][n_paths + 1], total in the last slot).
+__global__ void __launch_bounds__(128) tess_emit_kernel(DevicePaths P, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ shape_path_begin,
+                                                       uint32_t n_shapes, TessOutput out, uint32_t* __restrict__ err) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_paths) return;
+    const PathView pv = load_path(P, p);
+    const size_t stride = (size_t)P.n_paths + 1;
+    Sink<true> s;
+    s.init();
+    s.out = out;
+#pragma unroll
+    for (int c = 0; c < CNT_COUNT; ++c) s.base.v[c] = offsets[c * stride + p];
+    // shape of this path: last s with shape_path_begin[s] <= p
+    uint32_t lo = 0, hi = n_shapes;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (shape_path_begin[mid] <= p) lo = mid; else hi = mid; }
+    const uint32_t first_path = shape_path_begin[lo];
+    s.shape_base[0] = offsets[CAT_LINE * stride + first_path];
+    s.shape_base[1] = offsets[CAT_JOINT * stride + first_path];
+    s.shape_base[2] = offsets[CAT_SOLID * stride + first_path];
+    s.solid_total = offsets[CAT_SOLID * stride + p + 1] - s.base.v[CAT_SOLID];
+    if (pv.so.flags & CR_STROKE_FLAG_STROKED) stroke_path<true>(s, pv);
+    else fill_path<true>(s, pv);
+    if (s.err) atomicOr(err, s.err);
+}
+
+// Per-shape slice boundaries: cat_begin[c][s] = offsets[c][shape_path_begin[s]], s in [0, n_shapes].
+__global__ void shape_bounds_kernel(const uint32_t* __restrict__ offsets, uint32_t n_paths, const uint32_t* __restrict__ shape_path_begin, uint32_t n_shapes,
+                                    uint32_t* __restrict__ cat_begin) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_shapes) return;
+    const uint32_t p = shape_path_begin[s];
+    for (int c = 0; c < CNT_COUNT; ++c) cat_begin[(size_t)c * (n_shapes + 1) + s] = offsets[(size_t)c * (n_paths + 1) + p];
+}
+
+// ------------------------------------------------------------------------------------ convex_hull.rs on device
+// Lexicographic (x, then y) order of SafeFloat<f32, 2> (src/safe_float.rs:158-168).
+__device__ __forceinline__ bool lex_less(float2 a, float2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
+__device__ __forceinline__ float turn(float2 a, float2 b, float2 c) { return triple(from_vec(a.x, a.y), from_vec(b.x, b.y), from_vec(c.x, c.y)); }
+
+// In-place bitonic sort of n points with virtual +inf padding (all comparators put the minimum at the lower index).
+__device__ void block_sort_points(float2* pts, uint32_t n) {
+    uint32_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (uint32_t k = 2; k <= np2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < np2 / 2; t += blockDim.x) {
+                uint32_t lo, hi;
+                if (j == (k >> 1)) {  // flip step: i <-> block_end - 1 - offset
+                    const uint32_t block = t / j, off = t % j;
+                    lo = block * k + off;
+                    hi = block * k + k - 1 - off;
+                } else {
+                    const uint32_t block = t / j, off = t % j;
+                    lo = block * 2 * j + off;
+                    hi = lo + j;
+                }
+                if (hi < n) {
+                    const float2 a = pts[lo], b = pts[hi];
+                    if (lex_less(b, a)) { pts[lo] = b; pts[hi] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+// One monotone chain of convex_hull::andrew (src/convex_hull.rs:14-24 / :27-38). Returns the stack size.
+__device__ uint32_t hull_chain(const float2* pts, uint32_t n, bool reverse, float2* stack) {
+    uint32_t len = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const float2 p = pts[reverse ? n - 1 - k : k];
+        while (len > 1 && turn(stack[len - 2], stack[len - 1], p) <= CR_ERROR_MARGIN) --len;
+        stack[len++] = p;
+    }
+    return len;
+}
+#define HULL_SMEM_POINTS 1024
+// One CTA per shape. proto: the shape's proto_hull slice (sorted in place); scratch: same-size arrays for the two
+// chain stacks; hull_out: slice with capacity = proto count; hull_count[s] = number of hull vertices (strip order).
+__global__ void __launch_bounds__(128) hull_kernel(float2* __restrict__ proto, float2* __restrict__ scratch_a, float2* __restrict__ scratch_b,
+                                                   const uint32_t* __restrict__ proto_begin, uint32_t n_shapes, float2* __restrict__ hull_out,
+                                                   uint32_t* __restrict__ hull_count) {
+    __shared__ float2 sh_pts[HULL_SMEM_POINTS];
+    __shared__ float2 sh_a[HULL_SMEM_POINTS];
+    __shared__ float2 sh_b[HULL_SMEM_POINTS];
+    __shared__ uint32_t sh_len[2];
+    const uint32_t s = blockIdx.x;
+    const uint32_t begin = proto_begin[s], n = proto_begin[s + 1] - begin;
+    float2* out = hull_out + begin;
+    if (n < 3) {  // returned as-is (src/convex_hull.rs:9-11); fan->strip of <= 2 points is the identity
+        if (threadIdx.x < n) out[threadIdx.x] = proto[begin + threadIdx.x];
+        if (threadIdx.x == 0) hull_count[s] = n;
+        return;
+    }
+    const bool small = n <= HULL_SMEM_POINTS;
+    float2* pts = small ? sh_pts : proto + begin;
+    float2* sa = small ? sh_a : scratch_a + begin;
+    float2* sb = small ? sh_b : scratch_b + begin;
+    if (small) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pts[i] = proto[begin + i];
+        __syncthreads();
+    }
+    block_sort_points(pts, n);
+    if (threadIdx.x == 0) sh_len[0] = hull_chain(pts, n, false, sa) - 1;     // hull.pop()
+    if (threadIdx.x == 32) sh_len[1] = hull_chain(pts, n, true, sb) - 1;     // hull.pop()
+    __syncthreads();
+    const uint32_t la = sh_len[0], lb = sh_len[1], total = la + lb;
+    // triangle_fan_to_strip(andrew(..)) (src/renderer.rs:197, src/vertex.rs:28-35)
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint32_t src = (i & 1u) == 0 ? (i >> 1) : total - 1 - (i >> 1);
+        out[i] = src < la ? sa[src] : sb[src - la];
+    }
+    if (threadIdx.x == 0) hull_count[s] = total;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------- host launchers
+int cr_tess_count(cudaStream_t stream, const DevicePaths& paths, uint32_t n_groups, uint32_t* counts, uint32_t* err_flag) {
+    if (paths.n_paths == 0) return CR_OK;
+    tess_count_kernel<<<(paths.n_paths + 127) / 128, 128, 0, stream>>>(paths, n_groups, counts, err_flag);
+    g_cr_kernel_launches += 1;
+    CR_CUDA_TRY(cudaGetLastError());
+    return CR_OK;
+}
+int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t n_paths, const uint32_t* shape_path_begin, uint32_t n_shapes, uint32_t* cat_begin) {
+    shape_bounds_kernel<<<(n_shapes + 1 + 127) / 128, 128, 0, stream>>>(offsets, n_paths, shape_path_begin, n_shapes, cat_begin);
+    g_cr_kernel_launches += 1;
+    CR_CUDA_TRY(cudaGetLastError());
+    return CR_OK;
+}
+int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* offsets, const uint32_t* shape_path_begin, uint32_t n_shapes,
+                 const TessOutput& out, uint32_t* err_flag) {
+    if (paths.n_paths == 0) return CR_OK;
+    tess_emit_kernel<<<(paths.n_paths + 127) / 128, 128, 0, stream>>>(paths, offsets, shape_path_begin, n_shapes, out, err_flag);
+    g_cr_kernel_launches += 1;
+    CR_CUDA_TRY(cudaGetLastError());
+    return CR_OK;
+}
+int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
+                 float2* hull_out, uint32_t* hull_count) {
+    if (n_shapes == 0) return CR_OK;
+    hull_kernel<<<n_shapes, 128, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out, hull_count);
+    g_cr_kernel_launches += 1;
+    CR_CUDA_TRY(cudaGetLastError());
+    return CR_OK;
+}

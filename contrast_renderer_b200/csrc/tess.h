@@ -1,0 +1,32 @@
+// tess.h — host-visible interface of tess.cu (K1/K2 tessellation, scans, hull).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/contrast_b200.h"
+
+// cr_path_soa with every pointer in device memory.
+struct DevicePaths {
+    uint32_t n_paths;
+    uint32_t n_segments;
+    const float* start;
+    const uint32_t* segment_begin;
+    const uint8_t* segment_types;
+    const uint32_t* type_begin;        // [5][n_paths + 1]
+    const float* seg[5];               // line, integral quadratic, integral cubic, rational quadratic, rational cubic
+    const cr_stroke_options* stroke_options;
+};
+
+// Destination arrays of the emit pass (whole batch).
+struct TessOutput {
+    void* vtx[7];        // CAT_LINE .. CAT_RC, packed exactly like src/vertex.rs
+    float2* proto;       // proto_hull points
+    uint32_t* idx[3];    // line, joint, solid: (shape-relative vertex index << 1) | strip parity, CR_RESTART between strips
+};
+
+int cr_tess_count(cudaStream_t stream, const DevicePaths& paths, uint32_t n_groups, uint32_t* counts, uint32_t* err_flag);
+int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t n_paths, const uint32_t* shape_path_begin, uint32_t n_shapes,
+                         uint32_t* cat_begin);
+int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* offsets, const uint32_t* shape_path_begin, uint32_t n_shapes,
+                 const TessOutput& out, uint32_t* err_flag);
+int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
+                 float2* hull_out, uint32_t* hull_count);
