@@ -1,0 +1,869 @@
+// api.cu — the C-ABI of libcontrast_b200.so (include/contrast_b200.h): object lifetimes, host<->device staging and
+// the launch sequences that string the kernels of tess.cu / raster.cu / prims.cu together.
+//
+// Mirrors, entry point by entry point, the Rust public API of the reference for this path:
+//   Renderer::new / resize_internal_buffers / set_clip_depth / save_alpha_context / restore_alpha_context
+//   (src/renderer.rs:432,892,932,941,979), Shape::from_paths / render / set_dynamic_stroke_options
+//   (src/renderer.rs:177,267,360), convert_dynamic_stroke_options (src/renderer.rs:29-60).
+// There is NO CPU fallback anywhere in this file: without a CUDA device every entry point that would compute
+// returns CR_ERR_NO_DEVICE / CR_ERR_CUDA.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <memory>
+#include <new>
+#include <vector>
+#include "device_common.cuh"
+#include "prims.h"
+#include "raster.h"
+#include "tess.h"
+
+// ----------------------------------------------------------------------------------------------- error plumbing
+static thread_local char g_error_message[512] = "";
+void cr_set_error_message(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error_message, sizeof(g_error_message), fmt, ap);
+    va_end(ap);
+}
+#define CR_TRY(expr)                     \
+    do {                                 \
+        const int _st = (expr);          \
+        if (_st != CR_OK) return _st;    \
+    } while (0)
+static int fail(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error_message, sizeof(g_error_message), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+namespace {
+
+// A grow-only device allocation (stream-ordered allocator, so re-tessellating every frame does not synchronise).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(cudaStream_t stream, size_t bytes) {
+        if (bytes <= cap && p) return CR_OK;
+        if (p) CR_CUDA_TRY(cudaFreeAsync(p, stream));
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes < 256 ? 256 : bytes;
+        CR_CUDA_TRY(cudaMallocAsync(&p, want, stream));
+        cap = want;
+        return CR_OK;
+    }
+    void release(cudaStream_t stream) {
+        if (p) cudaFreeAsync(p, stream);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Descriptor48 {   // DynamicStrokeDescriptor (src/renderer.rs:18-27)
+    float gap_start[CR_MAX_DASH_INTERVALS];
+    float gap_end[CR_MAX_DASH_INTERVALS];
+    uint32_t caps;
+    uint32_t count_dashed_join;
+    float phase;
+    uint32_t _padding;
+};
+static_assert(sizeof(Descriptor48) == 48, "DynamicStrokeDescriptor is 48 bytes");
+
+// convert_dynamic_stroke_options (src/renderer.rs:29-60)
+int convert_dynamic_stroke_options(const cr_dynamic_stroke_options& o, Descriptor48& out) {
+    memset(&out, 0, sizeof(out));
+    if (o.join > CR_JOIN_ROUND) return fail(CR_ERR_INVALID_ARGUMENT, "join %u is not a cr_join", o.join);
+    if (o.dashed) {
+        if (o.pattern_len > CR_MAX_DASH_INTERVALS) return fail(CR_ERR_TOO_MANY_DASH_INTERVALS, "%u dash intervals > %d", o.pattern_len, CR_MAX_DASH_INTERVALS);
+        if (o.pattern_len == 0) return fail(CR_ERR_INVALID_ARGUMENT, "a dashed stroke needs at least one interval");
+        out.count_dashed_join = ((o.pattern_len - 1) << 3) | 4u | o.join;
+        out.phase = o.phase;
+        for (uint32_t i = 0; i < o.pattern_len; ++i) {
+            if (o.pattern[i].dash_start > CR_CAP_BUTT || o.pattern[i].dash_end > CR_CAP_BUTT) return fail(CR_ERR_INVALID_ARGUMENT, "bad cap");
+            out.gap_start[i] = o.pattern[i].gap_start;
+            out.gap_end[i] = o.pattern[i].gap_end;
+            out.caps |= o.pattern[i].dash_start << (((i + o.pattern_len - 1) % o.pattern_len) * 8);
+            out.caps |= o.pattern[i].dash_end << (i * 8 + 4);
+        }
+    } else {
+        if (o.start > CR_CAP_BUTT || o.end > CR_CAP_BUTT) return fail(CR_ERR_INVALID_ARGUMENT, "bad cap");
+        out.caps = o.start | (o.end << 4);
+        out.count_dashed_join = o.join;
+    }
+    return CR_OK;
+}
+
+int decode_device_error(uint32_t flags) {
+    if (flags & CR_DEVERR_GROUP_OOB) return fail(CR_ERR_DYNAMIC_STROKE_OPTIONS_INDEX_OUT_OF_BOUNDS, "a path references a dynamic stroke options group that does not exist");
+    if (flags & CR_DEVERR_NON_FINITE) return fail(CR_ERR_NON_FINITE, "tessellation produced a non-finite hull point");
+    if (flags & CR_DEVERR_STEPS) return fail(CR_ERR_CURVE_STEPS_CAPACITY, "more than %d tangent-angle steps in one curve interval", CR_MAX_STEPS_PER_INTERVAL);
+    if (flags & CR_DEVERR_CUBIC) return fail(CR_ERR_CUBIC_TRIANGULATION, "cubic control quadrilateral is in no recognised configuration");
+    return CR_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- objects
+struct cr_renderer {
+    cr_config config;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint32_t width = 0, height = 0, tiles_x = 0, tiles_y = 0;
+    DevBuf color, stencil, alpha_layers;
+    // scratch shared by every from_paths / submit of this renderer
+    DevBuf staging[10], counts, scan_scratch, shape_begin_dev, err_flag, hull_scratch_a, hull_scratch_b;
+    DevBuf cmds_dev, batches_dev, cmd_cands, cand_tiles, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, radix_scratch, tile_begin, inst_transforms, inst_colors,
+        covered_dev;
+    uint32_t* pinned = nullptr;   // small pinned read-back area
+    cr_stats stats{};
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // tess begin/end, bin begin/end, raster begin/end
+    bool ev_valid[3] = {false, false, false};
+    uint64_t live_objects = 0;
+};
+
+struct cr_shape {
+    cr_shape_batch* batch;
+    uint32_t index;
+    bool owns_batch;
+};
+
+struct cr_shape_batch {
+    cr_renderer* renderer = nullptr;
+    uint32_t n_shapes = 0, n_paths = 0, n_groups = 0;
+    DevBuf vtx[7], proto, hull, idx[3], cat_begin, hull_count, stroke, desc_dev;
+    std::vector<uint32_t> cat_begin_host;    // [CNT_COUNT][n_shapes + 1]
+    std::vector<uint32_t> hull_count_host;   // [n_shapes]
+    std::vector<cr_shape> views;
+    uint64_t totals[CNT_COUNT] = {};
+};
+
+struct InstanceSet {
+    const float* transforms;
+    const float* colors;
+    uint32_t count, space, base;
+};
+struct cr_pass {
+    cr_renderer* renderer;
+    std::vector<DeviceCommand> commands;
+    std::vector<cr_shape_batch*> batches;
+    std::vector<InstanceSet> instance_sets;
+    uint32_t instance_total = 0;
+    uint32_t clip_depth = 0, save_layer = 0, restore_layer = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int previous = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&previous) != cudaSuccess) { ok = false; return; }
+        if (previous != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (previous >= 0) cudaSetDevice(previous); }
+};
+#define CR_GUARD(r)                                                                    \
+    DeviceGuard _guard((r)->device);                                                   \
+    if (!_guard.ok) return fail(CR_ERR_CUDA, "cannot select CUDA device %d", (r)->device)
+
+void batch_release(cr_shape_batch* b) {
+    cudaStream_t st = b->renderer->stream;
+    for (auto& v : b->vtx) v.release(st);
+    for (auto& v : b->idx) v.release(st);
+    b->proto.release(st); b->hull.release(st); b->cat_begin.release(st); b->hull_count.release(st); b->stroke.release(st); b->desc_dev.release(st);
+}
+
+// Bring one input array to the device: host memory is staged (cudaMemcpyAsync on the renderer's stream), device
+// memory is used where it lies.
+template <typename T>
+int stage(cr_renderer* r, int slot, const T* src, size_t count, uint32_t space, const T** out) {
+    if (count == 0) { *out = nullptr; return CR_OK; }
+    if (!src) return fail(CR_ERR_INVALID_ARGUMENT, "null input array (slot %d)", slot);
+    if (space == CR_MEM_DEVICE) { *out = src; return CR_OK; }
+    CR_TRY(r->staging[slot].reserve(r->stream, count * sizeof(T)));
+    CR_CUDA_TRY(cudaMemcpyAsync(r->staging[slot].p, src, count * sizeof(T), cudaMemcpyHostToDevice, r->stream));
+    *out = r->staging[slot].as<T>();
+    return CR_OK;
+}
+
+int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t n_groups, const cr_path_soa* soa, const uint32_t* shape_path_begin,
+                uint32_t n_shapes, cr_shape_batch* b) {
+    if (!soa) return fail(CR_ERR_INVALID_ARGUMENT, "paths is null");
+    if (n_groups > 65536) return fail(CR_ERR_INVALID_ARGUMENT, "at most 65536 dynamic stroke option groups (the vertex flag word keeps the group in 16 bits, src/shaders.wgsl:273)");
+    if (n_groups && !groups) return fail(CR_ERR_INVALID_ARGUMENT, "dynamic_stroke_options is null");
+    if (soa->memory_space > CR_MEM_DEVICE) return fail(CR_ERR_INVALID_ARGUMENT, "bad memory_space");
+    if (n_shapes == 0 || !shape_path_begin) return fail(CR_ERR_INVALID_ARGUMENT, "a batch needs at least one shape");
+    if (shape_path_begin[0] != 0 || shape_path_begin[n_shapes] != soa->n_paths) return fail(CR_ERR_INVALID_ARGUMENT, "shape_path_begin must cover [0, n_paths]");
+    for (uint32_t s = 0; s < n_shapes; ++s)
+        if (shape_path_begin[s] > shape_path_begin[s + 1]) return fail(CR_ERR_INVALID_ARGUMENT, "shape_path_begin must be non-decreasing");
+    cudaStream_t st = r->stream;
+    const uint32_t n_paths = soa->n_paths;
+    const size_t stride = (size_t)n_paths + 1;
+
+    // descriptors first: TooManyDashIntervals is reported before any tessellation work (src/renderer.rs:210-215 runs
+    // after the loop in the reference, but both are pure functions of the input and an error discards the Shape)
+    std::vector<Descriptor48> descs(n_groups);
+    for (size_t i = 0; i < n_groups; ++i) CR_TRY(convert_dynamic_stroke_options(groups[i], descs[i]));
+
+    if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[0], st));
+    DevicePaths P{};
+    P.n_paths = n_paths;
+    P.n_segments = soa->n_segments;
+    uint32_t type_totals[5] = {0, 0, 0, 0, 0};
+    if (n_paths) {
+        if (!soa->type_begin) return fail(CR_ERR_INVALID_ARGUMENT, "type_begin is null");
+        if (soa->memory_space == CR_MEM_HOST) {
+            for (int t = 0; t < 5; ++t) type_totals[t] = soa->type_begin[t * stride + n_paths];
+        } else {
+            for (int t = 0; t < 5; ++t)
+                CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[t], soa->type_begin + t * stride + n_paths, 4, cudaMemcpyDeviceToHost, st));
+            CR_CUDA_TRY(cudaStreamSynchronize(st));
+            for (int t = 0; t < 5; ++t) type_totals[t] = r->pinned[t];
+        }
+    }
+    static const int kSegFloats[5] = {2, 4, 6, 5, 10};
+    CR_TRY(stage(r, 0, soa->start, 2 * (size_t)n_paths, soa->memory_space, &P.start));
+    CR_TRY(stage(r, 1, soa->segment_begin, n_paths ? stride : 0, soa->memory_space, &P.segment_begin));
+    CR_TRY(stage(r, 2, soa->segment_types, soa->n_segments, soa->memory_space, &P.segment_types));
+    CR_TRY(stage(r, 3, soa->type_begin, n_paths ? 5 * stride : 0, soa->memory_space, &P.type_begin));
+    const float* seg_src[5] = {soa->line_segments, soa->integral_quadratic, soa->integral_cubic, soa->rational_quadratic, soa->rational_cubic};
+    uint64_t input_bytes = 0;
+    for (int t = 0; t < 5; ++t) {
+        CR_TRY(stage(r, 4 + t, seg_src[t], (size_t)type_totals[t] * kSegFloats[t], soa->memory_space, &P.seg[t]));
+        input_bytes += (uint64_t)type_totals[t] * (1 + 4 * kSegFloats[t]);
+    }
+    if (n_paths && !soa->stroke_options) return fail(CR_ERR_INVALID_ARGUMENT, "stroke_options is null (use flags = 0 for filled paths)");
+    CR_TRY(stage(r, 9, soa->stroke_options, n_paths, soa->memory_space, &P.stroke_options));
+    input_bytes += 8ull * n_paths;
+
+    // ---- pass A: count, scan
+    CR_TRY(r->counts.reserve(st, CNT_COUNT * stride * sizeof(uint32_t)));
+    CR_TRY(r->scan_scratch.reserve(st, (size_t)cr_scan_scratch_words((uint32_t)stride, CNT_COUNT) * 4));
+    CR_TRY(r->err_flag.reserve(st, 4));
+    CR_CUDA_TRY(cudaMemsetAsync(r->err_flag.p, 0, 4, st));
+    uint32_t* counts = r->counts.as<uint32_t>();
+    CR_TRY(cr_tess_count(st, P, (uint32_t)n_groups, counts, r->err_flag.as<uint32_t>()));
+    CR_TRY(cr_scan_exclusive(st, counts, (uint32_t)stride, CNT_COUNT, r->scan_scratch.as<uint32_t>()));
+    for (int c = 0; c < CNT_COUNT; ++c)
+        CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[c], counts + c * stride + n_paths, 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[CNT_COUNT], r->err_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaStreamSynchronize(st));
+    CR_TRY(decode_device_error(r->pinned[CNT_COUNT]));
+    for (int c = 0; c < CNT_COUNT; ++c) b->totals[c] = r->pinned[c];
+
+    // ---- allocate the outputs, pass B: emit, hull
+    b->renderer = r;
+    b->n_shapes = n_shapes;
+    b->n_paths = n_paths;
+    b->n_groups = (uint32_t)n_groups;
+    for (int c = 0; c < 7; ++c) CR_TRY(b->vtx[c].reserve(st, b->totals[c] * (size_t)kCategoryStride[c]));
+    CR_TRY(b->proto.reserve(st, b->totals[CNT_PROTO] * 8));
+    CR_TRY(b->hull.reserve(st, b->totals[CNT_PROTO] * 8));
+    CR_TRY(r->hull_scratch_a.reserve(st, b->totals[CNT_PROTO] * 8));
+    CR_TRY(r->hull_scratch_b.reserve(st, b->totals[CNT_PROTO] * 8));
+    for (int k = 0; k < 3; ++k) CR_TRY(b->idx[k].reserve(st, b->totals[CNT_LINE_IDX + k] * 4));
+    CR_TRY(b->cat_begin.reserve(st, (size_t)CNT_COUNT * (n_shapes + 1) * 4));
+    CR_TRY(b->hull_count.reserve(st, (size_t)n_shapes * 4));
+    CR_TRY(b->stroke.reserve(st, n_groups * sizeof(Descriptor48)));
+    if (n_groups) CR_CUDA_TRY(cudaMemcpyAsync(b->stroke.p, descs.data(), n_groups * sizeof(Descriptor48), cudaMemcpyHostToDevice, st));
+    CR_TRY(r->shape_begin_dev.reserve(st, (size_t)(n_shapes + 1) * 4));
+    CR_CUDA_TRY(cudaMemcpyAsync(r->shape_begin_dev.p, shape_path_begin, (size_t)(n_shapes + 1) * 4, cudaMemcpyHostToDevice, st));
+    TessOutput out{};
+    for (int c = 0; c < 7; ++c) out.vtx[c] = b->vtx[c].p;
+    out.proto = b->proto.as<float2>();
+    for (int k = 0; k < 3; ++k) out.idx[k] = b->idx[k].as<uint32_t>();
+    CR_TRY(cr_tess_shape_bounds(st, counts, n_paths, r->shape_begin_dev.as<uint32_t>(), n_shapes, b->cat_begin.as<uint32_t>()));
+    CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, r->err_flag.as<uint32_t>()));
+    CR_TRY(cr_tess_hull(st, out.proto, r->hull_scratch_a.as<float2>(), r->hull_scratch_b.as<float2>(),
+                        b->cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, b->hull.as<float2>(), b->hull_count.as<uint32_t>()));
+    if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[1], st)); r->ev_valid[0] = true; }
+
+    // ---- the rasteriser's view of this batch + host mirrors of the slice tables
+    DeviceBatch db{};
+    for (int c = 0; c < 7; ++c) db.vtx[c] = b->vtx[c].p;
+    db.hull = b->hull.as<float2>();
+    for (int k = 0; k < 3; ++k) db.idx[k] = b->idx[k].as<uint32_t>();
+    db.cat_begin = b->cat_begin.as<uint32_t>();
+    db.hull_count = b->hull_count.as<uint32_t>();
+    db.stroke = b->stroke.p;
+    db.n_shapes = n_shapes;
+    db.n_groups = (uint32_t)n_groups;
+    CR_TRY(b->desc_dev.reserve(st, sizeof(DeviceBatch)));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->desc_dev.p, &db, sizeof(db), cudaMemcpyHostToDevice, st));
+    b->cat_begin_host.resize((size_t)CNT_COUNT * (n_shapes + 1));
+    b->hull_count_host.resize(n_shapes);
+    CR_CUDA_TRY(cudaMemcpyAsync(b->cat_begin_host.data(), b->cat_begin.p, b->cat_begin_host.size() * 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->hull_count_host.data(), b->hull_count.p, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[0], r->err_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaStreamSynchronize(st));
+    CR_TRY(decode_device_error(r->pinned[0]));
+    b->views.resize(n_shapes);
+    for (uint32_t s = 0; s < n_shapes; ++s) b->views[s] = cr_shape{b, s, false};
+
+    uint64_t out_bytes = 0;
+    for (int c = 0; c < 7; ++c) out_bytes += b->totals[c] * (uint64_t)kCategoryStride[c];
+    for (uint32_t s = 0; s < n_shapes; ++s) out_bytes += 8ull * b->hull_count_host[s];
+    for (int k = 0; k < 3; ++k) out_bytes += 2ull * b->totals[CNT_LINE_IDX + k];
+    // B_in of SURVEY §8d: 8 + 24 [stroked] per path; the stroked count is not known on the host for device inputs,
+    // so the 24 B record is counted for every path that carries one (all of them in this ABI).
+    r->stats.input_bytes = input_bytes + 24ull * n_paths;
+    r->stats.vertex_bytes = out_bytes;
+    r->stats.tessellated_paths = n_paths;
+    return CR_OK;
+}
+
+uint32_t slots_of_host(const cr_shape_batch* b, uint32_t shape, int cat) {
+    const size_t stride = (size_t)b->n_shapes + 1;
+    const uint32_t* cb = b->cat_begin_host.data();
+    if (cat <= 2) return cb[(CNT_LINE_IDX + cat) * stride + shape + 1] - cb[(CNT_LINE_IDX + cat) * stride + shape];
+    if (cat <= 6) return (cb[cat * stride + shape + 1] - cb[cat * stride + shape]) / 3u;
+    const uint32_t hc = b->hull_count_host[shape];
+    return hc >= 3 ? hc - 2 : 0u;
+}
+
+}  // namespace
+
+// ============================================================================================= exported C-ABI
+extern "C" {
+
+uint32_t cr_abi_version(void) { return 1; }
+const char* cr_last_error_message(void) { return g_error_message; }
+const char* cr_status_string(int status) {
+    switch (status) {
+        case CR_OK: return "Ok";
+        case CR_ERR_NUMBER_OF_STENCIL_BITS_IS_UNSUPPORTED: return "NumberOfStencilBitsIsUnsupported";
+        case CR_ERR_CLIP_STACK_OVERFLOW: return "ClipStackOverflow";
+        case CR_ERR_TOO_MANY_NESTED_OPACITY_GROUPS: return "TooManyNestedOpacityGroups";
+        case CR_ERR_TOO_MANY_DASH_INTERVALS: return "TooManyDashIntervals";
+        case CR_ERR_DYNAMIC_STROKE_OPTIONS_INDEX_OUT_OF_BOUNDS: return "DynamicStrokeOptionsIndexOutOfBounds";
+        case CR_ERR_INVALID_ARGUMENT: return "InvalidArgument";
+        case CR_ERR_CUDA: return "Cuda";
+        case CR_ERR_NON_FINITE: return "NonFinite";
+        case CR_ERR_CURVE_STEPS_CAPACITY: return "CurveStepsCapacity";
+        case CR_ERR_CUBIC_TRIANGULATION: return "CubicTriangulation";
+        case CR_ERR_NO_DEVICE: return "NoDevice";
+        case CR_ERR_NOT_RESIZED: return "NotResized";
+        default: return "Unknown";
+    }
+}
+
+// Renderer::new (src/renderer.rs:432-437)
+int cr_renderer_create(const cr_config* config, cr_renderer** out) {
+    if (!config || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (config->winding_counter_bits == 0 || config->clip_nesting_counter_bits + config->winding_counter_bits > 8)
+        return fail(CR_ERR_NUMBER_OF_STENCIL_BITS_IS_UNSUPPORTED, "winding_counter_bits = %u, clip_nesting_counter_bits = %u", config->winding_counter_bits,
+                    config->clip_nesting_counter_bits);
+    if (config->msaa_sample_count != 1 && config->msaa_sample_count != 4) return fail(CR_ERR_INVALID_ARGUMENT, "msaa_sample_count must be 1 or 4");
+    if (config->blending > CR_BLEND_REPLACE || config->cull_mode > CR_CULL_BACK) return fail(CR_ERR_INVALID_ARGUMENT, "bad blending / cull_mode");
+    int n_devices = 0;
+    if (cudaGetDeviceCount(&n_devices) != cudaSuccess || n_devices == 0) {
+        cudaGetLastError();
+        return fail(CR_ERR_NO_DEVICE, "no CUDA device: libcontrast_b200 has no CPU path");
+    }
+    int device = config->device;
+    if (device < 0) CR_CUDA_TRY(cudaGetDevice(&device));
+    if (device >= n_devices) return fail(CR_ERR_NO_DEVICE, "device %d of %d", device, n_devices);
+    std::unique_ptr<cr_renderer> r(new (std::nothrow) cr_renderer());
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "out of host memory");
+    r->config = *config;
+    r->config.device = device;
+    r->device = device;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CR_ERR_CUDA, "cannot select CUDA device %d", device);
+    CR_CUDA_TRY(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
+    r->stream = r->own_stream;
+    cudaMemPool_t pool;
+    CR_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = ~0ull;   // keep freed blocks cached: shape rebuilds every frame must not hit cudaMalloc
+    CR_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    CR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&r->pinned), 64 * sizeof(uint32_t)));
+    for (auto& e : r->ev) CR_CUDA_TRY(cudaEventCreate(&e));
+    *out = r.release();
+    return CR_OK;
+}
+
+void cr_renderer_destroy(cr_renderer* r) {
+    if (!r) return;
+    DeviceGuard guard(r->device);
+    cudaStreamSynchronize(r->stream);
+    cudaStream_t st = r->stream;
+    DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
+                     &r->hull_scratch_b, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->pair_tile, &r->pair_cand, &r->pair_tile_alt,
+                     &r->pair_cand_alt, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->covered_dev};
+    for (DevBuf* d : all) d->release(st);
+    for (auto& d : r->staging) d.release(st);
+    cudaStreamSynchronize(st);
+    for (auto& e : r->ev) if (e) cudaEventDestroy(e);
+    if (r->pinned) cudaFreeHost(r->pinned);
+    if (r->own_stream) cudaStreamDestroy(r->own_stream);
+    delete r;
+}
+
+int cr_renderer_get_config(const cr_renderer* r, cr_config* out) {
+    if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = r->config;
+    return CR_OK;
+}
+
+// Renderer::resize_internal_buffers (src/renderer.rs:892-929) + the caller-owned colour / depth-stencil textures.
+int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    if (width == 0 || height == 0 || width > 32768 || height > 32768) return fail(CR_ERR_INVALID_ARGUMENT, "bad extent %ux%u", width, height);
+    CR_GUARD(r);
+    const size_t samples = (size_t)width * height * r->config.msaa_sample_count;
+    CR_TRY(r->color.reserve(r->stream, samples * 16));
+    CR_TRY(r->stencil.reserve(r->stream, samples));
+    CR_TRY(r->alpha_layers.reserve(r->stream, samples * 4 * std::max<uint32_t>(1, r->config.alpha_layer_count)));
+    CR_TRY(r->covered_dev.reserve(r->stream, 8));
+    r->width = width;
+    r->height = height;
+    r->tiles_x = (width + CR_TILE - 1) / CR_TILE;
+    r->tiles_y = (height + CR_TILE - 1) / CR_TILE;
+    CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * 16, r->stream));
+    CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
+    CR_CUDA_TRY(cudaMemsetAsync(r->alpha_layers.p, 0, samples * 4 * std::max<uint32_t>(1, r->config.alpha_layer_count), r->stream));
+    return CR_OK;
+}
+
+int cr_renderer_set_stream(cr_renderer* r, void* cuda_stream) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    CR_GUARD(r);
+    CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    r->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : r->own_stream;
+    return CR_OK;
+}
+int cr_renderer_synchronize(cr_renderer* r) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    CR_GUARD(r);
+    CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    return CR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- shape building
+int cr_shape_batch_from_paths(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t n_groups, const cr_path_soa* paths,
+                              const uint32_t* shape_path_begin, uint32_t n_shapes, cr_shape_batch* existing, cr_shape_batch** out) {
+    if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    CR_GUARD(r);
+    cr_shape_batch* b = existing;   // consumed: its allocations are reused in place when large enough (Buffer::update, src/renderer.rs:89-95)
+    if (b && b->renderer != r) return fail(CR_ERR_INVALID_ARGUMENT, "existing batch belongs to another renderer");
+    if (!b) {
+        b = new (std::nothrow) cr_shape_batch();
+        if (!b) return fail(CR_ERR_INVALID_ARGUMENT, "out of host memory");
+        b->renderer = r;
+    }
+    const int st = build_batch(r, groups, n_groups, paths, shape_path_begin, n_shapes, b);
+    if (st != CR_OK) {
+        batch_release(b);
+        delete b;
+        return st;
+    }
+    *out = b;
+    return CR_OK;
+}
+void cr_shape_batch_destroy(cr_shape_batch* b) {
+    if (!b) return;
+    DeviceGuard guard(b->renderer->device);
+    batch_release(b);
+    delete b;
+}
+uint32_t cr_shape_batch_size(const cr_shape_batch* b) { return b ? b->n_shapes : 0; }
+cr_shape* cr_shape_batch_get(cr_shape_batch* b, uint32_t index) { return (b && index < b->n_shapes) ? &b->views[index] : nullptr; }
+
+// Shape::from_paths (src/renderer.rs:177-249)
+int cr_shape_from_paths(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t n_groups, const cr_path_soa* paths, cr_shape* existing,
+                        cr_shape** out) {
+    if (!r || !out || !paths) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (existing && !existing->owns_batch) return fail(CR_ERR_INVALID_ARGUMENT, "existing is a borrowed view of a batch");
+    const uint32_t begin[2] = {0, paths->n_paths};
+    cr_shape_batch* old_batch = existing ? existing->batch : nullptr;
+    cr_shape_batch* batch = nullptr;
+    const int st = cr_shape_batch_from_paths(r, groups, n_groups, paths, begin, 1, old_batch, &batch);
+    if (existing) delete existing;   // consumed either way; on failure its batch was released above
+    if (st != CR_OK) return st;
+    cr_shape* s = new (std::nothrow) cr_shape{batch, 0, true};
+    if (!s) { cr_shape_batch_destroy(batch); return fail(CR_ERR_INVALID_ARGUMENT, "out of host memory"); }
+    *out = s;
+    return CR_OK;
+}
+void cr_shape_destroy(cr_shape* s) {
+    if (!s || !s->owns_batch) return;
+    cr_shape_batch_destroy(s->batch);
+    delete s;
+}
+
+// Shape::set_dynamic_stroke_options (src/renderer.rs:360-376)
+int cr_shape_batch_set_dynamic_stroke_options(cr_shape_batch* b, size_t index, const cr_dynamic_stroke_options* options) {
+    if (!b || !options) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    if (index >= b->n_groups) return fail(CR_ERR_DYNAMIC_STROKE_OPTIONS_INDEX_OUT_OF_BOUNDS, "group %zu of %u", index, b->n_groups);
+    Descriptor48 d;
+    CR_TRY(convert_dynamic_stroke_options(*options, d));
+    CR_GUARD(b->renderer);
+    CR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(b->stroke.p) + index * sizeof(d), &d, sizeof(d), cudaMemcpyHostToDevice, b->renderer->stream));
+    CR_CUDA_TRY(cudaStreamSynchronize(b->renderer->stream));   // `d` lives on this stack frame
+    return CR_OK;
+}
+int cr_shape_set_dynamic_stroke_options(cr_shape* s, size_t index, const cr_dynamic_stroke_options* options) {
+    if (!s) return fail(CR_ERR_INVALID_ARGUMENT, "null shape");
+    return cr_shape_batch_set_dynamic_stroke_options(s->batch, index, options);
+}
+
+int cr_shape_get_layout(cr_shape* s, cr_shape_layout* out) {
+    if (!s || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    const cr_shape_batch* b = s->batch;
+    const size_t stride = (size_t)b->n_shapes + 1;
+    const uint32_t* cb = b->cat_begin_host.data();
+    uint64_t acc = 0;
+    for (int c = 0; c < 7; ++c) {
+        acc += (uint64_t)(cb[c * stride + s->index + 1] - cb[c * stride + s->index]) * kCategoryStride[c];
+        out->vertex_offsets[c] = acc;
+    }
+    acc += 8ull * b->hull_count_host[s->index];
+    out->vertex_offsets[7] = acc;
+    acc = 0;
+    for (int k = 0; k < 3; ++k) {
+        acc += 2ull * (cb[(CNT_LINE_IDX + k) * stride + s->index + 1] - cb[(CNT_LINE_IDX + k) * stride + s->index]);
+        out->index_offsets[k] = acc;
+    }
+    out->dynamic_stroke_options_count = b->n_groups;
+    out->proto_hull_points = cb[CNT_PROTO * stride + s->index + 1] - cb[CNT_PROTO * stride + s->index];
+    return CR_OK;
+}
+
+int cr_shape_read_vertex_buffer(cr_shape* s, void* dst, size_t capacity) {
+    if (!s || !dst) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    cr_shape_layout layout;
+    CR_TRY(cr_shape_get_layout(s, &layout));
+    if (capacity < layout.vertex_offsets[7]) return fail(CR_ERR_INVALID_ARGUMENT, "capacity %zu < %llu", capacity, (unsigned long long)layout.vertex_offsets[7]);
+    const cr_shape_batch* b = s->batch;
+    CR_GUARD(b->renderer);
+    cudaStream_t st = b->renderer->stream;
+    const size_t stride = (size_t)b->n_shapes + 1;
+    const uint32_t* cb = b->cat_begin_host.data();
+    char* d = static_cast<char*>(dst);
+    uint64_t at = 0;
+    for (int c = 0; c < 8; ++c) {
+        const uint64_t bytes = layout.vertex_offsets[c] - at;
+        if (bytes) {
+            const char* src = c < 7 ? static_cast<const char*>(b->vtx[c].p) + (size_t)cb[c * stride + s->index] * kCategoryStride[c]
+                                    : static_cast<const char*>(b->hull.p) + (size_t)cb[CNT_PROTO * stride + s->index] * 8;
+            CR_CUDA_TRY(cudaMemcpyAsync(d + at, src, bytes, cudaMemcpyDeviceToHost, st));
+        }
+        at = layout.vertex_offsets[c];
+    }
+    CR_CUDA_TRY(cudaStreamSynchronize(st));
+    return CR_OK;
+}
+
+int cr_shape_read_index_buffer(cr_shape* s, void* dst, size_t capacity) {
+    if (!s || !dst) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    cr_shape_layout layout;
+    CR_TRY(cr_shape_get_layout(s, &layout));
+    if (capacity < layout.index_offsets[2]) return fail(CR_ERR_INVALID_ARGUMENT, "capacity too small");
+    const cr_shape_batch* b = s->batch;
+    CR_GUARD(b->renderer);
+    cudaStream_t st = b->renderer->stream;
+    const size_t stride = (size_t)b->n_shapes + 1;
+    const uint32_t* cb = b->cat_begin_host.data();
+    uint16_t* d = static_cast<uint16_t*>(dst);
+    std::vector<uint32_t> wide;
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t begin = cb[(CNT_LINE_IDX + k) * stride + s->index], n = cb[(CNT_LINE_IDX + k) * stride + s->index + 1] - begin;
+        wide.resize(n);
+        if (n) CR_CUDA_TRY(cudaMemcpyAsync(wide.data(), b->idx[k].as<uint32_t>() + begin, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CR_CUDA_TRY(cudaStreamSynchronize(st));
+        // `start_index as u16` (src/stroke.rs:108,128, src/fill.rs:363): the reference's u16 indices wrap modulo 65536
+        for (uint32_t i = 0; i < n; ++i) *d++ = wide[i] == CR_RESTART ? (uint16_t)0xFFFF : (uint16_t)(wide[i] >> 1);
+    }
+    return CR_OK;
+}
+
+int cr_shape_read_stroke_buffer(cr_shape* s, void* dst, size_t capacity) {
+    if (!s || !dst) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    const cr_shape_batch* b = s->batch;
+    const size_t bytes = (size_t)b->n_groups * sizeof(Descriptor48);
+    if (capacity < bytes) return fail(CR_ERR_INVALID_ARGUMENT, "capacity too small");
+    CR_GUARD(b->renderer);
+    if (bytes) CR_CUDA_TRY(cudaMemcpyAsync(dst, b->stroke.p, bytes, cudaMemcpyDeviceToHost, b->renderer->stream));
+    CR_CUDA_TRY(cudaStreamSynchronize(b->renderer->stream));
+    return CR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- render pass
+int cr_pass_begin(cr_renderer* r, uint32_t clear_color, uint32_t clear_stencil, cr_pass** out) {
+    if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
+    CR_GUARD(r);
+    const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
+    if (clear_color) CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * 16, r->stream));
+    if (clear_stencil) CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
+    cr_pass* p = new (std::nothrow) cr_pass();
+    if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "out of host memory");
+    p->renderer = r;
+    *out = p;
+    return CR_OK;
+}
+
+int cr_pass_set_instances(cr_pass* p, const float* transforms, const float* colors, uint32_t count, uint32_t memory_space) {
+    if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "null pass");
+    if (count && !transforms) return fail(CR_ERR_INVALID_ARGUMENT, "null transforms");
+    if (memory_space > CR_MEM_DEVICE) return fail(CR_ERR_INVALID_ARGUMENT, "bad memory_space");
+    p->instance_sets.push_back(InstanceSet{transforms, colors, count, memory_space, p->instance_total});
+    p->instance_total += count;
+    return CR_OK;
+}
+
+// Renderer::set_clip_depth (src/renderer.rs:932-938)
+int cr_pass_set_clip_depth(cr_pass* p, uint32_t clip_depth) {
+    if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "null pass");
+    if (clip_depth >= (1u << p->renderer->config.clip_nesting_counter_bits)) return fail(CR_ERR_CLIP_STACK_OVERFLOW, "clip depth %u", clip_depth);
+    p->clip_depth = clip_depth;
+    return CR_OK;
+}
+// Renderer::save_alpha_context (src/renderer.rs:941-976)
+int cr_pass_save_alpha_context(cr_pass* p, uint32_t alpha_layer) {
+    if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "null pass");
+    if (alpha_layer >= p->renderer->config.alpha_layer_count) return fail(CR_ERR_TOO_MANY_NESTED_OPACITY_GROUPS, "alpha layer %u", alpha_layer);
+    p->save_layer = alpha_layer;
+    return CR_OK;
+}
+// Renderer::restore_alpha_context (src/renderer.rs:979-985)
+int cr_pass_restore_alpha_context(cr_pass* p, uint32_t alpha_layer) {
+    if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "null pass");
+    if (alpha_layer >= p->renderer->config.alpha_layer_count) return fail(CR_ERR_TOO_MANY_NESTED_OPACITY_GROUPS, "alpha layer %u", alpha_layer);
+    p->restore_layer = alpha_layer;
+    return CR_OK;
+}
+
+static int record(cr_pass* p, cr_shape_batch* b, uint32_t shape, uint32_t instance_begin, uint32_t instance_end, uint32_t op) {
+    if (op > CR_OP_RESTORE_ALPHA_CONTEXT) return fail(CR_ERR_INVALID_ARGUMENT, "bad render operation %u", op);
+    if (b->renderer != p->renderer) return fail(CR_ERR_INVALID_ARGUMENT, "shape belongs to another renderer");
+    if (shape >= b->n_shapes) return fail(CR_ERR_INVALID_ARGUMENT, "shape index %u of %u", shape, b->n_shapes);
+    if (p->instance_sets.empty()) return fail(CR_ERR_INVALID_ARGUMENT, "cr_pass_set_instances has not been called");
+    const InstanceSet& is = p->instance_sets.back();
+    if (instance_begin > instance_end || instance_end > is.count) return fail(CR_ERR_INVALID_ARGUMENT, "instances [%u, %u) of %u", instance_begin, instance_end, is.count);
+    const bool needs_color = op == CR_OP_COLOR || op == CR_OP_SCALE_ALPHA_CONTEXT || op == CR_OP_RESTORE_ALPHA_CONTEXT;
+    if (needs_color && !is.colors) return fail(CR_ERR_INVALID_ARGUMENT, "this operation reads the instance colour slot, which is not bound");
+    if ((op == CR_OP_SAVE_ALPHA_CONTEXT || op == CR_OP_RESTORE_ALPHA_CONTEXT) && p->renderer->config.alpha_layer_count == 0)
+        return fail(CR_ERR_TOO_MANY_NESTED_OPACITY_GROUPS, "alpha_layer_count is 0");
+    if (instance_begin == instance_end) return CR_OK;
+    uint32_t bi = 0;
+    for (; bi < p->batches.size(); ++bi) if (p->batches[bi] == b) break;
+    if (bi == p->batches.size()) p->batches.push_back(b);
+    DeviceCommand c{};
+    c.batch = bi;
+    c.shape = shape;
+    c.instance_begin = is.base + instance_begin;
+    c.instance_end = is.base + instance_end;
+    c.operation = op;
+    c.ref = p->clip_depth << p->renderer->config.winding_counter_bits;
+    c.save_layer = p->save_layer;
+    c.restore_layer = p->restore_layer;
+    p->commands.push_back(c);
+    return CR_OK;
+}
+
+// Shape::render (src/renderer.rs:267-355)
+int cr_shape_render(cr_pass* p, cr_shape* s, uint32_t instance_begin, uint32_t instance_end, uint32_t op) {
+    if (!p || !s) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    return record(p, s->batch, s->index, instance_begin, instance_end, op);
+}
+int cr_pass_render_batch(cr_pass* p, cr_shape_batch* b, const cr_draw_command* commands, size_t count) {
+    if (!p || !b || (count && !commands)) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    p->commands.reserve(p->commands.size() + count);
+    for (size_t i = 0; i < count; ++i)
+        CR_TRY(record(p, b, commands[i].shape_index, commands[i].instance_begin, commands[i].instance_end, commands[i].render_operation));
+    return CR_OK;
+}
+
+static int submit(cr_pass* p) {
+    cr_renderer* r = p->renderer;
+    cudaStream_t st = r->stream;
+    const uint32_t n_cmds = (uint32_t)p->commands.size();
+    if (n_cmds == 0) return CR_OK;
+    if (r->config.msaa_sample_count != 1) return fail(CR_ERR_INVALID_ARGUMENT, "the tile rasteriser currently implements msaa_sample_count = 1 only");
+    // ---- instance slots
+    const float* transforms = nullptr;
+    const float* colors = nullptr;
+    if (p->instance_sets.size() == 1 && p->instance_sets[0].space == CR_MEM_DEVICE) {
+        transforms = p->instance_sets[0].transforms;
+        colors = p->instance_sets[0].colors;
+    } else {
+        CR_TRY(r->inst_transforms.reserve(st, (size_t)p->instance_total * 64));
+        CR_TRY(r->inst_colors.reserve(st, (size_t)p->instance_total * 16));
+        bool any_color = false;
+        for (const InstanceSet& is : p->instance_sets) {
+            if (!is.count) continue;
+            const cudaMemcpyKind kind = is.space == CR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+            CR_CUDA_TRY(cudaMemcpyAsync(r->inst_transforms.as<float>() + 16 * (size_t)is.base, is.transforms, (size_t)is.count * 64, kind, st));
+            if (is.colors) {
+                CR_CUDA_TRY(cudaMemcpyAsync(r->inst_colors.as<float>() + 4 * (size_t)is.base, is.colors, (size_t)is.count * 16, kind, st));
+                any_color = true;
+            }
+        }
+        transforms = r->inst_transforms.as<float>();
+        colors = any_color ? r->inst_colors.as<float>() : nullptr;
+    }
+    // ---- scene description
+    std::vector<DeviceBatch> host_batches(p->batches.size());
+    CR_TRY(r->batches_dev.reserve(st, host_batches.size() * sizeof(DeviceBatch)));
+    for (size_t i = 0; i < p->batches.size(); ++i)
+        CR_CUDA_TRY(cudaMemcpyAsync(r->batches_dev.as<DeviceBatch>() + i, p->batches[i]->desc_dev.p, sizeof(DeviceBatch), cudaMemcpyDeviceToDevice, st));
+    CR_TRY(r->cmds_dev.reserve(st, (size_t)n_cmds * sizeof(DeviceCommand)));
+    CR_CUDA_TRY(cudaMemcpyAsync(r->cmds_dev.p, p->commands.data(), (size_t)n_cmds * sizeof(DeviceCommand), cudaMemcpyHostToDevice, st));
+    // candidates per command are known on the host (slice tables are mirrored), so the candidate scan needs no device pass
+    std::vector<uint32_t> cand_begin(n_cmds + 1);
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < n_cmds; ++c) {
+        cand_begin[c] = (uint32_t)total;
+        const DeviceCommand& cmd = p->commands[c];
+        const cr_shape_batch* b = p->batches[cmd.batch];
+        const uint64_t n_inst = cmd.instance_end - cmd.instance_begin;
+        uint64_t slots = 0;
+        if (cmd.operation == CR_OP_STENCIL) {
+            for (int cat = 0; cat < 7; ++cat)
+                if (cat >= 2 || b->n_groups > 0) slots += slots_of_host(b, cmd.shape, cat);
+        } else {
+            slots = slots_of_host(b, cmd.shape, 7);
+        }
+        total += slots * n_inst;
+        if (total >= 0xFFFFFFFFull) return fail(CR_ERR_INVALID_ARGUMENT, "more than 2^32 candidate primitives in one pass; submit in several passes");
+    }
+    cand_begin[n_cmds] = (uint32_t)total;
+    const uint32_t n_cands = (uint32_t)total;
+    if (n_cands == 0) return CR_OK;
+    CR_TRY(r->cmd_cands.reserve(st, (size_t)(n_cmds + 1) * 4));
+    CR_CUDA_TRY(cudaMemcpyAsync(r->cmd_cands.p, cand_begin.data(), (size_t)(n_cmds + 1) * 4, cudaMemcpyHostToDevice, st));
+
+    RasterScene sc{};
+    sc.batches = r->batches_dev.as<DeviceBatch>();
+    sc.commands = r->cmds_dev.as<DeviceCommand>();
+    sc.cmd_cand_begin = r->cmd_cands.as<uint32_t>();
+    sc.n_commands = n_cmds;
+    sc.transforms = transforms;
+    sc.colors = colors;
+    RasterTarget tg{};
+    tg.color = r->color.as<float4>();
+    tg.stencil = r->stencil.as<uint8_t>();
+    tg.alpha_layers = r->alpha_layers.as<float>();
+    tg.width = r->width; tg.height = r->height; tg.tiles_x = r->tiles_x; tg.tiles_y = r->tiles_y;
+    tg.wmask = (1u << r->config.winding_counter_bits) - 1u;
+    tg.cmask = ((1u << r->config.clip_nesting_counter_bits) - 1u) << r->config.winding_counter_bits;
+    tg.blending = r->config.blending;
+    tg.cull_mode = r->config.cull_mode;
+
+    // ---- bin: count, scan, emit, sort by tile (stable => draw order survives inside every tile)
+    if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[2], st));
+    CR_TRY(r->cand_tiles.reserve(st, (size_t)(n_cands + 1) * 4));
+    CR_TRY(r->scan_scratch.reserve(st, (size_t)cr_scan_scratch_words(n_cands + 1, 1) * 4));
+    CR_TRY(cr_raster_bin_count(st, sc, tg, n_cands, r->cand_tiles.as<uint32_t>()));
+    CR_TRY(cr_scan_exclusive(st, r->cand_tiles.as<uint32_t>(), n_cands + 1, 1, r->scan_scratch.as<uint32_t>()));
+    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[0], r->cand_tiles.as<uint32_t>() + n_cands, 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaStreamSynchronize(st));
+    const uint32_t n_pairs = r->pinned[0];
+    const uint32_t n_tiles = r->tiles_x * r->tiles_y;
+    r->stats.primitives = n_cands;
+    r->stats.tile_pairs = n_pairs;
+    CR_CUDA_TRY(cudaMemsetAsync(r->covered_dev.p, 0, 8, st));
+    if (n_pairs) {
+        CR_TRY(r->pair_tile.reserve(st, (size_t)n_pairs * 4));
+        CR_TRY(r->pair_cand.reserve(st, (size_t)n_pairs * 4));
+        CR_TRY(r->pair_tile_alt.reserve(st, (size_t)n_pairs * 4));
+        CR_TRY(r->pair_cand_alt.reserve(st, (size_t)n_pairs * 4));
+        CR_TRY(r->radix_scratch.reserve(st, (size_t)cr_radix_scratch_words(n_pairs) * 4));
+        CR_TRY(r->tile_begin.reserve(st, (size_t)(n_tiles + 1) * 4));
+        CR_TRY(cr_raster_bin_emit(st, sc, tg, n_cands, r->cand_tiles.as<uint32_t>(), r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>()));
+        uint32_t key_bits = 1;
+        while ((1u << key_bits) < n_tiles) ++key_bits;
+        uint32_t *sorted_tile = nullptr, *sorted_cand = nullptr;
+        CR_TRY(cr_radix_sort_pairs(st, r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>(), r->pair_tile_alt.as<uint32_t>(), r->pair_cand_alt.as<uint32_t>(),
+                                   n_pairs, key_bits, r->radix_scratch.as<uint32_t>(), &sorted_tile, &sorted_cand));
+        CR_TRY(cr_lower_bounds(st, sorted_tile, n_pairs, r->tile_begin.as<uint32_t>(), n_tiles + 1));
+        if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[3], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[4], st)); }
+        CR_TRY(cr_raster_tiles(st, sc, tg, r->tile_begin.as<uint32_t>(), sorted_cand, r->covered_dev.as<unsigned long long>()));
+        if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }
+    }
+    return CR_OK;
+}
+
+// queue.submit(encoder.finish()) (examples/showcase/main.rs:252)
+int cr_pass_submit(cr_pass* p) {
+    if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "null pass");
+    int st;
+    {
+        DeviceGuard guard(p->renderer->device);
+        st = guard.ok ? submit(p) : fail(CR_ERR_CUDA, "cannot select CUDA device");
+    }
+    delete p;
+    return st;
+}
+
+void cr_pass_abort(cr_pass* p) { delete p; }
+
+// ------------------------------------------------------------------------------------------------- read-back
+static int read_back(cr_renderer* r, const void* src, size_t bytes, void* dst, size_t capacity) {
+    if (!r || !dst) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
+    if (capacity < bytes) return fail(CR_ERR_INVALID_ARGUMENT, "capacity %zu < %zu", capacity, bytes);
+    CR_GUARD(r);
+    CR_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, r->stream));
+    CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    return CR_OK;
+}
+int cr_renderer_read_color(cr_renderer* r, float* dst, size_t capacity_bytes) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    return read_back(r, r->color.p, (size_t)r->width * r->height * r->config.msaa_sample_count * 16, dst, capacity_bytes);
+}
+int cr_renderer_read_stencil(cr_renderer* r, uint8_t* dst, size_t capacity_bytes) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    return read_back(r, r->stencil.p, (size_t)r->width * r->height * r->config.msaa_sample_count, dst, capacity_bytes);
+}
+int cr_renderer_read_alpha_layer(cr_renderer* r, uint32_t layer, float* dst, size_t capacity_bytes) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    if (layer >= r->config.alpha_layer_count) return fail(CR_ERR_TOO_MANY_NESTED_OPACITY_GROUPS, "alpha layer %u", layer);
+    const size_t layer_bytes = (size_t)r->width * r->height * r->config.msaa_sample_count * 4;
+    return read_back(r, static_cast<const char*>(r->alpha_layers.p) + layer * layer_bytes, layer_bytes, dst, capacity_bytes);
+}
+int cr_renderer_get_attachments(cr_renderer* r, void** color_dev, void** stencil_dev) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
+    if (color_dev) *color_dev = r->color.p;
+    if (stencil_dev) *stencil_dev = r->stencil.p;
+    return CR_OK;
+}
+
+int cr_renderer_enable_timing(cr_renderer* r, uint32_t enabled) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    r->timing = enabled != 0;
+    r->ev_valid[0] = r->ev_valid[1] = r->ev_valid[2] = false;
+    return CR_OK;
+}
+int cr_renderer_get_stats(cr_renderer* r, cr_stats* out) {
+    if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    CR_GUARD(r);
+    CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->covered_dev.p) {
+        unsigned long long covered = 0;
+        CR_CUDA_TRY(cudaMemcpy(&covered, r->covered_dev.p, 8, cudaMemcpyDeviceToHost));
+        r->stats.covered_samples = covered;
+    }
+    r->stats.kernel_launches = g_cr_kernel_launches;
+    float ms = 0.0f;
+    r->stats.last_tess_ms = (r->ev_valid[0] && cudaEventElapsedTime(&ms, r->ev[0], r->ev[1]) == cudaSuccess) ? ms : 0.0f;
+    r->stats.last_bin_ms = (r->ev_valid[1] && cudaEventElapsedTime(&ms, r->ev[2], r->ev[3]) == cudaSuccess) ? ms : 0.0f;
+    r->stats.last_raster_ms = (r->ev_valid[2] && cudaEventElapsedTime(&ms, r->ev[4], r->ev[5]) == cudaSuccess) ? ms : 0.0f;
+    cudaGetLastError();
+    *out = r->stats;
+    return CR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+"""Seeded synthetic scenes for the configurations named in BASELINE.json, built directly as `PathSoA`
+with vectorised numpy so that 10^5..10^6 paths are generated in well under a second.
+
+Every generator is a pure function of its arguments (PCG64 seeded with 0xC0FFEE + config index by default), so the
+CPU oracle and the CUDA path — and the GPU box and this container — see bit-identical inputs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+from .path import Cap, DashInterval, DynamicStrokeOptions, Join, PathSoA
+
+SEED0 = 0xC0FFEE
+
+# MODEL UNITS. The reference's tolerances are absolute (ERROR_MARGIN = 1e-4, src/error.rs:19, compared against signed
+# AREAS in src/fill.rs:127,153 and src/convex_hull.rs:16), so it is only usable with path coordinates of order 1-10 —
+# its own demo draws 2.7-unit glyphs and a 5.8-unit rectangle (examples/showcase/main.rs:59-94) and leaves the
+# mapping to pixels to the instance matrix. With raw pixel coordinates (areas ~1e4, f32 ulp ~1e-3) the enclosing-
+# triangle test of fill.rs:151-156 fails by rounding and the assert at fill.rs:174 panics. The generators therefore
+# emit model units and a scene-wide `pixels_per_unit` that goes into the instance transform; scenes with cubic fills
+# additionally keep every Shape in LOCAL coordinates around its own origin (areas are differences of products of
+# absolute coordinates) and place it with a per-instance translation, as the reference's demo does.
+
+
+@dataclass
+class Scene:
+    paths: PathSoA
+    shape_path_begin: np.ndarray          # [n_shapes + 1] u32
+    dynamic_stroke_options: List[DynamicStrokeOptions]
+    width: int
+    height: int
+    colors: Optional[np.ndarray] = None   # [n_shapes, 4] f32 straight-alpha rgba (one instance per shape)
+    name: str = ""
+    pixels_per_unit: float = 1.0          # path coordinates are in model units (see MODEL UNITS below)
+    origins: Optional[np.ndarray] = None  # [n_shapes, 2] model-space position of each shape's local origin (None: all zero)
+
+    def transform(self) -> np.ndarray:
+        """The instance mat4 (16 floats, column vectors) that maps model units to this scene's framebuffer."""
+        from .renderer import orthographic_transform
+        return orthographic_transform(self.width / self.pixels_per_unit, self.height / self.pixels_per_unit)
+
+    def transforms(self) -> np.ndarray:
+        """[n_shapes, 16]: instance i = scene transform * translate(origins[i]) (column vectors, src/shaders.wgsl:13-27)."""
+        m = np.tile(self.transform(), (self.n_shapes, 1))
+        if self.origins is not None:
+            o = np.asarray(self.origins, np.float64)
+            m[:, 12] = (m[:, 0].astype(np.float64) * o[:, 0] + m[:, 12]).astype(np.float32)
+            m[:, 13] = (m[:, 5].astype(np.float64) * o[:, 1] + m[:, 13]).astype(np.float32)
+        return np.ascontiguousarray(m, np.float32)
+
+    @property
+    def n_shapes(self) -> int:
+        return len(self.shape_path_begin) - 1
+
+
+def _assemble(start: np.ndarray, seg_counts: np.ndarray, seg_types: np.ndarray, payload: List[np.ndarray], stroke: np.ndarray) -> PathSoA:
+    """payload[t]: rows (in global segment order) of the segments whose type is t."""
+    n = len(seg_counts)
+    segment_begin = np.zeros(n + 1, np.uint32)
+    np.cumsum(seg_counts, out=segment_begin[1:])
+    seg_path = np.repeat(np.arange(n), seg_counts)
+    type_begin = np.zeros((5, n + 1), np.uint32)
+    for t in range(5):
+        per_path = np.bincount(seg_path[seg_types == t], minlength=n)
+        np.cumsum(per_path, out=type_begin[t, 1:])
+    segments = [np.ascontiguousarray(payload[t], dtype=np.float32).reshape(-1, _abi.SEGMENT_FLOATS[t]) for t in range(5)]
+    # SafeFloat canonicalisation of the inputs (src/safe_float.rs:46-49): -0.0 -> +0.0
+    segments = [s + np.float32(0.0) for s in segments]
+    return PathSoA(np.ascontiguousarray(start, np.float32) + np.float32(0.0), segment_begin, np.ascontiguousarray(seg_types, np.uint8), type_begin, segments,
+                   stroke)
+
+
+def _stroke_records(n: int, width, offset=0.0, miter_clip=4.0, closed=True, group=0, angle_step: Optional[float] = 0.1, steps: int = 0) -> np.ndarray:
+    rec = np.zeros(n, PathSoA.STROKE_DTYPE)
+    rec["width"] = width
+    rec["offset"] = offset
+    rec["miter_clip"] = miter_clip
+    flags = _abi.CR_STROKE_FLAG_STROKED | (_abi.CR_STROKE_FLAG_CLOSED if closed else 0)
+    if angle_step is not None:
+        flags |= _abi.CR_STROKE_FLAG_UNIFORM_TANGENT_ANGLE
+        rec["approx"] = np.float32(angle_step).view(np.uint32)
+    else:
+        rec["approx"] = steps
+    rec["flags"] = flags
+    rec["group"] = group
+    return rec
+
+
+def _blob_geometry(rng: np.random.Generator, centre: np.ndarray, radius: np.ndarray, seg_counts: np.ndarray):
+    """Star-convex closed outlines: anchors at increasing angles around `centre`. Returns per-segment (a, b, na, nb):
+    endpoints and outward unit normals at the endpoints, in global segment order, plus the path starts."""
+    n = len(seg_counts)
+    total = int(seg_counts.sum())
+    seg_path = np.repeat(np.arange(n), seg_counts)
+    first = np.zeros(n + 1, np.int64)
+    np.cumsum(seg_counts, out=first[1:])
+    local = np.arange(total) - first[seg_path]
+    k = seg_counts[seg_path].astype(np.float64)
+    phase = rng.uniform(0.0, 2.0 * np.pi, n)[seg_path]
+    jitter = rng.uniform(-0.25, 0.25, total)
+    ang = phase + (local + jitter) * (2.0 * np.pi / k)
+    rad = radius[seg_path] * rng.uniform(0.55, 1.0, total)
+    pts = centre[seg_path] + np.stack([np.cos(ang), np.sin(ang)], 1) * rad[:, None]
+    nxt = np.where(local + 1 == seg_counts[seg_path], first[seg_path], np.arange(total) + 1)
+    a, b = pts, pts[nxt]
+    out_a = np.stack([np.cos(ang), np.sin(ang)], 1)
+    out_b = out_a[nxt]
+    return a, b, out_a, out_b, pts[first[:-1]], seg_path
+
+
+def _shape_layout(rng: np.random.Generator, n_paths: int, paths_per_shape: int, extent, ppu: float, spread: np.ndarray):
+    """Shapes of `paths_per_shape` consecutive paths; returns (shape_path_begin, shape origins in model units, path
+    centres in the LOCAL coordinates of their shape: zero for single-path shapes, else within +-1.5 * spread)."""
+    begin = np.arange(0, n_paths + 1, paths_per_shape, dtype=np.uint32)
+    if begin[-1] != n_paths:
+        begin = np.append(begin, np.uint32(n_paths))
+    n_shapes = len(begin) - 1
+    origins = np.stack([rng.uniform(0, extent[0], n_shapes), rng.uniform(0, extent[1], n_shapes)], 1) / ppu
+    local = rng.uniform(-1.5, 1.5, (n_paths, 2)) * np.asarray(spread, np.float64).reshape(-1, 1)
+    if paths_per_shape == 1:
+        local[:] = 0.0
+    return begin, origins, local
+
+
+# ------------------------------------------------------------------------------------------------------ config 1
+def _rotate(v: np.ndarray, angle: np.ndarray) -> np.ndarray:
+    c, s = np.cos(angle)[:, None], np.sin(angle)[:, None]
+    return np.concatenate([v[:, :1] * c - v[:, 1:] * s, v[:, :1] * s + v[:, 1:] * c], 1)
+
+
+def closed_cubic_strokes(n_paths: int = 1000, seed: int = SEED0 + 1, extent: Tuple[int, int] = (1920, 1080), paths_per_shape: int = 1,
+                         pixels_per_unit: float = 40.0) -> Scene:
+    """BASELINE config 1: closed paths of 4 integral cubics, width U[1,8] px, miter clip 4, UniformTangentAngle(0.1).
+    Handles are rotated off the blob tangent by U[-0.7, 0.7] rad, so most anchors are corners (miter joins)."""
+    rng = np.random.default_rng(seed)
+    ppu = float(pixels_per_unit)
+    seg_counts = np.full(n_paths, 4, np.int64)
+    radius = rng.uniform(20.0, 200.0, n_paths) / ppu
+    begin, origins, centre = _shape_layout(rng, n_paths, paths_per_shape, extent, ppu, spread=radius)
+    a, b, na, nb, start, _ = _blob_geometry(rng, centre, radius, seg_counts)
+    chord = b - a
+    tang = _rotate(np.stack([-na[:, 1], na[:, 0]], 1), rng.uniform(-0.7, 0.7, len(a)))   # counter-clockwise tangent at a, perturbed
+    tang_b = _rotate(np.stack([-nb[:, 1], nb[:, 0]], 1), rng.uniform(-0.7, 0.7, len(a)))
+    clen = np.linalg.norm(chord, axis=1, keepdims=True)
+    h0 = rng.uniform(0.2, 0.6, (len(a), 1)) * clen
+    h1 = rng.uniform(0.2, 0.6, (len(a), 1)) * clen
+    cubic = np.concatenate([a + tang * h0, b - tang_b * h1, b], 1)
+    types = np.full(len(a), _abi.CR_SEG_INTEGRAL_CUBIC, np.uint8)
+    payload = [np.zeros((0, 2)), np.zeros((0, 4)), cubic, np.zeros((0, 5)), np.zeros((0, 10))]
+    stroke = _stroke_records(n_paths, (rng.uniform(1.0, 8.0, n_paths) / ppu).astype(np.float32))
+    soa = _assemble(start, seg_counts, types, payload, stroke)
+    n_shapes = len(begin) - 1
+    colors = np.concatenate([rng.uniform(0, 1, (n_shapes, 3)), np.ones((n_shapes, 1))], 1).astype(np.float32)
+    return Scene(soa, begin, [DynamicStrokeOptions.Solid(Join.Miter, Cap.Butt, Cap.Butt)], extent[0], extent[1], colors, "closed_cubic_strokes", ppu,
+                 origins)
+
+
+def _det3(a, b, c):
+    return (a[:, 0] * (b[:, 1] * c[:, 2] - b[:, 2] * c[:, 1]) - a[:, 1] * (b[:, 0] * c[:, 2] - b[:, 2] * c[:, 0])
+            + a[:, 2] * (b[:, 0] * c[:, 1] - b[:, 1] * c[:, 0]))
+
+
+def cubic_fill_is_safe(points: np.ndarray, weights: Optional[np.ndarray] = None) -> np.ndarray:
+    """Which cubic segments the reference's FillBuilder can digest (float64 screening of the generator's output).
+
+    points: [n, 4, 2] control points including the start; weights: [n, 4] or None (integral).
+    The reference panics (assert_eq!/assert_ne! at src/fill.rs:174,178) or mis-triangulates when
+      * the control quadrilateral is (nearly) degenerate, so the signs of the four sub-triangle areas are noise;
+      * a loop's double point has exactly one parameter in (0, 1) that lies close to 0 or 1: split_curve_at!
+        (src/fill.rs:206-216,232-241) then produces a sliver quadrilateral with noise signs;
+      * a RATIONAL cubic has a concave control quadrilateral: the areas are computed from weighted points
+        (the `.signum()` normalisation is commented out at src/fill.rs:143), so the enclosing-triangle identity
+        of src/fill.rs:151-156 no longer holds.
+    Generators demote such segments to lower-order ones; parity tests additionally check every scene with the oracle."""
+    n = len(points)
+    w = np.ones((n, 4)) if weights is None else np.asarray(weights, np.float64)
+    h = np.concatenate([w[:, :, None], points * w[:, :, None]], 2)          # (w, wx, wy)
+    pb = [h[:, 0], -3 * h[:, 0] + 3 * h[:, 1], 3 * h[:, 0] - 6 * h[:, 1] + 3 * h[:, 2], -h[:, 0] + 3 * h[:, 1] - 3 * h[:, 2] + h[:, 3]]
+    d = np.stack([_det3(pb[1], pb[2], pb[3]), -_det3(pb[0], pb[2], pb[3]), _det3(pb[0], pb[1], pb[3]), -_det3(pb[0], pb[1], pb[2])], 1)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-300)
+    integral = np.abs(d[:, 0]) <= 1e-4
+    with np.errstate(all="ignore"):
+        disc_i = 3 * d[:, 2] ** 2 - 4 * d[:, 1] * d[:, 3]
+        sq = np.sqrt(np.maximum(-disc_i, 0))
+        ri = np.stack([(d[:, 2] + sq) / (2 * d[:, 1]), (d[:, 2] - sq) / (2 * d[:, 1])], 1)
+        c0, c1, c2 = d[:, 1] * d[:, 3] - d[:, 2] ** 2, d[:, 1] * d[:, 2] - d[:, 0] * d[:, 3], d[:, 0] * d[:, 2] - d[:, 1] ** 2
+        disc_r = c1 * c1 - 4 * c2 * c0
+        sr = np.sqrt(np.maximum(disc_r, 0))
+        rr = np.stack([(-c1 - sr) / (2 * c2), (-c1 + sr) / (2 * c2)], 1)
+    loop = np.where(integral, (disc_i < 0) & (np.abs(d[:, 1]) > 1e-4), disc_r > 0)
+    roots = np.where(integral[:, None], ri, rr)
+    roots = np.where(np.isfinite(roots), roots, 1e9)
+    near = ((np.abs(roots) < 0.2) | (np.abs(roots - 1) < 0.2)).any(1)
+    # rational loops also carry ONE real inflection point (root of -d3 + 3 d2 t - 3 d1 t^2 + d0 t^3); when it is the only
+    # root in (0, 1) the reference splits there (find_double_point_issue, src/fill.rs:14-32) and the split
+    # quadrilaterals have a zero-area sub-triangle by construction => noise signs => panic
+    bad_inflection = np.zeros(n, bool)
+    if weights is not None:
+        for i in np.nonzero(loop & ~integral)[0]:
+            r = np.roots([d[i, 0], -3 * d[i, 1], 3 * d[i, 2], -d[i, 3]])
+            r = r[np.abs(r.imag) < 1e-9].real
+            bad_inflection[i] = bool(((r > -0.05) & (r < 1.05)).any())
+    bad_loop = loop & (near | bad_inflection)
+    # nearly singular classification (cusp-like or almost-quadratic) is where f32 and f64 disagree: stay clear of it
+    fragile = np.where(integral, np.abs(disc_i) < 1e-3, np.abs(disc_r) < 1e-3) | (~integral & (np.abs(d[:, 0]) < 1e-3))
+    u = np.concatenate([np.ones((n, 4, 1)), points], 2)
+    ua = np.stack([_det3(u[:, 1], u[:, 2], u[:, 3]), _det3(u[:, 0], u[:, 2], u[:, 3]), _det3(u[:, 0], u[:, 1], u[:, 3]), _det3(u[:, 0], u[:, 1], u[:, 2])], 1)
+    wa = ua * np.stack([w[:, 1] * w[:, 2] * w[:, 3], w[:, 0] * w[:, 2] * w[:, 3], w[:, 0] * w[:, 1] * w[:, 3], w[:, 0] * w[:, 1] * w[:, 2]], 1)
+    degenerate = np.abs(wa).min(1) < 1e-2
+    concave = 2 * np.abs(ua).max(1) > 0.97 * np.abs(ua).sum(1)
+    bad = bad_loop | fragile | degenerate
+    if weights is not None:
+        bad |= concave
+    return ~bad
+
+
+# ------------------------------------------------------------------------------------------------------ config 2
+def mixed_fills(n_paths: int = 10000, seed: int = SEED0 + 2, extent: Tuple[int, int] = (1920, 1080), size: Tuple[float, float] = (10.0, 150.0),
+                seg_range: Tuple[int, int] = (3, 12), types=(0, 1, 2), paths_per_shape: int = 1, rational: bool = False,
+                pixels_per_unit: float = 40.0) -> Scene:
+    """BASELINE config 2: filled closed paths of 3..12 segments drawn from {line, integral quadratic, integral cubic}
+    (or, with rational=True, also the rational kinds with weights U[0.5, 2])."""
+    rng = np.random.default_rng(seed)
+    ppu = float(pixels_per_unit)
+    seg_counts = rng.integers(seg_range[0], seg_range[1] + 1, n_paths).astype(np.int64)
+    radius = rng.uniform(size[0], size[1], n_paths) / ppu
+    begin, origins, centre = _shape_layout(rng, n_paths, paths_per_shape, extent, ppu, spread=radius)
+    a, b, na, nb, start, _ = _blob_geometry(rng, centre, radius, seg_counts)
+    total = len(a)
+    kinds = np.asarray(types if not rational else (0, 1, 2, 3, 4), np.uint8)
+    seg_types = kinds[rng.integers(0, len(kinds), total)]
+    chord = b - a
+    clen = np.linalg.norm(chord, axis=1, keepdims=True)
+    mid = 0.5 * (a + b)
+    bulge = rng.uniform(-0.15, 0.45, (total, 1)) * clen
+    nmid = na + nb
+    nmid /= np.maximum(np.linalg.norm(nmid, axis=1, keepdims=True), 1e-9)
+    quad_c = mid + nmid * bulge
+    tang = np.stack([-na[:, 1], na[:, 0]], 1)
+    tang_b = np.stack([-nb[:, 1], nb[:, 0]], 1)
+    h0 = rng.uniform(0.15, 0.7, (total, 1)) * clen
+    h1 = rng.uniform(0.15, 0.7, (total, 1)) * clen
+    s0 = rng.uniform(-0.3, 0.5, (total, 1)) * clen
+    s1 = rng.uniform(-0.3, 0.5, (total, 1)) * clen
+    c1 = a + tang * h0 + na * s0
+    c2 = b - tang_b * h1 + nb * s1
+    wq = rng.uniform(0.5, 2.0, (total, 1))
+    wc = rng.uniform(0.5, 2.0, (total, 4))
+    # cubics the reference's fill builder cannot digest become quadratics of the same kind (see cubic_fill_is_safe)
+    quad_pts = np.stack([a, c1, c2, b], 1)
+    ic, rc = seg_types == _abi.CR_SEG_INTEGRAL_CUBIC, seg_types == _abi.CR_SEG_RATIONAL_CUBIC
+    seg_types = np.where(ic & ~cubic_fill_is_safe(quad_pts), _abi.CR_SEG_INTEGRAL_QUADRATIC, seg_types)
+    seg_types = np.where(rc & ~cubic_fill_is_safe(quad_pts, wc), _abi.CR_SEG_RATIONAL_QUADRATIC, seg_types).astype(np.uint8)
+    sel = [seg_types == t for t in range(5)]
+    payload = [b[sel[0]], np.concatenate([quad_c, b], 1)[sel[1]], np.concatenate([c1, c2, b], 1)[sel[2]], np.concatenate([wq, quad_c, b], 1)[sel[3]],
+               np.concatenate([wc, c1, c2, b], 1)[sel[4]]]
+    stroke = np.zeros(n_paths, PathSoA.STROKE_DTYPE)
+    soa = _assemble(start, seg_counts, seg_types, payload, stroke)
+    n_shapes = len(begin) - 1
+    colors = np.concatenate([rng.uniform(0, 1, (n_shapes, 3)), np.ones((n_shapes, 1))], 1).astype(np.float32)
+    return Scene(soa, begin, [], extent[0], extent[1], colors, "mixed_fills", ppu, origins)
+
+
+# ------------------------------------------------------------------------------------------------------ config 3
+def glyph_like_fills(n_glyphs: int = 100000, seed: int = SEED0 + 3, extent: Tuple[int, int] = (3840, 2160), em: float = 20.0,
+                     glyphs_per_shape: int = 400, pixels_per_unit: float = 10.0) -> Scene:
+    """BASELINE config 3 stand-in until the text front-end lands: glyph-sized closed contours of lines and
+    integral quadratics (TrueType outlines are quadratic) with the measured OpenSans statistics — 1.44 contours and 20.9
+    outline points per glyph — laid out on text lines; one Shape per run of `glyphs_per_shape` glyphs,
+    like `paths_of_text` output chunked per line. Inner contours are reversed (counter shapes), so non-zero and
+    even-odd fills differ from a plain union."""
+    rng = np.random.default_rng(seed)
+    ppu = float(pixels_per_unit)
+    has_inner = rng.uniform(0, 1, n_glyphs) < 0.44
+    n_paths = int(n_glyphs + has_inner.sum())
+    glyph_of_path = np.concatenate([np.arange(n_glyphs), np.nonzero(has_inner)[0]])
+    inner = np.concatenate([np.zeros(n_glyphs, bool), np.ones(int(has_inner.sum()), bool)])
+    order = np.lexsort((inner, glyph_of_path))   # outer contour first, then its inner contour
+    glyph_of_path, inner = glyph_of_path[order], inner[order]
+    advance = 0.6 * em
+    line_height = 1.36 * em   # OpenSans: (ascender - descender + gap) / unitsPerEm = 2789 / 2048
+    per_line = max(1, int((extent[0] - 2 * em) // advance))
+    col, row = glyph_of_path % per_line, glyph_of_path // per_line
+    n_rows_fit = max(1, int((extent[1] - em) // line_height))
+    centre = np.stack([em + (col + 0.5) * advance, em * 0.8 + (row % n_rows_fit) * line_height], 1).astype(np.float64) / ppu
+    radius = np.where(inner, 0.16 * em, 0.36 * em) * rng.uniform(0.8, 1.0, n_paths) / ppu
+    seg_counts = np.where(inner, rng.integers(4, 9, n_paths), rng.integers(8, 15, n_paths)).astype(np.int64)
+    a, b, na, nb, start, seg_path = _blob_geometry(rng, centre, radius, seg_counts)
+    total = len(a)
+    seg_types = np.where(rng.uniform(0, 1, total) < 0.55, _abi.CR_SEG_INTEGRAL_QUADRATIC, _abi.CR_SEG_LINE).astype(np.uint8)
+    clen = np.linalg.norm(b - a, axis=1, keepdims=True)
+    nmid = na + nb
+    nmid /= np.maximum(np.linalg.norm(nmid, axis=1, keepdims=True), 1e-9)
+    quad_c = 0.5 * (a + b) + nmid * rng.uniform(-0.1, 0.4, (total, 1)) * clen
+    # reverse inner contours: walk the same outline backwards (src/path.rs:445-488 `reverse` does this in the showcase)
+    rev = inner[seg_path]
+    if rev.any():
+        first = np.zeros(n_paths + 1, np.int64)
+        np.cumsum(seg_counts, out=first[1:])
+        local = np.arange(total) - first[seg_path]
+        mirror = first[seg_path] + (seg_counts[seg_path] - 1 - local)
+        src = np.where(rev, mirror, np.arange(total))
+        a2, b2 = np.where(rev[:, None], b[src], a[src]), np.where(rev[:, None], a[src], b[src])
+        quad_c, seg_types = quad_c[src], seg_types[src]
+        a, b = a2, b2
+        start = a[first[:-1]]
+    sel = [seg_types == t for t in range(5)]
+    payload = [b[sel[0]], np.concatenate([quad_c, b], 1)[sel[1]], np.zeros((0, 6)), np.zeros((0, 5)), np.zeros((0, 10))]
+    stroke = np.zeros(n_paths, PathSoA.STROKE_DTYPE)
+    soa = _assemble(start, seg_counts, seg_types, payload, stroke)
+    # shapes = runs of glyphs_per_shape glyphs (paths of one glyph stay together)
+    glyph_first_path = np.searchsorted(glyph_of_path, np.arange(0, n_glyphs, glyphs_per_shape))
+    begin = np.append(glyph_first_path, n_paths).astype(np.uint32)
+    n_shapes = len(begin) - 1
+    colors = np.concatenate([rng.uniform(0, 0.8, (n_shapes, 3)), np.ones((n_shapes, 1))], 1).astype(np.float32)
+    return Scene(soa, begin, [], extent[0], extent[1], colors, "glyph_like_fills", ppu)
+
+
+# ------------------------------------------------------------------------------------------------------ config 5
+def dashed_rational_strokes(n_paths: int = 1000000, seed: int = SEED0 + 5, extent: Tuple[int, int] = (7680, 4320), paths_per_shape: int = 1000,
+                            angle_step: float = 0.2, pixels_per_unit: float = 10.0) -> Scene:
+    """BASELINE config 5: open paths of 2 rational cubics (weights U[0.5,2]), width U[1,4], round joins and caps,
+    two-interval dash pattern, UniformTangentAngle(0.2)."""
+    rng = np.random.default_rng(seed)
+    ppu = float(pixels_per_unit)
+    seg_counts = np.full(n_paths, 2, np.int64)
+    p0 = np.stack([rng.uniform(0, extent[0], n_paths), rng.uniform(0, extent[1], n_paths)], 1) / ppu
+    step = rng.uniform(8.0, 30.0, (n_paths, 1)) / ppu
+    direction = rng.uniform(0, 2 * np.pi, n_paths)
+    d = np.stack([np.cos(direction), np.sin(direction)], 1)
+    nrm = np.stack([-d[:, 1], d[:, 0]], 1)
+
+    def wiggle(scale):
+        return nrm * rng.uniform(-1.0, 1.0, (n_paths, 1)) * step * scale
+
+    q1 = p0 + d * step + wiggle(0.8)
+    q2 = p0 + d * step * 2 + wiggle(0.8)
+    q3 = p0 + d * step * 3 + wiggle(0.3)
+    turn = rng.uniform(-0.9, 0.9, n_paths)
+    d2 = np.stack([np.cos(direction + turn), np.sin(direction + turn)], 1)
+    n2 = np.stack([-d2[:, 1], d2[:, 0]], 1)
+    r1 = q3 + d2 * step + n2 * rng.uniform(-1.0, 1.0, (n_paths, 1)) * step * 0.8
+    r2 = q3 + d2 * step * 2 + n2 * rng.uniform(-1.0, 1.0, (n_paths, 1)) * step * 0.8
+    r3 = q3 + d2 * step * 3
+    w = rng.uniform(0.5, 2.0, (n_paths, 2, 4))
+    seg = np.stack([np.concatenate([w[:, 0], q1, q2, q3], 1), np.concatenate([w[:, 1], r1, r2, r3], 1)], 1).reshape(-1, 10)
+    types = np.full(2 * n_paths, _abi.CR_SEG_RATIONAL_CUBIC, np.uint8)
+    payload = [np.zeros((0, 2)), np.zeros((0, 4)), np.zeros((0, 6)), np.zeros((0, 5)), seg]
+    stroke = _stroke_records(n_paths, (rng.uniform(1.0, 4.0, n_paths) / ppu).astype(np.float32), miter_clip=1.0, closed=False, angle_step=angle_step)
+    soa = _assemble(p0, seg_counts, types, payload, stroke)
+    begin = np.arange(0, n_paths + 1, paths_per_shape, dtype=np.uint32)
+    if begin[-1] != n_paths:
+        begin = np.append(begin, np.uint32(n_paths))
+    n_shapes = len(begin) - 1
+    colors = np.concatenate([rng.uniform(0, 1, (n_shapes, 3)), np.full((n_shapes, 1), 0.8)], 1).astype(np.float32)
+    dso = DynamicStrokeOptions.Dashed(Join.Round, [DashInterval(2.0, 3.0, Cap.Round, Cap.Round), DashInterval(5.0, 5.5, Cap.Round, Cap.Round)],
+                                      float(rng.uniform(0, 6)))
+    return Scene(soa, begin, [dso], extent[0], extent[1], colors, "dashed_rational_strokes", ppu)
+
+
+def stencil_cover_commands(n_shapes: int) -> np.ndarray:
+    """One Stencil + one Color per shape, shape i drawn with instance i (examples/showcase/main.rs:236-249)."""
+    cmds = np.zeros((2 * n_shapes, 4), np.uint32)
+    idx = np.arange(n_shapes, dtype=np.uint32)
+    cmds[0::2] = np.stack([idx, idx, idx + 1, np.zeros_like(idx)], 1)
+    cmds[1::2] = np.stack([idx, idx, idx + 1, np.full_like(idx, 3)], 1)
+    return cmds

@@ -240,6 +240,8 @@ int cr_pass_render_batch(cr_pass* pass, cr_shape_batch* batch, const cr_draw_com
 /* queue.submit(encoder.finish()) (examples/showcase/main.rs:252): bins, sorts and rasterises everything
  * recorded, asynchronously on the renderer's stream. The pass object is consumed. */
 int cr_pass_submit(cr_pass* pass);
+/* Dropping a wgpu::RenderPass / CommandEncoder without submitting it: frees the pass, runs nothing. */
+void cr_pass_abort(cr_pass* pass);
 
 /* Attachment read-back (tests / image dump). color: [height][width][samples][4] f32 premultiplied;
  * stencil: [height][width][samples] u8 (clip bits << winding bits | winding bits);

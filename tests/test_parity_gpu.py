@@ -1,0 +1,443 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded inputs.
+Bit-exact for everything (vertex bytes, u16 indices, 48-byte descriptors, u8 stencil, f32 colour bit patterns): both
+sides compute in f32 with the shared arithmetic contract (csrc/arith/cr_arith.h), FMA contraction off."""
+import numpy as np
+import pytest
+
+from contrast_renderer_b200 import _abi, scenes
+from contrast_renderer_b200.path import (Cap, CurveApproximation, DashInterval, DynamicStrokeOptions, Join, Path, PathSoA,
+                                         RationalCubicCurveSegment, RationalQuadraticCurveSegment, StrokeOptions)
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_shapes(oracle, scene):
+    return [oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
+            for i in range(scene.n_shapes)]
+
+
+def assert_shape_equal(oracle, shape, ref, tag=""):
+    layout = shape.layout()
+    assert list(layout.vertex_offsets) == ref.vertex_offsets, f"{tag}: vertex_offsets"
+    assert list(layout.index_offsets) == ref.index_offsets, f"{tag}: index_offsets"
+    assert int(layout.proto_hull_points) == ref.proto_hull_points, f"{tag}: proto hull size"
+    got_v, want_v = shape.vertex_buffer(), ref.vertex_buffer
+    if not np.array_equal(got_v, want_v):
+        got, want = oracle.split_vertex_buffer(got_v, ref.vertex_offsets), oracle.split_vertex_buffer(want_v, ref.vertex_offsets)
+        for name, g, w in zip(oracle.CATEGORY_NAMES, got, want):
+            if g.tobytes() != w.tobytes():
+                bad = [i for i in range(len(g)) if g[i].tobytes() != w[i].tobytes()]
+                raise AssertionError(f"{tag}: {name} vertices differ at {bad[:5]} of {len(g)}: got {g[bad[0]]} want {w[bad[0]]}")
+    assert np.array_equal(shape.index_buffer(), ref.index_buffer), f"{tag}: index buffer"
+    assert np.array_equal(shape.stroke_buffer(), ref.stroke_buffer), f"{tag}: stroke descriptors"
+
+
+def render_both(cr, oracle, scene, config=None, commands=None, transforms=None, colors=None, per_command_state=None):
+    """Tessellates + renders `scene` on the GPU and with the oracle; returns ((color, stencil, covered), (ref...))."""
+    config = config or cr.Configuration()
+    rnd = cr.Renderer(config)
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, scene.dynamic_stroke_options, scene.paths, scene.shape_path_begin)
+    refs = oracle_shapes(oracle, scene)
+    cmds = scenes.stencil_cover_commands(scene.n_shapes) if commands is None else np.asarray(commands, np.uint32)
+    transforms = scene.transforms() if transforms is None else transforms
+    colors = scene.colors if colors is None else colors
+    rp = rnd.begin_render_pass()
+    rp.set_instances(transforms, colors)
+    rp.render_batch(batch, cmds)
+    rp.submit()
+    got = (rnd.read_color(), rnd.read_stencil(), int(rnd.stats().covered_samples))
+    ocmds = [(int(c[0]), int(c[1]), int(c[2]), int(c[3]), 0, 0, 0) for c in cmds]
+    ref_color, ref_stencil, _, ref_covered = oracle.render(config.to_c(), scene.width, scene.height, refs, ocmds, transforms, colors, threads=4)
+    batch.close()
+    rnd.close()
+    return got, (ref_color, ref_stencil, ref_covered)
+
+
+def assert_frames_equal(got, want):
+    (color, stencil, covered), (ref_color, ref_stencil, ref_covered) = got, want
+    assert np.array_equal(stencil, ref_stencil), f"stencil differs at {np.argwhere(stencil != ref_stencil)[:5]}"
+    diff = color.view(np.uint32) != ref_color.view(np.uint32)
+    assert not diff.any(), f"colour differs at {np.argwhere(diff)[:5]}"
+    assert covered == ref_covered
+
+
+# ----------------------------------------------------------------------------------------------- tessellation
+@pytest.mark.parametrize("maker", [
+    lambda: scenes.closed_cubic_strokes(200),                                   # BASELINE config 1 (reduced count)
+    lambda: scenes.mixed_fills(600),                                            # config 2 kinds: line / quad / cubic
+    lambda: scenes.mixed_fills(600, rational=True, seed=77),                    # all five segment kinds
+    lambda: scenes.mixed_fills(300, rational=True, paths_per_shape=7, seed=5),  # multi-path shapes (hull over many paths)
+    lambda: scenes.glyph_like_fills(1500, glyphs_per_shape=100),                # config 3 kinds
+    lambda: scenes.dashed_rational_strokes(300, paths_per_shape=25),            # config 5 kinds
+], ids=["cubic_strokes", "mixed_fills", "all_kinds", "multi_path_shapes", "glyphs", "dashed_rational_strokes"])
+def test_tessellation_matches_oracle(cr, oracle, maker):
+    scene = maker()
+    rnd = cr.Renderer()
+    batch = cr.ShapeBatch(rnd, scene.dynamic_stroke_options, scene.paths, scene.shape_path_begin)
+    assert len(batch) == scene.n_shapes
+    for i, ref in enumerate(oracle_shapes(oracle, scene)):
+        assert_shape_equal(oracle, batch[i], ref, f"{scene.name} shape {i}")
+    batch.close()
+    rnd.close()
+
+
+def test_config1_full_size_tessellation(cr, oracle):
+    """BASELINE config 1 at its full size: 1k closed cubic paths, stroke tessellation to vertex buffers only."""
+    scene = scenes.closed_cubic_strokes(1000)
+    rnd = cr.Renderer()
+    batch = cr.ShapeBatch(rnd, scene.dynamic_stroke_options, scene.paths, scene.shape_path_begin)
+    for i, ref in enumerate(oracle_shapes(oracle, scene)):
+        assert_shape_equal(oracle, batch[i], ref, f"shape {i}")
+    batch.close()
+    rnd.close()
+
+
+def stroke_path(points_and_kinds, start, **so):
+    p = Path(start, StrokeOptions(**so))
+    for kind, data in points_and_kinds:
+        if kind == "L":
+            p.push_line(data)
+        elif kind == "Q":
+            p.push_integral_quadratic_curve(data)
+        elif kind == "C":
+            p.push_integral_cubic_curve(data)
+        elif kind == "RQ":
+            p.push_rational_quadratic_curve(RationalQuadraticCurveSegment(*data))
+        else:
+            p.push_rational_cubic_curve(RationalCubicCurveSegment(*data))
+    return p
+
+
+STROKE_VARIANTS = [
+    dict(width=0.3, offset=0.0, miter_clip=1.0, closed=False),
+    dict(width=0.3, offset=0.5, miter_clip=4.0, closed=True),
+    dict(width=0.2, offset=-0.25, miter_clip=0.6, closed=True, curve_approximation=CurveApproximation.UniformlySpacedParameters(7)),
+    dict(width=0.5, offset=0.1, miter_clip=2.0, closed=False, curve_approximation=CurveApproximation.UniformTangentAngle(0.35)),
+]
+
+
+@pytest.mark.parametrize("so", STROKE_VARIANTS, ids=["open", "closed_offset", "uniform_params", "coarse_angle"])
+def test_single_shape_api_strokes_every_segment_kind(cr, oracle, so):
+    """cr_shape_from_paths (Shape::from_paths) on hand-built paths: every segment kind, straight runs (no join),
+    reversals (anti-parallel join), cusps of an S-cubic, both curve approximations, offsets, open and closed."""
+    w = 0.70710678
+    paths = [
+        stroke_path([("L", [2, 0]), ("L", [2, 1]), ("L", [0, 1])], [0, 0], **so),                          # rectangle corners
+        stroke_path([("L", [1, 0]), ("L", [2, 0]), ("L", [1, 0])], [0, 0], **so),                          # collinear then reversal
+        stroke_path([("Q", [[1, 1.5], [2, 0]]), ("C", [[3, -1], [4, 2], [5, 0]])], [0, 0], **so),          # quad + S cubic (inflection)
+        stroke_path([("RQ", (w, [[1, 1], [0, 1]])), ("RQ", (w, [[-1, 1], [-1, 0]]))], [1, 0], **so),       # two quarter circles
+        stroke_path([("RC", ([1, 0.6, 1.7, 1], [[0.5, 1.5], [2.5, 1.2], [3, 0]])), ("L", [3, -1])], [0, 0], **so),
+        stroke_path([("C", [[3, 2], [-1, 2], [2, 0]])], [0, 0], **so),                                     # loop cubic
+    ]
+    dso = [DynamicStrokeOptions.Solid(Join.Round, Cap.Round, Cap.Square)]
+    soa = PathSoA.from_paths(paths)
+    rnd = cr.Renderer()
+    shape = cr.Shape.from_paths(rnd, dso, soa)
+    assert_shape_equal(oracle, shape, oracle.shape_from_paths(dso, soa), "strokes")
+    shape.close()
+    rnd.close()
+
+
+def test_mixed_stroke_and_fill_in_one_shape(cr, oracle):
+    fill = Path([0, 0])
+    fill.push_line([3, 0])
+    fill.push_integral_quadratic_curve([[3.5, 1.5], [2, 2]])
+    fill.push_integral_cubic_curve([[1.5, 3], [0.5, 1], [0, 2]])
+    fill.close()
+    stroke = stroke_path([("L", [1, 2]), ("Q", [[2, 3], [3, 1]])], [0.5, 0.5], width=0.2, closed=True, dynamic_stroke_options_group=1)
+    dso = [DynamicStrokeOptions.Solid(Join.Miter, Cap.Butt, Cap.Butt),
+           DynamicStrokeOptions.Dashed(Join.Bevel, [DashInterval(0.5, 1.0, Cap.Out, Cap.In), DashInterval(1.5, 2.0, Cap.Left, Cap.Right)], 0.25)]
+    soa = PathSoA.from_paths([fill, stroke, fill])
+    rnd = cr.Renderer()
+    shape = cr.Shape.from_paths(rnd, dso, soa)
+    ref = oracle.shape_from_paths(dso, soa)
+    assert_shape_equal(oracle, shape, ref, "mixed")
+    # Shape::set_dynamic_stroke_options: in-place 48-byte update, no re-tessellation
+    new = DynamicStrokeOptions.Dashed(Join.Round, [DashInterval(0.1, 0.2, Cap.Round, Cap.Round)], 0.75)
+    shape.set_dynamic_stroke_options(1, new)
+    ref.set_dynamic_stroke_options(1, new)
+    assert np.array_equal(shape.stroke_buffer(), ref.stroke_buffer)
+    with pytest.raises(cr.DynamicStrokeOptionsIndexOutOfBounds):
+        shape.set_dynamic_stroke_options(2, new)
+    # existing shape is consumed and rebuilt in place
+    soa2 = PathSoA.from_paths([stroke, fill])
+    shape2 = cr.Shape.from_paths(rnd, dso, soa2, existing=shape)
+    assert_shape_equal(oracle, shape2, oracle.shape_from_paths(dso, soa2), "rebuilt")
+    shape2.close()
+    rnd.close()
+
+
+def test_edge_cases(cr, oracle):
+    """Empty inputs, paths without segments, a single point, fewer than three hull points."""
+    rnd = cr.Renderer()
+    empty = PathSoA.from_paths([])
+    shape = cr.Shape.from_paths(rnd, [], empty)
+    assert_shape_equal(oracle, shape, oracle.shape_from_paths([], empty), "no paths")
+    shape.close()
+    lonely = PathSoA.from_paths([Path([1, 2])])                       # a filled path with no segments
+    shape = cr.Shape.from_paths(rnd, [], lonely)
+    assert_shape_equal(oracle, shape, oracle.shape_from_paths([], lonely), "no segments")
+    shape.close()
+    two = Path([0, 0])
+    two.push_line([1, 1])
+    soa = PathSoA.from_paths([two])
+    shape = cr.Shape.from_paths(rnd, [], soa)
+    assert_shape_equal(oracle, shape, oracle.shape_from_paths([], soa), "two points")
+    shape.close()
+    # ragged batch: empty shapes between populated ones
+    scene = scenes.mixed_fills(40, rational=True)
+    begin = np.array([0, 0, 13, 13, 13, 40, 40], np.uint32)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, begin)
+    for i in range(len(begin) - 1):
+        assert_shape_equal(oracle, batch[i], oracle.shape_from_paths([], scene.paths, int(begin[i]), int(begin[i + 1])), f"ragged {i}")
+    batch.close()
+    rnd.close()
+
+
+def test_error_codes(cr, oracle):
+    """Error behaviour of the reference API (src/error.rs:5-16, src/renderer.rs:32,189,366,433,933,947)."""
+    with pytest.raises(cr.NumberOfStencilBitsIsUnsupported):
+        cr.Renderer(cr.Configuration(winding_counter_bits=0))
+    with pytest.raises(cr.NumberOfStencilBitsIsUnsupported):
+        cr.Renderer(cr.Configuration(winding_counter_bits=5, clip_nesting_counter_bits=4))
+    rnd = cr.Renderer(cr.Configuration(clip_nesting_counter_bits=2, winding_counter_bits=6, alpha_layer_count=1))
+    p = stroke_path([("L", [1, 0])], [0, 0], width=0.1, dynamic_stroke_options_group=1)
+    soa = PathSoA.from_paths([p])
+    with pytest.raises(cr.DynamicStrokeOptionsIndexOutOfBounds):
+        cr.Shape.from_paths(rnd, [DynamicStrokeOptions.Solid(Join.Miter, Cap.Butt, Cap.Butt)], soa)
+    five = DynamicStrokeOptions.Dashed(Join.Miter, [DashInterval(i, i + 0.5) for i in range(5)], 0.0)
+    with pytest.raises(cr.TooManyDashIntervals):
+        cr.Shape.from_paths(rnd, [five, five], soa)
+    with pytest.raises(cr.Error) as e:
+        rnd.begin_render_pass()
+    assert e.value.status == _abi.CR_ERR_NOT_RESIZED
+    rnd.resize_internal_buffers(64, 64)
+    rp = rnd.begin_render_pass()
+    rp.set_clip_depth(3)
+    with pytest.raises(cr.ClipStackOverflow):
+        rp.set_clip_depth(4)
+    rp.save_alpha_context(0)
+    with pytest.raises(cr.TooManyNestedOpacityGroups):
+        rp.save_alpha_context(1)
+    with pytest.raises(cr.TooManyNestedOpacityGroups):
+        rp.restore_alpha_context(1)
+    rp.submit()
+    # a curve with more tangent-angle steps than the device-side capacity is reported, not truncated silently
+    tight = stroke_path([("Q", [[1, 2], [2, 0]])], [0, 0], width=0.1, curve_approximation=CurveApproximation.UniformTangentAngle(0.001))
+    with pytest.raises(cr.Error) as e:
+        cr.Shape.from_paths(rnd, [DynamicStrokeOptions.Solid(Join.Miter, Cap.Butt, Cap.Butt)], PathSoA.from_paths([tight]))
+    assert e.value.status == _abi.CR_ERR_CURVE_STEPS_CAPACITY
+    rnd.close()
+
+
+def test_device_resident_inputs_match_host_inputs(cr, oracle):
+    """CR_MEM_DEVICE inputs (zero-copy) give the same bytes as CR_MEM_HOST inputs."""
+    import torch
+    scene = scenes.mixed_fills(200, rational=True)
+    rnd = cr.Renderer()
+    host = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    tensors = [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).cuda() for a in scene.paths.arrays()]
+    ptrs = [t.data_ptr() if t.numel() else 0 for t in tensors]
+    torch.cuda.synchronize()
+    dev = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin, memory_space=_abi.CR_MEM_DEVICE, pointers=ptrs)
+    for i in range(scene.n_shapes):
+        assert np.array_equal(host[i].vertex_buffer(), dev[i].vertex_buffer())
+        assert np.array_equal(host[i].index_buffer(), dev[i].index_buffer())
+    host.close()
+    dev.close()
+    rnd.close()
+
+
+# ---------------------------------------------------------------------------------------------------- raster
+@pytest.mark.parametrize("winding_bits", [1, 4], ids=["even_odd", "non_zero"])
+def test_config2_fill_rules(cr, oracle, winding_bits):
+    """BASELINE config 2 (reduced count, same generator): mixed filled paths, even-odd (1 winding bit) and non-zero."""
+    scene = scenes.mixed_fills(400, extent=(640, 360), size=(8.0, 90.0))
+    cfg = cr.Configuration(winding_counter_bits=winding_bits, clip_nesting_counter_bits=4)
+    got, want = render_both(cr, oracle, scene, cfg)
+    assert want[2] > 10000
+    assert_frames_equal(got, want)
+
+
+def test_all_segment_kinds_translucent(cr, oracle):
+    scene = scenes.mixed_fills(300, extent=(512, 384), size=(8.0, 100.0), rational=True, seed=99)
+    scene.colors[:, 3] = np.linspace(0.2, 1.0, scene.n_shapes, dtype=np.float32)
+    got, want = render_both(cr, oracle, scene)
+    assert_frames_equal(got, want)
+
+
+def test_glyph_scene(cr, oracle):
+    scene = scenes.glyph_like_fills(1200, extent=(640, 240), glyphs_per_shape=60)
+    got, want = render_both(cr, oracle, scene)
+    assert want[2] > 5000
+    assert_frames_equal(got, want)
+
+
+@pytest.mark.parametrize("dashed", [False, True], ids=["solid", "dashed"])
+@pytest.mark.parametrize("join", [Join.Miter, Join.Bevel, Join.Round])
+def test_strokes_joins_caps_dashes(cr, oracle, join, dashed):
+    scene = scenes.closed_cubic_strokes(60, extent=(512, 384), pixels_per_unit=24.0)
+    scene.paths.stroke_options["width"] *= 2.0
+    if dashed:
+        scene.dynamic_stroke_options = [DynamicStrokeOptions.Dashed(join, [DashInterval(1.0, 2.0, Cap.Round, Cap.Out), DashInterval(3.5, 4.0, Cap.In, Cap.Square)], 0.3)]
+    else:
+        scene.dynamic_stroke_options = [DynamicStrokeOptions.Solid(join, Cap.Round, Cap.Square)]
+    got, want = render_both(cr, oracle, scene)
+    assert want[2] > 2000
+    assert_frames_equal(got, want)
+
+
+@pytest.mark.parametrize("caps", [(Cap.Square, Cap.Round), (Cap.Out, Cap.In), (Cap.Right, Cap.Left), (Cap.Butt, Cap.Butt)], ids=lambda c: f"{c[0].name}_{c[1].name}")
+def test_open_strokes_caps(cr, oracle, caps):
+    scene = scenes.dashed_rational_strokes(150, extent=(512, 384), paths_per_shape=10, pixels_per_unit=4.0)
+    scene.dynamic_stroke_options = [DynamicStrokeOptions.Solid(Join.Round, caps[0], caps[1])]
+    got, want = render_both(cr, oracle, scene)
+    assert want[2] > 1000
+    assert_frames_equal(got, want)
+
+
+def test_config5_kind_dashed_round(cr, oracle):
+    """BASELINE config 5 (reduced count, same generator): dashed open rational-cubic strokes, round joins and caps."""
+    scene = scenes.dashed_rational_strokes(400, extent=(768, 432), paths_per_shape=40, pixels_per_unit=5.0)
+    got, want = render_both(cr, oracle, scene)
+    assert want[2] > 1000
+    assert_frames_equal(got, want)
+
+
+def test_instancing_and_perspective(cr, oracle):
+    """One shape drawn with several instance matrices, including a perspective one (w != 1) and a culled back face."""
+    scene = scenes.mixed_fills(12, extent=(384, 256), size=(20.0, 60.0), rational=True, paths_per_shape=12, seed=3)
+    base = scene.transforms()[0].reshape(4, 4).T.astype(np.float64)   # columns -> matrix
+    mats = []
+    for k in range(5):
+        a = 0.5 * k
+        rot = np.array([[np.cos(a), -np.sin(a), 0, 0], [np.sin(a), np.cos(a), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+        persp = np.eye(4)
+        persp[3, 0] = 0.02 * k
+        persp[3, 1] = -0.015 * k
+        shift = np.eye(4)
+        shift[0, 3] = 0.8 * k - 1.5
+        shift[1, 3] = 0.4 * k - 0.6
+        mats.append((persp @ base @ shift @ rot).T.reshape(16))
+    mirror = np.diag([-1.0, 1.0, 1.0, 1.0])
+    mats.append((base @ mirror).T.reshape(16))                           # flips the facing of every triangle
+    transforms = np.asarray(mats, np.float32)
+    colors = np.random.default_rng(1).uniform(0.1, 1.0, (len(mats), 4)).astype(np.float32)
+    cmds = []
+    for i in range(len(mats)):
+        cmds += [(0, i, i + 1, 0), (0, i, i + 1, 3)]
+    for cull in (cr.CullMode.Off, cr.CullMode.Back, cr.CullMode.Front):
+        got, want = render_both(cr, oracle, scene, cr.Configuration(cull_mode=cull), cmds, transforms, colors)
+        assert_frames_equal(got, want)
+    # one instanced Stencil over all instances, then one instanced Color (instance ranges, src/renderer.rs:271)
+    got, want = render_both(cr, oracle, scene, None, [(0, 0, len(mats), 0), (0, 0, len(mats), 3)], transforms, colors)
+    assert_frames_equal(got, want)
+
+
+def test_clip_and_opacity_protocols(cr, oracle):
+    """Nested clipping (Stencil -> Clip -> children -> UnClip) and group opacity (Save/Scale/RestoreAlphaContext),
+    src/renderer.rs:253-266, with the pass state (clip depth, alpha layer) changing between draws."""
+    scene = scenes.mixed_fills(6, extent=(320, 240), size=(40.0, 90.0), seed=11)
+    scene.origins[:] = np.array([[4.0, 3.0], [4.5, 3.2], [3.6, 2.8], [4.2, 3.5], [3.9, 2.6], [4.4, 3.1]])
+    config = cr.Configuration(alpha_layer_count=2)
+    transforms, colors = scene.transforms(), scene.colors.copy()
+    colors[:, 3] = [1.0, 0.6, 0.5, 0.7, 0.4, 0.8]
+    S, CLIP, UNCLIP, COLOR, SAVE, SCALE, RESTORE = range(7)
+    # (shape, op, clip_depth, save_layer, restore_layer)
+    script = [
+        (0, S, 0, 0, 0), (0, CLIP, 1, 0, 0),                       # clip to shape 0
+        (1, S, 1, 0, 0), (1, COLOR, 1, 0, 0),                      # child inside the clip
+        (2, S, 1, 0, 0), (2, CLIP, 2, 0, 0),                       # nested clip
+        (3, S, 2, 0, 0), (3, SAVE, 2, 0, 0), (3, SCALE, 2, 0, 0),  # opacity group over shape 3's area
+        (4, S, 2, 0, 0), (4, COLOR, 2, 0, 0),
+        (3, S, 2, 0, 0), (3, RESTORE, 2, 0, 0),
+        (2, S, 1, 0, 0), (2, UNCLIP, 1, 0, 0),                     # leave the nested clip
+        (5, S, 1, 0, 0), (5, COLOR, 1, 0, 0),
+        (0, S, 0, 0, 0), (0, UNCLIP, 0, 0, 0),
+    ]
+    rnd = cr.Renderer(config)
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    refs = oracle_shapes(oracle, scene)
+    rp = rnd.begin_render_pass()
+    rp.set_instances(transforms, colors)
+    ocmds = []
+    for shape, op, depth, save, restore in script:
+        rp.set_clip_depth(depth)
+        rp.save_alpha_context(save)
+        rp.restore_alpha_context(restore)
+        batch[shape].render(rp, range(shape, shape + 1), cr.RenderOperation(op))
+        ocmds.append((shape, shape, shape + 1, op, depth, save, restore))
+    rp.submit()
+    color, stencil, layer = rnd.read_color(), rnd.read_stencil(), rnd.read_alpha_layer(0)
+    ref_color, ref_stencil, ref_layers, _ = oracle.render(config.to_c(), scene.width, scene.height, refs, ocmds, transforms, colors)
+    assert np.array_equal(stencil, ref_stencil)
+    assert np.array_equal(color.view(np.uint32), ref_color.view(np.uint32))
+    assert np.array_equal(layer.view(np.uint32), ref_layers[0].view(np.uint32))
+    assert (stencil == 0).all(), "clip and winding bits are back to zero after the matching UnClip"
+    batch.close()
+    rnd.close()
+
+
+def test_load_op_keeps_previous_pass(cr, oracle):
+    """A second pass with LoadOp::Load composites over the first; two submits == one submit of both command lists."""
+    scene = scenes.mixed_fills(80, extent=(320, 200), size=(10.0, 60.0), seed=21)
+    scene.colors[:, 3] = 0.5
+    cmds = scenes.stencil_cover_commands(scene.n_shapes)
+    rnd = cr.Renderer()
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    half = len(cmds) // 2
+    for k, part in enumerate((cmds[:half], cmds[half:])):
+        rp = rnd.begin_render_pass(clear_color=(k == 0), clear_stencil=(k == 0))
+        rp.set_instances(scene.transforms(), scene.colors)
+        rp.render_batch(batch, part)
+        rp.submit()
+    two = (rnd.read_color(), rnd.read_stencil())
+    rp = rnd.begin_render_pass()
+    rp.set_instances(scene.transforms(), scene.colors)
+    rp.render_batch(batch, cmds)
+    rp.submit()
+    one = (rnd.read_color(), rnd.read_stencil())
+    assert np.array_equal(one[1], two[1]) and np.array_equal(one[0].view(np.uint32), two[0].view(np.uint32))
+    batch.close()
+    rnd.close()
+
+
+# -------------------------------------------------------------------- size-independent properties at full size
+def test_full_size_config3_matches_oracle_and_properties(cr, oracle):
+    """BASELINE config 3 at full size (100k glyphs, 144k paths, 3840x2160): bit-exact against the oracle, plus
+    size-independent properties: rendering twice gives identical bits (the raster has no order-dependent atomics),
+    opaque covers leave alpha in {0, 1}, the cover zeroes the winding bits (src/renderer.rs:747-752).
+
+    The last property holds up to the reference's own hull tolerance: convex_hull::andrew pops points whose turn area is
+    <= 1e-4 (src/convex_hull.rs:16) in f32 on absolute coordinates, so a hull may miss a boundary pixel of its own shape
+    and the winding bits stay set there. The oracle reproduces exactly the same pixels (17 for this seed)."""
+    scene = scenes.glyph_like_fills(100000)
+    rnd = cr.Renderer()
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    cmds = scenes.stencil_cover_commands(scene.n_shapes)
+    frames = []
+    for _ in range(2):
+        rp = rnd.begin_render_pass()
+        rp.set_instances(scene.transforms(), scene.colors)
+        rp.render_batch(batch, cmds)
+        rp.submit()
+        frames.append((rnd.read_color(), rnd.read_stencil(), int(rnd.stats().covered_samples)))
+    (c0, s0, n0), (c1, s1, n1) = frames
+    assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32)) and np.array_equal(s0, s1) and n0 == n1
+    assert int((s0 != 0).sum()) < 100
+    alpha = c0[..., 3]
+    assert set(np.unique(alpha)) <= {0.0, 1.0}
+    assert n0 >= int((alpha == 1.0).sum()) > 1000000
+    refs = oracle_shapes(oracle, scene)
+    for i in (0, 1, scene.n_shapes // 2, scene.n_shapes - 1):
+        assert_shape_equal(oracle, batch[i], refs[i], f"shape {i}")
+    ocmds = [(int(c[0]), int(c[1]), int(c[2]), int(c[3]), 0, 0, 0) for c in cmds]
+    ref_color, ref_stencil, _, ref_covered = oracle.render(rnd.config.to_c(), scene.width, scene.height, refs, ocmds, scene.transforms(), scene.colors,
+                                                           threads=oracle.max_threads())
+    assert_frames_equal((c0, s0, n0), (ref_color, ref_stencil, ref_covered))
+    batch.close()
+    rnd.close()
