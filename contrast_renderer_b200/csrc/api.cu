@@ -117,7 +117,7 @@ struct cr_renderer {
     DevBuf color, stencil, alpha_layers;
     // scratch shared by every from_paths / submit of this renderer
     DevBuf staging[10], counts, scan_scratch, shape_begin_dev, err_flag, hull_scratch_a, hull_scratch_b;
-    DevBuf cmds_dev, batches_dev, cmd_cands, cand_tiles, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, radix_scratch, tile_begin, inst_transforms, inst_colors,
+    DevBuf cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, radix_scratch, tile_begin, inst_transforms, inst_colors,
         covered_dev;
     uint32_t* pinned = nullptr;   // small pinned read-back area
     cr_stats stats{};
@@ -242,20 +242,25 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     CR_TRY(stage(r, 9, soa->stroke_options, n_paths, soa->memory_space, &P.stroke_options));
     input_bytes += 8ull * n_paths;
 
-    // ---- pass A: count, scan
+    // ---- pass A: count, scan, per-shape slice boundaries
     CR_TRY(r->counts.reserve(st, CNT_COUNT * stride * sizeof(uint32_t)));
     CR_TRY(r->scan_scratch.reserve(st, (size_t)cr_scan_scratch_words((uint32_t)stride, CNT_COUNT) * 4));
-    CR_TRY(r->err_flag.reserve(st, 4));
-    CR_CUDA_TRY(cudaMemsetAsync(r->err_flag.p, 0, 4, st));
+    CR_TRY(r->err_flag.reserve(st, 8));   // [0] error bits, [1] largest proto-hull slice of any shape
+    CR_CUDA_TRY(cudaMemsetAsync(r->err_flag.p, 0, 8, st));
+    CR_TRY(r->shape_begin_dev.reserve(st, (size_t)(n_shapes + 1) * 4));
+    CR_CUDA_TRY(cudaMemcpyAsync(r->shape_begin_dev.p, shape_path_begin, (size_t)(n_shapes + 1) * 4, cudaMemcpyHostToDevice, st));
+    CR_TRY(b->cat_begin.reserve(st, (size_t)CNT_COUNT * (n_shapes + 1) * 4));
     uint32_t* counts = r->counts.as<uint32_t>();
     CR_TRY(cr_tess_count(st, P, (uint32_t)n_groups, counts, r->err_flag.as<uint32_t>()));
     CR_TRY(cr_scan_exclusive(st, counts, (uint32_t)stride, CNT_COUNT, r->scan_scratch.as<uint32_t>()));
+    CR_TRY(cr_tess_shape_bounds(st, counts, n_paths, r->shape_begin_dev.as<uint32_t>(), n_shapes, b->cat_begin.as<uint32_t>(), r->err_flag.as<uint32_t>() + 1));
     for (int c = 0; c < CNT_COUNT; ++c)
         CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[c], counts + c * stride + n_paths, 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[CNT_COUNT], r->err_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[CNT_COUNT], r->err_flag.p, 8, cudaMemcpyDeviceToHost, st));
     CR_CUDA_TRY(cudaStreamSynchronize(st));
     CR_TRY(decode_device_error(r->pinned[CNT_COUNT]));
     for (int c = 0; c < CNT_COUNT; ++c) b->totals[c] = r->pinned[c];
+    const uint32_t max_proto = r->pinned[CNT_COUNT + 1];
 
     // ---- allocate the outputs, pass B: emit, hull
     b->renderer = r;
@@ -268,20 +273,16 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     CR_TRY(r->hull_scratch_a.reserve(st, b->totals[CNT_PROTO] * 8));
     CR_TRY(r->hull_scratch_b.reserve(st, b->totals[CNT_PROTO] * 8));
     for (int k = 0; k < 3; ++k) CR_TRY(b->idx[k].reserve(st, b->totals[CNT_LINE_IDX + k] * 4));
-    CR_TRY(b->cat_begin.reserve(st, (size_t)CNT_COUNT * (n_shapes + 1) * 4));
     CR_TRY(b->hull_count.reserve(st, (size_t)n_shapes * 4));
     CR_TRY(b->stroke.reserve(st, n_groups * sizeof(Descriptor48)));
     if (n_groups) CR_CUDA_TRY(cudaMemcpyAsync(b->stroke.p, descs.data(), n_groups * sizeof(Descriptor48), cudaMemcpyHostToDevice, st));
-    CR_TRY(r->shape_begin_dev.reserve(st, (size_t)(n_shapes + 1) * 4));
-    CR_CUDA_TRY(cudaMemcpyAsync(r->shape_begin_dev.p, shape_path_begin, (size_t)(n_shapes + 1) * 4, cudaMemcpyHostToDevice, st));
     TessOutput out{};
     for (int c = 0; c < 7; ++c) out.vtx[c] = b->vtx[c].p;
     out.proto = b->proto.as<float2>();
     for (int k = 0; k < 3; ++k) out.idx[k] = b->idx[k].as<uint32_t>();
-    CR_TRY(cr_tess_shape_bounds(st, counts, n_paths, r->shape_begin_dev.as<uint32_t>(), n_shapes, b->cat_begin.as<uint32_t>()));
     CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, r->err_flag.as<uint32_t>()));
     CR_TRY(cr_tess_hull(st, out.proto, r->hull_scratch_a.as<float2>(), r->hull_scratch_b.as<float2>(),
-                        b->cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, b->hull.as<float2>(), b->hull_count.as<uint32_t>()));
+                        b->cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, b->hull.as<float2>(), b->hull_count.as<uint32_t>(), max_proto));
     if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[1], st)); r->ev_valid[0] = true; }
 
     // ---- the rasteriser's view of this batch + host mirrors of the slice tables
@@ -395,7 +396,7 @@ void cr_renderer_destroy(cr_renderer* r) {
     cudaStreamSynchronize(r->stream);
     cudaStream_t st = r->stream;
     DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
-                     &r->hull_scratch_b, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->pair_tile, &r->pair_cand, &r->pair_tile_alt,
+                     &r->hull_scratch_b, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand, &r->pair_tile_alt,
                      &r->pair_cand_alt, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->covered_dev};
     for (DevBuf* d : all) d->release(st);
     for (auto& d : r->staging) d.release(st);
@@ -661,13 +662,24 @@ static int record(cr_pass* p, cr_shape_batch* b, uint32_t shape, uint32_t instan
     if (bi == p->batches.size()) p->batches.push_back(b);
     DeviceCommand c{};
     c.batch = bi;
-    c.shape = shape;
     c.instance_begin = is.base + instance_begin;
-    c.instance_end = is.base + instance_end;
+    c.instance_count = instance_end - instance_begin;
     c.operation = op;
     c.ref = p->clip_depth << p->renderer->config.winding_counter_bits;
-    c.save_layer = p->save_layer;
-    c.restore_layer = p->restore_layer;
+    c.layers = p->save_layer | (p->restore_layer << 16);
+    // candidates of this command, category by category in the draw order of src/renderer.rs:275-354
+    const size_t stride = (size_t)b->n_shapes + 1;
+    const uint32_t* cb = b->cat_begin_host.data();
+    uint64_t total = 0;
+    for (int cat = 0; cat < 8; ++cat) {
+        const bool drawn = op == CR_OP_STENCIL ? (cat < 7 && (cat >= 2 || b->n_groups > 0)) : cat == 7;
+        c.slots[cat] = drawn ? slots_of_host(b, shape, cat) : 0u;
+        total += (uint64_t)c.slots[cat] * c.instance_count;
+        if (total >= 0xFFFFFFFFull) return fail(CR_ERR_INVALID_ARGUMENT, "more than 2^32 candidate primitives in one draw");
+        c.cat_end[cat] = (uint32_t)total;
+        c.vbase[cat] = cb[(cat < 7 ? cat : (int)CNT_PROTO) * stride + shape];
+        if (cat < 3) c.ibase[cat] = cb[(CNT_LINE_IDX + cat) * stride + shape];
+    }
     p->commands.push_back(c);
     return CR_OK;
 }
@@ -725,17 +737,7 @@ static int submit(cr_pass* p) {
     uint64_t total = 0;
     for (uint32_t c = 0; c < n_cmds; ++c) {
         cand_begin[c] = (uint32_t)total;
-        const DeviceCommand& cmd = p->commands[c];
-        const cr_shape_batch* b = p->batches[cmd.batch];
-        const uint64_t n_inst = cmd.instance_end - cmd.instance_begin;
-        uint64_t slots = 0;
-        if (cmd.operation == CR_OP_STENCIL) {
-            for (int cat = 0; cat < 7; ++cat)
-                if (cat >= 2 || b->n_groups > 0) slots += slots_of_host(b, cmd.shape, cat);
-        } else {
-            slots = slots_of_host(b, cmd.shape, 7);
-        }
-        total += slots * n_inst;
+        total += p->commands[c].cat_end[7];
         if (total >= 0xFFFFFFFFull) return fail(CR_ERR_INVALID_ARGUMENT, "more than 2^32 candidate primitives in one pass; submit in several passes");
     }
     cand_begin[n_cmds] = (uint32_t)total;
@@ -764,8 +766,10 @@ static int submit(cr_pass* p) {
     // ---- bin: count, scan, emit, sort by tile (stable => draw order survives inside every tile)
     if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[2], st));
     CR_TRY(r->cand_tiles.reserve(st, (size_t)(n_cands + 1) * 4));
+    CR_TRY(r->records.reserve(st, (size_t)n_cands * sizeof(PrimRecord)));
     CR_TRY(r->scan_scratch.reserve(st, (size_t)cr_scan_scratch_words(n_cands + 1, 1) * 4));
-    CR_TRY(cr_raster_bin_count(st, sc, tg, n_cands, r->cand_tiles.as<uint32_t>()));
+    CR_TRY(r->big_list.reserve(st, (size_t)(n_cands + 1) * 4));
+    CR_TRY(cr_raster_setup(st, sc, tg, n_cands, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>()));
     CR_TRY(cr_scan_exclusive(st, r->cand_tiles.as<uint32_t>(), n_cands + 1, 1, r->scan_scratch.as<uint32_t>()));
     CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[0], r->cand_tiles.as<uint32_t>() + n_cands, 4, cudaMemcpyDeviceToHost, st));
     CR_CUDA_TRY(cudaStreamSynchronize(st));
@@ -781,7 +785,8 @@ static int submit(cr_pass* p) {
         CR_TRY(r->pair_cand_alt.reserve(st, (size_t)n_pairs * 4));
         CR_TRY(r->radix_scratch.reserve(st, (size_t)cr_radix_scratch_words(n_pairs) * 4));
         CR_TRY(r->tile_begin.reserve(st, (size_t)(n_tiles + 1) * 4));
-        CR_TRY(cr_raster_bin_emit(st, sc, tg, n_cands, r->cand_tiles.as<uint32_t>(), r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>()));
+        CR_TRY(cr_raster_bin_emit(st, tg, n_cands, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), r->pair_tile.as<uint32_t>(),
+                                  r->pair_cand.as<uint32_t>()));
         uint32_t key_bits = 1;
         while ((1u << key_bits) < n_tiles) ++key_bits;
         uint32_t *sorted_tile = nullptr, *sorted_cand = nullptr;
@@ -789,7 +794,7 @@ static int submit(cr_pass* p) {
                                    n_pairs, key_bits, r->radix_scratch.as<uint32_t>(), &sorted_tile, &sorted_cand));
         CR_TRY(cr_lower_bounds(st, sorted_tile, n_pairs, r->tile_begin.as<uint32_t>(), n_tiles + 1));
         if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[3], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[4], st)); }
-        CR_TRY(cr_raster_tiles(st, sc, tg, r->tile_begin.as<uint32_t>(), sorted_cand, r->covered_dev.as<unsigned long long>()));
+        CR_TRY(cr_raster_tiles(st, sc, tg, r->records.as<PrimRecord>(), r->tile_begin.as<uint32_t>(), sorted_cand, r->covered_dev.as<unsigned long long>()));
         if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }
     }
     return CR_OK;

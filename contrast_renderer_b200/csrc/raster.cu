@@ -1,15 +1,22 @@
-// raster.cu — the binner and K3, the software stencil-then-cover tile rasteriser for sm_100a.
+// raster.cu — primitive setup, the binner and K3, the software stencil-then-cover tile rasteriser for sm_100a.
 //
 // Replaces the wgpu render pass of the reference: Shape::render draw recording (src/renderer.rs:267-355), the 13
 // pipeline stencil / blend states (src/renderer.rs:565-861) and every entry point of src/shaders.wgsl.
 //
-// Data flow (all in HBM, no host round trips except one pair-count read-back):
-//   commands --count--> candidate primitives (one per index slot / list triangle / hull strip triangle, in exact
-//   draw order) --bin--> (tile, candidate) pairs --stable radix sort by tile--> per-tile ranges --K3--> framebuffer.
-// K3: one CTA per 16x16 tile, one thread per pixel. The pixel's stencil byte and RGBA colour live in REGISTERS for
-// the whole pass; triangles are set up cooperatively (one thread per triangle) into shared memory in chunks of 256
-// and then every pixel walks the chunk in draw order (shared-memory broadcast reads, warp-uniform branches). The
-// tile is read once and written once with 128-bit accesses, so overdraw costs no HBM traffic.
+// Data flow (all in HBM, one 4-byte read-back of the pair count):
+//   commands -> candidates (one per index slot / list triangle / hull-strip triangle, numbered in exact draw order)
+//   --prim_setup--> 48-byte PrimRecords (vertex stage done once) + tiles touched per candidate --scan-->
+//   --bin_emit--> (tile, candidate) pairs --stable radix sort by tile--> per-tile ranges in draw order --K3--> framebuffer.
+//
+// K3: one CTA per 16x16 tile. The pixel's stencil byte and RGBA colour live in the REGISTERS of "its" thread for the whole
+// pass, so the tile is read once and written once (128-bit accesses) and overdraw costs no HBM traffic. The tile's
+// primitives are walked in draw order in chunks; inside a chunk, maximal runs of primitives whose stencil effect
+// commutes are executed in parallel over (primitive, pixel row) pairs into a shared-memory accumulator:
+//   * fill stencil (src/renderer.rs:577-582): the test only looks at the clip bits, the op is +-1 mod 2^winding_bits
+//     => the run's net effect on a pixel is the signed count of covering front/back faces;
+//   * stroke stencil (src/renderer.rs:571-576): passes only while the winding bits are still equal to the reference
+//     (zero), then sets them to one => the run's net effect is "any primitive covers".
+// Cover operations (colour, clip, alpha contexts) are order dependent and run one thread per pixel.
 //
 // Rasterisation contract: see the header comment of oracle/raster.hpp (written independently, same rules).
 #include "device_common.cuh"
@@ -18,7 +25,8 @@
 
 namespace {
 
-#define CHUNK 256
+#define RCHUNK 128            // primitives staged in shared memory at a time
+#define BIG_TILE_BOX 8        // candidates touching more tiles than this are binned by the whole warp
 
 struct Descriptor {   // DynamicStrokeDescriptor, src/renderer.rs:18-27 (48 B)
     float gap_start[4];
@@ -33,99 +41,11 @@ enum Pipe : uint32_t {
     P_STROKE_LINE = 0, P_STROKE_JOINT = 1, P_FILL_SOLID = 2, P_FILL_IQ = 3, P_FILL_IC = 4, P_FILL_RQ = 5, P_FILL_RC = 6,
     P_CLIP = 7, P_UNCLIP = 8, P_COLOR = 9, P_SAVE_ALPHA = 10, P_SCALE_ALPHA = 11, P_RESTORE_ALPHA = 12
 };
+#define META_FRONT 16u
+#define META_SWAPPED 32u
+#define META_VALID 64u
+#define META_FULL 2048u   // (tile-local) every pixel centre of the tile is inside the primitive
 
-__device__ __forceinline__ uint32_t slots_of(const DeviceBatch& b, uint32_t shape, int cat) {
-    const size_t stride = (size_t)b.n_shapes + 1;
-    if (cat <= 2) {
-        const size_t row = (size_t)(CNT_LINE_IDX + cat) * stride;
-        return b.cat_begin[row + shape + 1] - b.cat_begin[row + shape];
-    }
-    if (cat <= 6) {
-        const size_t row = (size_t)cat * stride;
-        return (b.cat_begin[row + shape + 1] - b.cat_begin[row + shape]) / 3u;
-    }
-    const uint32_t hc = b.hull_count[shape];
-    return hc >= 3 ? hc - 2 : 0u;
-}
-__device__ __forceinline__ bool cat_drawn(const DeviceBatch& b, int cat) { return cat >= 2 || b.n_groups > 0; }   // src/renderer.rs:276
-
-// Candidate primitives of one command: Stencil = 7 instanced draws in category order (src/renderer.rs:275-336),
-// everything else = one instanced hull draw (:345-354).
-__global__ void count_candidates_kernel(const DeviceBatch* __restrict__ batches, const DeviceCommand* __restrict__ commands, uint32_t n, uint32_t* __restrict__ out) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    const DeviceCommand cmd = commands[c];
-    const DeviceBatch& b = batches[cmd.batch];
-    const uint32_t n_inst = cmd.instance_end > cmd.instance_begin ? cmd.instance_end - cmd.instance_begin : 0u;
-    uint32_t total = 0;
-    if (cmd.operation == CR_OP_STENCIL) {
-        for (int cat = 0; cat < 7; ++cat)
-            if (cat_drawn(b, cat)) total += slots_of(b, cmd.shape, cat) * n_inst;
-    } else {
-        total = slots_of(b, cmd.shape, 7) * n_inst;
-    }
-    out[c] = total;
-}
-
-struct Candidate {
-    uint32_t cmd;
-    uint32_t cat;      // 0..7
-    uint32_t instance;
-    uint32_t local;    // slot / triangle number inside the category
-};
-__device__ Candidate decode_candidate(const RasterScene& sc, uint32_t cand, DeviceCommand& cmd_out) {
-    uint32_t lo = 0, hi = sc.n_commands;   // last command with begin <= cand
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sc.cmd_cand_begin[mid] <= cand) lo = mid; else hi = mid; }
-    Candidate k;
-    k.cmd = lo;
-    const DeviceCommand cmd = sc.commands[lo];
-    cmd_out = cmd;
-    const DeviceBatch& b = sc.batches[cmd.batch];
-    uint32_t rem = cand - sc.cmd_cand_begin[lo];
-    const uint32_t n_inst = cmd.instance_end - cmd.instance_begin;
-    k.cat = 7;
-    if (cmd.operation == CR_OP_STENCIL) {
-        for (int cat = 0; cat < 7; ++cat) {
-            if (!cat_drawn(b, cat)) continue;
-            const uint32_t n = slots_of(b, cmd.shape, cat);
-            const uint32_t tot = n * n_inst;
-            if (rem < tot) { k.cat = cat; k.instance = cmd.instance_begin + rem / n; k.local = rem % n; return k; }
-            rem -= tot;
-        }
-    }
-    const uint32_t n = slots_of(b, cmd.shape, 7);
-    k.instance = cmd.instance_begin + rem / n;
-    k.local = rem % n;
-    return k;
-}
-
-// The three vertex numbers (absolute, inside the batch-wide category array) of a candidate; false if the slot is
-// not a triangle (restart inside, strip too short).
-__device__ bool candidate_vertices(const DeviceBatch& b, uint32_t shape, const Candidate& k, uint32_t v[3], bool& odd) {
-    const size_t stride = (size_t)b.n_shapes + 1;
-    if (k.cat <= 2) {
-        const size_t irow = (size_t)(CNT_LINE_IDX + k.cat) * stride;
-        const uint32_t ib = b.cat_begin[irow + shape], ie = b.cat_begin[irow + shape + 1];
-        if (k.local + 2 >= ie - ib) return false;
-        const uint32_t* idx = b.idx[k.cat] + ib + k.local;
-        const uint32_t i0 = idx[0], i1 = idx[1], i2 = idx[2];
-        if (i0 == CR_RESTART || i1 == CR_RESTART || i2 == CR_RESTART) return false;
-        const uint32_t vb = b.cat_begin[(size_t)k.cat * stride + shape];
-        v[0] = vb + (i0 >> 1); v[1] = vb + (i1 >> 1); v[2] = vb + (i2 >> 1);
-        odd = (i0 & 1u) != 0;
-        return true;
-    }
-    if (k.cat <= 6) {
-        const uint32_t vb = b.cat_begin[(size_t)k.cat * stride + shape];
-        v[0] = vb + 3 * k.local; v[1] = v[0] + 1; v[2] = v[0] + 2;
-        odd = false;
-        return true;
-    }
-    const uint32_t vb = b.cat_begin[(size_t)CNT_PROTO * stride + shape];
-    v[0] = vb + k.local; v[1] = v[0] + 1; v[2] = v[0] + 2;
-    odd = (k.local & 1u) != 0;
-    return true;
-}
 __device__ __forceinline__ const float* vertex_ptr(const DeviceBatch& b, uint32_t cat, uint32_t v) {
     switch (cat) {
         case 0: return reinterpret_cast<const float*>(b.vtx[0]) + (size_t)v * 5;
@@ -139,134 +59,254 @@ __device__ __forceinline__ const float* vertex_ptr(const DeviceBatch& b, uint32_
     }
 }
 
-struct SnapVertex { int X, Y; float invw; bool ok; };
+struct SnapVertex { int X, Y; bool ok; };
 // vertex shader + viewport transform + 1/256 px snapping (src/shaders.wgsl:66-74)
+__device__ __forceinline__ float clip_w(const float* __restrict__ m, float x, float y) { return (m[3] * x + m[7] * y) + m[15]; }
 __device__ __forceinline__ SnapVertex snap_vertex(const float* __restrict__ m, float x, float y, uint32_t W, uint32_t H) {
     SnapVertex v;
     const float cx = (m[0] * x + m[4] * y) + m[12];
     const float cy = (m[1] * x + m[5] * y) + m[13];
-    const float cw = (m[3] * x + m[7] * y) + m[15];
+    const float cw = clip_w(m, x, y);
     v.ok = cw > 0.0f;
-    v.invw = 1.0f / cw;
-    const float fx = ((cx * v.invw) * 0.5f + 0.5f) * (float)W;
-    const float fy = (0.5f - (cy * v.invw) * 0.5f) * (float)H;
+    const float invw = 1.0f / cw;
+    const float fx = ((cx * invw) * 0.5f + 0.5f) * (float)W;
+    const float fy = (0.5f - (cy * invw) * 0.5f) * (float)H;
     if (!(cr::fabs_f(fx) <= 2097152.0f) || !(cr::fabs_f(fy) <= 2097152.0f)) v.ok = false;
     v.X = v.ok ? (int)cr::floor_f(fx * 256.0f + 0.5f) : 0;
     v.Y = v.ok ? (int)cr::floor_f(fy * 256.0f + 0.5f) : 0;
     return v;
 }
 
-// A triangle oriented clockwise on screen (positive doubled area in y-down pixels) with its three edge functions
-// E_e(P) = A_e * (P.y - Y_e) - B_e * (P.x - X_e), inside when E_e + bias_e >= 0 (top-left rule).
-struct Tri {
-    int X[3], Y[3];
-    int A[3], B[3];
-    int bias[3];
-    bool front, swapped;
-};
-__device__ __forceinline__ bool make_tri(const SnapVertex& a, const SnapVertex& b, const SnapVertex& c, bool odd, Tri& t) {
-    if (!a.ok || !b.ok || !c.ok) return false;
-    long long area2 = (long long)(b.X - a.X) * (c.Y - a.Y) - (long long)(c.X - a.X) * (b.Y - a.Y);
-    if (area2 == 0) return false;
-    t.front = (area2 < 0) != odd;
-    t.swapped = area2 < 0;
-    t.X[0] = a.X; t.Y[0] = a.Y;
-    if (t.swapped) { t.X[1] = c.X; t.Y[1] = c.Y; t.X[2] = b.X; t.Y[2] = b.Y; }
-    else { t.X[1] = b.X; t.Y[1] = b.Y; t.X[2] = c.X; t.Y[2] = c.Y; }
+// Edge e runs from vertex e to vertex e+1 of a clockwise (y down) triangle: E_e(P) = A_e (P.y - Y_e) - B_e (P.x - X_e),
+// inside when E_e + bias_e >= 0 (top-left rule: bias 0 on top and left edges, -1 otherwise).
+struct Edges { int A[3], B[3], bias[3]; };
+__device__ __forceinline__ Edges make_edges(const int* X, const int* Y) {
+    Edges t;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
         const int n = e == 2 ? 0 : e + 1;
-        t.A[e] = t.X[n] - t.X[e];
-        t.B[e] = t.Y[n] - t.Y[e];
+        t.A[e] = X[n] - X[e];
+        t.B[e] = Y[n] - Y[e];
         t.bias[e] = ((t.B[e] == 0 && t.A[e] > 0) || t.B[e] < 0) ? 0 : -1;
     }
+    return t;
+}
+
+// Pixel and tile extent of a triangle: pixel centres are at 256 p + 128.
+struct Extent { int px0, px1, py0, py1, tx0, tx1, ty0, ty1; bool empty; };
+__device__ __forceinline__ Extent extent_of(const int* X, const int* Y, const RasterTarget& tg) {
+    Extent x;
+    const int minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+    const int minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+    x.px0 = max(0, (minX - 128 + 255) >> 8); x.px1 = min((int)tg.width - 1, (maxX - 128) >> 8);
+    x.py0 = max(0, (minY - 128 + 255) >> 8); x.py1 = min((int)tg.height - 1, (maxY - 128) >> 8);
+    x.empty = x.px0 > x.px1 || x.py0 > x.py1;
+    x.tx0 = x.px0 / CR_TILE; x.tx1 = x.px1 / CR_TILE; x.ty0 = x.py0 / CR_TILE; x.ty1 = x.py1 / CR_TILE;
+    return x;
+}
+// Can any pixel centre of tile (tx, ty), restricted to the triangle's pixel extent, be inside? (per-edge trivial reject)
+__device__ __forceinline__ bool tile_hit(const int* X, const int* Y, const Edges& t, const Extent& x, int tx, int ty) {
+    const int ylo = max(x.py0, ty * CR_TILE) * 256 + 128, yhi = min(x.py1, ty * CR_TILE + CR_TILE - 1) * 256 + 128;
+    const int xlo = max(x.px0, tx * CR_TILE) * 256 + 128, xhi = min(x.px1, tx * CR_TILE + CR_TILE - 1) * 256 + 128;
+    bool hit = true;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int PX = t.B[e] < 0 ? xhi : xlo, PY = t.A[e] > 0 ? yhi : ylo;   // corner maximising E_e
+        const long long E = (long long)t.A[e] * (PY - Y[e]) - (long long)t.B[e] * (PX - X[e]);
+        if (E + t.bias[e] < 0) hit = false;
+    }
+    return hit;
+}
+
+// ------------------------------------------------------------------------------------------ vertex stage
+// Which command a candidate belongs to: last command whose first candidate is <= cand.
+__device__ __forceinline__ uint32_t find_command(const uint32_t* __restrict__ begin, uint32_t n_commands, uint32_t cand) {
+    uint32_t lo = 0, hi = n_commands;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (begin[mid] <= cand) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__device__ bool build_record(const RasterScene& sc, const RasterTarget& tg, uint32_t cand, const uint32_t* __restrict__ cmd_begin, PrimRecord& rec) {
+    rec.meta = 0;
+    const uint32_t ci = find_command(cmd_begin, sc.n_commands, cand);
+    const DeviceCommand& cmd = sc.commands[ci];
+    uint32_t rem = cand - cmd_begin[ci];
+    uint32_t cat = 0, prev_end = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { const uint32_t e = cmd.cat_end[c]; if (rem >= e) { cat = c + 1; prev_end = e; } }
+    if (cat > 7) return false;
+    rem -= prev_end;
+    const uint32_t n = cmd.slots[cat];
+    const uint32_t inst = rem / n, local = rem - inst * n;
+    const DeviceBatch& b = sc.batches[cmd.batch];
+    uint32_t v[3];
+    bool odd = false;
+    if (cat <= 2) {   // indexed triangle strips with primitive restart (src/renderer.rs:476)
+        if (local + 2 >= n) return false;
+        const uint32_t* idx = b.idx[cat] + cmd.ibase[cat] + local;
+        const uint32_t i0 = idx[0], i1 = idx[1], i2 = idx[2];
+        if (i0 == CR_RESTART || i1 == CR_RESTART || i2 == CR_RESTART) return false;
+        v[0] = cmd.vbase[cat] + (i0 >> 1); v[1] = cmd.vbase[cat] + (i1 >> 1); v[2] = cmd.vbase[cat] + (i2 >> 1);
+        odd = (i0 & 1u) != 0;
+    } else if (cat <= 6) {   // triangle lists
+        v[0] = cmd.vbase[cat] + 3 * local; v[1] = v[0] + 1; v[2] = v[0] + 2;
+    } else {   // non-indexed hull strip (src/renderer.rs:354)
+        v[0] = cmd.vbase[7] + local; v[1] = v[0] + 1; v[2] = v[0] + 2;
+        odd = (local & 1u) != 0;
+    }
+    const uint32_t instance = cmd.instance_begin + inst;
+    const float* m = sc.transforms + 16 * (size_t)instance;
+    SnapVertex sv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float* p = vertex_ptr(b, cat, v[i]);   // 20- and 24-byte vertices are only 4-byte aligned
+        sv[i] = snap_vertex(m, p[0], p[1], tg.width, tg.height);
+    }
+    if (!sv[0].ok || !sv[1].ok || !sv[2].ok) return false;
+    const long long area2 = (long long)(sv[1].X - sv[0].X) * (sv[2].Y - sv[0].Y) - (long long)(sv[2].X - sv[0].X) * (sv[1].Y - sv[0].Y);
+    if (area2 == 0) return false;
+    const bool front = (area2 < 0) != odd;   // counter-clockwise in NDC (y up) = negative area in y-down pixels; odd strip triangles flip
+    const bool swapped = area2 < 0;
+    if (cmd.operation == CR_OP_COLOR) {   // cull_mode applies to the colour cover only (src/renderer.rs:743)
+        if (tg.cull_mode == CR_CULL_BACK && !front) return false;
+        if (tg.cull_mode == CR_CULL_FRONT && front) return false;
+    }
+    const uint32_t pipe = cmd.operation == CR_OP_STENCIL ? cat : P_CLIP + (cmd.operation - CR_OP_CLIP);   // CLIP..RESTORE follow the enum order
+    rec.X[0] = sv[0].X; rec.Y[0] = sv[0].Y;
+    rec.X[1] = swapped ? sv[2].X : sv[1].X; rec.Y[1] = swapped ? sv[2].Y : sv[1].Y;
+    rec.X[2] = swapped ? sv[1].X : sv[2].X; rec.Y[2] = swapped ? sv[1].Y : sv[2].Y;
+    rec.meta = pipe | (front ? META_FRONT : 0u) | (swapped ? META_SWAPPED : 0u) | META_VALID | (cat << 8);
+    rec.cmd = ci;
+    rec.instance = instance;
+    rec.v[0] = v[0]; rec.v[1] = v[1]; rec.v[2] = v[2];
     return true;
 }
-__device__ __forceinline__ int floor_div256(int v) { return v >> 8; }   // arithmetic shift = floor for negatives
 
-// Visit every tile whose sample centres can be inside the triangle (bounding box + per-edge trivial reject).
-template <typename F>
-__device__ __forceinline__ void for_each_tile(const Tri& t, const RasterTarget& tg, F f) {
-    const int minX = min(t.X[0], min(t.X[1], t.X[2])), maxX = max(t.X[0], max(t.X[1], t.X[2]));
-    const int minY = min(t.Y[0], min(t.Y[1], t.Y[2])), maxY = max(t.Y[0], max(t.Y[1], t.Y[2]));
-    // pixel centres are at 256*p + 128: first centre >= minX, last centre <= maxX
-    const int px0 = max(0, (minX - 128 + 255) >> 8), px1 = min((int)tg.width - 1, (maxX - 128) >> 8);
-    const int py0 = max(0, (minY - 128 + 255) >> 8), py1 = min((int)tg.height - 1, (maxY - 128) >> 8);
-    if (px0 > px1 || py0 > py1) return;
-    const int tx0 = px0 / CR_TILE, tx1 = px1 / CR_TILE, ty0 = py0 / CR_TILE, ty1 = py1 / CR_TILE;
-    for (int ty = ty0; ty <= ty1; ++ty) {
-        const int ylo = max(py0, ty * CR_TILE) * 256 + 128, yhi = min(py1, ty * CR_TILE + CR_TILE - 1) * 256 + 128;
-        for (int tx = tx0; tx <= tx1; ++tx) {
-            const int xlo = max(px0, tx * CR_TILE) * 256 + 128, xhi = min(px1, tx * CR_TILE + CR_TILE - 1) * 256 + 128;
-            bool out = false;
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                const int PX = t.B[e] < 0 ? xhi : xlo, PY = t.A[e] > 0 ? yhi : ylo;   // corner maximising E_e
-                const long long E = (long long)t.A[e] * (PY - t.Y[e]) - (long long)t.B[e] * (PX - t.X[e]);
-                if (E + t.bias[e] < 0) out = true;
+__device__ __forceinline__ void store_record(PrimRecord* dst, const PrimRecord& rec) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4((uint32_t)rec.X[0], (uint32_t)rec.X[1], (uint32_t)rec.X[2], (uint32_t)rec.Y[0]);
+    d[1] = make_uint4((uint32_t)rec.Y[1], (uint32_t)rec.Y[2], rec.meta, rec.cmd);
+    d[2] = make_uint4(rec.instance, rec.v[0], rec.v[1], rec.v[2]);
+}
+__device__ __forceinline__ PrimRecord load_record(const PrimRecord* src) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    const uint4 a = s[0], b = s[1], c = s[2];
+    PrimRecord r;
+    r.X[0] = (int)a.x; r.X[1] = (int)a.y; r.X[2] = (int)a.z; r.Y[0] = (int)a.w;
+    r.Y[1] = (int)b.x; r.Y[2] = (int)b.y; r.meta = b.z; r.cmd = b.w;
+    r.instance = c.x; r.v[0] = c.y; r.v[1] = c.z; r.v[2] = c.w;
+    return r;
+}
+
+// Tiles touched by a triangle whose tile box is small: walked by its own thread.
+// EMIT == false: returns the count. EMIT == true: also writes (tile, cand) pairs starting at `at`.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t walk_tiles_small(const int* X, const int* Y, const Extent& x, const RasterTarget& tg, uint32_t cand, uint32_t at,
+                                                     uint32_t* __restrict__ pair_tile, uint32_t* __restrict__ pair_cand) {
+    const Edges t = make_edges(X, Y);
+    uint32_t count = 0;
+    for (int ty = x.ty0; ty <= x.ty1; ++ty)
+        for (int tx = x.tx0; tx <= x.tx1; ++tx)
+            if (tile_hit(X, Y, t, x, tx, ty)) {
+                if (EMIT) { pair_tile[at + count] = (uint32_t)(ty * (int)tg.tiles_x + tx); pair_cand[at + count] = cand; }
+                ++count;
             }
-            if (!out) f((uint32_t)(ty * (int)tg.tiles_x + tx));
+    return count;
+}
+// Tiles touched by a triangle with a large tile box (hull covers, big fans): walked by a whole warp, 32 tiles per step.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t walk_tiles_warp(const int* X, const int* Y, const RasterTarget& tg, uint32_t cand, uint32_t at,
+                                                    uint32_t* __restrict__ pair_tile, uint32_t* __restrict__ pair_cand) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const Extent x = extent_of(X, Y, tg);
+    const Edges t = make_edges(X, Y);
+    const int w = x.tx1 - x.tx0 + 1, total = w * (x.ty1 - x.ty0 + 1);
+    uint32_t running = 0;
+    int ty = x.ty0 + (int)lane / w, tx = x.tx0 + (int)lane % w;   // 32 consecutive tiles of the box, advanced incrementally
+    const int dy = 32 / w, dx = 32 % w;
+    for (int base = 0; base < total; base += 32) {
+        const bool hit = base + (int)lane < total && tile_hit(X, Y, t, x, tx, ty);
+        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+        if (EMIT && hit) {
+            const uint32_t pos = at + running + __popc(hits & ((1u << lane) - 1u));
+            pair_tile[pos] = (uint32_t)(ty * (int)tg.tiles_x + tx);
+            pair_cand[pos] = cand;
+        }
+        running += __popc(hits);
+        ty += dy; tx += dx;
+        if (tx > x.tx1) { tx -= w; ty += 1; }
+    }
+    return running;
+}
+
+#define SETUP_THREADS 256
+#define SETUP_CMD_CACHE 2048
+#define META_BIG 128u
+// big[0] = number of big candidates, big[1 ...] = their candidate numbers
+__global__ void __launch_bounds__(SETUP_THREADS) prim_setup_kernel(RasterScene sc, RasterTarget tg, uint32_t n, PrimRecord* __restrict__ records,
+                                                                   uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ big) {
+    __shared__ uint32_t sh_begin[SETUP_CMD_CACHE + 1];
+    const uint32_t* cmd_begin = sc.cmd_cand_begin;
+    if (sc.n_commands <= SETUP_CMD_CACHE) {
+        for (uint32_t i = threadIdx.x; i <= sc.n_commands; i += blockDim.x) sh_begin[i] = sc.cmd_cand_begin[i];
+        __syncthreads();
+        cmd_begin = sh_begin;
+    }
+    const uint32_t cand = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cand >= n) return;
+    PrimRecord rec;
+    uint32_t count = 0;
+    if (build_record(sc, tg, cand, cmd_begin, rec)) {
+        const Extent x = extent_of(rec.X, rec.Y, tg);
+        if (x.empty) rec.meta = 0;
+        else if ((x.tx1 - x.tx0 + 1) * (x.ty1 - x.ty0 + 1) <= BIG_TILE_BOX) count = walk_tiles_small<false>(rec.X, rec.Y, x, tg, cand, 0, nullptr, nullptr);
+        else { rec.meta |= META_BIG; big[1 + atomicAdd(big, 1u)] = cand; }   // counted by bin_big_kernel<false>
+    }
+    store_record(records + cand, rec);
+    cand_tiles[cand] = count;
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS) bin_emit_kernel(RasterTarget tg, uint32_t n, const PrimRecord* __restrict__ records,
+                                                                 const uint32_t* __restrict__ begin, uint32_t* __restrict__ pair_tile,
+                                                                 uint32_t* __restrict__ pair_cand) {
+    const uint32_t cand = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cand >= n) return;
+    const uint32_t at = begin[cand];
+    if (begin[cand + 1] == at) return;
+    const PrimRecord rec = load_record(records + cand);
+    if (!(rec.meta & META_VALID) || (rec.meta & META_BIG)) return;
+    walk_tiles_small<true>(rec.X, rec.Y, extent_of(rec.X, rec.Y, tg), tg, cand, at, pair_tile, pair_cand);
+}
+
+// One warp per big candidate (grid-stride over the list built by prim_setup_kernel).
+template <bool EMIT>
+__global__ void __launch_bounds__(128) bin_big_kernel(RasterTarget tg, const PrimRecord* __restrict__ records, const uint32_t* __restrict__ big,
+                                                      uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ pair_tile, uint32_t* __restrict__ pair_cand) {
+    const uint32_t n_big = big[0];
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_big; i += warps) {
+        const uint32_t cand = big[1 + i];
+        const PrimRecord rec = load_record(records + cand);
+        if (EMIT) walk_tiles_warp<true>(rec.X, rec.Y, tg, cand, cand_tiles[cand], pair_tile, pair_cand);   // cand_tiles now holds the exclusive scan
+        else {
+            const uint32_t count = walk_tiles_warp<false>(rec.X, rec.Y, tg, cand, 0, nullptr, nullptr);
+            if ((threadIdx.x & 31u) == 0) cand_tiles[cand] = count;
         }
     }
 }
 
-// Geometry of a candidate as the binner needs it (positions only). Returns false if nothing can be drawn.
-__device__ bool candidate_triangle(const RasterScene& sc, const RasterTarget& tg, uint32_t cand, Tri& tri) {
-    DeviceCommand cmd;
-    const Candidate k = decode_candidate(sc, cand, cmd);
-    const DeviceBatch& b = sc.batches[cmd.batch];
-    uint32_t v[3];
-    bool odd;
-    if (!candidate_vertices(b, cmd.shape, k, v, odd)) return false;
-    const float* m = sc.transforms + 16 * (size_t)k.instance;
-    SnapVertex sv[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float* p = vertex_ptr(b, k.cat, v[i]);
-        sv[i] = snap_vertex(m, p[0], p[1], tg.width, tg.height);
-    }
-    if (!make_tri(sv[0], sv[1], sv[2], odd, tri)) return false;
-    if (cmd.operation == CR_OP_COLOR) {   // cull_mode applies to the colour cover only (src/renderer.rs:743)
-        if (tg.cull_mode == CR_CULL_BACK && !tri.front) return false;
-        if (tg.cull_mode == CR_CULL_FRONT && tri.front) return false;
-    }
-    return true;
-}
-
-__global__ void __launch_bounds__(128) bin_count_kernel(RasterScene sc, RasterTarget tg, uint32_t n, uint32_t* __restrict__ cand_tiles) {
-    const uint32_t cand = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cand >= n) return;
-    Tri tri;
-    uint32_t count = 0;
-    if (candidate_triangle(sc, tg, cand, tri)) for_each_tile(tri, tg, [&](uint32_t) { ++count; });
-    cand_tiles[cand] = count;
-}
-__global__ void __launch_bounds__(128) bin_emit_kernel(RasterScene sc, RasterTarget tg, uint32_t n, const uint32_t* __restrict__ begin, uint32_t* __restrict__ pair_tile,
-                                                      uint32_t* __restrict__ pair_cand) {
-    const uint32_t cand = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cand >= n) return;
-    if (begin[cand + 1] == begin[cand]) return;
-    Tri tri;
-    if (!candidate_triangle(sc, tg, cand, tri)) return;
-    uint32_t at = begin[cand];
-    for_each_tile(tri, tg, [&](uint32_t tile) { pair_tile[at] = tile; pair_cand[at] = cand; ++at; });
-}
-
 // ------------------------------------------------------------------------------------------- K3: tile raster
-struct PrimSetup {
-    long long e0[3];        // edge functions (with top-left bias folded in) at the tile's first pixel centre
-    int A[3], B[3];         // per-pixel steps are 256*A (y) and -256*B (x)
+struct TilePrim {
+    long long e0[3];        // edge functions, top-left bias folded in, at the centre of the tile's pixel (0, 0)
+    int A[3], B[3];         // per-pixel steps: +256 A per row, -256 B per column
     int bias[3];
     float invw[3];
     float attr[3][4];
     uint32_t flat_u;
     float flat_f;
-    uint32_t pipe;          // Pipe | front << 8 | valid << 9
-    uint32_t ref;
-    uint32_t instance;
-    uint32_t batch;
-    uint32_t layers;        // save_layer | restore_layer << 16
+    uint32_t meta;          // PrimRecord::meta; META_VALID cleared if nothing of it can land in this tile
     uint32_t bbox;          // x0 | y0 << 8 | x1 << 16 | y1 << 24 in tile pixels
+    uint32_t ref, instance, batch, layers, cmd;
 };
 
 __device__ __forceinline__ bool cap_test(float tx, float ty, uint32_t cap_type) {   // src/shaders.wgsl:165-189
@@ -302,61 +342,101 @@ __device__ bool stroke_dashed(const Descriptor& d, float tx, float ty) {   // sr
     return true;
 }
 
-__device__ void setup_primitive(const RasterScene& sc, const RasterTarget& tg, uint32_t cand, int tile_px, int tile_py, PrimSetup& ps) {
-    ps.pipe = 0;
-    DeviceCommand cmd;
-    const Candidate k = decode_candidate(sc, cand, cmd);
-    const DeviceBatch& b = sc.batches[cmd.batch];
-    uint32_t v[3];
-    bool odd;
-    if (!candidate_vertices(b, cmd.shape, k, v, odd)) return;
-    const float* m = sc.transforms + 16 * (size_t)k.instance;
-    const int n_attr = (int)((0x04332032u >> (4u * k.cat)) & 15u);   // attribute floats per category: 2,3,0,2,3,3,4,0
-    SnapVertex sv[3];
-    float attr[3][4];
-    uint32_t flat_u = 0;
+// Fragment stage of the stencil pipelines (src/shaders.wgsl:233-300): perspective-correct attributes at the sample and
+// the sample_mask predicate. E[] are the biased edge values at the sample.
+__device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TilePrim& ps, uint32_t pipe, const long long* E) {
+    const float e0 = (float)(E[1] - ps.bias[1]) * ps.invw[0], e1 = (float)(E[2] - ps.bias[2]) * ps.invw[1], e2 = (float)(E[0] - ps.bias[0]) * ps.invw[2];
+    const float den = (e0 + e1) + e2;
+    float a[4];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float* p = vertex_ptr(b, k.cat, v[i]);
-        sv[i] = snap_vertex(m, p[0], p[1], tg.width, tg.height);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) attr[i][a] = a < n_attr ? p[2 + a] : 0.0f;
-        if (i == 0 && k.cat <= 1) flat_u = __float_as_uint(p[2 + n_attr]);
+    for (int q = 0; q < 4; ++q) a[q] = ((e0 * ps.attr[0][q] + e1 * ps.attr[1][q]) + e2 * ps.attr[2][q]) / den;
+    switch (pipe) {
+        case P_FILL_IQ: return a[0] * a[0] - a[1] <= 0.0f;
+        case P_FILL_IC: return a[0] * a[0] * a[0] - a[1] * a[2] <= 0.0f;
+        case P_FILL_RQ: return a[0] * a[0] - a[1] * a[2] <= 0.0f;
+        case P_FILL_RC: return a[0] * a[0] * a[0] - a[1] * a[2] * a[3] <= 0.0f;
+        case P_STROKE_LINE: {   // src/shaders.wgsl:268-285
+            const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[ps.batch].stroke)[ps.flat_u & 65535u];
+            if ((d.count_dashed_join & 4u) != 0u) return stroke_dashed(d, a[0], a[1]);
+            if ((ps.flat_u & 65536u) != 0u) return cap_test(a[0], a[1] - ps.flat_f, d.caps >> 4u);
+            if (a[1] < 0.0f) return cap_test(a[0], -a[1], d.caps);
+            return true;
+        }
+        default: {              // P_STROKE_JOINT, src/shaders.wgsl:287-300
+            const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[ps.batch].stroke)[ps.flat_u & 65535u];
+            const float radius = cr::sqrt_f(a[0] * a[0] + a[1] * a[1]);
+            const uint32_t kind = d.count_dashed_join & 3u;
+            bool keep = kind == 1u ? (ps.flat_u & 65536u) != 0u : (kind == 2u ? radius <= 0.5f : true);
+            if (keep && (d.count_dashed_join & 4u) != 0u) keep = stroke_dashed(d, radius, a[2] + cr::atan2_f(a[1], a[0]) / 6.28318548202514648438f);
+            return keep;
+        }
     }
-    Tri t;
-    if (!make_tri(sv[0], sv[1], sv[2], odd, t)) return;
-    uint32_t pipe;
-    if (cmd.operation == CR_OP_STENCIL) pipe = k.cat;
-    else pipe = P_CLIP + (cmd.operation - CR_OP_CLIP);   // CLIP, UNCLIP, COLOR, SAVE, SCALE, RESTORE follow the enum order
-    ps.flat_u = flat_u;
-    ps.flat_f = attr[0][1];
-    const int i1 = t.swapped ? 2 : 1, i2 = t.swapped ? 1 : 2;
-    ps.invw[0] = sv[0].invw; ps.invw[1] = sv[i1].invw; ps.invw[2] = sv[i2].invw;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) { ps.attr[0][a] = attr[0][a]; ps.attr[1][a] = attr[i1][a]; ps.attr[2][a] = attr[i2][a]; }
+}
+
+// Stage one primitive of this tile into shared memory (one thread per primitive).
+__device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, const PrimRecord& rec, int tile_px, int tile_py, TilePrim& ps) {
+    ps.meta = 0;
+    if (!(rec.meta & META_VALID)) return;
+    const uint32_t pipe = rec.meta & 15u, cat = (rec.meta >> 8) & 7u;
+    const DeviceCommand& cmd = sc.commands[rec.cmd];
+    const Edges t = make_edges(rec.X, rec.Y);
     const int PX = tile_px * 256 + 128, PY = tile_py * 256 + 128;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
         ps.A[e] = t.A[e]; ps.B[e] = t.B[e]; ps.bias[e] = t.bias[e];
-        ps.e0[e] = (long long)t.A[e] * (PY - t.Y[e]) - (long long)t.B[e] * (PX - t.X[e]) + t.bias[e];
+        ps.e0[e] = (long long)t.A[e] * (PY - rec.Y[e]) - (long long)t.B[e] * (PX - rec.X[e]) + t.bias[e];
     }
-    // pixel bounding box clipped to this tile
-    const int minX = min(t.X[0], min(t.X[1], t.X[2])), maxX = max(t.X[0], max(t.X[1], t.X[2]));
-    const int minY = min(t.Y[0], min(t.Y[1], t.Y[2])), maxY = max(t.Y[0], max(t.Y[1], t.Y[2]));
-    const int x0 = max(0, ((minX - 128 + 255) >> 8) - tile_px), x1 = min(CR_TILE - 1, ((maxX - 128) >> 8) - tile_px);
-    const int y0 = max(0, ((minY - 128 + 255) >> 8) - tile_py), y1 = min(CR_TILE - 1, ((maxY - 128) >> 8) - tile_py);
+    // pixel bounding box clipped to this tile and to the target
+    const int minX = min(rec.X[0], min(rec.X[1], rec.X[2])), maxX = max(rec.X[0], max(rec.X[1], rec.X[2]));
+    const int minY = min(rec.Y[0], min(rec.Y[1], rec.Y[2])), maxY = max(rec.Y[0], max(rec.Y[1], rec.Y[2]));
+    const int x0 = max(0, ((minX - 128 + 255) >> 8) - tile_px), x1 = min(min(CR_TILE - 1, (int)tg.width - 1 - tile_px), ((maxX - 128) >> 8) - tile_px);
+    const int y0 = max(0, ((minY - 128 + 255) >> 8) - tile_py), y1 = min(min(CR_TILE - 1, (int)tg.height - 1 - tile_py), ((maxY - 128) >> 8) - tile_py);
     if (x0 > x1 || y0 > y1) return;
     ps.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+    bool full = true;   // minimum of every edge function over the tile's pixel centres is still inside
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const long long emin = ps.e0[e] + (t.A[e] < 0 ? (long long)t.A[e] * ((CR_TILE - 1) * 256) : 0) - (t.B[e] > 0 ? (long long)t.B[e] * ((CR_TILE - 1) * 256) : 0);
+        if (emin < 0) full = false;
+    }
     ps.ref = cmd.ref;
-    ps.instance = k.instance;
+    ps.instance = rec.instance;
     ps.batch = cmd.batch;
-    ps.layers = cmd.save_layer | (cmd.restore_layer << 16);
-    ps.pipe = pipe | (t.front ? 256u : 0u) | 512u;
+    ps.layers = cmd.layers;
+    ps.cmd = rec.cmd;
+    ps.flat_u = 0;
+    ps.flat_f = 0.0f;
+    if (pipe <= P_FILL_RC && pipe != P_FILL_SOLID) {   // pipelines with a fragment predicate need the vertex attributes
+        const DeviceBatch& b = sc.batches[cmd.batch];
+        const float* m = sc.transforms + 16 * (size_t)rec.instance;
+        const int n_attr = (int)((0x04332032u >> (4u * cat)) & 15u);   // attribute floats per category: 2,3,0,2,3,3,4,0
+        const bool swapped = (rec.meta & META_SWAPPED) != 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int src = i == 0 ? 0 : (swapped ? 3 - i : i);   // stored vertex order is (0, 2, 1) when swapped
+            const float* p = vertex_ptr(b, cat, rec.v[src]);
+            ps.invw[i] = 1.0f / clip_w(m, p[0], p[1]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) ps.attr[i][a] = a < n_attr ? p[2 + a] : 0.0f;
+            if (i == 0) {   // flat attributes come from the first (provoking) vertex
+                if (cat <= 1) ps.flat_u = __float_as_uint(p[2 + n_attr]);
+                ps.flat_f = n_attr > 1 ? p[3] : 0.0f;
+            }
+        }
+    }
+    ps.meta = rec.meta | (full ? META_FULL : 0u);
 }
 
-__global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const uint32_t* __restrict__ tile_begin,
-                                                                         const uint32_t* __restrict__ pair_cand, unsigned long long* __restrict__ covered_out) {
-    __shared__ PrimSetup sh[CHUNK];
+// Run kinds: primitives of one run commute (see the file header).
+__device__ __forceinline__ uint32_t run_kind(uint32_t pipe) { return pipe <= P_STROKE_JOINT ? 0u : (pipe <= P_FILL_RC ? 1u : 2u); }
+
+__global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
+                                                                         const uint32_t* __restrict__ tile_begin, const uint32_t* __restrict__ pair_cand,
+                                                                         unsigned long long* __restrict__ covered_out) {
+    __shared__ TilePrim sh[RCHUNK];
+    __shared__ int acc[CR_TILE * CR_TILE];
+    __shared__ uint32_t run_mask[RCHUNK / 32];
+    __shared__ uint8_t run_start[RCHUNK + 1];
     const uint32_t tile = blockIdx.x;
     const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];
     if (begin == end) return;
@@ -369,96 +449,139 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterS
     float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in_fb) { s = tg.stencil[pix]; col = tg.color[pix]; }
     const uint32_t W = tg.wmask, C = tg.cmask, M = W | C;
-    const int warp_y0 = (threadIdx.x >> 5) * (32 / CR_TILE), warp_y1 = warp_y0 + (32 / CR_TILE) - 1;
     uint32_t covered = 0;
     const size_t layer_stride = (size_t)tg.width * tg.height;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    acc[threadIdx.x] = 0;
 
-    for (uint32_t chunk = begin; chunk < end; chunk += CHUNK) {
-        const uint32_t n = min((uint32_t)CHUNK, end - chunk);
+    for (uint32_t chunk = begin; chunk < end; chunk += RCHUNK) {
+        const uint32_t n = min((uint32_t)RCHUNK, end - chunk);
         __syncthreads();
-        if (threadIdx.x < n) setup_primitive(sc, tg, pair_cand[chunk + threadIdx.x], tile_px, tile_py, sh[threadIdx.x]);
+        // ---- stage the chunk (one thread per primitive) and find the run boundaries
+        bool boundary = false;
+        if (threadIdx.x < n) {
+            const PrimRecord rec = load_record(records + pair_cand[chunk + threadIdx.x]);
+            stage_primitive(sc, tg, rec, tile_px, tile_py, sh[threadIdx.x]);
+        }
         __syncthreads();
-        for (uint32_t k = 0; k < n; ++k) {
-            const PrimSetup& ps = sh[k];
-            const uint32_t meta = ps.pipe;
-            if (!(meta & 512u)) continue;
-            const uint32_t bbox = ps.bbox;
-            const int by0 = (bbox >> 8) & 255, by1 = bbox >> 24;
-            if (by1 < warp_y0 || by0 > warp_y1) continue;                      // warp-uniform reject
-            const int bx0 = bbox & 255, bx1 = (bbox >> 16) & 255;
-            if (lx < bx0 || lx > bx1 || ly < by0 || ly > by1 || !in_fb) continue;
-            long long E[3];
-            bool inside = true;
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                E[e] = ps.e0[e] + (long long)ps.A[e] * (ly * 256) - (long long)ps.B[e] * (lx * 256);
-                if (E[e] < 0) inside = false;
-            }
-            if (!inside) continue;
-            const uint32_t pipe = meta & 255u;
-            const bool front = (meta & 256u) != 0;
-            // ---- fragment stage: perspective-correct attributes at the sample + sample_mask predicate
-            bool keep = true;
-            if (pipe != P_FILL_SOLID && pipe < P_CLIP) {
-                const float e0 = (float)(E[1] - ps.bias[1]) * ps.invw[0], e1 = (float)(E[2] - ps.bias[2]) * ps.invw[1], e2 = (float)(E[0] - ps.bias[0]) * ps.invw[2];
-                const float den = (e0 + e1) + e2;
-                float a[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) a[q] = ((e0 * ps.attr[0][q] + e1 * ps.attr[1][q]) + e2 * ps.attr[2][q]) / den;
-                switch (pipe) {
-                    case P_FILL_IQ: keep = a[0] * a[0] - a[1] <= 0.0f; break;
-                    case P_FILL_IC: keep = a[0] * a[0] * a[0] - a[1] * a[2] <= 0.0f; break;
-                    case P_FILL_RQ: keep = a[0] * a[0] - a[1] * a[2] <= 0.0f; break;
-                    case P_FILL_RC: keep = a[0] * a[0] * a[0] - a[1] * a[2] * a[3] <= 0.0f; break;
-                    case P_STROKE_LINE: {   // src/shaders.wgsl:268-285
-                        const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[ps.batch].stroke)[ps.flat_u & 65535u];
-                        if ((d.count_dashed_join & 4u) != 0u) keep = stroke_dashed(d, a[0], a[1]);
-                        else if ((ps.flat_u & 65536u) != 0u) keep = cap_test(a[0], a[1] - ps.flat_f, d.caps >> 4u);
-                        else if (a[1] < 0.0f) keep = cap_test(a[0], -a[1], d.caps);
-                    } break;
-                    default: {              // P_STROKE_JOINT, src/shaders.wgsl:287-300
-                        const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[ps.batch].stroke)[ps.flat_u & 65535u];
-                        const float radius = cr::sqrt_f(a[0] * a[0] + a[1] * a[1]);
-                        const uint32_t kind = d.count_dashed_join & 3u;
-                        keep = kind == 1u ? (ps.flat_u & 65536u) != 0u : (kind == 2u ? radius <= 0.5f : true);
-                        if (keep && (d.count_dashed_join & 4u) != 0u)
-                            keep = stroke_dashed(d, radius, a[2] + cr::atan2_f(a[1], a[0]) / 6.28318548202514648438f);
-                    } break;
+        if (threadIdx.x < RCHUNK) {
+            if (threadIdx.x < n) {
+                if (threadIdx.x == 0) boundary = true;
+                else {
+                    const TilePrim &p = sh[threadIdx.x - 1], &q = sh[threadIdx.x];
+                    // staged-out primitives (meta == 0) join whatever run surrounds them: they do nothing
+                    const uint32_t kp = run_kind(p.meta & 15u), kq = run_kind(q.meta & 15u);
+                    const bool pv = (p.meta & META_VALID) != 0, qv = (q.meta & META_VALID) != 0;
+                    if (pv && qv) boundary = kp != kq || (kq < 2u ? p.ref != q.ref : (p.cmd != q.cmd || p.instance != q.instance));
+                    else boundary = qv;   // a valid primitive after an invalid one conservatively opens a run
                 }
             }
-            if (!keep) continue;
-            // ---- output merger: stencil test / op and colour blend (src/renderer.rs:571-861)
-            const uint32_t ref = ps.ref;
-            if (pipe <= P_STROKE_JOINT) {
-                if ((ref & M) == (s & M)) s = (s & ~W) | ((s + 1u) & W);
-            } else if (pipe <= P_FILL_RC) {
-                if ((ref & M) <= (s & M)) s = (s & ~W) | ((front ? s + 1u : s - 1u) & W);
-            } else if (pipe == P_COLOR) {
-                if ((ref & M) < (s & M)) {
-                    const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
-                    const float sa = ic.w;
-                    const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
-                    if (tg.blending == CR_BLEND_PREMULTIPLIED_OVER) {
-                        const float kk = 1.0f - sa;
-                        col.x = sr + col.x * kk; col.y = sg + col.y * kk; col.z = sb + col.z * kk; col.w = sa + col.w * kk;
-                    } else { col.x = sr; col.y = sg; col.z = sb; col.w = sa; }
-                    covered += 1;
+            const uint32_t m = __ballot_sync(0xffffffffu, boundary);
+            if (lane == 0) run_mask[warp] = m;
+        }
+        __syncthreads();
+        uint32_t n_runs = 0;
+        {
+            uint32_t before = 0;
+#pragma unroll
+            for (int w = 0; w < RCHUNK / 32; ++w) { const uint32_t m = run_mask[w]; if ((uint32_t)w < warp) before += __popc(m); n_runs += __popc(m); }
+            if (boundary) run_start[before + __popc(run_mask[warp] & ((1u << lane) - 1u))] = (uint8_t)threadIdx.x;
+            if (threadIdx.x == 0) run_start[n_runs] = (uint8_t)n;   // n <= 128 fits
+        }
+        __syncthreads();
+        // ---- execute the runs in draw order
+        for (uint32_t r = 0; r < n_runs; ++r) {
+            const uint32_t a = run_start[r], b = run_start[r + 1];
+            // first valid primitive decides the run's kind and reference
+            uint32_t first = a;   // only the chunk's first run can start with staged-out primitives (see `boundary`)
+            if (r == 0) { while (first < b && !(sh[first].meta & META_VALID)) ++first; }
+            if (first == b) continue;
+            const uint32_t kind = run_kind(sh[first].meta & 15u);
+            if (kind < 2u) {
+                // stencil run: (primitive, row) work items, 16 primitives x 16 rows per sweep
+                for (uint32_t base = a; base < b; base += CR_TILE) {
+                    const uint32_t k = base + (threadIdx.x >> 4);
+                    if (k >= b) continue;
+                    const TilePrim& ps = sh[k];
+                    const uint32_t meta = ps.meta;
+                    if (!(meta & META_VALID)) continue;
+                    const uint32_t bbox = ps.bbox;
+                    const int y = (int)((bbox >> 8) & 255u) + (int)(threadIdx.x & 15u);
+                    if (y > (int)(bbox >> 24)) continue;
+                    const int x0 = (int)(bbox & 255u), x1 = (int)((bbox >> 16) & 255u);
+                    const uint32_t pipe = meta & 15u;
+                    long long E[3], step[3];
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        step[e] = (long long)ps.B[e] * 256;
+                        E[e] = ps.e0[e] + (long long)ps.A[e] * (y * 256) - step[e] * x0;
+                    }
+                    const int delta = kind == 0u ? 1 : ((meta & META_FRONT) ? 1 : -1);
+                    for (int x = x0; x <= x1; ++x) {
+                        if ((E[0] | E[1] | E[2]) >= 0) {
+                            if (pipe == P_FILL_SOLID || fragment_keep(sc, ps, pipe, E)) {
+                                if (kind == 0u) atomicOr(&acc[y * CR_TILE + x], 1);
+                                else atomicAdd(&acc[y * CR_TILE + x], delta);
+                            }
+                        }
+                        E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
+                    }
                 }
-                s = s & ~W;
-            } else if (pipe == P_CLIP) {
-                if ((ref & W) != (s & W)) s = (s & ~M) | (ref & M);
-            } else if (pipe == P_UNCLIP) {
-                if ((ref & C) < (s & C)) s = (s & ~M) | (ref & M);
-            } else if ((ref & M) <= (s & M)) {   // the three alpha-context covers share one stencil state (:761-766)
-                if (pipe == P_SAVE_ALPHA) {
-                    tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix] = col.w;
-                } else if (pipe == P_SCALE_ALPHA) {
-                    const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
-                    col.w = sa + col.w * (1.0f - sa);
-                } else {
-                    const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix];
-                    const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
-                    col.w = col.w - sa;
+                __syncthreads();
+                const int net = acc[threadIdx.x];
+                if (net != 0) {
+                    const uint32_t ref = sh[first].ref;
+                    if (kind == 0u) { if ((ref & M) == (s & M)) s = (s & ~W) | ((s + 1u) & W); }            // src/renderer.rs:571-576
+                    else if ((ref & M) <= (s & M)) s = (s & ~W) | ((s + (uint32_t)net) & W);                 // src/renderer.rs:577-582
+                    acc[threadIdx.x] = 0;
+                }
+                __syncthreads();
+            } else {
+                // cover run: one (command, instance) hull draw; order dependent, one thread per pixel
+                for (uint32_t k = a; k < b; ++k) {
+                    const TilePrim& ps = sh[k];
+                    const uint32_t meta = ps.meta;
+                    if (!(meta & META_VALID)) continue;
+                    const uint32_t bbox = ps.bbox;
+                    if (lx < (int)(bbox & 255u) || lx > (int)((bbox >> 16) & 255u) || ly < (int)((bbox >> 8) & 255u) || ly > (int)(bbox >> 24)) continue;
+                    bool inside = true;
+                    if (!(meta & META_FULL)) {
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) {
+                            const long long E = ps.e0[e] + (long long)ps.A[e] * (ly * 256) - (long long)ps.B[e] * (lx * 256);
+                            if (E < 0) inside = false;
+                        }
+                    }
+                    if (!inside || !in_fb) continue;
+                    const uint32_t pipe = meta & 15u, ref = ps.ref;
+                    if (pipe == P_COLOR) {                                                                   // src/renderer.rs:736-754
+                        if ((ref & M) < (s & M)) {
+                            const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
+                            const float sa = ic.w;
+                            const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
+                            if (tg.blending == CR_BLEND_PREMULTIPLIED_OVER) {
+                                const float kk = 1.0f - sa;
+                                col.x = sr + col.x * kk; col.y = sg + col.y * kk; col.z = sb + col.z * kk; col.w = sa + col.w * kk;
+                            } else { col.x = sr; col.y = sg; col.z = sb; col.w = sa; }
+                            covered += 1;
+                        }
+                        s = s & ~W;
+                    } else if (pipe == P_CLIP) {                                                             // src/renderer.rs:692-710
+                        if ((ref & W) != (s & W)) s = (s & ~M) | (ref & M);
+                    } else if (pipe == P_UNCLIP) {                                                           // src/renderer.rs:711-729
+                        if ((ref & C) < (s & C)) s = (s & ~M) | (ref & M);
+                    } else if ((ref & M) <= (s & M)) {   // the three alpha-context covers share one stencil state (src/renderer.rs:761-766)
+                        if (pipe == P_SAVE_ALPHA) {
+                            tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix] = col.w;
+                        } else if (pipe == P_SCALE_ALPHA) {
+                            const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
+                            col.w = sa + col.w * (1.0f - sa);
+                        } else {
+                            const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix];
+                            const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
+                            col.w = col.w - sa;
+                        }
+                    }
                 }
             }
         }
@@ -467,38 +590,36 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterS
     // covered-sample statistic: warp reduce, one atomic per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xffffffffu, covered, o);
-    if ((threadIdx.x & 31u) == 0 && covered) atomicAdd(covered_out, (unsigned long long)covered);
+    if (lane == 0 && covered) atomicAdd(covered_out, (unsigned long long)covered);
 }
 
 }  // namespace
 
-int cr_raster_count_candidates(cudaStream_t stream, const DeviceBatch* batches, const DeviceCommand* commands, uint32_t n_commands, uint32_t* cmd_cands) {
-    if (n_commands == 0) return CR_OK;
-    count_candidates_kernel<<<(n_commands + 255) / 256, 256, 0, stream>>>(batches, commands, n_commands, cmd_cands);
-    g_cr_kernel_launches += 1;
-    CR_CUDA_TRY(cudaGetLastError());
-    return CR_OK;
-}
-int cr_raster_bin_count(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, uint32_t* cand_tiles) {
+#define BIG_GRID (148 * 8)
+int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, PrimRecord* records, uint32_t* cand_tiles,
+                    uint32_t* big_list) {
     if (n_candidates == 0) return CR_OK;
-    bin_count_kernel<<<(n_candidates + 127) / 128, 128, 0, stream>>>(scene, target, n_candidates, cand_tiles);
-    g_cr_kernel_launches += 1;
+    CR_CUDA_TRY(cudaMemsetAsync(big_list, 0, 4, stream));
+    prim_setup_kernel<<<(n_candidates + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(scene, target, n_candidates, records, cand_tiles, big_list);
+    bin_big_kernel<false><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, cand_tiles, nullptr, nullptr);
+    g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }
-int cr_raster_bin_emit(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, const uint32_t* cand_pair_begin,
-                       uint32_t* pair_tile, uint32_t* pair_cand) {
+int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t n_candidates, const PrimRecord* records, const uint32_t* cand_pair_begin,
+                       const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand) {
     if (n_candidates == 0) return CR_OK;
-    bin_emit_kernel<<<(n_candidates + 127) / 128, 128, 0, stream>>>(scene, target, n_candidates, cand_pair_begin, pair_tile, pair_cand);
-    g_cr_kernel_launches += 1;
+    bin_emit_kernel<<<(n_candidates + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(target, n_candidates, records, cand_pair_begin, pair_tile, pair_cand);
+    bin_big_kernel<true><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, const_cast<uint32_t*>(cand_pair_begin), pair_tile, pair_cand);
+    g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }
-int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const uint32_t* tile_begin, const uint32_t* pair_cand,
-                    unsigned long long* covered_samples) {
+int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* tile_begin,
+                    const uint32_t* pair_cand, unsigned long long* covered_samples) {
     const uint32_t n_tiles = target.tiles_x * target.tiles_y;
     if (n_tiles == 0) return CR_OK;
-    raster_tiles_kernel<<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, tile_begin, pair_cand, covered_samples);
+    raster_tiles_kernel<<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, covered_samples);
     g_cr_kernel_launches += 1;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;

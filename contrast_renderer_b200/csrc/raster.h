@@ -1,4 +1,4 @@
-// raster.h — host-visible interface of raster.cu (binner + K3 tile rasteriser).
+// raster.h — host-visible interface of raster.cu (primitive setup, binner, K3 tile rasteriser).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,15 +18,33 @@ struct DeviceBatch {
     uint32_t n_groups;
 };
 
-// One recorded Shape::render call (src/renderer.rs:267) with the pass state current at record time.
+// One recorded Shape::render call (src/renderer.rs:267) with the pass state current at record time, expanded on the
+// host (the slice tables are mirrored there) so that device code needs no further table walks. A "candidate" is one
+// index slot of a strip, one triangle of a list, or one triangle of the hull strip, times the instance count; the
+// candidates of a command are numbered category by category in the draw order of src/renderer.rs:275-354.
 struct DeviceCommand {
+    uint32_t cat_end[8];          // cumulative candidate end of each vertex category, relative to the command's first candidate
+    uint32_t slots[8];            // candidates per instance in each category (0 if the category is not drawn)
+    uint32_t vbase[8];            // first vertex of the shape's slice in the batch-wide category array ([7]: hull slice)
+    uint32_t ibase[3];            // first index slot of the shape's slice (line, joint, solid)
     uint32_t batch;
-    uint32_t shape;
-    uint32_t instance_begin, instance_end;
+    uint32_t instance_begin, instance_count;
     uint32_t operation;           // cr_render_operation
     uint32_t ref;                 // stencil reference = clip_depth << winding_counter_bits (src/renderer.rs:936)
-    uint32_t save_layer, restore_layer;
+    uint32_t layers;              // save_layer | restore_layer << 16
+    uint32_t _pad[3];
 };
+static_assert(sizeof(DeviceCommand) == 144, "DeviceCommand layout");
+
+// One candidate after the vertex stage: transformed, snapped to 1/256 px, oriented clockwise on screen. 48 bytes.
+struct PrimRecord {
+    int X[3], Y[3];
+    uint32_t meta;                // pipe (bits 0-3) | front << 4 | swapped << 5 | valid << 6 | category << 8
+    uint32_t cmd;
+    uint32_t instance;
+    uint32_t v[3];                // vertex numbers in the batch-wide category array, in submission order
+};
+static_assert(sizeof(PrimRecord) == 48, "PrimRecord layout");
 
 struct RasterTarget {
     float4* color;                // [height][width] premultiplied RGBA32F
@@ -40,15 +58,18 @@ struct RasterTarget {
 struct RasterScene {
     const DeviceBatch* batches;
     const DeviceCommand* commands;
-    const uint32_t* cmd_cand_begin;   // [n_commands + 1] exclusive scan of candidate primitives per command
+    const uint32_t* cmd_cand_begin;   // [n_commands + 1] first candidate of each command
     uint32_t n_commands;
     const float* transforms;          // [n_instances][16]
     const float* colors;              // [n_instances][4] or null
 };
 
-int cr_raster_count_candidates(cudaStream_t stream, const DeviceBatch* batches, const DeviceCommand* commands, uint32_t n_commands, uint32_t* cmd_cands);
-int cr_raster_bin_count(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, uint32_t* cand_tiles);
-int cr_raster_bin_emit(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, const uint32_t* cand_pair_begin,
-                       uint32_t* pair_tile, uint32_t* pair_cand);
-int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const uint32_t* tile_begin, const uint32_t* pair_cand,
-                    unsigned long long* covered_samples);
+// Vertex stage + tile counting: fills records[0..n) and cand_tiles[0..n). big_list: n + 1 words of scratch (candidates
+// whose tile box is large are listed there and binned one warp each).
+int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, PrimRecord* records, uint32_t* cand_tiles,
+                    uint32_t* big_list);
+// (tile, candidate) pairs of every valid record, at cand_pair_begin[candidate].
+int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t n_candidates, const PrimRecord* records, const uint32_t* cand_pair_begin,
+                       const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand);
+int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* tile_begin,
+                    const uint32_t* pair_cand, unsigned long long* covered_samples);

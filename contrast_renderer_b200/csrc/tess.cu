@@ -858,11 +858,15 @@ __global__ void __launch_bounds__(128) tess_emit_kernel(DevicePaths P, const uin
 
 // Per-shape slice boundaries: cat_begin[c][s] = offsets[c][shape_path_begin[s]], s in [0, n_shapes].
 __global__ void shape_bounds_kernel(const uint32_t* __restrict__ offsets, uint32_t n_paths, const uint32_t* __restrict__ shape_path_begin, uint32_t n_shapes,
-                                    uint32_t* __restrict__ cat_begin) {
+                                    uint32_t* __restrict__ cat_begin, uint32_t* __restrict__ max_proto) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s > n_shapes) return;
     const uint32_t p = shape_path_begin[s];
     for (int c = 0; c < CNT_COUNT; ++c) cat_begin[(size_t)c * (n_shapes + 1) + s] = offsets[(size_t)c * (n_paths + 1) + p];
+    if (s < n_shapes) {
+        const uint32_t q = shape_path_begin[s + 1];
+        atomicMax(max_proto, offsets[(size_t)CNT_PROTO * (n_paths + 1) + q] - offsets[(size_t)CNT_PROTO * (n_paths + 1) + p]);
+    }
 }
 
 // ------------------------------------------------------------------------------------ convex_hull.rs on device
@@ -870,23 +874,21 @@ __global__ void shape_bounds_kernel(const uint32_t* __restrict__ offsets, uint32
 __device__ __forceinline__ bool lex_less(float2 a, float2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
 __device__ __forceinline__ float turn(float2 a, float2 b, float2 c) { return triple(from_vec(a.x, a.y), from_vec(b.x, b.y), from_vec(c.x, c.y)); }
 
-// In-place bitonic sort of n points with virtual +inf padding (all comparators put the minimum at the lower index).
+// In-place bitonic sort of n points with virtual +inf padding (every comparator puts the minimum at the lower index, so
+// comparators whose upper element is padding are no-ops and whole blocks of padding are skipped).
 __device__ void block_sort_points(float2* pts, uint32_t n) {
-    uint32_t np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (uint32_t k = 2; k <= np2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = threadIdx.x; t < np2 / 2; t += blockDim.x) {
-                uint32_t lo, hi;
-                if (j == (k >> 1)) {  // flip step: i <-> block_end - 1 - offset
-                    const uint32_t block = t / j, off = t % j;
-                    lo = block * k + off;
-                    hi = block * k + k - 1 - off;
-                } else {
-                    const uint32_t block = t / j, off = t % j;
-                    lo = block * 2 * j + off;
-                    hi = lo + j;
-                }
+    uint32_t log_np2 = 0;
+    while ((1u << log_np2) < n) ++log_np2;
+    for (uint32_t lk = 1; lk <= log_np2; ++lk) {          // k = 1 << lk: size of the bitonic blocks being merged
+        for (uint32_t lj = lk; lj-- > 0;) {               // j = 1 << lj: comparator distance
+            // comparators are numbered t = block * j + off; only blocks of size 2j that start below n can hold a real upper element
+            const uint32_t blocks = (n + (2u << lj) - 1) >> (lj + 1);
+            const uint32_t count = blocks << lj;
+            const bool flip = lj + 1 == lk;
+            for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) {
+                const uint32_t block = t >> lj, off = t & ((1u << lj) - 1u);
+                const uint32_t lo = (block << (lj + 1)) + off;
+                const uint32_t hi = flip ? (block << (lj + 1)) + (2u << lj) - 1u - off : lo + (1u << lj);
                 if (hi < n) {
                     const float2 a = pts[lo], b = pts[hi];
                     if (lex_less(b, a)) { pts[lo] = b; pts[hi] = a; }
@@ -896,25 +898,44 @@ __device__ void block_sort_points(float2* pts, uint32_t n) {
         }
     }
 }
-// One monotone chain of convex_hull::andrew (src/convex_hull.rs:14-24 / :27-38). Returns the stack size.
-__device__ uint32_t hull_chain(const float2* pts, uint32_t n, bool reverse, float2* stack) {
+// One monotone chain of convex_hull::andrew (src/convex_hull.rs:14-24 / :27-38): a strictly sequential stack machine
+// (the pop test has a tolerance, so the result depends on the transient stack states and must be replayed exactly).
+// The top two stack entries and the line through them stay in registers; `stack` may be shared or global memory.
+// Returns the stack size, or HULL_OVERFLOW if it would exceed `capacity`.
+#define HULL_OVERFLOW 0xFFFFFFFFu
+__device__ uint32_t hull_chain(const float2* pts, uint32_t n, bool reverse, float2* stack, uint32_t capacity) {
     uint32_t len = 0;
+    float2 a = make_float2(0.f, 0.f), b = a;
+    Ln line = mk_ln(0.f, 0.f, 0.f);   // join(a, b), valid while len >= 2
+    float2 p = pts[reverse ? n - 1 : 0];
     for (uint32_t k = 0; k < n; ++k) {
-        const float2 p = pts[reverse ? n - 1 - k : k];
-        while (len > 1 && turn(stack[len - 2], stack[len - 1], p) <= CR_ERROR_MARGIN) --len;
+        const float2 next = (k + 1 < n) ? pts[reverse ? n - 2 - k : k + 1] : p;   // prefetch: independent of the stack
+        while (len > 1) {
+            const float t = incidence(from_vec(p.x, p.y), line);   // == triple(a, b, p)
+            if (!(t <= CR_ERROR_MARGIN)) break;
+            --len;
+            b = a;
+            if (len > 1) { a = stack[len - 2]; line = join(from_vec(a.x, a.y), from_vec(b.x, b.y)); }
+        }
+        if (len >= capacity) return HULL_OVERFLOW;
         stack[len++] = p;
+        a = b;
+        b = p;
+        if (len > 1) line = join(from_vec(a.x, a.y), from_vec(b.x, b.y));
+        p = next;
     }
     return len;
 }
-#define HULL_SMEM_POINTS 1024
-// One CTA per shape. proto: the shape's proto_hull slice (sorted in place); scratch: same-size arrays for the two
-// chain stacks; hull_out: slice with capacity = proto count; hull_count[s] = number of hull vertices (strip order).
-__global__ void __launch_bounds__(128) hull_kernel(float2* __restrict__ proto, float2* __restrict__ scratch_a, float2* __restrict__ scratch_b,
-                                                   const uint32_t* __restrict__ proto_begin, uint32_t n_shapes, float2* __restrict__ hull_out,
-                                                   uint32_t* __restrict__ hull_count) {
-    __shared__ float2 sh_pts[HULL_SMEM_POINTS];
-    __shared__ float2 sh_a[HULL_SMEM_POINTS];
-    __shared__ float2 sh_b[HULL_SMEM_POINTS];
+#define HULL_THREADS 512
+#define HULL_STACK 2048
+// One CTA per shape. Shapes with up to `cap` proto-hull points are sorted and chained entirely in shared memory
+// (dynamic: cap points + two HULL_STACK-entry stacks); larger ones, or chains deeper than HULL_STACK, use the global
+// scratch arrays. proto: the shape's proto_hull slice; hull_out: slice with capacity = proto count;
+// hull_count[s] = number of hull vertices, already in triangle_fan_to_strip order.
+__global__ void __launch_bounds__(HULL_THREADS) hull_kernel(float2* __restrict__ proto, float2* __restrict__ scratch_a, float2* __restrict__ scratch_b,
+                                                            const uint32_t* __restrict__ proto_begin, uint32_t n_shapes, float2* __restrict__ hull_out,
+                                                            uint32_t* __restrict__ hull_count, uint32_t cap) {
+    extern __shared__ float2 hull_smem[];
     __shared__ uint32_t sh_len[2];
     const uint32_t s = blockIdx.x;
     const uint32_t begin = proto_begin[s], n = proto_begin[s + 1] - begin;
@@ -924,19 +945,28 @@ __global__ void __launch_bounds__(128) hull_kernel(float2* __restrict__ proto, f
         if (threadIdx.x == 0) hull_count[s] = n;
         return;
     }
-    const bool small = n <= HULL_SMEM_POINTS;
-    float2* pts = small ? sh_pts : proto + begin;
-    float2* sa = small ? sh_a : scratch_a + begin;
-    float2* sb = small ? sh_b : scratch_b + begin;
+    const bool small = n <= cap;
+    float2* pts = small ? hull_smem : proto + begin;
+    float2* sa = small ? hull_smem + cap : scratch_a + begin;
+    float2* sb = small ? hull_smem + cap + HULL_STACK : scratch_b + begin;
     if (small) {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pts[i] = proto[begin + i];
         __syncthreads();
     }
     block_sort_points(pts, n);
-    if (threadIdx.x == 0) sh_len[0] = hull_chain(pts, n, false, sa) - 1;     // hull.pop()
-    if (threadIdx.x == 32) sh_len[1] = hull_chain(pts, n, true, sb) - 1;     // hull.pop()
+    const uint32_t capacity = small ? HULL_STACK : n;
+    if (threadIdx.x == 0) sh_len[0] = hull_chain(pts, n, false, sa, capacity);
+    if (threadIdx.x == 32) sh_len[1] = hull_chain(pts, n, true, sb, capacity);
     __syncthreads();
-    const uint32_t la = sh_len[0], lb = sh_len[1], total = la + lb;
+    if (sh_len[0] == HULL_OVERFLOW || sh_len[1] == HULL_OVERFLOW) {   // a hull with more than HULL_STACK vertices: redo with global stacks
+        __syncthreads();
+        sa = scratch_a + begin;
+        sb = scratch_b + begin;
+        if (threadIdx.x == 0) sh_len[0] = hull_chain(pts, n, false, sa, n);
+        if (threadIdx.x == 32) sh_len[1] = hull_chain(pts, n, true, sb, n);
+        __syncthreads();
+    }
+    const uint32_t la = sh_len[0] - 1, lb = sh_len[1] - 1, total = la + lb;   // hull.pop() after each chain
     // triangle_fan_to_strip(andrew(..)) (src/renderer.rs:197, src/vertex.rs:28-35)
     for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
         const uint32_t src = (i & 1u) == 0 ? (i >> 1) : total - 1 - (i >> 1);
@@ -955,8 +985,9 @@ int cr_tess_count(cudaStream_t stream, const DevicePaths& paths, uint32_t n_grou
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }
-int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t n_paths, const uint32_t* shape_path_begin, uint32_t n_shapes, uint32_t* cat_begin) {
-    shape_bounds_kernel<<<(n_shapes + 1 + 127) / 128, 128, 0, stream>>>(offsets, n_paths, shape_path_begin, n_shapes, cat_begin);
+int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t n_paths, const uint32_t* shape_path_begin, uint32_t n_shapes, uint32_t* cat_begin,
+                         uint32_t* max_proto) {
+    shape_bounds_kernel<<<(n_shapes + 1 + 127) / 128, 128, 0, stream>>>(offsets, n_paths, shape_path_begin, n_shapes, cat_begin, max_proto);
     g_cr_kernel_launches += 1;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
@@ -970,9 +1001,21 @@ int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* 
     return CR_OK;
 }
 int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
-                 float2* hull_out, uint32_t* hull_count) {
+                 float2* hull_out, uint32_t* hull_count, uint32_t max_points) {
     if (n_shapes == 0) return CR_OK;
-    hull_kernel<<<n_shapes, 128, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out, hull_count);
+    // shared-memory capacity tier: enough for the largest shape if that fits (two CTAs per SM up to 9728 points, one up to
+    // 24576), else the largest tier for the shapes that do fit
+    static bool attr_set = false;
+    const uint32_t max_cap = 24576;
+    if (!attr_set) {
+        CR_CUDA_TRY(cudaFuncSetAttribute(hull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((max_cap + 2 * HULL_STACK) * sizeof(float2))));
+        attr_set = true;
+    }
+    static const uint32_t tiers[5] = {1024, 2048, 4096, 9728, max_cap};
+    uint32_t cap = max_cap;
+    for (int i = 4; i >= 0; --i) if (max_points <= tiers[i]) cap = tiers[i];
+    hull_kernel<<<n_shapes, HULL_THREADS, (size_t)(cap + 2 * HULL_STACK) * sizeof(float2), stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out,
+                                                                                                     hull_count, cap);
     g_cr_kernel_launches += 1;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;

@@ -24,9 +24,10 @@ struct TessOutput {
 };
 
 int cr_tess_count(cudaStream_t stream, const DevicePaths& paths, uint32_t n_groups, uint32_t* counts, uint32_t* err_flag);
+// Also stores max over shapes of the proto-hull point count into *max_proto (device word, zeroed by the caller).
 int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t n_paths, const uint32_t* shape_path_begin, uint32_t n_shapes,
-                         uint32_t* cat_begin);
+                         uint32_t* cat_begin, uint32_t* max_proto);
 int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* offsets, const uint32_t* shape_path_begin, uint32_t n_shapes,
                  const TessOutput& out, uint32_t* err_flag);
 int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
-                 float2* hull_out, uint32_t* hull_count);
+                 float2* hull_out, uint32_t* hull_count, uint32_t max_points);
