@@ -29,10 +29,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "100k glyph-sized filled paths-of-text (lines + integral quadratics, 1.44 contours / 20.9 points per glyph), 3840x2160, Stencil+Color per 400-glyph shape"
+WORKLOAD = "100k glyph-sized filled paths-of-text (lines + integral quadratics, 1.44 contours / 20.9 points per glyph), 3840x2160, one Shape (Stencil+Color) per 316-glyph text line"
 N_GLYPHS = 100000
 EXTENT = (3840, 2160)
-GLYPHS_PER_SHAPE = 400
+GLYPHS_PER_SHAPE = 316   # (3840 - 2 * 20) // (0.6 * 20): one text line of 20 px glyphs, the chunking BASELINE.md names for config 3
 
 
 def make_scene(rank: int, n_glyphs: int = N_GLYPHS):

@@ -5,7 +5,7 @@
 //
 // Data flow (all in HBM, one 4-byte read-back of the pair count):
 //   commands -> candidates (one per index slot / list triangle / hull-strip triangle, numbered in exact draw order)
-//   --prim_setup--> 48-byte PrimRecords (vertex stage done once) + tiles touched per candidate --scan-->
+//   --prim_setup--> 64-byte PrimRecords (vertex stage done once) + tiles touched per candidate --scan-->
 //   --bin_emit--> (tile, candidate) pairs --stable radix sort by tile--> per-tile ranges in draw order --K3--> framebuffer.
 //
 // K3: one CTA per 16x16 tile. The pixel's stencil byte and RGBA colour live in the REGISTERS of "its" thread for the whole
@@ -179,6 +179,7 @@ __device__ bool build_record(const RasterScene& sc, const RasterTarget& tg, uint
     rec.cmd = ci;
     rec.instance = instance;
     rec.v[0] = v[0]; rec.v[1] = v[1]; rec.v[2] = v[2];
+    rec.ref = cmd.ref; rec.layers = cmd.layers; rec.batch = cmd.batch; rec._pad = 0;
     return true;
 }
 
@@ -187,14 +188,20 @@ __device__ __forceinline__ void store_record(PrimRecord* dst, const PrimRecord& 
     d[0] = make_uint4((uint32_t)rec.X[0], (uint32_t)rec.X[1], (uint32_t)rec.X[2], (uint32_t)rec.Y[0]);
     d[1] = make_uint4((uint32_t)rec.Y[1], (uint32_t)rec.Y[2], rec.meta, rec.cmd);
     d[2] = make_uint4(rec.instance, rec.v[0], rec.v[1], rec.v[2]);
+    d[3] = make_uint4(rec.ref, rec.layers, rec.batch, 0u);
 }
+template <bool FULL>   // FULL == false: only the geometry half (X, Y, meta, cmd) that the binner needs
 __device__ __forceinline__ PrimRecord load_record(const PrimRecord* src) {
     const uint4* s = reinterpret_cast<const uint4*>(src);
-    const uint4 a = s[0], b = s[1], c = s[2];
+    const uint4 a = s[0], b = s[1];
     PrimRecord r;
     r.X[0] = (int)a.x; r.X[1] = (int)a.y; r.X[2] = (int)a.z; r.Y[0] = (int)a.w;
     r.Y[1] = (int)b.x; r.Y[2] = (int)b.y; r.meta = b.z; r.cmd = b.w;
-    r.instance = c.x; r.v[0] = c.y; r.v[1] = c.z; r.v[2] = c.w;
+    if (FULL) {
+        const uint4 c = s[2], d = s[3];
+        r.instance = c.x; r.v[0] = c.y; r.v[1] = c.z; r.v[2] = c.w;
+        r.ref = d.x; r.layers = d.y; r.batch = d.z;
+    }
     return r;
 }
 
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) bin_emit_kernel(RasterTarget tg
     if (cand >= n) return;
     const uint32_t at = begin[cand];
     if (begin[cand + 1] == at) return;
-    const PrimRecord rec = load_record(records + cand);
+    const PrimRecord rec = load_record<false>(records + cand);
     if (!(rec.meta & META_VALID) || (rec.meta & META_BIG)) return;
     walk_tiles_small<true>(rec.X, rec.Y, extent_of(rec.X, rec.Y, tg), tg, cand, at, pair_tile, pair_cand);
 }
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(128) bin_big_kernel(RasterTarget tg, const Pri
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_big; i += warps) {
         const uint32_t cand = big[1 + i];
-        const PrimRecord rec = load_record(records + cand);
+        const PrimRecord rec = load_record<false>(records + cand);
         if (EMIT) walk_tiles_warp<true>(rec.X, rec.Y, tg, cand, cand_tiles[cand], pair_tile, pair_cand);   // cand_tiles now holds the exclusive scan
         else {
             const uint32_t count = walk_tiles_warp<false>(rec.X, rec.Y, tg, cand, 0, nullptr, nullptr);
@@ -347,9 +354,11 @@ __device__ bool stroke_dashed(const Descriptor& d, float tx, float ty) {   // sr
 __device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TilePrim& ps, uint32_t pipe, const long long* E) {
     const float e0 = (float)(E[1] - ps.bias[1]) * ps.invw[0], e1 = (float)(E[2] - ps.bias[2]) * ps.invw[1], e2 = (float)(E[0] - ps.bias[0]) * ps.invw[2];
     const float den = (e0 + e1) + e2;
-    float a[4];
+    float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int needed = (pipe == P_FILL_IQ || pipe == P_STROKE_LINE) ? 2 : (pipe == P_FILL_RC ? 4 : 3);   // attributes the predicate reads
 #pragma unroll
-    for (int q = 0; q < 4; ++q) a[q] = ((e0 * ps.attr[0][q] + e1 * ps.attr[1][q]) + e2 * ps.attr[2][q]) / den;
+    for (int q = 0; q < 4; ++q)
+        if (q < needed) a[q] = ((e0 * ps.attr[0][q] + e1 * ps.attr[1][q]) + e2 * ps.attr[2][q]) / den;
     switch (pipe) {
         case P_FILL_IQ: return a[0] * a[0] - a[1] <= 0.0f;
         case P_FILL_IC: return a[0] * a[0] * a[0] - a[1] * a[2] <= 0.0f;
@@ -378,7 +387,6 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
     ps.meta = 0;
     if (!(rec.meta & META_VALID)) return;
     const uint32_t pipe = rec.meta & 15u, cat = (rec.meta >> 8) & 7u;
-    const DeviceCommand& cmd = sc.commands[rec.cmd];
     const Edges t = make_edges(rec.X, rec.Y);
     const int PX = tile_px * 256 + 128, PY = tile_py * 256 + 128;
 #pragma unroll
@@ -399,15 +407,15 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
         const long long emin = ps.e0[e] + (t.A[e] < 0 ? (long long)t.A[e] * ((CR_TILE - 1) * 256) : 0) - (t.B[e] > 0 ? (long long)t.B[e] * ((CR_TILE - 1) * 256) : 0);
         if (emin < 0) full = false;
     }
-    ps.ref = cmd.ref;
+    ps.ref = rec.ref;
     ps.instance = rec.instance;
-    ps.batch = cmd.batch;
-    ps.layers = cmd.layers;
+    ps.batch = rec.batch;
+    ps.layers = rec.layers;
     ps.cmd = rec.cmd;
     ps.flat_u = 0;
     ps.flat_f = 0.0f;
     if (pipe <= P_FILL_RC && pipe != P_FILL_SOLID) {   // pipelines with a fragment predicate need the vertex attributes
-        const DeviceBatch& b = sc.batches[cmd.batch];
+        const DeviceBatch& b = sc.batches[rec.batch];
         const float* m = sc.transforms + 16 * (size_t)rec.instance;
         const int n_attr = (int)((0x04332032u >> (4u * cat)) & 15u);   // attribute floats per category: 2,3,0,2,3,3,4,0
         const bool swapped = (rec.meta & META_SWAPPED) != 0;
@@ -430,13 +438,14 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
 // Run kinds: primitives of one run commute (see the file header).
 __device__ __forceinline__ uint32_t run_kind(uint32_t pipe) { return pipe <= P_STROKE_JOINT ? 0u : (pipe <= P_FILL_RC ? 1u : 2u); }
 
-__global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
-                                                                         const uint32_t* __restrict__ tile_begin, const uint32_t* __restrict__ pair_cand,
-                                                                         unsigned long long* __restrict__ covered_out) {
+__global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
+                                                                            const uint32_t* __restrict__ tile_begin, const uint32_t* __restrict__ pair_cand,
+                                                                            unsigned long long* __restrict__ covered_out) {
     __shared__ TilePrim sh[RCHUNK];
-    __shared__ int acc[CR_TILE * CR_TILE];
+    __shared__ int acc[2][CR_TILE * CR_TILE];   // per-pixel result of a stencil run; double buffered so that one barrier per run suffices
     __shared__ uint32_t run_mask[RCHUNK / 32];
     __shared__ uint8_t run_start[RCHUNK + 1];
+    __shared__ uint16_t cov[CR_TILE][CR_TILE];   // row coverage masks of the cover primitives of one sweep
     const uint32_t tile = blockIdx.x;
     const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];
     if (begin == end) return;
@@ -452,15 +461,30 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterS
     uint32_t covered = 0;
     const size_t layer_stride = (size_t)tg.width * tg.height;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    acc[threadIdx.x] = 0;
+    acc[0][threadIdx.x] = 0;
+    acc[1][threadIdx.x] = 0;
+    // A finished stencil run whose per-pixel result has not been folded into `s` yet (block-uniform state).
+    int pending = -1;            // accumulator buffer of the pending run, or -1
+    uint32_t pending_kind = 0, pending_ref = 0;
+    int cur = 0;                 // buffer the next stencil run accumulates into
+    auto apply_pending = [&]() {
+        if (pending < 0) return;
+        const int net = acc[pending][threadIdx.x];
+        if (net != 0) {
+            if (pending_kind == 0u) { if ((pending_ref & M) == (s & M)) s = (s & ~W) | ((s + 1u) & W); }        // src/renderer.rs:571-576
+            else if ((pending_ref & M) <= (s & M)) s = (s & ~W) | ((s + (uint32_t)net) & W);                     // src/renderer.rs:577-582
+            acc[pending][threadIdx.x] = 0;   // ready for the run after next (a barrier separates)
+        }
+        pending = -1;
+    };
 
     for (uint32_t chunk = begin; chunk < end; chunk += RCHUNK) {
         const uint32_t n = min((uint32_t)RCHUNK, end - chunk);
-        __syncthreads();
+        __syncthreads();   // everybody is done with the previous chunk's shared records
         // ---- stage the chunk (one thread per primitive) and find the run boundaries
         bool boundary = false;
         if (threadIdx.x < n) {
-            const PrimRecord rec = load_record(records + pair_cand[chunk + threadIdx.x]);
+            const PrimRecord rec = load_record<true>(records + pair_cand[chunk + threadIdx.x]);
             stage_primitive(sc, tg, rec, tile_px, tile_py, sh[threadIdx.x]);
         }
         __syncthreads();
@@ -469,11 +493,11 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterS
                 if (threadIdx.x == 0) boundary = true;
                 else {
                     const TilePrim &p = sh[threadIdx.x - 1], &q = sh[threadIdx.x];
-                    // staged-out primitives (meta == 0) join whatever run surrounds them: they do nothing
+                    // staged-out primitives (meta == 0) join whatever run precedes them: they do nothing
                     const uint32_t kp = run_kind(p.meta & 15u), kq = run_kind(q.meta & 15u);
                     const bool pv = (p.meta & META_VALID) != 0, qv = (q.meta & META_VALID) != 0;
                     if (pv && qv) boundary = kp != kq || (kq < 2u ? p.ref != q.ref : (p.cmd != q.cmd || p.instance != q.instance));
-                    else boundary = qv;   // a valid primitive after an invalid one conservatively opens a run
+                    else boundary = qv;   // a valid primitive after a staged-out one conservatively opens a run
                 }
             }
             const uint32_t m = __ballot_sync(0xffffffffu, boundary);
@@ -492,13 +516,14 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterS
         // ---- execute the runs in draw order
         for (uint32_t r = 0; r < n_runs; ++r) {
             const uint32_t a = run_start[r], b = run_start[r + 1];
-            // first valid primitive decides the run's kind and reference
             uint32_t first = a;   // only the chunk's first run can start with staged-out primitives (see `boundary`)
             if (r == 0) { while (first < b && !(sh[first].meta & META_VALID)) ++first; }
             if (first == b) continue;
             const uint32_t kind = run_kind(sh[first].meta & 15u);
+            apply_pending();
             if (kind < 2u) {
                 // stencil run: (primitive, row) work items, 16 primitives x 16 rows per sweep
+                int* const out = acc[cur];
                 for (uint32_t base = a; base < b; base += CR_TILE) {
                     const uint32_t k = base + (threadIdx.x >> 4);
                     if (k >= b) continue;
@@ -520,72 +545,90 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE) raster_tiles_kernel(RasterS
                     for (int x = x0; x <= x1; ++x) {
                         if ((E[0] | E[1] | E[2]) >= 0) {
                             if (pipe == P_FILL_SOLID || fragment_keep(sc, ps, pipe, E)) {
-                                if (kind == 0u) atomicOr(&acc[y * CR_TILE + x], 1);
-                                else atomicAdd(&acc[y * CR_TILE + x], delta);
+                                if (kind == 0u) atomicOr(&out[y * CR_TILE + x], 1);
+                                else atomicAdd(&out[y * CR_TILE + x], delta);
                             }
                         }
                         E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
                     }
                 }
                 __syncthreads();
-                const int net = acc[threadIdx.x];
-                if (net != 0) {
-                    const uint32_t ref = sh[first].ref;
-                    if (kind == 0u) { if ((ref & M) == (s & M)) s = (s & ~W) | ((s + 1u) & W); }            // src/renderer.rs:571-576
-                    else if ((ref & M) <= (s & M)) s = (s & ~W) | ((s + (uint32_t)net) & W);                 // src/renderer.rs:577-582
-                    acc[threadIdx.x] = 0;
-                }
-                __syncthreads();
+                pending = cur;
+                pending_kind = kind;
+                pending_ref = sh[first].ref;
+                cur ^= 1;
             } else {
-                // cover run: one (command, instance) hull draw; order dependent, one thread per pixel
-                for (uint32_t k = a; k < b; ++k) {
-                    const TilePrim& ps = sh[k];
-                    const uint32_t meta = ps.meta;
-                    if (!(meta & META_VALID)) continue;
-                    const uint32_t bbox = ps.bbox;
-                    if (lx < (int)(bbox & 255u) || lx > (int)((bbox >> 16) & 255u) || ly < (int)((bbox >> 8) & 255u) || ly > (int)(bbox >> 24)) continue;
-                    bool inside = true;
-                    if (!(meta & META_FULL)) {
+                // cover run: one (command, instance) hull draw. Order dependent, so the stencil / blend ops run one thread per
+                // pixel, but coverage is found first by (primitive, row) work items as 16-bit row masks, 16 primitives a sweep.
+                for (uint32_t base = a; base < b; base += CR_TILE) {
+                    {
+                        const uint32_t k = base + (threadIdx.x >> 4);
+                        uint32_t mask = 0;
+                        if (k < b) {
+                            const TilePrim& ps = sh[k];
+                            const uint32_t meta = ps.meta;
+                            const uint32_t bbox = ps.bbox;
+                            const int y = (int)(threadIdx.x & 15u);
+                            if ((meta & META_VALID) && y >= (int)((bbox >> 8) & 255u) && y <= (int)(bbox >> 24)) {
+                                const int x0 = (int)(bbox & 255u), x1 = (int)((bbox >> 16) & 255u);
+                                if (meta & META_FULL) mask = ((2u << x1) - 1u) & ~((1u << x0) - 1u);
+                                else {
+                                    long long E[3], step[3];
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) {
-                            const long long E = ps.e0[e] + (long long)ps.A[e] * (ly * 256) - (long long)ps.B[e] * (lx * 256);
-                            if (E < 0) inside = false;
+                                    for (int e = 0; e < 3; ++e) {
+                                        step[e] = (long long)ps.B[e] * 256;
+                                        E[e] = ps.e0[e] + (long long)ps.A[e] * (y * 256) - step[e] * x0;
+                                    }
+                                    for (int x = x0; x <= x1; ++x) {
+                                        if ((E[0] | E[1] | E[2]) >= 0) mask |= 1u << x;
+                                        E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
+                                    }
+                                }
+                            }
+                        }
+                        cov[threadIdx.x >> 4][threadIdx.x & 15u] = (uint16_t)mask;
+                    }
+                    __syncthreads();
+                    const uint32_t count = min((uint32_t)CR_TILE, b - base);
+                    for (uint32_t j = 0; j < count; ++j) {
+                        if (!((cov[j][ly] >> lx) & 1u)) continue;
+                        const TilePrim& ps = sh[base + j];
+                        const uint32_t pipe = ps.meta & 15u, ref = ps.ref;
+                        if (pipe == P_COLOR) {                                                                   // src/renderer.rs:736-754
+                            if ((ref & M) < (s & M)) {
+                                const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
+                                const float sa = ic.w;
+                                const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
+                                if (tg.blending == CR_BLEND_PREMULTIPLIED_OVER) {
+                                    const float kk = 1.0f - sa;
+                                    col.x = sr + col.x * kk; col.y = sg + col.y * kk; col.z = sb + col.z * kk; col.w = sa + col.w * kk;
+                                } else { col.x = sr; col.y = sg; col.z = sb; col.w = sa; }
+                                covered += 1;
+                            }
+                            s = s & ~W;
+                        } else if (pipe == P_CLIP) {                                                             // src/renderer.rs:692-710
+                            if ((ref & W) != (s & W)) s = (s & ~M) | (ref & M);
+                        } else if (pipe == P_UNCLIP) {                                                           // src/renderer.rs:711-729
+                            if ((ref & C) < (s & C)) s = (s & ~M) | (ref & M);
+                        } else if ((ref & M) <= (s & M)) {   // the three alpha-context covers share one stencil state (src/renderer.rs:761-766)
+                            if (pipe == P_SAVE_ALPHA) {
+                                tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix] = col.w;
+                            } else if (pipe == P_SCALE_ALPHA) {
+                                const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
+                                col.w = sa + col.w * (1.0f - sa);
+                            } else {
+                                const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix];
+                                const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
+                                col.w = col.w - sa;
+                            }
                         }
                     }
-                    if (!inside || !in_fb) continue;
-                    const uint32_t pipe = meta & 15u, ref = ps.ref;
-                    if (pipe == P_COLOR) {                                                                   // src/renderer.rs:736-754
-                        if ((ref & M) < (s & M)) {
-                            const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
-                            const float sa = ic.w;
-                            const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
-                            if (tg.blending == CR_BLEND_PREMULTIPLIED_OVER) {
-                                const float kk = 1.0f - sa;
-                                col.x = sr + col.x * kk; col.y = sg + col.y * kk; col.z = sb + col.z * kk; col.w = sa + col.w * kk;
-                            } else { col.x = sr; col.y = sg; col.z = sb; col.w = sa; }
-                            covered += 1;
-                        }
-                        s = s & ~W;
-                    } else if (pipe == P_CLIP) {                                                             // src/renderer.rs:692-710
-                        if ((ref & W) != (s & W)) s = (s & ~M) | (ref & M);
-                    } else if (pipe == P_UNCLIP) {                                                           // src/renderer.rs:711-729
-                        if ((ref & C) < (s & C)) s = (s & ~M) | (ref & M);
-                    } else if ((ref & M) <= (s & M)) {   // the three alpha-context covers share one stencil state (src/renderer.rs:761-766)
-                        if (pipe == P_SAVE_ALPHA) {
-                            tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix] = col.w;
-                        } else if (pipe == P_SCALE_ALPHA) {
-                            const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
-                            col.w = sa + col.w * (1.0f - sa);
-                        } else {
-                            const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix];
-                            const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
-                            col.w = col.w - sa;
-                        }
-                    }
+                    __syncthreads();   // the next sweep overwrites the row masks
                 }
             }
         }
     }
+    apply_pending();
     if (in_fb) { tg.stencil[pix] = (uint8_t)s; tg.color[pix] = col; }
     // covered-sample statistic: warp reduce, one atomic per warp
 #pragma unroll

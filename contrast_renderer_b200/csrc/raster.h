@@ -36,15 +36,20 @@ struct DeviceCommand {
 };
 static_assert(sizeof(DeviceCommand) == 144, "DeviceCommand layout");
 
-// One candidate after the vertex stage: transformed, snapped to 1/256 px, oriented clockwise on screen. 48 bytes.
+// One candidate after the vertex stage: transformed, snapped to 1/256 px, oriented clockwise on screen. 64 bytes; the
+// binner only reads the first 32.
 struct PrimRecord {
     int X[3], Y[3];
-    uint32_t meta;                // pipe (bits 0-3) | front << 4 | swapped << 5 | valid << 6 | category << 8
+    uint32_t meta;                // pipe (bits 0-3) | front << 4 | swapped << 5 | valid << 6 | big << 7 | category << 8
     uint32_t cmd;
     uint32_t instance;
     uint32_t v[3];                // vertex numbers in the batch-wide category array, in submission order
+    uint32_t ref;                 // the command's stencil reference, alpha layers and batch (so K3 never reads the command)
+    uint32_t layers;
+    uint32_t batch;
+    uint32_t _pad;
 };
-static_assert(sizeof(PrimRecord) == 48, "PrimRecord layout");
+static_assert(sizeof(PrimRecord) == 64, "PrimRecord layout");
 
 struct RasterTarget {
     float4* color;                // [height][width] premultiplied RGBA32F

@@ -903,25 +903,41 @@ __device__ void block_sort_points(float2* pts, uint32_t n) {
 // The top two stack entries and the line through them stay in registers; `stack` may be shared or global memory.
 // Returns the stack size, or HULL_OVERFLOW if it would exceed `capacity`.
 #define HULL_OVERFLOW 0xFFFFFFFFu
-__device__ uint32_t hull_chain(const float2* pts, uint32_t n, bool reverse, float2* stack, uint32_t capacity) {
-    uint32_t len = 0;
-    float2 a = make_float2(0.f, 0.f), b = a;
-    Ln line = mk_ln(0.f, 0.f, 0.f);   // join(a, b), valid while len >= 2
-    float2 p = pts[reverse ? n - 1 : 0];
-    for (uint32_t k = 0; k < n; ++k) {
-        const float2 next = (k + 1 < n) ? pts[reverse ? n - 2 - k : k + 1] : p;   // prefetch: independent of the stack
+template <int DIR>   // +1: points in ascending order (lower chain), -1: descending (upper chain)
+__device__ __noinline__ uint32_t hull_chain(const float2* pts, uint32_t n, float2* stack, uint32_t capacity) {
+    // This loop runs on ONE thread and is pure dependent-issue latency, so it is written for minimum instruction count:
+    // the two top stack entries (a, b) and the line through them (l0 + l1 x + l2 y, == join(a, b) of device_common.cuh
+    // for unit-weight points) live in registers, the point stream is walked by pointer and prefetched one ahead.
+    const float2* src = DIR > 0 ? pts : pts + (n - 1);
+    float2 a = *src;
+    stack[0] = a;
+    if (n < 2) return n;
+    src += DIR;
+    float2 b = *src;
+    stack[1] = b;                       // no test while the stack holds fewer than two points
+    uint32_t len = 2;
+    float l0 = a.y * b.x - a.x * b.y, l1 = b.y - a.y, l2 = a.x - b.x;
+    if (n < 3) return len;
+    src += DIR;
+    float2 p = *src;
+    for (uint32_t k = 2; k < n; ++k) {
+        const float2 next = src[k + 1 < n ? DIR : 0];   // independent of the stack: overlaps the tests below
+        src += DIR;
         while (len > 1) {
-            const float t = incidence(from_vec(p.x, p.y), line);   // == triple(a, b, p)
+            const float t = (l0 + p.x * l1) + p.y * l2;   // == (a v b) v p, src/convex_hull.rs:16-19
             if (!(t <= CR_ERROR_MARGIN)) break;
             --len;
             b = a;
-            if (len > 1) { a = stack[len - 2]; line = join(from_vec(a.x, a.y), from_vec(b.x, b.y)); }
+            if (len > 1) {
+                a = stack[len - 2];
+                l0 = a.y * b.x - a.x * b.y; l1 = b.y - a.y; l2 = a.x - b.x;
+            }
         }
         if (len >= capacity) return HULL_OVERFLOW;
         stack[len++] = p;
         a = b;
         b = p;
-        if (len > 1) line = join(from_vec(a.x, a.y), from_vec(b.x, b.y));
+        l0 = a.y * b.x - a.x * b.y; l1 = b.y - a.y; l2 = a.x - b.x;
         p = next;
     }
     return len;
@@ -955,15 +971,15 @@ __global__ void __launch_bounds__(HULL_THREADS) hull_kernel(float2* __restrict__
     }
     block_sort_points(pts, n);
     const uint32_t capacity = small ? HULL_STACK : n;
-    if (threadIdx.x == 0) sh_len[0] = hull_chain(pts, n, false, sa, capacity);
-    if (threadIdx.x == 32) sh_len[1] = hull_chain(pts, n, true, sb, capacity);
+    if (threadIdx.x == 0) sh_len[0] = hull_chain<1>(pts, n, sa, capacity);
+    if (threadIdx.x == 32) sh_len[1] = hull_chain<-1>(pts, n, sb, capacity);
     __syncthreads();
     if (sh_len[0] == HULL_OVERFLOW || sh_len[1] == HULL_OVERFLOW) {   // a hull with more than HULL_STACK vertices: redo with global stacks
         __syncthreads();
         sa = scratch_a + begin;
         sb = scratch_b + begin;
-        if (threadIdx.x == 0) sh_len[0] = hull_chain(pts, n, false, sa, n);
-        if (threadIdx.x == 32) sh_len[1] = hull_chain(pts, n, true, sb, n);
+        if (threadIdx.x == 0) sh_len[0] = hull_chain<1>(pts, n, sa, n);
+        if (threadIdx.x == 32) sh_len[1] = hull_chain<-1>(pts, n, sb, n);
         __syncthreads();
     }
     const uint32_t la = sh_len[0] - 1, lb = sh_len[1] - 1, total = la + lb;   // hull.pop() after each chain

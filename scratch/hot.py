@@ -1,6 +1,7 @@
 """Attribute ncu SASS-level samples to CUDA source lines. usage: hot.py <ncu sass csv> <cubin> <kernel substring> [top]"""
 import csv, re, subprocess, sys, collections
 sass_csv, cubin, kern = sys.argv[1:4]
+SORT = 1 if "--inst" in sys.argv else 0
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 rows = list(csv.reader(open(sass_csv)))
 hdr = rows[1]
@@ -30,5 +31,5 @@ def src(f, ln):
         c = glob.glob('/root/repo/contrast_renderer_b200/csrc/**/' + f, recursive=True)
         srcs[f] = open(c[0]).read().splitlines() if c else []
     return srcs[f][ln - 1].strip()[:100] if ln and ln <= len(srcs[f]) else ''
-for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][SORT])[:top]:
     print(f"{f}:{ln:<5} samples {100*v[0]/ts:5.1f}%  inst {100*v[1]/ti:5.1f}%   {src(f, ln)}")
