@@ -338,6 +338,43 @@ CR_HD Roots solve_quadratic(float c0, float c1, float c2, float margin) {
     o.r[1] = make_root(-c1 + q.re, q.im, 2.0f * c2);
     return o;
 }
+// The cubic and quartic closed forms lose most of their digits to cancellation in binary32 (root errors of 0.1 were seen
+// on well-conditioned stroke quartics), so they are evaluated in binary64 complex arithmetic — built, like everything in
+// this header, from correctly rounded operations only — and rounded to binary32 once at the end.
+struct ComplexD {
+    double re, im;
+};
+CR_HD ComplexD cplxd(double re, double im) { ComplexD c; c.re = re; c.im = im; return c; }
+CR_HD ComplexD operator+(ComplexD a, ComplexD b) { return cplxd(a.re + b.re, a.im + b.im); }
+CR_HD ComplexD operator-(ComplexD a, ComplexD b) { return cplxd(a.re - b.re, a.im - b.im); }
+CR_HD ComplexD operator-(ComplexD a) { return cplxd(-a.re, -a.im); }
+CR_HD ComplexD operator*(ComplexD a, double s) { return cplxd(a.re * s, a.im * s); }
+CR_HD ComplexD cmul_d(ComplexD a, ComplexD b) { return cplxd(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+CR_HD ComplexD cdiv_d(ComplexD a, ComplexD b) {
+    const double d = b.re * b.re + b.im * b.im;
+    return cplxd((a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d);
+}
+CR_HD bool is_zero_d(ComplexD a) { return a.re == 0.0 && a.im == 0.0; }
+CR_HD double cabs_d(ComplexD a) { return sqrt_d(a.re * a.re + a.im * a.im); }
+CR_HD ComplexD csqrt_d(ComplexD a) {
+    if (a.im == 0.0) return a.re >= 0.0 ? cplxd(sqrt_d(a.re), 0.0) : cplxd(0.0, sqrt_d(-a.re));
+    const double m = cabs_d(a);
+    if (a.re >= 0.0) {
+        const double t = sqrt_d((m + a.re) * 0.5);
+        return cplxd(t, a.im / (2.0 * t));
+    }
+    const double t = sqrt_d((m - a.re) * 0.5);
+    return cplxd(fabs_d(a.im) / (2.0 * t), (f64_bits(a.im) >> 63) ? -t : t);
+}
+CR_HD ComplexD ccbrt_d(ComplexD a) {
+    const double m = cabs_d(a);
+    if (!(m > 0.0)) return cplxd(0.0, 0.0);
+    const double r = exp_d(log_d(m) / 3.0);
+    double s, c;
+    sincos_d(atan2_d(a.im, a.re) / 3.0, &s, &c);
+    return cplxd(r * c, r * s);
+}
+
 /// 0 = c0 + c1 x + c2 x^2 + c3 x^3 (general cubic formula). discriminant > 0: three real roots (serpentine),
 /// = 0: repeated root (cusp), < 0: one real root (loop) — the Loop-Blinn convention used by src/fill.rs:53-65.
 CR_HD Roots solve_cubic(float c0, float c1, float c2, float c3, float margin) {
@@ -348,80 +385,88 @@ CR_HD Roots solve_cubic(float c0, float c1, float c2, float c3, float margin) {
     }
     Roots o;
     for (int i = 0; i < 4; ++i) o.r[i] = no_root();
-    const float a = c3, b = c2, c = c1, d = c0;
-    const float d0 = b * b - 3.0f * a * c;
-    const float d1 = 2.0f * b * b * b - 9.0f * a * b * c + 27.0f * a * a * d;
-    const float inner = d1 * d1 - 4.0f * d0 * d0 * d0;
-    o.discriminant = -inner / (27.0f * a * a);
-    const Complex s = csqrt(cplx(inner, 0.0f));
-    Complex cc = ccbrt((cplx(d1, 0.0f) + s) * 0.5f);
-    if (cc.re == 0.0f && cc.im == 0.0f) cc = ccbrt((cplx(d1, 0.0f) - s) * 0.5f);
-    const float den = 3.0f * a;
+    const double a = c3, b = c2, c = c1, d = c0;
+    const double d0 = b * b - 3.0 * a * c;
+    const double d1 = 2.0 * b * b * b - 9.0 * a * b * c + 27.0 * a * a * d;
+    const double inner = d1 * d1 - 4.0 * d0 * d0 * d0;
+    o.discriminant = (float)(-inner / (27.0 * a * a));
+    const ComplexD s = csqrt_d(cplxd(inner, 0.0));
+    ComplexD cc = ccbrt_d((cplxd(d1, 0.0) + s) * 0.5);
+    if (is_zero_d(cc)) cc = ccbrt_d((cplxd(d1, 0.0) - s) * 0.5);
+    const float den = (float)(3.0 * a);
     o.count = 3;
-    if (cc.re == 0.0f && cc.im == 0.0f) {  // triple root
-        for (int k = 0; k < 3; ++k) o.r[k] = make_root(-b, 0.0f, den);
+    if (is_zero_d(cc)) {  // triple root
+        for (int k = 0; k < 3; ++k) o.r[k] = make_root((float)-b, 0.0f, den);
         o.real_root = 0;
         return o;
     }
-    const Complex xi = cplx(-0.5f, 0.86602540378443864676f);
-    Complex u = cc;
-    float best = 0.0f;
+    const ComplexD xi = cplxd(-0.5, 0.86602540378443864676);
+    ComplexD u = cc;
+    double best = 0.0;
     o.real_root = 0;
     for (int k = 0; k < 3; ++k) {
-        const Complex t = cdiv(cplx(d0, 0.0f), u);
-        const Complex n = -(cplx(b, 0.0f) + u + t);
-        o.r[k] = make_root(n.re, n.im, den);
-        if (k == 0 || fabs_f(n.im) < best) { best = fabs_f(n.im); o.real_root = k; }
-        u = cmul(u, xi);
+        const ComplexD t = cdiv_d(cplxd(d0, 0.0), u);
+        const ComplexD n = -(cplxd(b, 0.0) + u + t);
+        o.r[k] = make_root((float)n.re, (float)n.im, den);
+        if (k == 0 || fabs_d(n.im) < best) { best = fabs_d(n.im); o.real_root = k; }
+        u = cmul_d(u, xi);
     }
     return o;
 }
 /// 0 = c0 + ... + c4 x^4 (Ferrari / general quartic formula in complex arithmetic).
+/// Contract: roots are returned most-real first (stable insertion sort on |Im|). The callers take the FIRST root whose
+/// real part lies in [0, 1] without looking at the imaginary part (src/curve.rs:239-247), so a complex pair must not shadow
+/// a genuine real solution.
 CR_HD Roots solve_quartic(float c0, float c1, float c2, float c3, float c4, float margin) {
     if (fabs_f(c4) <= margin) return solve_cubic(c0, c1, c2, c3, margin);
     Roots o; o.real_root = 0;
     for (int i = 0; i < 4; ++i) o.r[i] = no_root();
-    const float a = c4, b = c3, c = c2, d = c1, e = c0;
-    const float p = (8.0f * a * c - 3.0f * b * b) / (8.0f * a * a);
-    const float q = (b * b * b - 4.0f * a * b * c + 8.0f * a * a * d) / (8.0f * a * a * a);
-    const float d0 = c * c - 3.0f * b * d + 12.0f * a * e;
-    const float d1 = 2.0f * c * c * c - 9.0f * b * c * d + 27.0f * b * b * e + 27.0f * a * d * d - 72.0f * a * c * e;
-    const float inner = d1 * d1 - 4.0f * d0 * d0 * d0;
-    o.discriminant = -inner / 27.0f;
-    const Complex sq = csqrt(cplx(inner, 0.0f));
-    Complex qq = ccbrt((cplx(d1, 0.0f) + sq) * 0.5f);
-    if (qq.re == 0.0f && qq.im == 0.0f) qq = ccbrt((cplx(d1, 0.0f) - sq) * 0.5f);
-    const Complex xi = cplx(-0.5f, 0.86602540378443864676f);
-    const float m23p = -2.0f / 3.0f * p;
-    Complex S = cplx(0.0f, 0.0f);
+    const double a = c4, b = c3, c = c2, d = c1, e = c0;
+    const double p = (8.0 * a * c - 3.0 * b * b) / (8.0 * a * a);
+    const double q = (b * b * b - 4.0 * a * b * c + 8.0 * a * a * d) / (8.0 * a * a * a);
+    const double d0 = c * c - 3.0 * b * d + 12.0 * a * e;
+    const double d1 = 2.0 * c * c * c - 9.0 * b * c * d + 27.0 * b * b * e + 27.0 * a * d * d - 72.0 * a * c * e;
+    const double inner = d1 * d1 - 4.0 * d0 * d0 * d0;
+    o.discriminant = (float)(-inner / 27.0);
+    const ComplexD sq = csqrt_d(cplxd(inner, 0.0));
+    ComplexD qq = ccbrt_d((cplxd(d1, 0.0) + sq) * 0.5);
+    if (is_zero_d(qq)) qq = ccbrt_d((cplxd(d1, 0.0) - sq) * 0.5);
+    const ComplexD xi = cplxd(-0.5, 0.86602540378443864676);
+    const double m23p = -2.0 / 3.0 * p;
+    ComplexD S = cplxd(0.0, 0.0);
     for (int k = 0; k < 3; ++k) {  // pick the first cube root that gives S != 0
-        Complex t = cplx(0.0f, 0.0f);
-        if (!(qq.re == 0.0f && qq.im == 0.0f)) t = (qq + cdiv(cplx(d0, 0.0f), qq)) * (1.0f / (3.0f * a));
-        S = csqrt(cplx(m23p, 0.0f) + t) * 0.5f;
-        if (!(S.re == 0.0f && S.im == 0.0f)) break;
-        qq = cmul(qq, xi);
+        ComplexD t = cplxd(0.0, 0.0);
+        if (!is_zero_d(qq)) t = (qq + cdiv_d(cplxd(d0, 0.0), qq)) * (1.0 / (3.0 * a));
+        S = csqrt_d(cplxd(m23p, 0.0) + t) * 0.5;
+        if (!is_zero_d(S)) break;
+        qq = cmul_d(qq, xi);
     }
-    const float mb4a = -b / (4.0f * a);
+    const double mb4a = -b / (4.0 * a);
     o.count = 4;
-    if (S.re == 0.0f && S.im == 0.0f) {  // depressed quartic y^4 + p y^2 + r = 0 with q == 0 and S == 0: biquadratic
-        const Complex h = csqrt(cplx(-2.0f * p, 0.0f)) * 0.5f;  // roots -b/4a ± sqrt(-2p)/2 (double)
-        o.r[0] = make_root(mb4a + h.re, h.im, 1.0f);
-        o.r[1] = make_root(mb4a - h.re, -h.im, 1.0f);
-        o.r[2] = o.r[0];
-        o.r[3] = o.r[1];
-        return o;
+    ComplexD r[4];
+    if (is_zero_d(S)) {  // depressed quartic y^4 + p y^2 + r = 0 with q == 0 and S == 0: biquadratic
+        const ComplexD h = csqrt_d(cplxd(-2.0 * p, 0.0)) * 0.5;  // roots -b/4a ± sqrt(-2p)/2 (double)
+        r[0] = cplxd(mb4a + h.re, h.im);
+        r[1] = cplxd(mb4a - h.re, -h.im);
+        r[2] = r[0];
+        r[3] = r[1];
+    } else {
+        const ComplexD s2 = cmul_d(S, S);
+        const ComplexD base = cplxd(-2.0 * p, 0.0) - s2 * 4.0;
+        const ComplexD qs = cdiv_d(cplxd(q, 0.0), S);
+        const ComplexD h1 = csqrt_d(base + qs) * 0.5;
+        const ComplexD h2 = csqrt_d(base - qs) * 0.5;
+        const ComplexD m = cplxd(mb4a, 0.0);
+        r[0] = m - S + h1; r[1] = m - S - h1; r[2] = m + S + h2; r[3] = m + S - h2;
     }
-    const Complex s2 = cmul(S, S);
-    const Complex base = cplx(-2.0f * p, 0.0f) - s2 * 4.0f;
-    const Complex qs = cdiv(cplx(q, 0.0f), S);
-    const Complex h1 = csqrt(base + qs) * 0.5f;
-    const Complex h2 = csqrt(base - qs) * 0.5f;
-    const Complex m = cplx(mb4a, 0.0f);
-    const Complex r0 = m - S + h1, r1 = m - S - h1, r2 = m + S + h2, r3 = m + S - h2;
-    o.r[0] = make_root(r0.re, r0.im, 1.0f);
-    o.r[1] = make_root(r1.re, r1.im, 1.0f);
-    o.r[2] = make_root(r2.re, r2.im, 1.0f);
-    o.r[3] = make_root(r3.re, r3.im, 1.0f);
+    for (int i = 1; i < 4; ++i) {
+        const ComplexD key = r[i];
+        const double k = fabs_d(key.im);
+        int j = i - 1;
+        while (j >= 0 && fabs_d(r[j].im) > k) { r[j + 1] = r[j]; --j; }
+        r[j + 1] = key;
+    }
+    for (int i = 0; i < 4; ++i) o.r[i] = make_root((float)r[i].re, (float)r[i].im, 1.0f);
     return o;
 }
 

@@ -221,9 +221,10 @@ def cubic_fill_is_safe(points: np.ndarray, weights: Optional[np.ndarray] = None)
 # ------------------------------------------------------------------------------------------------------ config 2
 def mixed_fills(n_paths: int = 10000, seed: int = SEED0 + 2, extent: Tuple[int, int] = (1920, 1080), size: Tuple[float, float] = (10.0, 150.0),
                 seg_range: Tuple[int, int] = (3, 12), types=(0, 1, 2), paths_per_shape: int = 1, rational: bool = False,
-                pixels_per_unit: float = 40.0) -> Scene:
+                pixels_per_unit: float = 40.0, mirror: bool = False) -> Scene:
     """BASELINE config 2: filled closed paths of 3..12 segments drawn from {line, integral quadratic, integral cubic}
-    (or, with rational=True, also the rational kinds with weights U[0.5, 2])."""
+    (or, with rational=True, also the rational kinds with weights U[0.5, 2]). Outlines run with increasing angle in model
+    space; mirror=True negates the local x coordinates, i.e. the same outlines traversed in the opposite sense."""
     rng = np.random.default_rng(seed)
     ppu = float(pixels_per_unit)
     seg_counts = rng.integers(seg_range[0], seg_range[1] + 1, n_paths).astype(np.int64)
@@ -233,6 +234,9 @@ def mixed_fills(n_paths: int = 10000, seed: int = SEED0 + 2, extent: Tuple[int, 
     total = len(a)
     kinds = np.asarray(types if not rational else (0, 1, 2, 3, 4), np.uint8)
     seg_types = kinds[rng.integers(0, len(kinds), total)]
+    if mirror:
+        flip = np.array([-1.0, 1.0])
+        a, b, na, nb, start = a * flip, b * flip, na * flip, nb * flip, start * flip
     chord = b - a
     clen = np.linalg.norm(chord, axis=1, keepdims=True)
     mid = 0.5 * (a + b)
@@ -240,8 +244,9 @@ def mixed_fills(n_paths: int = 10000, seed: int = SEED0 + 2, extent: Tuple[int, 
     nmid = na + nb
     nmid /= np.maximum(np.linalg.norm(nmid, axis=1, keepdims=True), 1e-9)
     quad_c = mid + nmid * bulge
-    tang = np.stack([-na[:, 1], na[:, 0]], 1)
-    tang_b = np.stack([-nb[:, 1], nb[:, 0]], 1)
+    turn = -1.0 if mirror else 1.0   # tangent along the direction of travel
+    tang = np.stack([-na[:, 1], na[:, 0]], 1) * turn
+    tang_b = np.stack([-nb[:, 1], nb[:, 0]], 1) * turn
     h0 = rng.uniform(0.15, 0.7, (total, 1)) * clen
     h1 = rng.uniform(0.15, 0.7, (total, 1)) * clen
     s0 = rng.uniform(-0.3, 0.5, (total, 1)) * clen
