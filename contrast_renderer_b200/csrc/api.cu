@@ -124,7 +124,8 @@ struct cr_renderer {
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // tess begin/end, bin begin/end, raster begin/end
     bool ev_valid[3] = {false, false, false};
-    uint64_t live_objects = 0;
+    uint64_t live_objects = 0;        // shape batches and passes that still point at this renderer
+    bool destroy_requested = false;   // cr_renderer_destroy was called while live_objects > 0: the last child frees it
 };
 
 struct cr_shape {
@@ -390,8 +391,7 @@ int cr_renderer_create(const cr_config* config, cr_renderer** out) {
     return CR_OK;
 }
 
-void cr_renderer_destroy(cr_renderer* r) {
-    if (!r) return;
+static void renderer_free(cr_renderer* r) {
     DeviceGuard guard(r->device);
     cudaStreamSynchronize(r->stream);
     cudaStream_t st = r->stream;
@@ -405,6 +405,17 @@ void cr_renderer_destroy(cr_renderer* r) {
     if (r->pinned) cudaFreeHost(r->pinned);
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
     delete r;
+}
+// Shapes and passes hold a pointer to their renderer (Rust: a borrow). Destroying the renderer first is tolerated: it is
+// kept alive until its last child is gone.
+static void renderer_release_child(cr_renderer* r) {
+    if (r->live_objects > 0) --r->live_objects;
+    if (r->destroy_requested && r->live_objects == 0) renderer_free(r);
+}
+void cr_renderer_destroy(cr_renderer* r) {
+    if (!r) return;
+    if (r->live_objects > 0) { r->destroy_requested = true; return; }
+    renderer_free(r);
 }
 
 int cr_renderer_get_config(const cr_renderer* r, cr_config* out) {
@@ -459,11 +470,13 @@ int cr_shape_batch_from_paths(cr_renderer* r, const cr_dynamic_stroke_options* g
         b = new (std::nothrow) cr_shape_batch();
         if (!b) return fail(CR_ERR_INVALID_ARGUMENT, "out of host memory");
         b->renderer = r;
+        ++r->live_objects;
     }
     const int st = build_batch(r, groups, n_groups, paths, shape_path_begin, n_shapes, b);
     if (st != CR_OK) {
         batch_release(b);
         delete b;
+        renderer_release_child(r);
         return st;
     }
     *out = b;
@@ -471,9 +484,13 @@ int cr_shape_batch_from_paths(cr_renderer* r, const cr_dynamic_stroke_options* g
 }
 void cr_shape_batch_destroy(cr_shape_batch* b) {
     if (!b) return;
-    DeviceGuard guard(b->renderer->device);
-    batch_release(b);
+    cr_renderer* r = b->renderer;
+    {
+        DeviceGuard guard(r->device);
+        batch_release(b);
+    }
     delete b;
+    renderer_release_child(r);
 }
 uint32_t cr_shape_batch_size(const cr_shape_batch* b) { return b ? b->n_shapes : 0; }
 cr_shape* cr_shape_batch_get(cr_shape_batch* b, uint32_t index) { return (b && index < b->n_shapes) ? &b->views[index] : nullptr; }
@@ -610,6 +627,7 @@ int cr_pass_begin(cr_renderer* r, uint32_t clear_color, uint32_t clear_stencil, 
     cr_pass* p = new (std::nothrow) cr_pass();
     if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "out of host memory");
     p->renderer = r;
+    ++r->live_objects;
     *out = p;
     return CR_OK;
 }
@@ -808,11 +826,18 @@ int cr_pass_submit(cr_pass* p) {
         DeviceGuard guard(p->renderer->device);
         st = guard.ok ? submit(p) : fail(CR_ERR_CUDA, "cannot select CUDA device");
     }
+    cr_renderer* r = p->renderer;
     delete p;
+    renderer_release_child(r);
     return st;
 }
 
-void cr_pass_abort(cr_pass* p) { delete p; }
+void cr_pass_abort(cr_pass* p) {
+    if (!p) return;
+    cr_renderer* r = p->renderer;
+    delete p;
+    renderer_release_child(r);
+}
 
 // ------------------------------------------------------------------------------------------------- read-back
 static int read_back(cr_renderer* r, const void* src, size_t bytes, void* dst, size_t capacity) {

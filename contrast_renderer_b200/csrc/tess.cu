@@ -942,8 +942,58 @@ __device__ __noinline__ uint32_t hull_chain(const float2* pts, uint32_t n, float
     }
     return len;
 }
+// Shared-memory specialisation of hull_chain: explicit ld.shared / st.shared on 32-bit addresses (no generic-address
+// resolution, no 64-bit pointer arithmetic) and the loop unrolled by hand around the register-resident top of the stack.
+// The serial chain is the critical path of from_paths for large shapes: every instruction removed here is ~4 cycles
+// per proto-hull point on a lone warp.
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
+template <int DIR>
+__device__ __noinline__ uint32_t hull_chain_shared(const float2* pts, uint32_t n, float2* stack, uint32_t capacity) {
+    const uint32_t stack0 = (uint32_t)__cvta_generic_to_shared(stack);
+    uint32_t src = (uint32_t)__cvta_generic_to_shared(pts) + (DIR > 0 ? 0u : (n - 1) * 8u);
+    float2 a = lds_f2(src);
+    sts_f2(stack0, a);
+    if (n < 2) return n;
+    src += DIR * 8;
+    float2 b = lds_f2(src);
+    sts_f2(stack0 + 8, b);
+    if (n < 3) return 2;
+    float l0 = a.y * b.x - a.x * b.y, l1 = b.y - a.y, l2 = a.x - b.x;
+    uint32_t top = stack0 + 16;                    // address one past the top entry
+    const uint32_t limit = stack0 + capacity * 8;  // pushing at `limit` would overflow
+    const uint32_t floor2 = stack0 + 16;           // top == floor2  <=>  two entries
+    src += DIR * 8;
+    float2 p = lds_f2(src);
+    for (uint32_t k = 2; k < n; ++k) {
+        src += DIR * 8;
+        const float2 next = lds_f2(k + 1 < n ? src : src - DIR * 8);   // prefetch: independent of the stack
+        // pop while (a v b) v p <= margin (src/convex_hull.rs:16-19); a, b are the two top entries
+        float t = (l0 + p.x * l1) + p.y * l2;
+        while (t <= CR_ERROR_MARGIN) {
+            top -= 8;                 // drop b
+            b = a;
+            if (top < floor2) break;  // a single entry is left: nothing to test against
+            a = lds_f2(top - 16);
+            l0 = a.y * b.x - a.x * b.y; l1 = b.y - a.y; l2 = a.x - b.x;
+            t = (l0 + p.x * l1) + p.y * l2;
+        }
+        if (top >= limit) return HULL_OVERFLOW;
+        sts_f2(top, p);
+        top += 8;
+        a = b;
+        b = p;
+        l0 = a.y * b.x - a.x * b.y; l1 = b.y - a.y; l2 = a.x - b.x;
+        p = next;
+    }
+    return (top - stack0) >> 3;
+}
 #define HULL_THREADS 512
-#define HULL_STACK 2048
+#define HULL_STACK 512    // shared-memory chain stacks; deeper hulls (> 512 vertices on one chain) redo the chains with global stacks
 // One CTA per shape. Shapes with up to `cap` proto-hull points are sorted and chained entirely in shared memory
 // (dynamic: cap points + two HULL_STACK-entry stacks); larger ones, or chains deeper than HULL_STACK, use the global
 // scratch arrays. proto: the shape's proto_hull slice; hull_out: slice with capacity = proto count;
@@ -971,8 +1021,13 @@ __global__ void __launch_bounds__(HULL_THREADS) hull_kernel(float2* __restrict__
     }
     block_sort_points(pts, n);
     const uint32_t capacity = small ? HULL_STACK : n;
-    if (threadIdx.x == 0) sh_len[0] = hull_chain<1>(pts, n, sa, capacity);
-    if (threadIdx.x == 32) sh_len[1] = hull_chain<-1>(pts, n, sb, capacity);
+    if (small) {
+        if (threadIdx.x == 0) sh_len[0] = hull_chain_shared<1>(pts, n, sa, capacity);
+        if (threadIdx.x == 32) sh_len[1] = hull_chain_shared<-1>(pts, n, sb, capacity);
+    } else {
+        if (threadIdx.x == 0) sh_len[0] = hull_chain<1>(pts, n, sa, capacity);
+        if (threadIdx.x == 32) sh_len[1] = hull_chain<-1>(pts, n, sb, capacity);
+    }
     __syncthreads();
     if (sh_len[0] == HULL_OVERFLOW || sh_len[1] == HULL_OVERFLOW) {   // a hull with more than HULL_STACK vertices: redo with global stacks
         __syncthreads();
@@ -1019,17 +1074,17 @@ int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* 
 int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
                  float2* hull_out, uint32_t* hull_count, uint32_t max_points) {
     if (n_shapes == 0) return CR_OK;
-    // shared-memory capacity tier: enough for the largest shape if that fits (two CTAs per SM up to 9728 points, one up to
-    // 24576), else the largest tier for the shapes that do fit
+    // shared-memory capacity tier: enough for the largest shape if that fits (three CTAs per SM up to 7680 points, two up
+    // to 13312, one up to 27648), else the largest tier for the shapes that do fit
     static bool attr_set = false;
-    const uint32_t max_cap = 24576;
+    const uint32_t max_cap = 27648;
     if (!attr_set) {
         CR_CUDA_TRY(cudaFuncSetAttribute(hull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((max_cap + 2 * HULL_STACK) * sizeof(float2))));
         attr_set = true;
     }
-    static const uint32_t tiers[5] = {1024, 2048, 4096, 9728, max_cap};
+    static const uint32_t tiers[6] = {1024, 2048, 4096, 7680, 13312, max_cap};
     uint32_t cap = max_cap;
-    for (int i = 4; i >= 0; --i) if (max_points <= tiers[i]) cap = tiers[i];
+    for (int i = 5; i >= 0; --i) if (max_points <= tiers[i]) cap = tiers[i];
     hull_kernel<<<n_shapes, HULL_THREADS, (size_t)(cap + 2 * HULL_STACK) * sizeof(float2), stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out,
                                                                                                      hull_count, cap);
     g_cr_kernel_launches += 1;
