@@ -1,0 +1,76 @@
+"""The N > 1 path on CPU: world_size-2 gloo process group, batch sharding of one scene, measurement reductions."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from contrast_renderer_b200 import scenes, sharding
+
+
+def test_shard_range_is_a_partition():
+    for n in (0, 1, 7, 317, 1000):
+        for world in (1, 2, 3, 8):
+            slices = [sharding.shard_range(n, world, r) for r in range(world)]
+            assert slices[0][0] == 0 and slices[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(slices, slices[1:]))
+            sizes = [hi - lo for lo, hi in slices]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_sliced_paths_tessellate_like_the_whole(oracle):
+    """A rank's slice of the scene gives, Shape by Shape, the same vertex / index bytes as the unsharded scene."""
+    scene = scenes.mixed_fills(60, rational=True, paths_per_shape=4, seed=8)
+    whole = [oracle.shape_from_paths([], scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1])) for i in range(scene.n_shapes)]
+    seen = 0
+    for rank in range(3):
+        part = sharding.shard_scene(scene, 3, rank)
+        lo, hi = sharding.shard_range(scene.n_shapes, 3, rank)
+        assert part.n_shapes == hi - lo and np.array_equal(part.colors, scene.colors[lo:hi])
+        for i in range(part.n_shapes):
+            got = oracle.shape_from_paths([], part.paths, int(part.shape_path_begin[i]), int(part.shape_path_begin[i + 1]))
+            assert np.array_equal(got.vertex_buffer, whole[lo + i].vertex_buffer) and np.array_equal(got.index_buffer, whole[lo + i].index_buffer)
+            seen += 1
+    assert seen == scene.n_shapes
+
+
+def _worker(rank: int, world: int, port: int, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle
+        scene = scenes.glyph_like_fills(600, extent=(640, 240), glyphs_per_shape=50)
+        part = sharding.shard_scene(scene, world, rank)
+        # every rank tessellates its own slice (the CPU stand-in for its renderer) and reports its own clock
+        nbytes, _ = oracle.tessellate_batch([], part.paths, part.shape_path_begin, threads=1)
+        ms, paths, covered = sharding.reduce_measurement(10.0 * (rank + 1), part.paths.n_paths, nbytes)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (part.n_shapes, part.paths.n_paths))
+        dist.barrier()
+        if rank == 0:
+            out.put((ms, paths, covered, gathered, scene.n_shapes, scene.paths.n_paths))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_reduction(built):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ms, paths, nbytes, gathered, n_shapes, n_paths = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ms == 20.0                                     # max over ranks
+    assert paths == n_paths                               # every path is owned by exactly one rank
+    assert sum(g[0] for g in gathered) == n_shapes and sum(g[1] for g in gathered) == n_paths
+    assert nbytes > 0
