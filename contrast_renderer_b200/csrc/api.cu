@@ -720,7 +720,6 @@ static int submit(cr_pass* p) {
     cudaStream_t st = r->stream;
     const uint32_t n_cmds = (uint32_t)p->commands.size();
     if (n_cmds == 0) return CR_OK;
-    if (r->config.msaa_sample_count != 1) return fail(CR_ERR_INVALID_ARGUMENT, "the tile rasteriser currently implements msaa_sample_count = 1 only");
     // ---- instance slots
     const float* transforms = nullptr;
     const float* colors = nullptr;
@@ -776,6 +775,9 @@ static int submit(cr_pass* p) {
     tg.stencil = r->stencil.as<uint8_t>();
     tg.alpha_layers = r->alpha_layers.as<float>();
     tg.width = r->width; tg.height = r->height; tg.tiles_x = r->tiles_x; tg.tiles_y = r->tiles_y;
+    tg.samples = r->config.msaa_sample_count;
+    tg.sample_lo = tg.samples == 4 ? 32 : 128;
+    tg.sample_hi = tg.samples == 4 ? 224 : 128;
     tg.wmask = (1u << r->config.winding_counter_bits) - 1u;
     tg.cmask = ((1u << r->config.clip_nesting_counter_bits) - 1u) << r->config.winding_counter_bits;
     tg.blending = r->config.blending;

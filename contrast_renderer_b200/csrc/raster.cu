@@ -92,22 +92,22 @@ __device__ __forceinline__ Edges make_edges(const int* X, const int* Y) {
     return t;
 }
 
-// Pixel and tile extent of a triangle: pixel centres are at 256 p + 128.
+// Pixel and tile extent of a triangle: pixel p has its samples at 256 p + [sample_lo, sample_hi] (128 = the centre for 1x).
 struct Extent { int px0, px1, py0, py1, tx0, tx1, ty0, ty1; bool empty; };
 __device__ __forceinline__ Extent extent_of(const int* X, const int* Y, const RasterTarget& tg) {
     Extent x;
     const int minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
     const int minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
-    x.px0 = max(0, (minX - 128 + 255) >> 8); x.px1 = min((int)tg.width - 1, (maxX - 128) >> 8);
-    x.py0 = max(0, (minY - 128 + 255) >> 8); x.py1 = min((int)tg.height - 1, (maxY - 128) >> 8);
+    x.px0 = max(0, (minX - tg.sample_hi + 255) >> 8); x.px1 = min((int)tg.width - 1, (maxX - tg.sample_lo) >> 8);
+    x.py0 = max(0, (minY - tg.sample_hi + 255) >> 8); x.py1 = min((int)tg.height - 1, (maxY - tg.sample_lo) >> 8);
     x.empty = x.px0 > x.px1 || x.py0 > x.py1;
     x.tx0 = x.px0 / CR_TILE; x.tx1 = x.px1 / CR_TILE; x.ty0 = x.py0 / CR_TILE; x.ty1 = x.py1 / CR_TILE;
     return x;
 }
-// Can any pixel centre of tile (tx, ty), restricted to the triangle's pixel extent, be inside? (per-edge trivial reject)
-__device__ __forceinline__ bool tile_hit(const int* X, const int* Y, const Edges& t, const Extent& x, int tx, int ty) {
-    const int ylo = max(x.py0, ty * CR_TILE) * 256 + 128, yhi = min(x.py1, ty * CR_TILE + CR_TILE - 1) * 256 + 128;
-    const int xlo = max(x.px0, tx * CR_TILE) * 256 + 128, xhi = min(x.px1, tx * CR_TILE + CR_TILE - 1) * 256 + 128;
+// Can any sample of tile (tx, ty), restricted to the triangle's pixel extent, be inside? (per-edge trivial reject)
+__device__ __forceinline__ bool tile_hit(const int* X, const int* Y, const Edges& t, const Extent& x, int tx, int ty, const RasterTarget& tg) {
+    const int ylo = max(x.py0, ty * CR_TILE) * 256 + tg.sample_lo, yhi = min(x.py1, ty * CR_TILE + CR_TILE - 1) * 256 + tg.sample_hi;
+    const int xlo = max(x.px0, tx * CR_TILE) * 256 + tg.sample_lo, xhi = min(x.px1, tx * CR_TILE + CR_TILE - 1) * 256 + tg.sample_hi;
     bool hit = true;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
@@ -214,7 +214,7 @@ __device__ __forceinline__ uint32_t walk_tiles_small(const int* X, const int* Y,
     uint32_t count = 0;
     for (int ty = x.ty0; ty <= x.ty1; ++ty)
         for (int tx = x.tx0; tx <= x.tx1; ++tx)
-            if (tile_hit(X, Y, t, x, tx, ty)) {
+            if (tile_hit(X, Y, t, x, tx, ty, tg)) {
                 if (EMIT) { pair_tile[at + count] = (uint32_t)(ty * (int)tg.tiles_x + tx); pair_cand[at + count] = cand; }
                 ++count;
             }
@@ -232,7 +232,7 @@ __device__ __forceinline__ uint32_t walk_tiles_warp(const int* X, const int* Y, 
     int ty = x.ty0 + (int)lane / w, tx = x.tx0 + (int)lane % w;   // 32 consecutive tiles of the box, advanced incrementally
     const int dy = 32 / w, dx = 32 % w;
     for (int base = 0; base < total; base += 32) {
-        const bool hit = base + (int)lane < total && tile_hit(X, Y, t, x, tx, ty);
+        const bool hit = base + (int)lane < total && tile_hit(X, Y, t, x, tx, ty, tg);
         const uint32_t hits = __ballot_sync(0xffffffffu, hit);
         if (EMIT && hit) {
             const uint32_t pos = at + running + __popc(hits & ((1u << lane) - 1u));
@@ -382,13 +382,19 @@ __device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TileP
     }
 }
 
-// Stage one primitive of this tile into shared memory (one thread per primitive).
+// Sample positions inside a pixel in 1/256 px: the centre for 1x, the WebGPU standard pattern for 4x (same table as the oracle).
+template <int S> __device__ __forceinline__ int sample_x(int k) { return S == 1 ? 128 : (k == 0 ? 96 : (k == 1 ? 224 : (k == 2 ? 32 : 160))); }
+template <int S> __device__ __forceinline__ int sample_y(int k) { return S == 1 ? 128 : (k == 0 ? 32 : (k == 1 ? 96 : (k == 2 ? 160 : 224))); }
+
+// Stage one primitive of this tile into shared memory (one thread per primitive). The edge functions are evaluated at the
+// centre of the tile's pixel (0, 0) for 1x and at its top-left corner for 4x (sample offsets are added per sample).
+template <int S>
 __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, const PrimRecord& rec, int tile_px, int tile_py, TilePrim& ps) {
     ps.meta = 0;
     if (!(rec.meta & META_VALID)) return;
     const uint32_t pipe = rec.meta & 15u, cat = (rec.meta >> 8) & 7u;
     const Edges t = make_edges(rec.X, rec.Y);
-    const int PX = tile_px * 256 + 128, PY = tile_py * 256 + 128;
+    const int PX = tile_px * 256 + (S == 1 ? 128 : 0), PY = tile_py * 256 + (S == 1 ? 128 : 0);
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
         ps.A[e] = t.A[e]; ps.B[e] = t.B[e]; ps.bias[e] = t.bias[e];
@@ -397,14 +403,16 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
     // pixel bounding box clipped to this tile and to the target
     const int minX = min(rec.X[0], min(rec.X[1], rec.X[2])), maxX = max(rec.X[0], max(rec.X[1], rec.X[2]));
     const int minY = min(rec.Y[0], min(rec.Y[1], rec.Y[2])), maxY = max(rec.Y[0], max(rec.Y[1], rec.Y[2]));
-    const int x0 = max(0, ((minX - 128 + 255) >> 8) - tile_px), x1 = min(min(CR_TILE - 1, (int)tg.width - 1 - tile_px), ((maxX - 128) >> 8) - tile_px);
-    const int y0 = max(0, ((minY - 128 + 255) >> 8) - tile_py), y1 = min(min(CR_TILE - 1, (int)tg.height - 1 - tile_py), ((maxY - 128) >> 8) - tile_py);
+    const int slo = S == 1 ? 128 : 32, shi = S == 1 ? 128 : 224;   // sample offsets inside a pixel span [slo, shi]
+    const int x0 = max(0, ((minX - shi + 255) >> 8) - tile_px), x1 = min(min(CR_TILE - 1, (int)tg.width - 1 - tile_px), ((maxX - slo) >> 8) - tile_px);
+    const int y0 = max(0, ((minY - shi + 255) >> 8) - tile_py), y1 = min(min(CR_TILE - 1, (int)tg.height - 1 - tile_py), ((maxY - slo) >> 8) - tile_py);
     if (x0 > x1 || y0 > y1) return;
     ps.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
-    bool full = true;   // minimum of every edge function over the tile's pixel centres is still inside
+    bool full = true;   // minimum of every edge function over all sample positions of the tile is still inside
+    const int far = (CR_TILE - 1) * 256 + (S == 1 ? 0 : 224), near = S == 1 ? 0 : 32;   // sample offsets from the evaluation origin
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-        const long long emin = ps.e0[e] + (t.A[e] < 0 ? (long long)t.A[e] * ((CR_TILE - 1) * 256) : 0) - (t.B[e] > 0 ? (long long)t.B[e] * ((CR_TILE - 1) * 256) : 0);
+        const long long emin = ps.e0[e] + (long long)t.A[e] * (t.A[e] < 0 ? far : near) - (long long)t.B[e] * (t.B[e] > 0 ? far : near);
         if (emin < 0) full = false;
     }
     ps.ref = rec.ref;
@@ -438,14 +446,16 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
 // Run kinds: primitives of one run commute (see the file header).
 __device__ __forceinline__ uint32_t run_kind(uint32_t pipe) { return pipe <= P_STROKE_JOINT ? 0u : (pipe <= P_FILL_RC ? 1u : 2u); }
 
-__global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
-                                                                            const uint32_t* __restrict__ tile_begin, const uint32_t* __restrict__ pair_cand,
-                                                                            unsigned long long* __restrict__ covered_out) {
+template <int S>
+__global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
+                                                                                         const uint32_t* __restrict__ tile_begin,
+                                                                                         const uint32_t* __restrict__ pair_cand,
+                                                                                         unsigned long long* __restrict__ covered_out) {
     __shared__ TilePrim sh[RCHUNK];
-    __shared__ int acc[2][CR_TILE * CR_TILE];   // per-pixel result of a stencil run; double buffered so that one barrier per run suffices
+    __shared__ int acc[2][CR_TILE * CR_TILE * S];   // per-sample result of a stencil run; double buffered so that one barrier per run suffices
     __shared__ uint32_t run_mask[RCHUNK / 32];
     __shared__ uint8_t run_start[RCHUNK + 1];
-    __shared__ uint16_t cov[CR_TILE][CR_TILE];   // row coverage masks of the cover primitives of one sweep
+    __shared__ unsigned long long cov[CR_TILE][CR_TILE];   // row coverage masks (bit x * S + k) of the cover primitives of one sweep
     const uint32_t tile = blockIdx.x;
     const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];
     if (begin == end) return;
@@ -453,27 +463,41 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(Rast
     const int lx = threadIdx.x & (CR_TILE - 1), ly = threadIdx.x / CR_TILE;
     const int px = tile_px + lx, py = tile_py + ly;
     const bool in_fb = px < (int)tg.width && py < (int)tg.height;
-    const size_t pix = (size_t)py * tg.width + px;
-    uint32_t s = 0;
-    float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in_fb) { s = tg.stencil[pix]; col = tg.color[pix]; }
+    const size_t pix = ((size_t)py * tg.width + px) * S;   // first sample of this thread's pixel
+    uint32_t s[S];
+    float4 col[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) { s[k] = 0; col[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (in_fb) {
+        if (S == 1) s[0] = tg.stencil[pix];
+        else {
+            const uint32_t packed = *reinterpret_cast<const uint32_t*>(tg.stencil + pix);   // 4 samples = 4 bytes, 4-byte aligned
+#pragma unroll
+            for (int k = 0; k < S; ++k) s[k] = (packed >> (8 * k)) & 255u;
+        }
+#pragma unroll
+        for (int k = 0; k < S; ++k) col[k] = tg.color[pix + k];
+    }
     const uint32_t W = tg.wmask, C = tg.cmask, M = W | C;
     uint32_t covered = 0;
-    const size_t layer_stride = (size_t)tg.width * tg.height;
+    const size_t layer_stride = (size_t)tg.width * tg.height * S;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    acc[0][threadIdx.x] = 0;
-    acc[1][threadIdx.x] = 0;
-    // A finished stencil run whose per-pixel result has not been folded into `s` yet (block-uniform state).
+#pragma unroll
+    for (int k = 0; k < S; ++k) { acc[0][threadIdx.x * S + k] = 0; acc[1][threadIdx.x * S + k] = 0; }
+    // A finished stencil run whose per-sample result has not been folded into `s` yet (block-uniform state).
     int pending = -1;            // accumulator buffer of the pending run, or -1
     uint32_t pending_kind = 0, pending_ref = 0;
     int cur = 0;                 // buffer the next stencil run accumulates into
     auto apply_pending = [&]() {
         if (pending < 0) return;
-        const int net = acc[pending][threadIdx.x];
-        if (net != 0) {
-            if (pending_kind == 0u) { if ((pending_ref & M) == (s & M)) s = (s & ~W) | ((s + 1u) & W); }        // src/renderer.rs:571-576
-            else if ((pending_ref & M) <= (s & M)) s = (s & ~W) | ((s + (uint32_t)net) & W);                     // src/renderer.rs:577-582
-            acc[pending][threadIdx.x] = 0;   // ready for the run after next (a barrier separates)
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            const int net = acc[pending][threadIdx.x * S + k];
+            if (net != 0) {
+                if (pending_kind == 0u) { if ((pending_ref & M) == (s[k] & M)) s[k] = (s[k] & ~W) | ((s[k] + 1u) & W); }        // src/renderer.rs:571-576
+                else if ((pending_ref & M) <= (s[k] & M)) s[k] = (s[k] & ~W) | ((s[k] + (uint32_t)net) & W);                     // src/renderer.rs:577-582
+                acc[pending][threadIdx.x * S + k] = 0;   // ready for the run after next (a barrier separates)
+            }
         }
         pending = -1;
     };
@@ -485,7 +509,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(Rast
         bool boundary = false;
         if (threadIdx.x < n) {
             const PrimRecord rec = load_record<true>(records + pair_cand[chunk + threadIdx.x]);
-            stage_primitive(sc, tg, rec, tile_px, tile_py, sh[threadIdx.x]);
+            stage_primitive<S>(sc, tg, rec, tile_px, tile_py, sh[threadIdx.x]);
         }
         __syncthreads();
         if (threadIdx.x < RCHUNK) {
@@ -543,10 +567,17 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(Rast
                     }
                     const int delta = kind == 0u ? 1 : ((meta & META_FRONT) ? 1 : -1);
                     for (int x = x0; x <= x1; ++x) {
-                        if ((E[0] | E[1] | E[2]) >= 0) {
-                            if (pipe == P_FILL_SOLID || fragment_keep(sc, ps, pipe, E)) {
-                                if (kind == 0u) atomicOr(&out[y * CR_TILE + x], 1);
-                                else atomicAdd(&out[y * CR_TILE + x], delta);
+#pragma unroll
+                        for (int q = 0; q < S; ++q) {
+                            long long Es[3];
+#pragma unroll
+                            for (int e = 0; e < 3; ++e)
+                                Es[e] = S == 1 ? E[e] : E[e] + (long long)ps.A[e] * sample_y<S>(q) - (long long)ps.B[e] * sample_x<S>(q);
+                            if ((Es[0] | Es[1] | Es[2]) >= 0) {
+                                if (pipe == P_FILL_SOLID || fragment_keep(sc, ps, pipe, Es)) {
+                                    if (kind == 0u) atomicOr(&out[(y * CR_TILE + x) * S + q], 1);
+                                    else atomicAdd(&out[(y * CR_TILE + x) * S + q], delta);
+                                }
                             }
                         }
                         E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
@@ -559,11 +590,11 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(Rast
                 cur ^= 1;
             } else {
                 // cover run: one (command, instance) hull draw. Order dependent, so the stencil / blend ops run one thread per
-                // pixel, but coverage is found first by (primitive, row) work items as 16-bit row masks, 16 primitives a sweep.
+                // pixel, but coverage is found first by (primitive, row) work items as row masks, 16 primitives a sweep.
                 for (uint32_t base = a; base < b; base += CR_TILE) {
                     {
                         const uint32_t k = base + (threadIdx.x >> 4);
-                        uint32_t mask = 0;
+                        unsigned long long mask = 0;
                         if (k < b) {
                             const TilePrim& ps = sh[k];
                             const uint32_t meta = ps.meta;
@@ -571,7 +602,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(Rast
                             const int y = (int)(threadIdx.x & 15u);
                             if ((meta & META_VALID) && y >= (int)((bbox >> 8) & 255u) && y <= (int)(bbox >> 24)) {
                                 const int x0 = (int)(bbox & 255u), x1 = (int)((bbox >> 16) & 255u);
-                                if (meta & META_FULL) mask = ((2u << x1) - 1u) & ~((1u << x0) - 1u);
+                                if (meta & META_FULL) mask = (x1 * S + S >= 64 ? ~0ull : ((1ull << (x1 * S + S)) - 1ull)) & ~((1ull << (x0 * S)) - 1ull);
                                 else {
                                     long long E[3], step[3];
 #pragma unroll
@@ -580,46 +611,58 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(Rast
                                         E[e] = ps.e0[e] + (long long)ps.A[e] * (y * 256) - step[e] * x0;
                                     }
                                     for (int x = x0; x <= x1; ++x) {
-                                        if ((E[0] | E[1] | E[2]) >= 0) mask |= 1u << x;
+#pragma unroll
+                                        for (int q = 0; q < S; ++q) {
+                                            long long any = 0;
+#pragma unroll
+                                            for (int e = 0; e < 3; ++e)
+                                                any |= S == 1 ? E[e] : E[e] + (long long)ps.A[e] * sample_y<S>(q) - (long long)ps.B[e] * sample_x<S>(q);
+                                            if (any >= 0) mask |= 1ull << (x * S + q);
+                                        }
                                         E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
                                     }
                                 }
                             }
                         }
-                        cov[threadIdx.x >> 4][threadIdx.x & 15u] = (uint16_t)mask;
+                        cov[threadIdx.x >> 4][threadIdx.x & 15u] = mask;
                     }
                     __syncthreads();
                     const uint32_t count = min((uint32_t)CR_TILE, b - base);
                     for (uint32_t j = 0; j < count; ++j) {
-                        if (!((cov[j][ly] >> lx) & 1u)) continue;
+                        const uint32_t hit = (uint32_t)(cov[j][ly] >> (lx * S)) & ((1u << S) - 1u);
+                        if (!hit) continue;
                         const TilePrim& ps = sh[base + j];
                         const uint32_t pipe = ps.meta & 15u, ref = ps.ref;
-                        if (pipe == P_COLOR) {                                                                   // src/renderer.rs:736-754
-                            if ((ref & M) < (s & M)) {
-                                const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
-                                const float sa = ic.w;
-                                const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
-                                if (tg.blending == CR_BLEND_PREMULTIPLIED_OVER) {
-                                    const float kk = 1.0f - sa;
-                                    col.x = sr + col.x * kk; col.y = sg + col.y * kk; col.z = sb + col.z * kk; col.w = sa + col.w * kk;
-                                } else { col.x = sr; col.y = sg; col.z = sb; col.w = sa; }
-                                covered += 1;
-                            }
-                            s = s & ~W;
-                        } else if (pipe == P_CLIP) {                                                             // src/renderer.rs:692-710
-                            if ((ref & W) != (s & W)) s = (s & ~M) | (ref & M);
-                        } else if (pipe == P_UNCLIP) {                                                           // src/renderer.rs:711-729
-                            if ((ref & C) < (s & C)) s = (s & ~M) | (ref & M);
-                        } else if ((ref & M) <= (s & M)) {   // the three alpha-context covers share one stencil state (src/renderer.rs:761-766)
-                            if (pipe == P_SAVE_ALPHA) {
-                                tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix] = col.w;
-                            } else if (pipe == P_SCALE_ALPHA) {
-                                const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
-                                col.w = sa + col.w * (1.0f - sa);
-                            } else {
-                                const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix];
-                                const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
-                                col.w = col.w - sa;
+#pragma unroll
+                        for (int q = 0; q < S; ++q) {
+                            if (!((hit >> q) & 1u)) continue;
+                            if (pipe == P_COLOR) {                                                                   // src/renderer.rs:736-754
+                                if ((ref & M) < (s[q] & M)) {
+                                    const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
+                                    const float sa = ic.w;
+                                    const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
+                                    if (tg.blending == CR_BLEND_PREMULTIPLIED_OVER) {
+                                        const float kk = 1.0f - sa;
+                                        col[q].x = sr + col[q].x * kk; col[q].y = sg + col[q].y * kk; col[q].z = sb + col[q].z * kk; col[q].w = sa + col[q].w * kk;
+                                    } else { col[q].x = sr; col[q].y = sg; col[q].z = sb; col[q].w = sa; }
+                                    covered += 1;
+                                }
+                                s[q] = s[q] & ~W;
+                            } else if (pipe == P_CLIP) {                                                             // src/renderer.rs:692-710
+                                if ((ref & W) != (s[q] & W)) s[q] = (s[q] & ~M) | (ref & M);
+                            } else if (pipe == P_UNCLIP) {                                                           // src/renderer.rs:711-729
+                                if ((ref & C) < (s[q] & C)) s[q] = (s[q] & ~M) | (ref & M);
+                            } else if ((ref & M) <= (s[q] & M)) {   // the three alpha-context covers share one stencil state (src/renderer.rs:761-766)
+                                if (pipe == P_SAVE_ALPHA) {
+                                    tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix + q] = col[q].w;
+                                } else if (pipe == P_SCALE_ALPHA) {
+                                    const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
+                                    col[q].w = sa + col[q].w * (1.0f - sa);
+                                } else {
+                                    const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix + q];
+                                    const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
+                                    col[q].w = col[q].w - sa;
+                                }
                             }
                         }
                     }
@@ -629,7 +672,17 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, 5) raster_tiles_kernel(Rast
         }
     }
     apply_pending();
-    if (in_fb) { tg.stencil[pix] = (uint8_t)s; tg.color[pix] = col; }
+    if (in_fb) {
+        if (S == 1) tg.stencil[pix] = (uint8_t)s[0];
+        else {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int k = 0; k < S; ++k) packed |= (s[k] & 255u) << (8 * k);
+            *reinterpret_cast<uint32_t*>(tg.stencil + pix) = packed;
+        }
+#pragma unroll
+        for (int k = 0; k < S; ++k) tg.color[pix + k] = col[k];
+    }
     // covered-sample statistic: warp reduce, one atomic per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xffffffffu, covered, o);
@@ -662,7 +715,8 @@ int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterT
                     const uint32_t* pair_cand, unsigned long long* covered_samples) {
     const uint32_t n_tiles = target.tiles_x * target.tiles_y;
     if (n_tiles == 0) return CR_OK;
-    raster_tiles_kernel<<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, covered_samples);
+    if (target.samples == 4) raster_tiles_kernel<4><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, covered_samples);
+    else raster_tiles_kernel<1><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, covered_samples);
     g_cr_kernel_launches += 1;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;

@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include "../../include/contrast_b200.h"
 
-#define CR_TILE 16   // pixels per tile edge (1 sample per pixel) — one CTA of 256 threads owns one tile
+#define CR_TILE 16   // pixels per tile edge — one CTA of 256 threads owns one tile, one thread per pixel (all of its samples)
 
 // One tessellated cr_shape_batch as the rasteriser sees it.
 struct DeviceBatch {
@@ -52,10 +52,12 @@ struct PrimRecord {
 static_assert(sizeof(PrimRecord) == 64, "PrimRecord layout");
 
 struct RasterTarget {
-    float4* color;                // [height][width] premultiplied RGBA32F
-    uint8_t* stencil;             // [height][width]
-    float* alpha_layers;          // [layer][height][width]
+    float4* color;                // [height][width][samples] premultiplied RGBA32F
+    uint8_t* stencil;             // [height][width][samples]
+    float* alpha_layers;          // [layer][height][width][samples]
     uint32_t width, height, tiles_x, tiles_y;
+    uint32_t samples;             // 1 (pixel centre) or 4 (WebGPU standard pattern (6,2),(14,6),(2,10),(10,14) / 16)
+    int sample_lo, sample_hi;     // smallest / largest sample offset inside a pixel in 1/256 px: 128,128 or 32,224
     uint32_t wmask, cmask;        // winding_counter_mask / clip_nesting_counter_mask (src/renderer.rs:565-566)
     uint32_t blending, cull_mode;
 };

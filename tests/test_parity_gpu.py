@@ -333,6 +333,54 @@ def test_config5_kind_dashed_round(cr, oracle):
     assert_frames_equal(got, want)
 
 
+@pytest.mark.parametrize("maker", [
+    lambda: scenes.mixed_fills(250, extent=(400, 300), size=(8.0, 80.0), rational=True, seed=41),
+    lambda: scenes.glyph_like_fills(900, extent=(512, 200), glyphs_per_shape=60),
+    lambda: scenes.closed_cubic_strokes(50, extent=(400, 300), pixels_per_unit=20.0),
+    lambda: scenes.dashed_rational_strokes(200, extent=(400, 300), paths_per_shape=20, pixels_per_unit=4.0),
+], ids=["all_kinds", "glyphs", "cubic_strokes", "dashed_strokes"])
+def test_msaa4_matches_oracle(cr, oracle, maker):
+    """msaa_sample_count = 4 (the reference demo's setting, examples/showcase/main.rs:11): four stencil bytes and four
+    colours per pixel at the WebGPU standard sample positions, shaded per sample (src/shaders.wgsl:35)."""
+    scene = maker()
+    scene.colors[:, 3] = np.linspace(0.3, 1.0, scene.n_shapes, dtype=np.float32)
+    got, want = render_both(cr, oracle, scene, cr.Configuration(msaa_sample_count=4))
+    assert got[0].shape == (scene.height, scene.width, 4, 4) and want[2] > 4000
+    assert_frames_equal(got, want)
+    # the samples of an edge pixel differ (that is the point of multisampling)
+    alpha = got[0][..., 3]
+    assert np.any(alpha.max(axis=2) != alpha.min(axis=2))
+
+
+def test_msaa4_clip_and_opacity(cr, oracle):
+    scene = scenes.mixed_fills(4, extent=(200, 160), size=(30.0, 70.0), seed=17)
+    scene.origins[:] = np.array([[2.5, 2.0], [2.8, 2.2], [2.2, 1.8], [2.6, 2.4]])
+    config = cr.Configuration(msaa_sample_count=4, alpha_layer_count=1)
+    colors = scene.colors.copy()
+    colors[:, 3] = [1.0, 0.6, 0.5, 0.7]
+    S, CLIP, UNCLIP, COLOR, SAVE, SCALE, RESTORE = range(7)
+    script = [(0, S, 0), (0, CLIP, 1), (1, S, 1), (1, COLOR, 1), (2, S, 1), (2, SAVE, 1), (2, SCALE, 1), (3, S, 1), (3, COLOR, 1),
+              (2, S, 1), (2, RESTORE, 1), (0, S, 0), (0, UNCLIP, 0)]
+    rnd = cr.Renderer(config)
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    refs = oracle_shapes(oracle, scene)
+    rp = rnd.begin_render_pass()
+    rp.set_instances(scene.transforms(), colors)
+    ocmds = []
+    for shape, op, depth in script:
+        rp.set_clip_depth(depth)
+        batch[shape].render(rp, range(shape, shape + 1), cr.RenderOperation(op))
+        ocmds.append((shape, shape, shape + 1, op, depth, 0, 0))
+    rp.submit()
+    color, stencil, layer = rnd.read_color(), rnd.read_stencil(), rnd.read_alpha_layer(0)
+    ref_color, ref_stencil, ref_layers, _ = oracle.render(config.to_c(), scene.width, scene.height, refs, ocmds, scene.transforms(), colors)
+    assert np.array_equal(stencil, ref_stencil) and np.array_equal(color.view(np.uint32), ref_color.view(np.uint32))
+    assert np.array_equal(layer.view(np.uint32), ref_layers[0].view(np.uint32))
+    batch.close()
+    rnd.close()
+
+
 def test_instancing_and_perspective(cr, oracle):
     """One shape drawn with several instance matrices, including a perspective one (w != 1) and a culled back face."""
     scene = scenes.mixed_fills(12, extent=(384, 256), size=(20.0, 60.0), rational=True, paths_per_shape=12, seed=3)
