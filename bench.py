@@ -29,16 +29,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "100k glyph-sized filled paths-of-text (lines + integral quadratics, 1.44 contours / 20.9 points per glyph), 3840x2160, one Shape (Stencil+Color) per 316-glyph text line"
+WORKLOAD = ("100k TTF glyph instances via the text front-end (paths_of_text layout, OpenSans outlines: 143.6k contour paths, 1.6M line + integral-quadratic "
+            "segments), 12 px glyphs, 3840x2160, one Shape (Stencil+Color) per 160-glyph run")
 N_GLYPHS = 100000
 EXTENT = (3840, 2160)
 RASTER_DRAM_BYTES_R01 = 413364224   # raster_tiles_kernel, one launch on this workload: 307.96 MB read + 105.41 MB written (ncu)
-GLYPHS_PER_SHAPE = 316   # (3840 - 2 * 20) // (0.6 * 20): one text line of 20 px glyphs, the chunking BASELINE.md names for config 3
+GLYPHS_PER_SHAPE = 160
 
 
 def make_scene(rank: int, n_glyphs: int = N_GLYPHS):
     from contrast_renderer_b200 import scenes
-    return scenes.glyph_like_fills(n_glyphs, seed=scenes.SEED0 + 3 + 1000 * rank, extent=EXTENT, glyphs_per_shape=GLYPHS_PER_SHAPE)
+    return scenes.text_glyphs(n_glyphs, seed=scenes.SEED0 + 3 + 1000 * rank, extent=EXTENT, glyphs_per_shape=GLYPHS_PER_SHAPE)
 
 
 def measured_peak_gbs():

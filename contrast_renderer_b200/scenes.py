@@ -37,9 +37,12 @@ class Scene:
     name: str = ""
     pixels_per_unit: float = 1.0          # path coordinates are in model units (see MODEL UNITS below)
     origins: Optional[np.ndarray] = None  # [n_shapes, 2] model-space position of each shape's local origin (None: all zero)
+    base_transform: Optional[np.ndarray] = None   # overrides the default y-down orthographic mapping (16 floats)
 
     def transform(self) -> np.ndarray:
         """The instance mat4 (16 floats, column vectors) that maps model units to this scene's framebuffer."""
+        if self.base_transform is not None:
+            return np.asarray(self.base_transform, np.float32)
         from .renderer import orthographic_transform
         return orthographic_transform(self.width / self.pixels_per_unit, self.height / self.pixels_per_unit)
 
@@ -323,6 +326,42 @@ def glyph_like_fills(n_glyphs: int = 100000, seed: int = SEED0 + 3, extent: Tupl
     n_shapes = len(begin) - 1
     colors = np.concatenate([rng.uniform(0, 0.8, (n_shapes, 3)), np.ones((n_shapes, 1))], 1).astype(np.float32)
     return Scene(soa, begin, [], extent[0], extent[1], colors, "glyph_like_fills", ppu)
+
+
+def text_glyphs(n_glyphs: int = 100000, seed: int = SEED0 + 3, extent: Tuple[int, int] = (3840, 2160), size_px: float = 12.0, chars_per_line: int = 640,
+                pixels_per_unit: float = 60.0, glyphs_per_shape: int = 160) -> Scene:
+    """BASELINE config 3 through the text front-end (src/text.rs): `n_glyphs` printable ASCII characters (U+0021..U+007E,
+    64-bit LCG), a newline every `chars_per_line`, laid out by `paths_of_text` semantics with OpenSans outlines
+    (tests/golden/opensans_ascii.npz, extracted from the reference's demo font), one Shape per run of `glyphs_per_shape`
+    characters (a phrase; the reference's demo puts one string into one Shape). Text is y-up and centred on the origin like
+    the reference's demo; the instance matrix maps it to the centre of the target without mirroring. 100 000 glyphs at 12 px
+    fill 157 lines of a 3840x2160 target. pixels_per_unit = 60 keeps the model coordinates of the whole page within +-30
+    units, where the reference's absolute 1e-4 hull tolerance (src/convex_hull.rs:16) still removes collinear baseline
+    points; at +-260 units f32 noise exceeds the tolerance and every line's hull keeps ~1000 vertices."""
+    import os
+    from .text import Alignment, FixtureFace, Layout, Orientation, text_to_soa
+    fixture = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "opensans_ascii.npz")
+    face = FixtureFace(dict(np.load(fixture)))
+    state = np.uint64(seed)
+    codes = np.empty(n_glyphs, np.int64)
+    with np.errstate(over="ignore"):
+        for i in range(n_glyphs):   # Knuth MMIX LCG, high bits
+            state = state * np.uint64(6364136223846793005) + np.uint64(1442695040888963407)
+            codes[i] = 33 + int(state >> np.uint64(33)) % 94
+    chars = [chr(c) for c in codes]
+    lines = ["".join(chars[i:i + chars_per_line]) for i in range(0, n_glyphs, chars_per_line)]
+    text = "\n".join(lines)
+    ppu = float(pixels_per_unit)
+    layout = Layout(size_px / ppu, Orientation.LeftToRight, Alignment.Center, Alignment.Center)
+    soa, occ_first_path = text_to_soa(face, layout, text)
+    shape_first_glyph = np.arange(0, n_glyphs, glyphs_per_shape)
+    begin = np.append(occ_first_path[shape_first_glyph], soa.n_paths).astype(np.uint32)
+    n_shapes = len(begin) - 1
+    rng = np.random.default_rng(seed)
+    colors = np.concatenate([rng.uniform(0, 0.8, (n_shapes, 3)), np.ones((n_shapes, 1))], 1).astype(np.float32)
+    m = np.zeros(16, np.float32)
+    m[0], m[5], m[10], m[15] = 2.0 * ppu / extent[0], 2.0 * ppu / extent[1], 1.0, 1.0
+    return Scene(soa, begin, [], extent[0], extent[1], colors, "text_glyphs", ppu, None, m)
 
 
 # ------------------------------------------------------------------------------------------------------ config 5

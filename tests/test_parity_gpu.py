@@ -302,6 +302,20 @@ def test_glyph_scene(cr, oracle):
     assert_frames_equal(got, want)
 
 
+def test_text_scene(cr, oracle):
+    """BASELINE config 3 generator at reduced size: OpenSans text through the text front-end (src/text.rs)."""
+    scene = scenes.text_glyphs(3000, extent=(1024, 256), chars_per_line=160, glyphs_per_shape=80)
+    rnd = cr.Renderer()
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    for i, ref in enumerate(oracle_shapes(oracle, scene)):
+        assert_shape_equal(oracle, batch[i], ref, f"text shape {i}")
+    batch.close()
+    rnd.close()
+    got, want = render_both(cr, oracle, scene)
+    assert want[2] > 15000
+    assert_frames_equal(got, want)
+
+
 @pytest.mark.parametrize("dashed", [False, True], ids=["solid", "dashed"])
 @pytest.mark.parametrize("join", [Join.Miter, Join.Bevel, Join.Round])
 def test_strokes_joins_caps_dashes(cr, oracle, join, dashed):
@@ -482,8 +496,35 @@ def test_load_op_keeps_previous_pass(cr, oracle):
 
 
 # -------------------------------------------------------------------- size-independent properties at full size
+def test_full_size_config3_text_matches_oracle(cr, oracle):
+    """BASELINE config 3 at full size through the text front-end (the benchmark workload): 100k OpenSans glyph instances,
+    143.6k contour paths, 1.6M segments, 3840x2160 — tessellation of sampled Shapes and the whole frame bit-exact."""
+    scene = scenes.text_glyphs(100000)
+    assert scene.paths.n_paths == 143596 and scene.paths.n_segments == 1599370 and scene.n_shapes == 625
+    rnd = cr.Renderer()
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    cmds = scenes.stencil_cover_commands(scene.n_shapes)
+    rp = rnd.begin_render_pass()
+    rp.set_instances(scene.transforms(), scene.colors)
+    rp.render_batch(batch, cmds)
+    rp.submit()
+    got = (rnd.read_color(), rnd.read_stencil(), int(rnd.stats().covered_samples))
+    refs = oracle_shapes(oracle, scene)
+    for i in (0, 1, scene.n_shapes // 2, scene.n_shapes - 1):
+        assert_shape_equal(oracle, batch[i], refs[i], f"shape {i}")
+    ocmds = [(int(c[0]), int(c[1]), int(c[2]), int(c[3]), 0, 0, 0) for c in cmds]
+    ref_color, ref_stencil, _, ref_covered = oracle.render(rnd.config.to_c(), scene.width, scene.height, refs, ocmds, scene.transforms(), scene.colors,
+                                                           threads=oracle.max_threads())
+    assert ref_covered > 500000
+    assert_frames_equal(got, (ref_color, ref_stencil, ref_covered))
+    batch.close()
+    rnd.close()
+
+
 def test_full_size_config3_matches_oracle_and_properties(cr, oracle):
-    """BASELINE config 3 at full size (100k glyphs, 144k paths, 3840x2160): bit-exact against the oracle, plus
+    """A synthetic stand-in of config 3 at full size (100k glyph-sized contour groups, 144k paths, 3840x2160) with model
+    coordinates of +-200 units, where f32 noise exceeds the reference's tolerances: bit-exact against the oracle, plus
     size-independent properties: rendering twice gives identical bits (the raster has no order-dependent atomics),
     opaque covers leave alpha in {0, 1}, the cover zeroes the winding bits (src/renderer.rs:747-752).
 
