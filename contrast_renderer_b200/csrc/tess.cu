@@ -942,102 +942,241 @@ __device__ __noinline__ uint32_t hull_chain(const float2* pts, uint32_t n, float
     }
     return len;
 }
-// Shared-memory specialisation of hull_chain: explicit ld.shared / st.shared on 32-bit addresses (no generic-address
-// resolution, no 64-bit pointer arithmetic) and the loop unrolled by hand around the register-resident top of the stack.
-// The serial chain is the critical path of from_paths for large shapes: every instruction removed here is ~4 cycles
-// per proto-hull point on a lone warp.
+// ---- shared-memory sort: register-tiled bitonic network
+// The network is the same data-oblivious one as block_sort_points (flip stage + half-cleaners, minimum to the lower index,
+// virtual +inf padding), but each thread carries 16 elements through up to four consecutive stages in registers, so a
+// merge of 2^lk elements costs 1 + ceil((lk - 1) / 4) shared-memory round trips instead of lk. Any correct sort gives the
+// same array (equal keys are identical points). Element i lives at slot i + (i >> 4): the padding makes the three access
+// strides used (1, 16, 256 elements) bank-conflict free for 8-byte accesses.
+__device__ __forceinline__ void cswap(float2& lo, float2& hi) {
+    const bool sw = hi.x < lo.x || (hi.x == lo.x && hi.y < lo.y);
+    const float2 l = lo, h = hi;
+    lo.x = sw ? h.x : l.x; lo.y = sw ? h.y : l.y;
+    hi.x = sw ? l.x : h.x; hi.y = sw ? l.y : h.y;
+}
+template <int LK> __device__ __forceinline__ void reg_flip(float2 (&v)[16]) {   // first stage of the merge of 2^LK-blocks
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int blk = t >> (LK - 1), off = t & ((1 << (LK - 1)) - 1);
+        cswap(v[(blk << LK) + off], v[(blk << LK) + (1 << LK) - 1 - off]);
+    }
+}
+template <int Q> __device__ __forceinline__ void reg_stage(float2 (&v)[16]) {   // half-cleaner at register distance 2^Q
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int lo = ((t >> Q) << (Q + 1)) | (t & ((1 << Q) - 1));
+        cswap(v[lo], v[lo + (1 << Q)]);
+    }
+}
+#define SORT_SLOT(i) ((i) + ((i) >> 4))
+// 16 elements i0 + m * s (m = 0..15) <-> registers; elements at or beyond n are +inf and never stored.
+__device__ __forceinline__ void sort_load16(const float2* sm, uint32_t n, uint32_t i0, uint32_t s, uint32_t ps, float2 (&v)[16]) {
+    const uint32_t p0 = SORT_SLOT(i0);
+    if (i0 + 15u * s < n) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = sm[p0 + m * ps];
+    } else {
+        const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = i0 + m * s < n ? sm[p0 + m * ps] : make_float2(inf, inf);
+    }
+}
+__device__ __forceinline__ void sort_store16(float2* sm, uint32_t n, uint32_t i0, uint32_t s, uint32_t ps, const float2 (&v)[16]) {
+    const uint32_t p0 = SORT_SLOT(i0);
+    if (i0 + 15u * s < n) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sm[p0 + m * ps] = v[m];
+    } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) if (i0 + m * s < n) sm[p0 + m * ps] = v[m];
+    }
+}
+__device__ void block_sort_points_shared(float2* sm, uint32_t n) {
+    uint32_t log_n2 = 4;
+    while ((1u << log_n2) < n) ++log_n2;
+    // runs of 16: sorted completely in registers
+    for (uint32_t t = threadIdx.x; t * 16u < n; t += blockDim.x) {
+        float2 v[16];
+        sort_load16(sm, n, t * 16u, 1u, 1u, v);
+        reg_flip<1>(v);
+        reg_flip<2>(v); reg_stage<0>(v);
+        reg_flip<3>(v); reg_stage<1>(v); reg_stage<0>(v);
+        reg_flip<4>(v); reg_stage<2>(v); reg_stage<1>(v); reg_stage<0>(v);
+        sort_store16(sm, n, t * 16u, 1u, 1u, v);
+    }
+    __syncthreads();
+    for (uint32_t lk = 5; lk <= log_n2; ++lk) {
+        {   // flip stage: off <-> 2^lk - 1 - off inside each block; only blocks that start below n hold real upper elements
+            const uint32_t half = 1u << (lk - 1);
+            const uint32_t count = ((n + (2u * half) - 1u) >> lk) << (lk - 1);
+            for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) {
+                const uint32_t blk = t >> (lk - 1), off = t & (half - 1u);
+                const uint32_t lo = (blk << lk) + off, hi = (blk << lk) + 2u * half - 1u - off;
+                if (hi < n) {
+                    float2 a = sm[SORT_SLOT(lo)], b = sm[SORT_SLOT(hi)];
+                    if (b.x < a.x || (b.x == a.x && b.y < a.y)) { sm[SORT_SLOT(lo)] = b; sm[SORT_SLOT(hi)] = a; }
+                }
+            }
+            __syncthreads();
+        }
+        for (int g = (int)(lk - 2) >> 2; g >= 0; --g) {   // half-cleaners lj = lk-2 .. 0, four at a time: group g holds lj = 4g .. 4g+3
+            const int top_q = min(3, (int)lk - 2 - 4 * g);
+            const uint32_t s = 1u << (4 * g), ps = g == 0 ? 1u : s + (s >> 4);
+            const uint32_t count = ((n + 16u * s - 1u) / (16u * s)) * s;
+            for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) {
+                const uint32_t i0 = ((t >> (4 * g)) << (4 * g + 4)) + (t & (s - 1u));
+                if (i0 >= n) continue;
+                float2 v[16];
+                sort_load16(sm, n, i0, s, ps, v);
+                if (top_q >= 3) reg_stage<3>(v);
+                if (top_q >= 2) reg_stage<2>(v);
+                if (top_q >= 1) reg_stage<1>(v);
+                reg_stage<0>(v);
+                sort_store16(sm, n, i0, s, ps, v);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Sort kernel: one CTA per shape; proto[begin, begin + n) is sorted in place (shared memory when it fits `cap` points).
+__global__ void __launch_bounds__(512) hull_sort_kernel(float2* __restrict__ proto, const uint32_t* __restrict__ proto_begin, uint32_t cap) {
+    extern __shared__ float2 hull_smem[];
+    const uint32_t s = blockIdx.x;
+    const uint32_t begin = proto_begin[s], n = proto_begin[s + 1] - begin;
+    if (n < 3) return;   // returned as-is, unsorted (src/convex_hull.rs:9-11)
+    if (n <= cap) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) hull_smem[SORT_SLOT(i)] = proto[begin + i];
+        __syncthreads();
+        block_sort_points_shared(hull_smem, n);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) proto[begin + i] = hull_smem[SORT_SLOT(i)];
+    } else {
+        block_sort_points(proto + begin, n);
+    }
+}
+
+// ---- the two monotone chains
+// One warp per chain, executed by lane 0 (the stack machine is strictly sequential, see hull_chain); the other lanes
+// stream the sorted points into a double-buffered shared-memory window ahead of it. The three top stack entries (c, a, b;
+// b on top) and the lines through (a, b) and (c, a) live in registers, and every point is tested against BOTH lines at
+// once, together with the two lines a push would create. The common outcomes — "keep b" and "pop b once" — then cost one
+// dependent test + select with no memory access on the critical path; only a point that pops two or more entries reloads
+// from the shared stack. The predicate evaluations that decide anything are exactly the reference's (the speculative
+// second test is only consulted after the first one failed). Chains run in their own kernel so that nothing else
+// competes for the issue slots of these latency-bound warps.
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
-template <int DIR>
-__device__ __noinline__ uint32_t hull_chain_shared(const float2* pts, uint32_t n, float2* stack, uint32_t capacity) {
-    const uint32_t stack0 = (uint32_t)__cvta_generic_to_shared(stack);
-    uint32_t src = (uint32_t)__cvta_generic_to_shared(pts) + (DIR > 0 ? 0u : (n - 1) * 8u);
-    float2 a = lds_f2(src);
-    sts_f2(stack0, a);
-    if (n < 2) return n;
-    src += DIR * 8;
-    float2 b = lds_f2(src);
-    sts_f2(stack0 + 8, b);
-    if (n < 3) return 2;
-    float l0 = a.y * b.x - a.x * b.y, l1 = b.y - a.y, l2 = a.x - b.x;
-    uint32_t top = stack0 + 16;                    // address one past the top entry
-    const uint32_t limit = stack0 + capacity * 8;  // pushing at `limit` would overflow
-    const uint32_t floor2 = stack0 + 16;           // top == floor2  <=>  two entries
-    src += DIR * 8;
-    float2 p = lds_f2(src);
-    for (uint32_t k = 2; k < n; ++k) {
-        src += DIR * 8;
-        const float2 next = lds_f2(k + 1 < n ? src : src - DIR * 8);   // prefetch: independent of the stack
-        // pop while (a v b) v p <= margin (src/convex_hull.rs:16-19); a, b are the two top entries
-        float t = (l0 + p.x * l1) + p.y * l2;
-        while (t <= CR_ERROR_MARGIN) {
-            top -= 8;                 // drop b
-            b = a;
-            if (top < floor2) break;  // a single entry is left: nothing to test against
-            a = lds_f2(top - 16);
-            l0 = a.y * b.x - a.x * b.y; l1 = b.y - a.y; l2 = a.x - b.x;
-            t = (l0 + p.x * l1) + p.y * l2;
-        }
-        if (top >= limit) return HULL_OVERFLOW;
-        sts_f2(top, p);
-        top += 8;
-        a = b;
-        b = p;
-        l0 = a.y * b.x - a.x * b.y; l1 = b.y - a.y; l2 = a.x - b.x;
-        p = next;
-    }
-    return (top - stack0) >> 3;
-}
-#define HULL_THREADS 512
-#define HULL_STACK 512    // shared-memory chain stacks; deeper hulls (> 512 vertices on one chain) redo the chains with global stacks
-// One CTA per shape. Shapes with up to `cap` proto-hull points are sorted and chained entirely in shared memory
-// (dynamic: cap points + two HULL_STACK-entry stacks); larger ones, or chains deeper than HULL_STACK, use the global
-// scratch arrays. proto: the shape's proto_hull slice; hull_out: slice with capacity = proto count;
-// hull_count[s] = number of hull vertices, already in triangle_fan_to_strip order.
-__global__ void __launch_bounds__(HULL_THREADS) hull_kernel(float2* __restrict__ proto, float2* __restrict__ scratch_a, float2* __restrict__ scratch_b,
-                                                            const uint32_t* __restrict__ proto_begin, uint32_t n_shapes, float2* __restrict__ hull_out,
-                                                            uint32_t* __restrict__ hull_count, uint32_t cap) {
-    extern __shared__ float2 hull_smem[];
+struct HullLine { float l0, l1, l2; };
+__device__ __forceinline__ HullLine hull_line(float2 a, float2 b) { return {a.y * b.x - a.x * b.y, b.y - a.y, a.x - b.x}; }   // == join(a, b), unit weights
+__device__ __forceinline__ float hull_side(const HullLine& l, float2 p) { return (l.l0 + p.x * l.l1) + p.y * l.l2; }           // == (a v b) v p
+
+#define HULL_STACK 1024     // shared-memory chain stacks; deeper chains are redone with global stacks
+#define CHAIN_WINDOW 256    // points per prefetch window
+#define CHAIN_THREADS 64
+__global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2* __restrict__ sorted, float2* __restrict__ scratch_a, float2* __restrict__ scratch_b,
+                                                                   const uint32_t* __restrict__ proto_begin, float2* __restrict__ hull_out,
+                                                                   uint32_t* __restrict__ hull_count) {
+    __shared__ float2 window[2][2][CHAIN_WINDOW];
+    __shared__ float2 stacks[2][HULL_STACK];
     __shared__ uint32_t sh_len[2];
     const uint32_t s = blockIdx.x;
     const uint32_t begin = proto_begin[s], n = proto_begin[s + 1] - begin;
     float2* out = hull_out + begin;
+    const float2* pts = sorted + begin;
     if (n < 3) {  // returned as-is (src/convex_hull.rs:9-11); fan->strip of <= 2 points is the identity
-        if (threadIdx.x < n) out[threadIdx.x] = proto[begin + threadIdx.x];
+        if (threadIdx.x < n) out[threadIdx.x] = pts[threadIdx.x];
         if (threadIdx.x == 0) hull_count[s] = n;
         return;
     }
-    const bool small = n <= cap;
-    float2* pts = small ? hull_smem : proto + begin;
-    float2* sa = small ? hull_smem + cap : scratch_a + begin;
-    float2* sb = small ? hull_smem + cap + HULL_STACK : scratch_b + begin;
-    if (small) {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pts[i] = proto[begin + i];
-        __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const bool descending = warp != 0;   // warp 0: lower chain (ascending points), warp 1: upper chain (descending)
+    // logical point k of this chain
+    auto fetch = [&](uint32_t w) {       // stream window w (points w * CHAIN_WINDOW ...) into window[warp][w & 1]
+        const uint32_t base = w * CHAIN_WINDOW;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&window[warp][w & 1u][0]);
+#pragma unroll
+        for (uint32_t i = 0; i < CHAIN_WINDOW / 32; ++i) {
+            const uint32_t k = base + lane + 32u * i;
+            if (k < n) {
+                const float2* src = pts + (descending ? n - 1u - k : k);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (lane + 32u * i) * 8u), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const uint32_t stack0 = (uint32_t)__cvta_generic_to_shared(&stacks[warp][0]);
+    const uint32_t floor2 = stack0 + 16;                 // top == floor2  <=>  two entries
+    const uint32_t limit = stack0 + HULL_STACK * 8;      // pushing at `limit` would overflow
+    uint32_t top = floor2;                               // address one past the top entry
+    float2 a = make_float2(0.f, 0.f), b = a, c = a;
+    HullLine lab = {0.f, 0.f, 0.f}, lca = lab;
+    bool overflow = false;
+    if (lane == 0) {
+        const uint32_t w0 = (uint32_t)__cvta_generic_to_shared(&window[warp][0][0]);
+        a = lds_f2(w0); b = lds_f2(w0 + 8);
+        sts_f2(stack0, a); sts_f2(stack0 + 8, b);
+        c = a; lab = hull_line(a, b); lca = lab;         // c, lca are meaningful only while the stack holds >= 3 entries
     }
-    block_sort_points(pts, n);
-    const uint32_t capacity = small ? HULL_STACK : n;
-    if (small) {
-        if (threadIdx.x == 0) sh_len[0] = hull_chain_shared<1>(pts, n, sa, capacity);
-        if (threadIdx.x == 32) sh_len[1] = hull_chain_shared<-1>(pts, n, sb, capacity);
-    } else {
-        if (threadIdx.x == 0) sh_len[0] = hull_chain<1>(pts, n, sa, capacity);
-        if (threadIdx.x == 32) sh_len[1] = hull_chain<-1>(pts, n, sb, capacity);
+    const uint32_t n_windows = (n + CHAIN_WINDOW - 1) / CHAIN_WINDOW;
+    for (uint32_t w = 0; w < n_windows; ++w) {
+        if (w + 1 < n_windows) fetch(w + 1);
+        if (lane == 0 && !overflow) {
+            uint32_t src = (uint32_t)__cvta_generic_to_shared(&window[warp][w & 1u][0]);
+            const uint32_t k0 = w == 0 ? 2u : 0u, k1 = min((uint32_t)CHAIN_WINDOW, n - w * CHAIN_WINDOW);
+            src += k0 * 8u;
+            for (uint32_t k = k0; k < k1; ++k, src += 8u) {
+                const float2 p = lds_f2(src);
+                // pop while (a v b) v p <= margin (src/convex_hull.rs:16-19); a, b are the two top entries
+                const float t1 = hull_side(lab, p), t2 = hull_side(lca, p);
+                const HullLine lbp = hull_line(b, p), lap = hull_line(a, p);
+                if (!(t1 <= CR_ERROR_MARGIN)) {                                // keep b:  .. c a b  ->  .. a b p
+                    if (top >= limit) { overflow = true; break; }
+                    sts_f2(top, p);
+                    top += 8;
+                    c = a; a = b; b = p;
+                    lca = lab; lab = lbp;
+                } else if (top == floor2 || !(t2 <= CR_ERROR_MARGIN)) {        // pop b only (a is the last entry, or a stays):  .. c a b  ->  .. c a p
+                    sts_f2(top - 8, p);
+                    b = p;
+                    lab = lap;
+                } else {                                                       // b and a are popped: continue on the shared stack, which now ends with c
+                    top -= 16;
+                    b = c;
+                    while (top >= floor2) {                                    // at least two entries are left
+                        a = lds_f2(top - 16);
+                        lab = hull_line(a, b);
+                        if (!(hull_side(lab, p) <= CR_ERROR_MARGIN)) break;
+                        top -= 8;
+                        b = a;
+                    }
+                    sts_f2(top, p);
+                    top += 8;
+                    a = b; b = p;
+                    lab = hull_line(a, b);
+                    if (top > floor2) { c = lds_f2(top - 24); lca = hull_line(c, a); }
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    if (lane == 0) {
+        uint32_t len = (top - stack0) >> 3;
+        if (overflow) len = descending ? hull_chain<-1>(pts, n, scratch_b + begin, n) : hull_chain<1>(pts, n, scratch_a + begin, n);
+        sh_len[warp] = len | (overflow ? 0x80000000u : 0u);
     }
     __syncthreads();
-    if (sh_len[0] == HULL_OVERFLOW || sh_len[1] == HULL_OVERFLOW) {   // a hull with more than HULL_STACK vertices: redo with global stacks
-        __syncthreads();
-        sa = scratch_a + begin;
-        sb = scratch_b + begin;
-        if (threadIdx.x == 0) sh_len[0] = hull_chain<1>(pts, n, sa, n);
-        if (threadIdx.x == 32) sh_len[1] = hull_chain<-1>(pts, n, sb, n);
-        __syncthreads();
-    }
-    const uint32_t la = sh_len[0] - 1, lb = sh_len[1] - 1, total = la + lb;   // hull.pop() after each chain
+    const bool ga = (sh_len[0] >> 31) != 0, gb = (sh_len[1] >> 31) != 0;
+    const float2* sa = ga ? scratch_a + begin : &stacks[0][0];
+    const float2* sb = gb ? scratch_b + begin : &stacks[1][0];
+    const uint32_t la = (sh_len[0] & 0x7fffffffu) - 1, lb = (sh_len[1] & 0x7fffffffu) - 1, total = la + lb;   // hull.pop() after each chain
     // triangle_fan_to_strip(andrew(..)) (src/renderer.rs:197, src/vertex.rs:28-35)
     for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
         const uint32_t src = (i & 1u) == 0 ? (i >> 1) : total - 1 - (i >> 1);
@@ -1074,20 +1213,19 @@ int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* 
 int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
                  float2* hull_out, uint32_t* hull_count, uint32_t max_points) {
     if (n_shapes == 0) return CR_OK;
-    // shared-memory capacity tier: enough for the largest shape if that fits (three CTAs per SM up to 7680 points, two up
-    // to 13312, one up to 27648), else the largest tier for the shapes that do fit
+    // Sort: shared-memory capacity (in points) = the largest shape rounded up to 512 if that fits one SM's shared memory
+    // (8.5 bytes per point with the bank padding), else the maximum — larger shapes sort in global memory.
     static bool attr_set = false;
-    const uint32_t max_cap = 27648;
+    const uint32_t max_cap = 26624;
     if (!attr_set) {
-        CR_CUDA_TRY(cudaFuncSetAttribute(hull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((max_cap + 2 * HULL_STACK) * sizeof(float2))));
+        CR_CUDA_TRY(cudaFuncSetAttribute(hull_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_SLOT(max_cap) * sizeof(float2))));
         attr_set = true;
     }
-    static const uint32_t tiers[6] = {1024, 2048, 4096, 7680, 13312, max_cap};
-    uint32_t cap = max_cap;
-    for (int i = 5; i >= 0; --i) if (max_points <= tiers[i]) cap = tiers[i];
-    hull_kernel<<<n_shapes, HULL_THREADS, (size_t)(cap + 2 * HULL_STACK) * sizeof(float2), stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out,
-                                                                                                     hull_count, cap);
-    g_cr_kernel_launches += 1;
+    const uint32_t cap = std::min<uint32_t>(max_cap, std::max<uint32_t>(512u, (max_points + 511u) / 512u * 512u));
+    const uint32_t threads = std::min<uint32_t>(512u, std::max<uint32_t>(64u, cap / 16u));   // one 16-element register tile per thread
+    hull_sort_kernel<<<n_shapes, threads, (size_t)SORT_SLOT(cap) * sizeof(float2), stream>>>(proto, proto_begin, cap);
+    hull_chain_kernel<<<n_shapes, CHAIN_THREADS, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, hull_out, hull_count);
+    g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }

@@ -199,8 +199,20 @@ def test_hull_paths_beyond_the_shared_memory_fast_path(cr, oracle):
     """convex_hull::andrew on the device has three regimes: shared-memory sort + chains, chains deeper than the
     shared-memory stacks (a hull with thousands of vertices), and shapes too large for shared memory (global sort)."""
     rnd = cr.Renderer()
-    # (1) a 1200-gon of radius 100 (turn areas ~1e-3 > ERROR_MARGIN): nearly every proto-hull point is a hull vertex -> the
-    # shared-memory chain stacks overflow and the chains are redone with global stacks
+    # (1) a 4000-gon of radius 200 (turn areas around ERROR_MARGIN): ~2600 proto-hull points stay hull vertices -> the
+    # 1024-entry shared-memory chain stacks overflow and the chains are redone with global stacks
+    ang = np.linspace(0.0, 2.0 * np.pi, 4000, endpoint=False)
+    ring = Path([200.0, 0.0])
+    for a in ang[1:]:
+        ring.push_line([200.0 * np.cos(a), 200.0 * np.sin(a)])
+    ring.close()
+    soa = PathSoA.from_paths([ring])
+    shape = cr.Shape.from_paths(rnd, [], soa)
+    ref = oracle.shape_from_paths([], soa)
+    assert ref.vertex_offsets[7] - ref.vertex_offsets[6] > 8 * 2200   # at least one chain is deeper than 1024
+    assert_shape_equal(oracle, shape, ref, "4000-gon")
+    shape.close()
+    # (1b) a 1200-gon of radius 100: both chains (~600 entries) stay in the shared-memory stacks
     ang = np.linspace(0.0, 2.0 * np.pi, 1200, endpoint=False)
     ring = Path([100.0, 0.0])
     for a in ang[1:]:
@@ -209,7 +221,6 @@ def test_hull_paths_beyond_the_shared_memory_fast_path(cr, oracle):
     soa = PathSoA.from_paths([ring])
     shape = cr.Shape.from_paths(rnd, [], soa)
     ref = oracle.shape_from_paths([], soa)
-    assert ref.vertex_offsets[7] - ref.vertex_offsets[6] > 8 * 1100
     assert_shape_equal(oracle, shape, ref, "1200-gon")
     shape.close()
     # (2) one shape with ~48k proto-hull points (2000 glyphs): sorted in global memory
@@ -217,7 +228,7 @@ def test_hull_paths_beyond_the_shared_memory_fast_path(cr, oracle):
     batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
     for i in range(scene.n_shapes):
         ref = oracle.shape_from_paths([], scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
-        assert ref.proto_hull_points > 27648
+        assert ref.proto_hull_points > 26624
         assert_shape_equal(oracle, batch[i], ref, f"big shape {i}")
     batch.close()
     rnd.close()
