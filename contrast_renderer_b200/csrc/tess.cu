@@ -1075,25 +1075,28 @@ __device__ __forceinline__ HullLine hull_line(float2 a, float2 b) { return {a.y 
 __device__ __forceinline__ float hull_side(const HullLine& l, float2 p) { return (l.l0 + p.x * l.l1) + p.y * l.l2; }           // == (a v b) v p
 
 #define HULL_STACK 1024     // shared-memory chain stacks; deeper chains are redone with global stacks
-#define CHAIN_WINDOW 256    // points per prefetch window
-#define CHAIN_THREADS 64
+#define CHAIN_WINDOW 128    // points per prefetch window
+#define CHAIN_SHAPES 2      // shapes per CTA: four chain warps, one per SM sub-partition
+#define CHAIN_THREADS (64 * CHAIN_SHAPES)
 __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2* __restrict__ sorted, float2* __restrict__ scratch_a, float2* __restrict__ scratch_b,
-                                                                   const uint32_t* __restrict__ proto_begin, float2* __restrict__ hull_out,
-                                                                   uint32_t* __restrict__ hull_count) {
-    __shared__ float2 window[2][2][CHAIN_WINDOW];
-    __shared__ float2 stacks[2][HULL_STACK];
-    __shared__ uint32_t sh_len[2];
-    const uint32_t s = blockIdx.x;
+                                                                   const uint32_t* __restrict__ proto_begin, uint32_t n_shapes,
+                                                                   float2* __restrict__ hull_out, uint32_t* __restrict__ hull_count) {
+    __shared__ float2 window[2 * CHAIN_SHAPES][2][CHAIN_WINDOW];
+    __shared__ float2 stacks[2 * CHAIN_SHAPES][HULL_STACK];
+    __shared__ uint32_t sh_len[2 * CHAIN_SHAPES];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t slot = warp >> 1, tid = threadIdx.x & 63u;   // the CTA's slot-th shape is handled by 64 threads
+    const uint32_t s = blockIdx.x * CHAIN_SHAPES + slot;
+    if (s >= n_shapes) return;
     const uint32_t begin = proto_begin[s], n = proto_begin[s + 1] - begin;
     float2* out = hull_out + begin;
     const float2* pts = sorted + begin;
     if (n < 3) {  // returned as-is (src/convex_hull.rs:9-11); fan->strip of <= 2 points is the identity
-        if (threadIdx.x < n) out[threadIdx.x] = pts[threadIdx.x];
-        if (threadIdx.x == 0) hull_count[s] = n;
+        if (tid < n) out[tid] = pts[tid];
+        if (tid == 0) hull_count[s] = n;
         return;
     }
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const bool descending = warp != 0;   // warp 0: lower chain (ascending points), warp 1: upper chain (descending)
+    const bool descending = (warp & 1u) != 0;   // even warp: lower chain (ascending points), odd warp: upper chain (descending)
     // logical point k of this chain
     auto fetch = [&](uint32_t w) {       // stream window w (points w * CHAIN_WINDOW ...) into window[warp][w & 1]
         const uint32_t base = w * CHAIN_WINDOW;
@@ -1131,25 +1134,32 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
             uint32_t src = (uint32_t)__cvta_generic_to_shared(&window[warp][w & 1u][0]);
             const uint32_t k0 = w == 0 ? 2u : 0u, k1 = min((uint32_t)CHAIN_WINDOW, n - w * CHAIN_WINDOW);
             src += k0 * 8u;
-            for (uint32_t k = k0; k < k1; ++k, src += 8u) {
-                const float2 p = lds_f2(src);
+            float2 pn = lds_f2(src);
+            for (uint32_t k = k0; k < k1; ++k) {
+                const float2 p = pn;
+                src += 8u;
+                pn = lds_f2(k + 1 < k1 ? src : src - 8u);   // next point: independent of the stack, overlaps the tests below
                 // pop while (a v b) v p <= margin (src/convex_hull.rs:16-19); a, b are the two top entries
                 const float t1 = hull_side(lab, p), t2 = hull_side(lca, p);
                 const HullLine lbp = hull_line(b, p), lap = hull_line(a, p);
-                if (!(t1 <= CR_ERROR_MARGIN)) {                                // keep b:  .. c a b  ->  .. a b p
-                    if (top >= limit) { overflow = true; break; }
-                    sts_f2(top, p);
-                    top += 8;
-                    c = a; a = b; b = p;
-                    lca = lab; lab = lbp;
-                } else if (top == floor2 || !(t2 <= CR_ERROR_MARGIN)) {        // pop b only (a is the last entry, or a stays):  .. c a b  ->  .. c a p
-                    sts_f2(top - 8, p);
+                const bool keep = !(t1 <= CR_ERROR_MARGIN);                        // keep b:  .. c a b  ->  .. a b p
+                const bool pop1 = top == floor2 || !(t2 <= CR_ERROR_MARGIN);       // else pop b only (a is the last entry, or a stays):  .. c a b  ->  .. c a p
+                if (keep ? top < limit : pop1) {                                   // the two common outcomes, branch free
+                    const uint32_t at = keep ? top : top - 8u;
+                    sts_f2(at, p);
+                    top = at + 8u;
+                    c.x = keep ? a.x : c.x; c.y = keep ? a.y : c.y;
+                    a.x = keep ? b.x : a.x; a.y = keep ? b.y : a.y;
+                    lca.l0 = keep ? lab.l0 : lca.l0; lca.l1 = keep ? lab.l1 : lca.l1; lca.l2 = keep ? lab.l2 : lca.l2;
+                    lab.l0 = keep ? lbp.l0 : lap.l0; lab.l1 = keep ? lbp.l1 : lap.l1; lab.l2 = keep ? lbp.l2 : lap.l2;
                     b = p;
-                    lab = lap;
-                } else {                                                       // b and a are popped: continue on the shared stack, which now ends with c
+                } else if (keep) {
+                    overflow = true;
+                    break;
+                } else {                                                           // b and a are popped: continue on the shared stack, which now ends with c
                     top -= 16;
                     b = c;
-                    while (top >= floor2) {                                    // at least two entries are left
+                    while (top >= floor2) {                                        // at least two entries are left
                         a = lds_f2(top - 16);
                         lab = hull_line(a, b);
                         if (!(hull_side(lab, p) <= CR_ERROR_MARGIN)) break;
@@ -1172,17 +1182,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
         if (overflow) len = descending ? hull_chain<-1>(pts, n, scratch_b + begin, n) : hull_chain<1>(pts, n, scratch_a + begin, n);
         sh_len[warp] = len | (overflow ? 0x80000000u : 0u);
     }
-    __syncthreads();
-    const bool ga = (sh_len[0] >> 31) != 0, gb = (sh_len[1] >> 31) != 0;
-    const float2* sa = ga ? scratch_a + begin : &stacks[0][0];
-    const float2* sb = gb ? scratch_b + begin : &stacks[1][0];
-    const uint32_t la = (sh_len[0] & 0x7fffffffu) - 1, lb = (sh_len[1] & 0x7fffffffu) - 1, total = la + lb;   // hull.pop() after each chain
+    asm volatile("bar.sync %0, 64;" ::"r"(1u + slot) : "memory");   // the two chain warps of this shape
+    const uint32_t len_a = sh_len[2 * slot], len_b = sh_len[2 * slot + 1];
+    const float2* sa = (len_a >> 31) ? scratch_a + begin : &stacks[2 * slot][0];
+    const float2* sb = (len_b >> 31) ? scratch_b + begin : &stacks[2 * slot + 1][0];
+    const uint32_t la = (len_a & 0x7fffffffu) - 1, lb = (len_b & 0x7fffffffu) - 1, total = la + lb;   // hull.pop() after each chain
     // triangle_fan_to_strip(andrew(..)) (src/renderer.rs:197, src/vertex.rs:28-35)
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+    for (uint32_t i = tid; i < total; i += 64u) {
         const uint32_t src = (i & 1u) == 0 ? (i >> 1) : total - 1 - (i >> 1);
         out[i] = src < la ? sa[src] : sb[src - la];
     }
-    if (threadIdx.x == 0) hull_count[s] = total;
+    if (tid == 0) hull_count[s] = total;
 }
 
 }  // namespace
@@ -1224,7 +1234,7 @@ int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* 
     const uint32_t cap = std::min<uint32_t>(max_cap, std::max<uint32_t>(512u, (max_points + 511u) / 512u * 512u));
     const uint32_t threads = std::min<uint32_t>(512u, std::max<uint32_t>(64u, cap / 16u));   // one 16-element register tile per thread
     hull_sort_kernel<<<n_shapes, threads, (size_t)SORT_SLOT(cap) * sizeof(float2), stream>>>(proto, proto_begin, cap);
-    hull_chain_kernel<<<n_shapes, CHAIN_THREADS, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, hull_out, hull_count);
+    hull_chain_kernel<<<(n_shapes + CHAIN_SHAPES - 1) / CHAIN_SHAPES, CHAIN_THREADS, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out, hull_count);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
