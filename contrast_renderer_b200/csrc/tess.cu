@@ -1130,6 +1130,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
     const uint32_t n_windows = (n + CHAIN_WINDOW - 1) / CHAIN_WINDOW;
     for (uint32_t w = 0; w < n_windows; ++w) {
         if (w + 1 < n_windows) fetch(w + 1);
+        // The stack grows by at most one entry per point: one capacity check per window keeps it out of the loop.
+        if (lane == 0 && !overflow && top + CHAIN_WINDOW * 8u > limit) overflow = true;
         if (lane == 0 && !overflow) {
             uint32_t src = (uint32_t)__cvta_generic_to_shared(&window[warp][w & 1u][0]);
             const uint32_t k0 = w == 0 ? 2u : 0u, k1 = min((uint32_t)CHAIN_WINDOW, n - w * CHAIN_WINDOW);
@@ -1143,9 +1145,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
                 const float t1 = hull_side(lab, p), t2 = hull_side(lca, p);
                 const HullLine lbp = hull_line(b, p), lap = hull_line(a, p);
                 const bool keep = !(t1 <= CR_ERROR_MARGIN);                        // keep b:  .. c a b  ->  .. a b p
-                const bool pop1 = top == floor2 || !(t2 <= CR_ERROR_MARGIN);       // else pop b only (a is the last entry, or a stays):  .. c a b  ->  .. c a p
-                if (keep ? top < limit : pop1) {                                   // the two common outcomes, branch free
-                    const uint32_t at = keep ? top : top - 8u;
+                if (keep || top == floor2 || !(t2 <= CR_ERROR_MARGIN)) {           // else pop b only (a is the last entry, or a stays):  .. c a b  ->  .. c a p
+                    const uint32_t at = keep ? top : top - 8u;                     // the two common outcomes, branch free
                     sts_f2(at, p);
                     top = at + 8u;
                     c.x = keep ? a.x : c.x; c.y = keep ? a.y : c.y;
@@ -1153,9 +1154,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
                     lca.l0 = keep ? lab.l0 : lca.l0; lca.l1 = keep ? lab.l1 : lca.l1; lca.l2 = keep ? lab.l2 : lca.l2;
                     lab.l0 = keep ? lbp.l0 : lap.l0; lab.l1 = keep ? lbp.l1 : lap.l1; lab.l2 = keep ? lbp.l2 : lap.l2;
                     b = p;
-                } else if (keep) {
-                    overflow = true;
-                    break;
                 } else {                                                           // b and a are popped: continue on the shared stack, which now ends with c
                     top -= 16;
                     b = c;
