@@ -222,6 +222,244 @@ class Path:
         """src/path.rs:630-635: a rational quadratic with middle weight 1/sqrt(2)."""
         self.push_rational_quadratic_curve(RationalQuadraticCurveSegment(np.float32(0.70710678118654752440), [tangent_crossing, to]))
 
+    # ---- src/path.rs:376-617: append, transform, reverse, conversions --------------------------------------------------
+    _N_WEIGHTS = (0, 0, 0, 1, 4)   # leading weight floats of a stored segment, by SegmentType
+
+    def _stores(self):
+        return (self.line_segments, self.integral_quadratic_curve_segments, self.integral_cubic_curve_segments,
+                self.rational_quadratic_curve_segments, self.rational_cubic_curve_segments)
+
+    def append(self, other: "Path") -> None:
+        """src/path.rs:376-384: concatenates the segment vectors and leaves `other` empty. The reference forgets
+        `segment_types`, which makes the appended segments unreachable; here they are appended
+        too, the evident intent."""
+        for mine, theirs in zip(self._stores(), other._stores()):
+            mine.extend(theirs)
+            theirs.clear()
+        self.segment_types.extend(other.segment_types)
+        other.segment_types.clear()
+
+    def transform(self, scale: float, motor) -> None:
+        """src/path.rs:387-439: every control point (start included) through `motor2d_to_mat3(motor)` whose two diagonal
+        entries are multiplied by `scale` (so `scale` is a uniform scale only for rotation-free motors, as in the reference)."""
+        from . import utils
+        t = utils.motor2d_to_mat3(motor)
+        t[0][0] *= np.float32(scale)
+        t[1][1] *= np.float32(scale)
+
+        def transform_point(q):
+            return safe_vec([t[2][0] + q[0] * t[0][0] + q[1] * t[1][0], t[2][1] + q[0] * t[0][1] + q[1] * t[1][1]])
+
+        self.start = transform_point(self.start)
+        for kind, store in enumerate(self._stores()):
+            w = Path._N_WEIGHTS[kind]
+            for seg in store:
+                for i in range(w, len(seg), 2):
+                    seg[i:i + 2] = transform_point(seg[i:i + 2])
+
+    def reverse(self) -> None:
+        """src/path.rs:445-488: swaps start and end, reverses every segment and the segment order."""
+        previous = self.start.copy()
+        cursors = [0] * 5
+        for kind in self.segment_types:
+            seg = self._stores()[kind][cursors[kind]]
+            cursors[kind] += 1
+            w = Path._N_WEIGHTS[kind]
+            if kind == SegmentType.RationalCubicCurve:
+                seg[0:4] = seg[0:4][::-1].copy()
+            if kind in (SegmentType.IntegralCubicCurve, SegmentType.RationalCubicCurve):   # control_points.swap(0, 1)
+                a = seg[w:w + 2].copy()
+                seg[w:w + 2] = seg[w + 2:w + 4]
+                seg[w + 2:w + 4] = a
+            end = seg[-2:].copy()
+            seg[-2:] = previous
+            previous = end
+        self.start = previous
+        self.segment_types.reverse()
+        for store in self._stores():
+            store.reverse()
+
+    def convert_integral_curves_to_rational_curves(self) -> None:
+        """src/path.rs:492-531: integral quadratics / cubics become rational ones with unit weights, in path order."""
+        cursors = [0] * 5
+        rq: List[np.ndarray] = []
+        rc: List[np.ndarray] = []
+        for i, kind in enumerate(self.segment_types):
+            seg = self._stores()[kind][cursors[kind]]
+            cursors[kind] += 1
+            if kind == SegmentType.IntegralQuadraticCurve:
+                rq.append(np.concatenate([np.ones(1, np.float32), seg]))
+                self.segment_types[i] = SegmentType.RationalQuadraticCurve
+            elif kind == SegmentType.IntegralCubicCurve:
+                rc.append(np.concatenate([np.ones(4, np.float32), seg]))
+                self.segment_types[i] = SegmentType.RationalCubicCurve
+            elif kind == SegmentType.RationalQuadraticCurve:
+                rq.append(seg)
+            elif kind == SegmentType.RationalCubicCurve:
+                rc.append(seg)
+        self.rational_quadratic_curve_segments[:] = rq
+        self.rational_cubic_curve_segments[:] = rc
+        self.integral_quadratic_curve_segments.clear()
+        self.integral_cubic_curve_segments.clear()
+
+    def convert_quadratic_curves_to_cubic_curves(self) -> None:
+        """src/path.rs:535-617: degree elevation; the rational case elevates the homogeneous control points and
+        normalises the two inner ones (weights [1, w1, w2, 1])."""
+        f = np.float32
+        cursors = [0] * 5
+        ic: List[np.ndarray] = []
+        rc: List[np.ndarray] = []
+        previous = self.start.copy()
+        two_thirds = f(2.0) / f(3.0)
+        for i, kind in enumerate(self.segment_types):
+            seg = self._stores()[kind][cursors[kind]]
+            cursors[kind] += 1
+            if kind == SegmentType.IntegralQuadraticCurve:
+                a, b = seg[0:2], seg[2:4]
+                # reference: previous + (a - previous) * 2.0 / 3.0 (two roundings: multiply, then divide)
+                c0 = previous + (a - previous) * f(2.0) / f(3.0)
+                c1 = b + (a - b) * f(2.0) / f(3.0)
+                ic.append(safe_vec(np.concatenate([c0, c1, b])))
+                self.segment_types[i] = SegmentType.IntegralCubicCurve
+            elif kind == SegmentType.IntegralCubicCurve:
+                ic.append(seg)
+            elif kind == SegmentType.RationalQuadraticCurve:
+                w = seg[0]
+                p0 = np.array([1.0, previous[0], previous[1]], np.float32)
+                p1 = np.array([w, seg[1] * w, seg[2] * w], np.float32)
+                p2 = np.array([1.0, seg[3], seg[4]], np.float32)
+                n0 = p0 + (p1 - p0) * two_thirds
+                n1 = p2 + (p1 - p2) * two_thirds
+                rc.append(safe_vec([1.0, n0[0], n1[0], 1.0, n0[1] / n0[0], n0[2] / n0[0], n1[1] / n1[0], n1[2] / n1[0], seg[3], seg[4]]))
+                self.segment_types[i] = SegmentType.RationalCubicCurve
+            elif kind == SegmentType.RationalCubicCurve:
+                rc.append(seg)
+            previous = seg[-2:].copy()
+        self.integral_cubic_curve_segments[:] = ic
+        self.rational_cubic_curve_segments[:] = rc
+        self.integral_quadratic_curve_segments.clear()
+        self.rational_quadratic_curve_segments.clear()
+
+    # ---- src/path.rs:637-815: arcs and shape constructors ---------------------------------------------------------------
+    def push_elliptical_arc(self, half_extent, rotation: float, large_arc: bool, sweep: bool, to) -> None:
+        """src/path.rs:638-703: SVG "arc to" (https://www.w3.org/TR/SVG/implnote.html) as rational quadratics of at most
+        120 degrees each."""
+        from . import utils as U
+        f = np.float32
+        radii = np.array([0.0, abs(f(half_extent[0])), abs(f(half_extent[1]))], np.float32)
+        if radii[1] == 0.0 or radii[2] == 0.0:
+            self.push_line(to)
+            return
+        frm = U.vec_to_point(self.get_end())
+        to_p = U.vec_to_point(safe_vec(to))
+        rotor = U.rotate2d(rotation)
+        vertex_unoriented = (to_p - frm) * f(0.5)                       # .dual(): component-wise identity
+        vertex = U.motor_transform_plane(U.motor_inverse(rotor), vertex_unoriented)
+        vertex_squared = vertex * vertex
+        radii_squared = radii * radii
+        scale_factor_squared = vertex_squared[1] / radii_squared[1] + vertex_squared[2] / radii_squared[2]
+        if scale_factor_squared > 1.0:                                  # radii too small to span from -> to: scale them up
+            radii = radii * np.sqrt(scale_factor_squared)
+            radii_squared = radii * radii
+        one_over_radii = np.array([0.0, f(1.0) / radii[1], f(1.0) / radii[2]], np.float32)
+        rsvs = radii_squared[1] * vertex_squared[2] + radii_squared[2] * vertex_squared[1]
+        offset = np.sqrt(max(f(0.0), (radii_squared[1] * radii_squared[2] - rsvs) / rsvs))
+        if large_arc == sweep:
+            offset = -offset
+        center_offset_unoriented = radii * U.rotate_90_degree_clockwise(vertex * one_over_radii) * offset
+        center = (to_p + frm) * f(0.5) + U.motor_transform_plane(rotor, center_offset_unoriented)
+        start_normal = (-vertex - center_offset_unoriented) * one_over_radii
+        end_normal = (vertex - center_offset_unoriented) * one_over_radii
+        polar_start = U.complex_signum([start_normal[1], start_normal[2]])
+        polar_end = U.complex_signum([end_normal[1], end_normal[2]])
+        polar_range = U.complex_div(polar_end, polar_start)
+        small_arc = U.complex_arg(polar_range)
+        if small_arc < 0.0:
+            polar_range = np.array([polar_range[0], -polar_range[1]], np.float32)   # reversal
+            small_arc = -small_arc
+        angle = small_arc
+        if large_arc:
+            angle = angle - U.TAU
+        step_radians = f(math.pi) * f(2.0) / f(3.0)
+        steps = int(math.ceil(float(abs(angle) / step_radians)))
+        if large_arc != sweep:
+            angle = -angle
+        polar_step = U.complex_powf(polar_range, angle / (small_arc * f(steps)))
+        half_polar_step_back = U.complex_powf(polar_step, -0.5)
+        weight = np.cos(abs(angle) / f(steps) * f(0.5))
+        tangent_crossing_radii = radii * (f(1.0) / weight)
+        for i in range(1, steps + 1):
+            interpolated = U.complex_mul(polar_start, U.complex_powi(polar_step, i))
+            v_unoriented = np.array([0.0, interpolated[0], interpolated[1]], np.float32) * radii
+            v = center + U.motor_transform_plane(rotor, v_unoriented)
+            interpolated = U.complex_mul(interpolated, half_polar_step_back)
+            tc_unoriented = np.array([0.0, interpolated[0], interpolated[1]], np.float32) * tangent_crossing_radii
+            tc = center + U.motor_transform_plane(rotor, tc_unoriented)
+            self.push_rational_quadratic_curve(RationalQuadraticCurveSegment(weight, [U.point_to_vec(tc), U.point_to_vec(v)]))
+
+    @staticmethod
+    def from_polygon(vertices, stroke_options: Optional[StrokeOptions] = None) -> "Path":
+        """src/path.rs:706-718"""
+        result = Path(vertices[0], stroke_options)
+        for v in vertices[1:]:
+            result.push_line(v)
+        return result
+
+    @staticmethod
+    def from_regular_polygon(center, radius: float, rotation: float, vertex_count: int, stroke_options: Optional[StrokeOptions] = None) -> "Path":
+        """src/path.rs:721-728"""
+        f = np.float32
+        vertices = []
+        for i in range(vertex_count):
+            angle = f(rotation) + f(i) / f(vertex_count) * f(math.pi) * f(2.0)
+            vertices.append([f(center[0]) + f(radius) * np.cos(angle), f(center[1]) + f(radius) * np.sin(angle)])
+        return Path.from_polygon(vertices, stroke_options)
+
+    @staticmethod
+    def from_rect(center, half_extent, stroke_options: Optional[StrokeOptions] = None) -> "Path":
+        """src/path.rs:731-738"""
+        f = np.float32
+        cx, cy, hx, hy = f(center[0]), f(center[1]), f(half_extent[0]), f(half_extent[1])
+        return Path.from_polygon([[cx - hx, cy - hy], [cx - hx, cy + hy], [cx + hx, cy + hy], [cx + hx, cy - hy]], stroke_options)
+
+    @staticmethod
+    def from_rounded_rect(center, half_extent, radius: float, stroke_options: Optional[StrokeOptions] = None) -> "Path":
+        """src/path.rs:741-776: four lines and four quarter circles, starting at the end of the last rounding."""
+        f = np.float32
+        cx, cy, hx, hy, r = f(center[0]), f(center[1]), f(half_extent[0]), f(half_extent[1]), f(radius)
+        vertices = [
+            ([cx - hx + r, cy - hy], [cx - hx, cy - hy], [cx - hx, cy - hy + r]),
+            ([cx - hx, cy + hy - r], [cx - hx, cy + hy], [cx - hx + r, cy + hy]),
+            ([cx + hx - r, cy + hy], [cx + hx, cy + hy], [cx + hx, cy + hy - r]),
+            ([cx + hx, cy - hy + r], [cx + hx, cy - hy], [cx + hx - r, cy - hy]),
+        ]
+        result = Path(vertices[3][2], stroke_options)
+        for frm, corner, to in vertices:
+            result.push_line(frm)
+            result.push_quarter_ellipse(corner, to)
+        return result
+
+    @staticmethod
+    def from_ellipse(center, half_extent, stroke_options: Optional[StrokeOptions] = None) -> "Path":
+        """src/path.rs:779-808: four quarter ellipses."""
+        f = np.float32
+        cx, cy, hx, hy = f(center[0]), f(center[1]), f(half_extent[0]), f(half_extent[1])
+        vertices = [
+            ([cx - hx, cy - hy], [cx - hx, cy]),
+            ([cx - hx, cy + hy], [cx, cy + hy]),
+            ([cx + hx, cy + hy], [cx + hx, cy]),
+            ([cx + hx, cy - hy], [cx, cy - hy]),
+        ]
+        result = Path(vertices[3][1], stroke_options)
+        for corner, to in vertices:
+            result.push_quarter_ellipse(corner, to)
+        return result
+
+    @staticmethod
+    def from_circle(center, radius: float, stroke_options: Optional[StrokeOptions] = None) -> "Path":
+        """src/path.rs:811-813"""
+        return Path.from_ellipse(center, [radius, radius], stroke_options)
+
 
 @dataclass
 class PathSoA:

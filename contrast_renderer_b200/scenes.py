@@ -413,3 +413,153 @@ def stencil_cover_commands(n_shapes: int) -> np.ndarray:
     cmds[0::2] = np.stack([idx, idx, idx + 1, np.zeros_like(idx)], 1)
     cmds[1::2] = np.stack([idx, idx, idx + 1, np.full_like(idx, 3)], 1)
     return cmds
+
+
+# ------------------------------------------------------------------------------------------------------ config 4
+OP_STENCIL, OP_CLIP, OP_UNCLIP, OP_COLOR, OP_SAVE_ALPHA, OP_SCALE_ALPHA, OP_RESTORE_ALPHA = range(7)   # RenderOperation, src/renderer.rs:144-174
+
+
+@dataclass
+class ScriptedScene:
+    """A scene whose draws carry pass state: `script` rows are (shape, instance_begin, instance_end, operation,
+    clip_depth, save_alpha_layer, restore_alpha_layer), the state being what `set_clip_depth` /
+    `save_alpha_context` / `restore_alpha_context` were last called with (src/renderer.rs:253-266,932-985)."""
+    paths: PathSoA
+    shape_path_begin: np.ndarray
+    dynamic_stroke_options: List[DynamicStrokeOptions]
+    width: int
+    height: int
+    transforms: np.ndarray     # [n_instances, 16]
+    colors: np.ndarray         # [n_instances, 4]
+    script: np.ndarray         # [n_commands, 7] u32
+    name: str = ""
+    alpha_layer_count: int = 2
+
+    @property
+    def n_shapes(self) -> int:
+        return len(self.shape_path_begin) - 1
+
+    def oracle_commands(self):
+        return [tuple(int(v) for v in row) for row in self.script]
+
+    def record(self, render_pass, batch) -> None:
+        """Replays the script into a RenderPass: state calls where the state changes, bulk recording in between."""
+        script = self.script
+        state = (None, None, None)
+        run_start = 0
+        for i in range(len(script) + 1):
+            new_state = tuple(int(v) for v in script[i, 4:7]) if i < len(script) else None
+            if new_state != state:
+                if i > run_start:
+                    render_pass.render_batch(batch, script[run_start:i, 0:4])
+                run_start = i
+                if new_state is not None:
+                    if new_state[0] != state[0]:
+                        render_pass.set_clip_depth(new_state[0])
+                    if new_state[1] != state[1]:
+                        render_pass.save_alpha_context(new_state[1])
+                    if new_state[2] != state[2]:
+                        render_pass.restore_alpha_context(new_state[2])
+                    state = new_state
+
+
+def tiger_like(n_instances: int = 1000, seed: int = SEED0 + 4, extent: Tuple[int, int] = (3840, 2160), paths_per_shape: int = 10,
+               instance_px: Tuple[float, float] = (60.0, 220.0)) -> ScriptedScene:
+    """BASELINE config 4, "tiger-style": `n_instances` placed copies (translation, rotation, scale) of one group of
+    24 Shapes x `paths_per_shape` paths built with the path constructors (src/path.rs:639-815: ellipses, circles, rounded
+    rectangles, elliptical-arc wedges -> rational quadratics; the same degree-elevated -> rational cubics). Every copy
+    runs three nested clips and two nested opacity groups (src/renderer.rs:253-266). Each (copy, Shape) pair is its own
+    instance (transform + colour), 24 per copy."""
+    from .path import Path
+    rng = np.random.default_rng(seed)
+    n_roles = 24
+
+    def decorations(cx, cy, rx, ry, count, cubic):
+        """`count` small conic outlines inside the box (cx +- rx, cy +- ry)."""
+        out = []
+        for k in range(count):
+            x, y = cx + rng.uniform(-0.6, 0.6) * rx, cy + rng.uniform(-0.6, 0.6) * ry
+            r = rng.uniform(0.12, 0.3) * min(rx, ry)
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                p = Path.from_circle([x, y], r)
+            elif kind == 1:
+                p = Path.from_ellipse([x, y], [r * 1.4, r * 0.7])
+            elif kind == 2:
+                p = Path.from_rounded_rect([x, y], [r * 1.3, r * 0.9], r * 0.35)
+            else:   # pie wedge: centre -> arc start -> elliptical arc -> implicit closing line
+                a0, a1 = rng.uniform(0, 2 * np.pi), rng.uniform(0.8, 4.5)
+                p = Path([x, y])
+                p.push_line([x + r * np.cos(a0), y + r * np.sin(a0)])
+                p.push_elliptical_arc([r, r], 0.0, a1 > np.pi, False, [x + r * np.cos(a0 + a1), y + r * np.sin(a0 + a1)])
+            if cubic and k % 2 == 0:
+                p.convert_quadratic_curves_to_cubic_curves()
+            out.append(p)
+        return out
+
+    # role geometry in the group's local frame (about +-4 x +-3 model units)
+    outlines = {
+        0: Path.from_rounded_rect([0.0, 0.0], [4.0, 3.0], 0.8),          # clip level 1
+        5: Path.from_ellipse([0.3, 0.1], [3.2, 2.3]),                     # clip level 2
+        9: Path.from_circle([-0.4, 0.0], 2.4),                            # opacity group 0
+        14: Path.from_rounded_rect([0.2, -0.1], [2.2, 1.6], 0.5),         # clip level 3
+        18: Path.from_ellipse([0.4, 0.0], [1.8, 1.2]),                    # opacity group 1
+    }
+    paths: List[Path] = []
+    for role in range(n_roles):
+        main = outlines.get(role)
+        if main is None:
+            cx, cy = rng.uniform(-2.0, 2.0), rng.uniform(-1.5, 1.5)
+            main = [Path.from_ellipse([cx, cy], [rng.uniform(0.6, 1.8), rng.uniform(0.5, 1.4)]),
+                    Path.from_rounded_rect([cx, cy], [rng.uniform(0.8, 1.8), rng.uniform(0.6, 1.3)], 0.3),
+                    Path.from_circle([cx, cy], rng.uniform(0.6, 1.5))][role % 3]
+            if role % 4 == 1:
+                main.convert_quadratic_curves_to_cubic_curves()
+        paths.append(main)
+        paths.extend(decorations(0.0, 0.0, 3.0, 2.2, paths_per_shape - 1, cubic=role % 2 == 0) if role not in outlines else
+                     decorations(0.0, 0.0, 0.1, 0.1, paths_per_shape - 1, cubic=False))   # clip / group outlines: tiny inner decorations only
+    soa = PathSoA.from_paths(paths)
+    begin = np.arange(0, n_roles * paths_per_shape + 1, paths_per_shape, dtype=np.uint32)
+
+    # per-copy placement: clip = ortho(W, H) * translate * rotate * scale, 2D affine in the instance mat4 (column vectors)
+    centre = np.stack([rng.uniform(0, extent[0], n_instances), rng.uniform(0, extent[1], n_instances)], 1)
+    scale = rng.uniform(instance_px[0], instance_px[1], n_instances) / 8.0   # the group is ~8 units wide
+    angle = rng.uniform(0, 2 * np.pi, n_instances)
+    c, s = np.cos(angle) * scale, np.sin(angle) * scale
+    sx, sy = 2.0 / extent[0], -2.0 / extent[1]
+    m = np.zeros((n_instances, 16))
+    m[:, 0], m[:, 1] = sx * c, sy * s
+    m[:, 4], m[:, 5] = -sx * s, sy * c
+    m[:, 10] = 1.0
+    m[:, 12], m[:, 13] = sx * centre[:, 0] - 1.0, sy * centre[:, 1] + 1.0
+    m[:, 15] = 1.0
+    transforms = np.repeat(m.astype(np.float32), n_roles, axis=0)
+    colors = np.concatenate([rng.uniform(0, 1, (n_instances * n_roles, 3)), rng.uniform(0.35, 1.0, (n_instances * n_roles, 1))], 1).astype(np.float32)
+
+    S, CLIP, UNCLIP, COLOR, SAVE, SCALE, RESTORE = range(7)
+
+    def fills(lo, hi, depth, l0=0, l1=0):
+        out = []
+        for k in range(lo, hi):
+            out += [(k, S, depth, l0, l1), (k, COLOR, depth, l0, l1)]
+        return out
+
+    group = ([(0, S, 0, 0, 0), (0, CLIP, 1, 0, 0)] + fills(1, 5, 1)
+             + [(5, S, 1, 0, 0), (5, CLIP, 2, 0, 0)] + fills(6, 9, 2)
+             + [(9, S, 2, 0, 0), (9, SAVE, 2, 0, 0), (9, SCALE, 2, 0, 0)] + fills(10, 14, 2)
+             + [(14, S, 2, 0, 0), (14, CLIP, 3, 0, 0)] + fills(15, 18, 3)
+             + [(18, S, 3, 1, 0), (18, SAVE, 3, 1, 0), (18, SCALE, 3, 1, 0)] + fills(19, 22, 3, 1, 0)
+             + [(18, S, 3, 1, 1), (18, RESTORE, 3, 1, 1)]
+             + [(14, S, 2, 1, 1), (14, UNCLIP, 2, 1, 1)]
+             + [(9, S, 2, 1, 0), (9, RESTORE, 2, 1, 0)]
+             + [(5, S, 1, 1, 0), (5, UNCLIP, 1, 1, 0)]
+             + [(0, S, 0, 1, 0), (0, UNCLIP, 0, 1, 0)] + fills(22, 24, 0, 1, 0))
+    g = np.array(group, np.int64)
+    script = np.zeros((n_instances, len(g), 7), np.uint32)
+    inst = (np.arange(n_instances)[:, None] * n_roles + g[None, :, 0])
+    script[:, :, 0] = g[None, :, 0]
+    script[:, :, 1] = inst
+    script[:, :, 2] = inst + 1
+    script[:, :, 3] = g[None, :, 1]
+    script[:, :, 4:7] = g[None, :, 2:5]
+    return ScriptedScene(soa, begin, [], extent[0], extent[1], np.ascontiguousarray(transforms), colors, script.reshape(-1, 7), "tiger_like", 2)

@@ -481,6 +481,74 @@ def test_clip_and_opacity_protocols(cr, oracle):
     rnd.close()
 
 
+@pytest.mark.parametrize("samples", [1, 4], ids=["1x", "msaa4"])
+def test_config4_tiger_like_nested_clips_and_opacity_groups(cr, oracle, samples):
+    """BASELINE config 4 at reduced size: placed copies of a 24-Shape group authored with the path constructors
+    (src/path.rs:639-815: rounded rectangles, ellipses, arc wedges as rational quadratics and, degree-elevated, as rational
+    cubics), every copy running three nested clips and two nested opacity groups (src/renderer.rs:253-266), copies
+    overlapping each other, rotated and scaled by their instance matrices."""
+    scene = scenes.tiger_like(14, extent=(640, 400), instance_px=(120.0, 330.0))
+    config = cr.Configuration(alpha_layer_count=2, msaa_sample_count=samples)
+    rnd = cr.Renderer(config)
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    refs = oracle_shapes(oracle, scene)
+    for i, ref in enumerate(refs):
+        assert_shape_equal(oracle, batch[i], ref, f"group shape {i}")
+    rp = rnd.begin_render_pass()
+    rp.set_instances(scene.transforms, scene.colors)
+    scene.record(rp, batch)
+    rp.submit()
+    color, stencil, covered = rnd.read_color(), rnd.read_stencil(), int(rnd.stats().covered_samples)
+    layers = [rnd.read_alpha_layer(k) for k in range(2)]
+    ref_color, ref_stencil, ref_layers, ref_covered = oracle.render(config.to_c(), scene.width, scene.height, refs, scene.oracle_commands(),
+                                                                    scene.transforms, scene.colors, threads=4)
+    assert np.array_equal(stencil, ref_stencil)
+    assert np.array_equal(color.view(np.uint32), ref_color.view(np.uint32))
+    for k in range(2):
+        assert np.array_equal(layers[k].view(np.uint32), ref_layers[k].view(np.uint32))
+    assert covered == ref_covered and covered > 20000
+    assert (stencil == 0).all(), "every copy leaves the clip and winding bits at zero"
+    batch.close()
+    rnd.close()
+
+
+def test_constructed_conics_cover_their_area(cr, oracle):
+    """A circle, an ellipse and a rounded rectangle from the constructors, as rational quadratics and degree-elevated to
+    rational cubics (src/path.rs:535-617), cover the pixels of the exact shape: the implicit tests u^2 - vw <= 0 and
+    k^3 - lmn <= 0 (src/shaders.wgsl:233-266) on constructor output, independent of the oracle."""
+    ppu, w, h = 40.0, 480, 360
+    for cubic in (False, True):
+        shapes = [Path.from_circle([3.0, 3.0], 2.0), Path.from_ellipse([8.5, 3.0], [2.5, 1.5]), Path.from_rounded_rect([5.0, 7.0], [3.0, 1.2], 0.6)]
+        if cubic:
+            for p in shapes:
+                p.convert_quadratic_curves_to_cubic_curves()
+        soa = PathSoA.from_paths(shapes)
+        rnd = cr.Renderer()
+        rnd.resize_internal_buffers(w, h)
+        batch = cr.ShapeBatch(rnd, [], soa, np.arange(4, dtype=np.uint32))
+        m = cr.orthographic_transform(w / ppu, h / ppu)
+        colors = np.array([[1, 0, 0, 1], [0, 1, 0, 1], [0, 0, 1, 1]], np.float32)
+        rp = rnd.begin_render_pass()
+        rp.set_instances(np.tile(m, (3, 1)), colors)
+        rp.render_batch(batch, scenes.stencil_cover_commands(3))
+        rp.submit()
+        color = rnd.read_color().reshape(h, w, 4)
+        ys, xs = np.mgrid[0:h, 0:w]
+        x, y = (xs + 0.5) / ppu, (ys + 0.5) / ppu
+        inside_circle = (x - 3.0) ** 2 + (y - 3.0) ** 2 < 4.0
+        inside_ellipse = ((x - 8.5) / 2.5) ** 2 + ((y - 3.0) / 1.5) ** 2 < 1.0
+        dx, dy = np.maximum(np.abs(x - 5.0) - 2.4, 0.0), np.maximum(np.abs(y - 7.0) - 0.6, 0.0)
+        inside_rrect = dx * dx + dy * dy < 0.36
+        for channel, inside in ((0, inside_circle), (1, inside_ellipse), (2, inside_rrect)):
+            got = color[:, :, channel] > 0.5
+            wrong = int((got != inside).sum())
+            assert wrong <= 6, f"cubic={cubic} channel {channel}: {wrong} pixels differ from the exact shape"   # centres within 1e-4 px of the outline
+            assert int(got.sum()) > 1000
+        batch.close()
+        rnd.close()
+
+
 def test_load_op_keeps_previous_pass(cr, oracle):
     """A second pass with LoadOp::Load composites over the first; two submits == one submit of both command lists."""
     scene = scenes.mixed_fills(80, extent=(320, 200), size=(10.0, 60.0), seed=21)
