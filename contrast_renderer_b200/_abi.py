@@ -74,6 +74,9 @@ class StatsC(C.Structure):
                 ("last_bin_ms", C.c_float), ("_reserved", C.c_float)]
 
 
+CR_IPC_HANDLE_BYTES = 64
+CR_TILE = 16
+
 # Every symbol include/contrast_b200.h declares (checked against the built library by tests/test_abi.py).
 EXPORTED_SYMBOLS = (
     "cr_renderer_create", "cr_renderer_destroy", "cr_renderer_get_config", "cr_renderer_resize", "cr_renderer_set_stream",
@@ -83,5 +86,6 @@ EXPORTED_SYMBOLS = (
     "cr_pass_begin", "cr_pass_set_instances", "cr_pass_set_clip_depth", "cr_pass_save_alpha_context",
     "cr_pass_restore_alpha_context", "cr_shape_render", "cr_pass_render_batch", "cr_pass_submit", "cr_pass_abort", "cr_renderer_read_color",
     "cr_renderer_read_stencil", "cr_renderer_read_alpha_layer", "cr_renderer_get_attachments", "cr_renderer_get_stats",
-    "cr_renderer_enable_timing", "cr_status_string", "cr_last_error_message", "cr_abi_version",
+    "cr_renderer_enable_timing", "cr_renderer_set_tile_sharding", "cr_renderer_export_attachments", "cr_renderer_import_peer_attachments",
+    "cr_status_string", "cr_last_error_message", "cr_abi_version",
 )

@@ -46,18 +46,19 @@ namespace {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool plain = false;   // cudaMalloc instead of the stream-ordered pool: such memory can be exported with cudaIpcGetMemHandle
     int reserve(cudaStream_t stream, size_t bytes) {
         if (bytes <= cap && p) return CR_OK;
-        if (p) CR_CUDA_TRY(cudaFreeAsync(p, stream));
-        p = nullptr;
-        cap = 0;
+        release(stream);
         const size_t want = bytes < 256 ? 256 : bytes;
-        CR_CUDA_TRY(cudaMallocAsync(&p, want, stream));
+        if (plain) CR_CUDA_TRY(cudaMalloc(&p, want));
+        else CR_CUDA_TRY(cudaMallocAsync(&p, want, stream));
         cap = want;
         return CR_OK;
     }
     void release(cudaStream_t stream) {
-        if (p) cudaFreeAsync(p, stream);
+        if (p && plain) { cudaStreamSynchronize(stream); cudaFree(p); }
+        else if (p) cudaFreeAsync(p, stream);
         p = nullptr;
         cap = 0;
     }
@@ -124,6 +125,9 @@ struct cr_renderer {
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // tess begin/end, bin begin/end, raster begin/end
     bool ev_valid[3] = {false, false, false};
+    uint32_t shard_world = 1, shard_rank = 0;              // tile sharding of one target across GPUs
+    void* peer_color[CR_MAX_PEERS] = {};                   // peer-mapped attachments of the other ranks, slot = rank - (rank > shard_rank)
+    void* peer_stencil[CR_MAX_PEERS] = {};
     uint64_t live_objects = 0;        // shape batches and passes that still point at this renderer
     bool destroy_requested = false;   // cr_renderer_destroy was called while live_objects > 0: the last child frees it
 };
@@ -391,9 +395,17 @@ int cr_renderer_create(const cr_config* config, cr_renderer** out) {
     return CR_OK;
 }
 
+static void close_peers(cr_renderer* r) {
+    for (int i = 0; i < CR_MAX_PEERS; ++i) {
+        if (r->peer_color[i]) cudaIpcCloseMemHandle(r->peer_color[i]);
+        if (r->peer_stencil[i]) cudaIpcCloseMemHandle(r->peer_stencil[i]);
+        r->peer_color[i] = r->peer_stencil[i] = nullptr;
+    }
+}
 static void renderer_free(cr_renderer* r) {
     DeviceGuard guard(r->device);
     cudaStreamSynchronize(r->stream);
+    close_peers(r);
     cudaStream_t st = r->stream;
     DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
                      &r->hull_scratch_b, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand, &r->pair_tile_alt,
@@ -430,6 +442,8 @@ int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
     if (width == 0 || height == 0 || width > 32768 || height > 32768) return fail(CR_ERR_INVALID_ARGUMENT, "bad extent %ux%u", width, height);
     CR_GUARD(r);
     const size_t samples = (size_t)width * height * r->config.msaa_sample_count;
+    if (r->peer_color[0] || r->peer_stencil[0]) return fail(CR_ERR_INVALID_ARGUMENT, "resize while peer attachments are imported: call cr_renderer_set_tile_sharding(r, 1, 0) first");
+    r->color.plain = r->stencil.plain = true;   // exportable to the other ranks of a tile-sharded target
     CR_TRY(r->color.reserve(r->stream, samples * 16));
     CR_TRY(r->stencil.reserve(r->stream, samples));
     CR_TRY(r->alpha_layers.reserve(r->stream, samples * 4 * std::max<uint32_t>(1, r->config.alpha_layer_count)));
@@ -782,6 +796,9 @@ static int submit(cr_pass* p) {
     tg.cmask = ((1u << r->config.clip_nesting_counter_bits) - 1u) << r->config.winding_counter_bits;
     tg.blending = r->config.blending;
     tg.cull_mode = r->config.cull_mode;
+    tg.shard_world = r->shard_world;
+    tg.shard_rank = r->shard_rank;
+    for (int i = 0; i < CR_MAX_PEERS; ++i) { tg.peer_color[i] = static_cast<float4*>(r->peer_color[i]); tg.peer_stencil[i] = static_cast<uint8_t*>(r->peer_stencil[i]); }
 
     // ---- bin: count, scan, emit, sort by tile (stable => draw order survives inside every tile)
     if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[2], st));
@@ -870,6 +887,40 @@ int cr_renderer_get_attachments(cr_renderer* r, void** color_dev, void** stencil
     if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
     if (color_dev) *color_dev = r->color.p;
     if (stencil_dev) *stencil_dev = r->stencil.p;
+    return CR_OK;
+}
+
+// ---- one render target spanning several GPUs: tile ownership + peer-mapped attachments
+int cr_renderer_set_tile_sharding(cr_renderer* r, uint32_t world, uint32_t rank) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    if (world == 0 || world > CR_MAX_PEERS + 1 || rank >= world) return fail(CR_ERR_INVALID_ARGUMENT, "bad tile sharding %u of %u (at most %d ranks)", rank, world, CR_MAX_PEERS + 1);
+    CR_GUARD(r);
+    CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    close_peers(r);
+    r->shard_world = world;
+    r->shard_rank = rank;
+    return CR_OK;
+}
+int cr_renderer_export_attachments(cr_renderer* r, uint8_t* color_handle, uint8_t* stencil_handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == CR_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    if (!r || !color_handle || !stencil_handle) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
+    CR_GUARD(r);
+    CR_CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(color_handle), r->color.p));
+    CR_CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(stencil_handle), r->stencil.p));
+    return CR_OK;
+}
+int cr_renderer_import_peer_attachments(cr_renderer* r, uint32_t peer_rank, const uint8_t* color_handle, const uint8_t* stencil_handle) {
+    if (!r || !color_handle || !stencil_handle) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    if (peer_rank >= r->shard_world || peer_rank == r->shard_rank) return fail(CR_ERR_INVALID_ARGUMENT, "peer rank %u is not another rank of a %u-rank target", peer_rank, r->shard_world);
+    CR_GUARD(r);
+    const uint32_t slot = peer_rank - (peer_rank > r->shard_rank ? 1u : 0u);
+    if (r->peer_color[slot] || r->peer_stencil[slot]) return fail(CR_ERR_INVALID_ARGUMENT, "peer rank %u is already imported", peer_rank);
+    cudaIpcMemHandle_t hc, hs;
+    memcpy(&hc, color_handle, sizeof(hc));
+    memcpy(&hs, stencil_handle, sizeof(hs));
+    CR_CUDA_TRY(cudaIpcOpenMemHandle(&r->peer_color[slot], hc, cudaIpcMemLazyEnablePeerAccess));
+    CR_CUDA_TRY(cudaIpcOpenMemHandle(&r->peer_stencil[slot], hs, cudaIpcMemLazyEnablePeerAccess));
     return CR_OK;
 }
 

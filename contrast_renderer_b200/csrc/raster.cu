@@ -214,7 +214,7 @@ __device__ __forceinline__ uint32_t walk_tiles_small(const int* X, const int* Y,
     uint32_t count = 0;
     for (int ty = x.ty0; ty <= x.ty1; ++ty)
         for (int tx = x.tx0; tx <= x.tx1; ++tx)
-            if (tile_hit(X, Y, t, x, tx, ty, tg)) {
+            if (cr_tile_owned(tg, tx, ty) && tile_hit(X, Y, t, x, tx, ty, tg)) {
                 if (EMIT) { pair_tile[at + count] = (uint32_t)(ty * (int)tg.tiles_x + tx); pair_cand[at + count] = cand; }
                 ++count;
             }
@@ -232,7 +232,7 @@ __device__ __forceinline__ uint32_t walk_tiles_warp(const int* X, const int* Y, 
     int ty = x.ty0 + (int)lane / w, tx = x.tx0 + (int)lane % w;   // 32 consecutive tiles of the box, advanced incrementally
     const int dy = 32 / w, dx = 32 % w;
     for (int base = 0; base < total; base += 32) {
-        const bool hit = base + (int)lane < total && tile_hit(X, Y, t, x, tx, ty, tg);
+        const bool hit = base + (int)lane < total && cr_tile_owned(tg, tx, ty) && tile_hit(X, Y, t, x, tx, ty, tg);
         const uint32_t hits = __ballot_sync(0xffffffffu, hit);
         if (EMIT && hit) {
             const uint32_t pos = at + running + __popc(hits & ((1u << lane) - 1u));
@@ -682,6 +682,22 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
         }
 #pragma unroll
         for (int k = 0; k < S; ++k) tg.color[pix + k] = col[k];
+        // tile sharding: the finished tile also goes to every other rank's attachments (P2P stores over NVLink)
+        for (uint32_t peer = 0; peer + 1 < tg.shard_world; ++peer) {
+            float4* pc = tg.peer_color[peer];
+            uint8_t* ps = tg.peer_stencil[peer];
+            if (pc == nullptr) continue;
+            if (S == 1) ps[pix] = (uint8_t)s[0];
+            else {
+                uint32_t packed = 0;
+#pragma unroll
+                for (int k = 0; k < S; ++k) packed |= (s[k] & 255u) << (8 * k);
+                *reinterpret_cast<uint32_t*>(ps + pix) = packed;
+            }
+#pragma unroll
+            for (int k = 0; k < S; ++k) pc[pix + k] = col[k];
+        }
+        if (tg.shard_world > 1u) __threadfence_system();
     }
     // covered-sample statistic: warp reduce, one atomic per warp
 #pragma unroll

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include "../../include/contrast_b200.h"
 
+#define CR_MAX_PEERS 7   // tile sharding: up to 8 GPUs of one node
 #define CR_TILE 16   // pixels per tile edge — one CTA of 256 threads owns one tile, one thread per pixel (all of its samples)
 
 // One tessellated cr_shape_batch as the rasteriser sees it.
@@ -60,7 +61,16 @@ struct RasterTarget {
     int sample_lo, sample_hi;     // smallest / largest sample offset inside a pixel in 1/256 px: 128,128 or 32,224
     uint32_t wmask, cmask;        // winding_counter_mask / clip_nesting_counter_mask (src/renderer.rs:565-566)
     uint32_t blending, cull_mode;
+    // One render target spanning several GPUs (tile sharding): tile (tx, ty) is owned by rank (tx + ty) % world.
+    // A rank bins and rasterises only the tiles it owns and K3 stores every finished tile into its own attachments AND,
+    // over NVLink, into the peer-mapped attachments of the other ranks, so each rank ends up with the complete frame.
+    uint32_t shard_world, shard_rank;             // world <= 1: not sharded
+    float4* peer_color[CR_MAX_PEERS];             // [world - 1] attachments of the other ranks (peer-mapped), or null
+    uint8_t* peer_stencil[CR_MAX_PEERS];
 };
+__host__ __device__ inline bool cr_tile_owned(const RasterTarget& tg, int tx, int ty) {
+    return tg.shard_world <= 1u || (uint32_t)(tx + ty) % tg.shard_world == tg.shard_rank;
+}
 
 struct RasterScene {
     const DeviceBatch* batches;

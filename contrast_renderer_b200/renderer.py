@@ -67,6 +67,9 @@ def lib():
             "cr_renderer_get_attachments": [vp, C.POINTER(vp), C.POINTER(vp)],
             "cr_renderer_get_stats": [vp, C.POINTER(_abi.StatsC)],
             "cr_renderer_enable_timing": [vp, u32],
+            "cr_renderer_set_tile_sharding": [vp, u32, u32],
+            "cr_renderer_export_attachments": [vp, vp, vp],
+            "cr_renderer_import_peer_attachments": [vp, u32, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(l, name)
@@ -212,6 +215,22 @@ class Renderer:
         color, stencil = C.c_void_p(), C.c_void_p()
         _check(lib().cr_renderer_get_attachments(self._h, C.byref(color), C.byref(stencil)))
         return color.value, stencil.value
+
+    # ---- one target spanning several GPUs (include/contrast_b200.h, "tile sharding"); orchestration in sharding.py
+    def set_tile_sharding(self, world: int, rank: int) -> None:
+        _check(lib().cr_renderer_set_tile_sharding(self._h, world, rank))
+
+    def export_attachments(self) -> bytes:
+        """The two 64-byte CUDA IPC handles (colour, stencil) of this renderer's attachments, concatenated."""
+        color, stencil = (C.c_uint8 * _abi.CR_IPC_HANDLE_BYTES)(), (C.c_uint8 * _abi.CR_IPC_HANDLE_BYTES)()
+        _check(lib().cr_renderer_export_attachments(self._h, color, stencil))
+        return bytes(color) + bytes(stencil)
+
+    def import_peer_attachments(self, peer_rank: int, handles: bytes) -> None:
+        n = _abi.CR_IPC_HANDLE_BYTES
+        assert len(handles) == 2 * n
+        color, stencil = (C.c_uint8 * n).from_buffer_copy(handles[:n]), (C.c_uint8 * n).from_buffer_copy(handles[n:])
+        _check(lib().cr_renderer_import_peer_attachments(self._h, peer_rank, color, stencil))
 
     def read_color(self) -> np.ndarray:
         out = np.empty((self.height, self.width, self.config.msaa_sample_count, 4), np.float32)

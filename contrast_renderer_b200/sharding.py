@@ -1,9 +1,16 @@
-"""Multi-GPU plumbing of the path: one process per GPU, path instances sharded by batch (north_star).
+"""Multi-GPU plumbing of the path: one process per GPU (north_star). Two ways to shard:
 
-Shapes are independent except for draw order into a shared target, so a batch of Shapes is cut into contiguous draw-order
-slices, one per rank; each rank tessellates and rasterises its slice with its own renderer into its own target. No
-collective is needed on the data path. torch.distributed (NCCL on GPUs, gloo in the CPU tests) only carries the barrier and
-the max-over-ranks / sum-over-ranks reductions of the measurements.
+* BATCH sharding (independent path instances, bench.py --gpus N): a batch of Shapes is cut into contiguous draw-order
+  slices, one per rank; each rank tessellates and rasterises its slice with its own renderer into its own target. No
+  collective on the data path.
+* TILE sharding (one render target spanning the box, BASELINE config 4): every rank holds the (small) geometry and records
+  the same pass; tile (tx, ty) is owned by rank (tx + ty) % world; a rank bins and rasterises its own tiles only and the
+  tile kernel stores every finished tile into all ranks' attachments with P2P stores over NVLink (CUDA IPC mappings of the
+  peers' attachments), so the "gather" is fused into the raster kernel's epilogue. `TileShardedTarget` does the handle
+  exchange and the two stream-ordered barriers per pass.
+
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) carries the handle exchange, the barriers and the max-over-ranks /
+sum-over-ranks reductions of the measurements.
 """
 from __future__ import annotations
 
@@ -57,3 +64,71 @@ def reduce_measurement(elapsed_ms: float, paths: int, covered: int, device=None)
     s = torch.tensor([paths, covered], dtype=torch.float64, device=device)
     dist.all_reduce(s, op=dist.ReduceOp.SUM)
     return float(t.item()), int(s[0].item()), int(s[1].item())
+
+
+# ------------------------------------------------------------------------------------------------ tile sharding
+def tile_owner(tx, ty, world: int):
+    """Owner rank of tile (tx, ty): the same function as cr_tile_owned (csrc/raster.h). Diagonal interleave: every rank
+    gets every world-th tile of every tile row and column, which balances any spatially coherent scene."""
+    return (np.asarray(tx) + np.asarray(ty)) % world
+
+
+def owned_tile_mask(width: int, height: int, world: int, rank: int, tile: int = 16) -> np.ndarray:
+    """[tiles_y, tiles_x] bool: the tiles `rank` rasterises."""
+    tiles_x, tiles_y = (width + tile - 1) // tile, (height + tile - 1) // tile
+    ty, tx = np.mgrid[0:tiles_y, 0:tiles_x]
+    return tile_owner(tx, ty, world) == rank
+
+
+def exchange_handles(local: bytes, group=None):
+    """all_gather of the ranks' IPC handle blobs; returns the list indexed by rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = [None] * world
+    dist.all_gather_object(out, local, group=group)
+    return out
+
+
+class TileShardedTarget:
+    """One render target spanning the ranks of the default process group. Usage, identically on every rank:
+
+        target = TileShardedTarget(renderer)            # after renderer.resize_internal_buffers(...)
+        rp = target.begin_render_pass()                 # clears, then barrier: nobody writes into a target still being cleared
+        ... record the same draws on every rank ...
+        target.submit(rp)                               # own tiles -> all ranks, then barrier: the frame is complete everywhere
+
+    The renderer is moved onto torch's current CUDA stream so that the NCCL barriers are ordered with its kernels on the
+    device; the host never blocks.
+    """
+
+    def __init__(self, renderer, group=None):
+        import torch
+        import torch.distributed as dist
+        self.renderer, self.group = renderer, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._token = torch.zeros(1, device=f"cuda:{renderer.config.device}")
+        renderer.set_stream(torch.cuda.current_stream().cuda_stream)
+        renderer.set_tile_sharding(self.world, self.rank)
+        handles = exchange_handles(renderer.export_attachments(), group)
+        for peer, blob in enumerate(handles):
+            if peer != self.rank:
+                renderer.import_peer_attachments(peer, blob)
+        self.barrier()
+
+    def barrier(self) -> None:
+        import torch.distributed as dist
+        dist.all_reduce(self._token, group=self.group)   # stream-ordered: completes once every rank's earlier work is done
+
+    def begin_render_pass(self, clear_color: bool = True, clear_stencil: bool = True):
+        rp = self.renderer.begin_render_pass(clear_color, clear_stencil)
+        self.barrier()
+        return rp
+
+    def submit(self, render_pass) -> None:
+        render_pass.submit()
+        self.barrier()
+
+    def close(self) -> None:
+        self.barrier()
+        self.renderer.synchronize()
+        self.renderer.set_tile_sharding(1, 0)

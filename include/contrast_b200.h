@@ -252,6 +252,24 @@ int cr_renderer_read_alpha_layer(cr_renderer* renderer, uint32_t layer, float* d
 /* Device pointers of the attachments (for zero-copy consumers and multi-GPU tile exchange). */
 int cr_renderer_get_attachments(cr_renderer* renderer, void** color_dev, void** stencil_dev);
 
+/* One render target spanning several GPUs of a node ("NCCL reduce of framebuffer tiles only when one render target spans
+ * the box", BASELINE north_star; SURVEY 8e tile sharding). No reference counterpart: wgpu renders on one device.
+ * Every rank creates a renderer of the same configuration and extent, records the SAME pass and submits it; tile
+ * (tx, ty) of the 16 x 16 pixel grid is owned by rank (tx + ty) % world. A rank bins and rasterises only its own tiles,
+ * and the tile kernel stores each finished tile into its own attachments and, with P2P stores over NVLink, into the
+ * imported attachments of every other rank: after all ranks have submitted (and a barrier), each rank holds the
+ * complete colour and stencil attachments. Alpha layers and cr_stats.covered_samples stay per-owner.
+ * The caller orders the ranks: a barrier between cr_pass_begin (which clears) and cr_pass_submit, and one after
+ * cr_pass_submit (contrast_renderer_b200/sharding.py does both with stream-ordered NCCL collectives).
+ * cr_renderer_set_tile_sharding(r, 1, 0) returns to a single-GPU target and closes the imported handles. */
+#define CR_IPC_HANDLE_BYTES 64
+int cr_renderer_set_tile_sharding(cr_renderer* renderer, uint32_t world, uint32_t rank);
+/* cudaIpcMemHandle_t of the colour / stencil attachments (valid until the next cr_renderer_resize). */
+int cr_renderer_export_attachments(cr_renderer* renderer, uint8_t color_handle[CR_IPC_HANDLE_BYTES], uint8_t stencil_handle[CR_IPC_HANDLE_BYTES]);
+/* Maps the attachments of rank `peer_rank` (handles from its cr_renderer_export_attachments, in another process). */
+int cr_renderer_import_peer_attachments(cr_renderer* renderer, uint32_t peer_rank, const uint8_t color_handle[CR_IPC_HANDLE_BYTES],
+                                        const uint8_t stencil_handle[CR_IPC_HANDLE_BYTES]);
+
 /* Counters of the last submitted pass / last from_paths call (synchronises the stream). */
 typedef struct cr_stats {
     uint64_t covered_samples;              /* samples that passed the stencil test of a COLOR cover */

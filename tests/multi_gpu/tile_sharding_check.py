@@ -1,0 +1,78 @@
+"""Tile-sharded single target on N GPUs (BASELINE config 4). Launch with
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/multi_gpu/tile_sharding_check.py
+Every rank renders the same scripted scene into ONE target spanning the ranks (own tiles only, finished tiles stored into
+all ranks' attachments by the tile kernel) and then checks that ITS copy of the complete frame is bit-identical to the
+frame a single-GPU renderer produces for the same scene. Prints one JSON line from rank 0; exit code 0 = identical."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from contrast_renderer_b200 import renderer as R, scenes, sharding  # noqa: E402
+
+
+def main() -> int:
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    n_instances = int(os.environ.get("CR_TILE_CHECK_INSTANCES", "200"))
+    extent = (1920, 1080)
+    scene = scenes.tiger_like(n_instances, extent=extent, instance_px=(60.0, 260.0))
+    config = R.Configuration(device=local, alpha_layer_count=2)
+
+    def render(sharded: bool, repeats: int = 1):
+        rnd = R.Renderer(config)
+        rnd.resize_internal_buffers(scene.width, scene.height)
+        target = sharding.TileShardedTarget(rnd) if sharded else None
+        batch = R.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = []
+        for _ in range(repeats):
+            torch.cuda.synchronize()
+            if sharded:
+                dist.barrier()
+            start.record()
+            rp = target.begin_render_pass() if sharded else rnd.begin_render_pass()
+            rp.set_instances(scene.transforms, scene.colors)
+            scene.record(rp, batch)
+            if sharded:
+                target.submit(rp)
+            else:
+                rp.submit()
+            stop.record()
+            rnd.synchronize()
+            torch.cuda.synchronize()
+            ms.append(start.elapsed_time(stop))
+        frame = (rnd.read_color(), rnd.read_stencil(), int(rnd.stats().covered_samples), int(rnd.stats().tile_pairs))
+        if sharded:
+            target.close()
+        batch.close()
+        rnd.close()
+        return frame, min(ms)
+
+    (color1, stencil1, covered1, pairs1), ms_single = render(False, 3)
+    (colorN, stencilN, coveredN, pairsN), ms_sharded = render(True, 3)
+    same = bool(np.array_equal(color1.view(np.uint32), colorN.view(np.uint32)) and np.array_equal(stencil1, stencilN))
+    stats = torch.tensor([coveredN, pairsN, int(same)], dtype=torch.int64, device=f"cuda:{local}")
+    total = stats.clone()
+    dist.all_reduce(total)
+    t = torch.tensor([ms_sharded], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = int(total[2].item()) == world and int(total[0].item()) == covered1 and int(total[1].item()) == pairs1
+    if rank == 0:
+        print(json.dumps({"check": "tile_sharded_target", "n_gpus": world, "identical_on_every_rank": int(total[2].item()) == world,
+                          "covered_samples_single": covered1, "covered_samples_sum_over_ranks": int(total[0].item()),
+                          "tile_pairs_single": pairs1, "tile_pairs_sum_over_ranks": int(total[1].item()),
+                          "ms_single_gpu": round(ms_single, 3), "ms_sharded_max_over_ranks": round(float(t.item()), 3),
+                          "scene": f"tiger_like({n_instances}) {extent[0]}x{extent[1]}, {len(scene.script)} draws", "ok": ok}))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

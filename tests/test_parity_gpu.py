@@ -641,3 +641,24 @@ def test_full_size_config3_matches_oracle_and_properties(cr, oracle):
     assert_frames_equal((c0, s0, n0), (ref_color, ref_stencil, ref_covered))
     batch.close()
     rnd.close()
+
+
+def test_tile_sharded_target_matches_single_gpu():
+    """One render target spanning the GPUs of the box (BASELINE config 4): every rank's copy of the frame is bit-identical
+    to the single-GPU frame. Needs >= 2 GPUs (`gpurun --gpus 2`); runs tests/multi_gpu/tile_sharding_check.py under torchrun."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", "29671",
+           os.path.join(root, "tests", "multi_gpu", "tile_sharding_check.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
+    result = json.loads(lines[-1])
+    assert result["ok"] and result["identical_on_every_rank"] and result["n_gpus"] == n

@@ -74,3 +74,60 @@ def test_two_rank_gloo_sharding_and_reduction(built):
     assert paths == n_paths                               # every path is owned by exactly one rank
     assert sum(g[0] for g in gathered) == n_shapes and sum(g[1] for g in gathered) == n_paths
     assert nbytes > 0
+
+
+# ------------------------------------------------------------------------------------------------ tile sharding (config 4)
+def test_tile_ownership_is_a_balanced_partition():
+    for width, height in ((3840, 2160), (640, 400), (17, 33)):
+        for world in (1, 2, 3, 4, 8):
+            masks = [sharding.owned_tile_mask(width, height, world, r) for r in range(world)]
+            total = np.sum(masks, axis=0)
+            assert (total == 1).all(), "every tile has exactly one owner"
+            counts = [int(m.sum()) for m in masks]
+            assert max(counts) - min(counts) <= max(masks[0].shape), "diagonal interleave is balanced to within one tile row"
+            if world > 1 and masks[0].shape[1] >= world:
+                assert all(m[0, :world].sum() == 1 for m in masks), "every rank owns one of any `world` consecutive tiles of a row"
+
+
+def _tile_worker(rank: int, world: int, port: int, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle
+        from contrast_renderer_b200 import renderer as R
+        # the CPU stand-in for a rank: the oracle renders the replicated scene, the rank keeps the tiles it owns and
+        # "stores" them into every rank's frame (here: an all_gather of the owned tiles), like K3's peer stores
+        scene = scenes.tiger_like(3, extent=(160, 96), instance_px=(60.0, 120.0))
+        refs = [oracle.shape_from_paths([], scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1])) for i in range(scene.n_shapes)]
+        config = R.Configuration(alpha_layer_count=2)
+        color, stencil, _, _ = oracle.render(config.to_c(), scene.width, scene.height, refs, scene.oracle_commands(), scene.transforms, scene.colors)
+        mask = np.kron(sharding.owned_tile_mask(scene.width, scene.height, world, rank), np.ones((16, 16), bool))[:scene.height, :scene.width]
+        mine = np.where(mask[..., None, None], color.reshape(scene.height, scene.width, 1, 4), 0.0)
+        handles = sharding.exchange_handles(bytes([rank]) * 128)
+        parts = [None] * world
+        dist.all_gather_object(parts, (mine, mask))
+        frame = np.zeros_like(mine)
+        for part, m in parts:
+            frame[m] = part[m]
+        if rank == 0:
+            out.put((handles, np.array_equal(frame.reshape(color.shape), color), float(np.abs(color).sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_tile_sharded_frame(built):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_tile_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    handles, same, energy = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert handles == [bytes([0]) * 128, bytes([1]) * 128]   # blobs arrive indexed by rank
+    assert same and energy > 0, "the owned tiles of the two ranks compose the whole frame"
