@@ -97,17 +97,21 @@ class TileShardedTarget:
         ... record the same draws on every rank ...
         target.submit(rp)                               # own tiles -> all ranks, then barrier: the frame is complete everywhere
 
-    The renderer is moved onto torch's current CUDA stream so that the NCCL barriers are ordered with its kernels on the
-    device; the host never blocks.
+    The renderer is moved onto `self.stream`, a torch CUDA stream of its own (the legacy default stream has handle 0,
+    which cr_renderer_set_stream reads as "use your own stream"), and the NCCL barriers are issued with that stream
+    current, so they are ordered with the renderer's kernels on the device; the host never blocks.
     """
 
-    def __init__(self, renderer, group=None):
+    def __init__(self, renderer, group=None, stream=None):
         import torch
         import torch.distributed as dist
         self.renderer, self.group = renderer, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self._token = torch.zeros(1, device=f"cuda:{renderer.config.device}")
-        renderer.set_stream(torch.cuda.current_stream().cuda_stream)
+        device = torch.device(f"cuda:{renderer.config.device}")
+        self.stream = stream if stream is not None else torch.cuda.Stream(device)
+        assert self.stream.cuda_stream != 0, "the legacy default stream cannot be shared with the renderer"
+        self._token = torch.zeros(1, device=device)
+        renderer.set_stream(self.stream.cuda_stream)
         renderer.set_tile_sharding(self.world, self.rank)
         handles = exchange_handles(renderer.export_attachments(), group)
         for peer, blob in enumerate(handles):
@@ -116,8 +120,10 @@ class TileShardedTarget:
         self.barrier()
 
     def barrier(self) -> None:
+        import torch
         import torch.distributed as dist
-        dist.all_reduce(self._token, group=self.group)   # stream-ordered: completes once every rank's earlier work is done
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self._token, group=self.group)   # stream-ordered: completes once every rank's earlier work is done
 
     def begin_render_pass(self, clear_color: bool = True, clear_stencil: bool = True):
         rp = self.renderer.begin_render_pass(clear_color, clear_stencil)

@@ -24,30 +24,39 @@ def main() -> int:
     scene = scenes.tiger_like(n_instances, extent=extent, instance_px=(60.0, 260.0))
     config = R.Configuration(device=local, alpha_layer_count=2)
 
+    kernel_ms = {}
+
     def render(sharded: bool, repeats: int = 1):
         rnd = R.Renderer(config)
         rnd.resize_internal_buffers(scene.width, scene.height)
-        target = sharding.TileShardedTarget(rnd) if sharded else None
+        stream = torch.cuda.Stream()                   # the renderer's work and the CUDA events below go to this stream
+        rnd.set_stream(stream.cuda_stream)
+        target = sharding.TileShardedTarget(rnd, stream=stream) if sharded else None
         batch = R.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+        rnd.enable_timing(True)
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ms = []
         for _ in range(repeats):
             torch.cuda.synchronize()
             if sharded:
                 dist.barrier()
-            start.record()
             rp = target.begin_render_pass() if sharded else rnd.begin_render_pass()
             rp.set_instances(scene.transforms, scene.colors)
-            scene.record(rp, batch)
+            scene.record(rp, batch)       # host-side recording (12 k draws through ctypes) is not what is being compared
+            torch.cuda.synchronize()
+            dist.barrier()                # the ranks finish recording at different times: start the clocks together
+            start.record(stream)
             if sharded:
                 target.submit(rp)
             else:
                 rp.submit()
-            stop.record()
+            stop.record(stream)
             rnd.synchronize()
             torch.cuda.synchronize()
             ms.append(start.elapsed_time(stop))
-        frame = (rnd.read_color(), rnd.read_stencil(), int(rnd.stats().covered_samples), int(rnd.stats().tile_pairs))
+        st = rnd.stats()
+        frame = (rnd.read_color(), rnd.read_stencil(), int(st.covered_samples), int(st.tile_pairs))
+        kernel_ms[sharded] = (round(float(st.last_bin_ms), 3), round(float(st.last_raster_ms), 3))
         if sharded:
             target.close()
         batch.close()
@@ -67,7 +76,8 @@ def main() -> int:
         print(json.dumps({"check": "tile_sharded_target", "n_gpus": world, "identical_on_every_rank": int(total[2].item()) == world,
                           "covered_samples_single": covered1, "covered_samples_sum_over_ranks": int(total[0].item()),
                           "tile_pairs_single": pairs1, "tile_pairs_sum_over_ranks": int(total[1].item()),
-                          "ms_single_gpu": round(ms_single, 3), "ms_sharded_max_over_ranks": round(float(t.item()), 3),
+                          "submit_ms_single_gpu": round(ms_single, 3), "submit_ms_sharded_max_over_ranks": round(float(t.item()), 3),
+                          "bin_raster_ms_single": kernel_ms[False], "bin_raster_ms_sharded_rank0": kernel_ms[True],
                           "scene": f"tiger_like({n_instances}) {extent[0]}x{extent[1]}, {len(scene.script)} draws", "ok": ok}))
     dist.barrier()
     dist.destroy_process_group()
