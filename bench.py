@@ -33,7 +33,8 @@ WORKLOAD = ("100k TTF glyph instances via the text front-end (paths_of_text layo
             "segments), 12 px glyphs, 3840x2160, one Shape (Stencil+Color) per 160-glyph run")
 N_GLYPHS = 100000
 EXTENT = (3840, 2160)
-RASTER_DRAM_BYTES_R01 = 413364224   # raster_tiles_kernel, one launch on this workload: 307.96 MB read + 105.41 MB written (ncu)
+RASTER_DRAM_BYTES_R01 = 274071808   # raster_tiles_kernel, one launch on this workload: 209.49 MB read + 64.58 MB written (ncu --set full, profiles/)
+CHAIN_DRAM_BYTES_R01 = 21055744     # hull_chain_kernel, one launch: 21.06 MB read + 0 written
 GLYPHS_PER_SHAPE = 160
 
 
@@ -208,13 +209,19 @@ def main():
     transforms = scene.transforms()
 
     rnd = R.Renderer(R.Configuration(device=local_rank))
-    stream = torch.cuda.current_stream(dev)
+    # The renderer and the CUDA events that time it share ONE stream. It must not be the legacy default stream: its handle is
+    # 0, which cr_renderer_set_stream reads as "use your own stream".
+    stream = torch.cuda.Stream(dev)
+    assert stream.cuda_stream != 0
+    torch.cuda.set_stream(stream)
     rnd.set_stream(stream.cuda_stream)
     rnd.resize_internal_buffers(scene.width, scene.height)
     rnd.enable_timing(True)
 
     # device-resident and pinned-host copies of every input array
     host_arrays = soa.arrays()
+    if not soa.any_stroked():
+        host_arrays[9] = host_arrays[9][:0]   # all paths are filled: cr_path_soa.stroke_options = NULL, nothing to copy
     pinned = [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).pin_memory() for a in host_arrays]
     resident = [t.to(dev) for t in pinned]
     inst_host = [torch.from_numpy(transforms.reshape(-1).copy()).pin_memory(), torch.from_numpy(scene.colors.reshape(-1).copy()).pin_memory()]
@@ -245,7 +252,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     def timed(device_resident: bool, steps: int, collect: bool):
-        kernel_ms = {"tess": [], "bin": [], "raster": []}
+        kernel_ms = {"tess": [], "bin": [], "raster": [], "hull_sort": [], "hull_chain": []}
         covered = 0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -258,6 +265,8 @@ def main():
                 kernel_ms["tess"].append(st.last_tess_ms)
                 kernel_ms["bin"].append(st.last_bin_ms)
                 kernel_ms["raster"].append(st.last_raster_ms)
+                kernel_ms["hull_sort"].append(st.last_hull_sort_ms)
+                kernel_ms["hull_chain"].append(st.last_hull_chain_ms)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -296,10 +305,25 @@ def main():
         tess_alg = int(st.input_bytes) + layout_bytes                         # SURVEY §8d B_tess
         mean = lambda xs: float(np.mean(xs)) if xs else 0.0
         k_ms = {k: mean(v) for k, v in kernel_ms.items()}
-        # The dominant single kernel of the step is K3, raster_tiles_kernel (43.7 % of the device time in the committed ncu
-        # launch list, profiles/launches_r01.csv); its algorithmic bytes are B_rast of SURVEY §8d / DESIGN.md §5.
-        achieved = raster_alg / (k_ms["raster"] * 1e-3) / 1e9 if k_ms["raster"] > 0 else 0.0
+        # Roofline of the DOMINANT single kernel, whichever of the two heavy ones took longer in this run (both are timed live
+        # with CUDA events on the renderer's stream; the committed ncu launch list profiles/launches_r01.csv shows the same
+        # shares): K3 raster_tiles_kernel with B_rast of SURVEY 8d, or hull_chain_kernel (convex_hull::andrew's chains) with
+        # 8 B per proto-hull point read + 8 B per hull vertex written. The other one is reported
+        # next to it as "roofline_other".
+        proto_points, hull_vertices = int(st.proto_hull_points), int(st.hull_vertices)
+        chain_alg = 8 * proto_points + 8 * hull_vertices
+
+        def roofline_of(name, alg, ms, formula, traffic):
+            ach = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak if peak else None,
+                    "algorithmic_bytes": alg, "algorithmic_bytes_formula": formula, "kernel_ms": ms, "traffic": traffic}
         default_workload = args.glyphs == N_GLYPHS
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/ncu_full_r01_summary.csv)
+        rooflines = [roofline_of("raster_tiles_kernel", raster_alg, k_ms["raster"], "vertex+index bytes + 80 B x instances + W x H x (1 B stencil + 16 B rgba32f)",
+                                 RASTER_DRAM_BYTES_R01 if default_workload else None),
+                     roofline_of("hull_chain_kernel", chain_alg, k_ms["hull_chain"], "8 B x proto-hull points + 8 B x hull vertices (latency-bound sequential stack machines, DESIGN.md section 7)",
+                                 CHAIN_DRAM_BYTES_R01 if default_workload else None)]
+        rooflines.sort(key=lambda r: -r["kernel_ms"])
         line = {
             "metric": "paths/sec", "value": total_paths * args.steps / (ms_dev * 1e-3), "unit": "paths/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,12 +338,8 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "kernel_ms_per_step": k_ms,
-            "roofline": {"kernel": "raster_tiles_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "algorithmic_bytes": raster_alg,
-                         "algorithmic_bytes_formula": "vertex+index bytes + 80 B x instances + W x H x (1 B stencil + 16 B rgba32f)",
-                         "kernel_ms": k_ms["raster"],
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/ncu_full_r01_summary.csv)
-                         "traffic": RASTER_DRAM_BYTES_R01 if default_workload else None},
+            "roofline": rooflines[0],
+            "roofline_other": rooflines[1],
             "stages": {"tessellation": {"ms": k_ms["tess"], "algorithmic_bytes": tess_alg, "achieved_gbs": tess_alg / (k_ms["tess"] * 1e-3) / 1e9 if k_ms["tess"] else 0.0},
                        "binning": {"ms": k_ms["bin"], "tile_pairs": int(st.tile_pairs), "primitives": int(st.primitives)},
                        "raster": {"ms": k_ms["raster"]}},

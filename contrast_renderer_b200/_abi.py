@@ -71,7 +71,8 @@ class StatsC(C.Structure):
     _fields_ = [("covered_samples", C.c_uint64), ("primitives", C.c_uint64), ("tile_pairs", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("tessellated_paths", C.c_uint64), ("vertex_bytes", C.c_uint64),
                 ("input_bytes", C.c_uint64), ("last_tess_ms", C.c_float), ("last_raster_ms", C.c_float),
-                ("last_bin_ms", C.c_float), ("_reserved", C.c_float)]
+                ("last_bin_ms", C.c_float), ("last_hull_sort_ms", C.c_float), ("last_hull_chain_ms", C.c_float), ("_reserved", C.c_float),
+                ("proto_hull_points", C.c_uint64), ("hull_vertices", C.c_uint64)]
 
 
 CR_IPC_HANDLE_BYTES = 64

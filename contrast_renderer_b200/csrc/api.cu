@@ -123,7 +123,7 @@ struct cr_renderer {
     uint32_t* pinned = nullptr;   // small pinned read-back area
     cr_stats stats{};
     bool timing = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // tess begin/end, bin begin/end, raster begin/end
+    cudaEvent_t ev[9] = {};   // tess begin/end, bin begin/end, raster begin/end, hull begin / after sort / end
     bool ev_valid[3] = {false, false, false};
     uint32_t shard_world = 1, shard_rank = 0;              // tile sharding of one target across GPUs
     void* peer_color[CR_MAX_PEERS] = {};                   // peer-mapped attachments of the other ranks, slot = rank - (rank > shard_rank)
@@ -243,8 +243,9 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
         CR_TRY(stage(r, 4 + t, seg_src[t], (size_t)type_totals[t] * kSegFloats[t], soa->memory_space, &P.seg[t]));
         input_bytes += (uint64_t)type_totals[t] * (1 + 4 * kSegFloats[t]);
     }
-    if (n_paths && !soa->stroke_options) return fail(CR_ERR_INVALID_ARGUMENT, "stroke_options is null (use flags = 0 for filled paths)");
-    CR_TRY(stage(r, 9, soa->stroke_options, n_paths, soa->memory_space, &P.stroke_options));
+    // stroke_options == NULL: every Path has `stroke_options: None` (src/path.rs:215), i.e. all paths are filled
+    if (soa->stroke_options) CR_TRY(stage(r, 9, soa->stroke_options, n_paths, soa->memory_space, &P.stroke_options));
+    else P.stroke_options = nullptr;
     input_bytes += 8ull * n_paths;
 
     // ---- pass A: count, scan, per-shape slice boundaries
@@ -286,9 +287,11 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     out.proto = b->proto.as<float2>();
     for (int k = 0; k < 3; ++k) out.idx[k] = b->idx[k].as<uint32_t>();
     CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, r->err_flag.as<uint32_t>()));
+    if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[6], st));
     CR_TRY(cr_tess_hull(st, out.proto, r->hull_scratch_a.as<float2>(), r->hull_scratch_b.as<float2>(),
-                        b->cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, b->hull.as<float2>(), b->hull_count.as<uint32_t>(), max_proto));
-    if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[1], st)); r->ev_valid[0] = true; }
+                        b->cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, b->hull.as<float2>(), b->hull_count.as<uint32_t>(), max_proto,
+                        r->timing ? r->ev[7] : nullptr));
+    if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[8], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[1], st)); r->ev_valid[0] = true; }
 
     // ---- the rasteriser's view of this batch + host mirrors of the slice tables
     DeviceBatch db{};
@@ -318,9 +321,12 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     for (int k = 0; k < 3; ++k) out_bytes += 2ull * b->totals[CNT_LINE_IDX + k];
     // B_in of SURVEY §8d: 8 + 24 [stroked] per path; the stroked count is not known on the host for device inputs,
     // so the 24 B record is counted for every path that carries one (all of them in this ABI).
-    r->stats.input_bytes = input_bytes + 24ull * n_paths;
+    r->stats.input_bytes = input_bytes + (soa->stroke_options ? 24ull * n_paths : 0ull);
     r->stats.vertex_bytes = out_bytes;
     r->stats.tessellated_paths = n_paths;
+    r->stats.proto_hull_points = b->totals[CNT_PROTO];
+    r->stats.hull_vertices = 0;
+    for (uint32_t s = 0; s < n_shapes; ++s) r->stats.hull_vertices += b->hull_count_host[s];
     return CR_OK;
 }
 
@@ -338,7 +344,7 @@ uint32_t slots_of_host(const cr_shape_batch* b, uint32_t shape, int cat) {
 // ============================================================================================= exported C-ABI
 extern "C" {
 
-uint32_t cr_abi_version(void) { return 1; }
+uint32_t cr_abi_version(void) { return 2; }
 const char* cr_last_error_message(void) { return g_error_message; }
 const char* cr_status_string(int status) {
     switch (status) {
@@ -944,6 +950,8 @@ int cr_renderer_get_stats(cr_renderer* r, cr_stats* out) {
     r->stats.last_tess_ms = (r->ev_valid[0] && cudaEventElapsedTime(&ms, r->ev[0], r->ev[1]) == cudaSuccess) ? ms : 0.0f;
     r->stats.last_bin_ms = (r->ev_valid[1] && cudaEventElapsedTime(&ms, r->ev[2], r->ev[3]) == cudaSuccess) ? ms : 0.0f;
     r->stats.last_raster_ms = (r->ev_valid[2] && cudaEventElapsedTime(&ms, r->ev[4], r->ev[5]) == cudaSuccess) ? ms : 0.0f;
+    r->stats.last_hull_sort_ms = (r->ev_valid[0] && cudaEventElapsedTime(&ms, r->ev[6], r->ev[7]) == cudaSuccess) ? ms : 0.0f;
+    r->stats.last_hull_chain_ms = (r->ev_valid[0] && cudaEventElapsedTime(&ms, r->ev[7], r->ev[8]) == cudaSuccess) ? ms : 0.0f;
     cudaGetLastError();
     *out = r->stats;
     return CR_OK;

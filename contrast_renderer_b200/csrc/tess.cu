@@ -807,7 +807,8 @@ __device__ __forceinline__ PathView load_path(const DevicePaths& P, uint32_t p) 
     pv.seg[2] = P.seg[2] + 6 * (size_t)P.type_begin[2 * stride + p];
     pv.seg[3] = P.seg[3] + 5 * (size_t)P.type_begin[3 * stride + p];
     pv.seg[4] = P.seg[4] + 10 * (size_t)P.type_begin[4 * stride + p];
-    pv.so = P.stroke_options[p];
+    if (P.stroke_options) pv.so = P.stroke_options[p];
+    else pv.so = cr_stroke_options{};   // no stroke options: a filled Path
     return pv;
 }
 
@@ -1219,7 +1220,7 @@ int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* 
     return CR_OK;
 }
 int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
-                 float2* hull_out, uint32_t* hull_count, uint32_t max_points) {
+                 float2* hull_out, uint32_t* hull_count, uint32_t max_points, cudaEvent_t after_sort) {
     if (n_shapes == 0) return CR_OK;
     // Sort: shared-memory capacity (in points) = the largest shape rounded up to 512 if that fits one SM's shared memory
     // (8.5 bytes per point with the bank padding), else the maximum — larger shapes sort in global memory.
@@ -1232,6 +1233,7 @@ int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* 
     const uint32_t cap = std::min<uint32_t>(max_cap, std::max<uint32_t>(512u, (max_points + 511u) / 512u * 512u));
     const uint32_t threads = std::min<uint32_t>(512u, std::max<uint32_t>(64u, cap / 16u));   // one 16-element register tile per thread
     hull_sort_kernel<<<n_shapes, threads, (size_t)SORT_SLOT(cap) * sizeof(float2), stream>>>(proto, proto_begin, cap);
+    if (after_sort) CR_CUDA_TRY(cudaEventRecord(after_sort, stream));
     hull_chain_kernel<<<(n_shapes + CHAIN_SHAPES - 1) / CHAIN_SHAPES, CHAIN_THREADS, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out, hull_count);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());

@@ -30,4 +30,4 @@ int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t 
 int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* offsets, const uint32_t* shape_path_begin, uint32_t n_shapes,
                  const TessOutput& out, uint32_t* err_flag);
 int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
-                 float2* hull_out, uint32_t* hull_count, uint32_t max_points);
+                 float2* hull_out, uint32_t* hull_count, uint32_t max_points, cudaEvent_t after_sort = nullptr);   // after_sort: optional event recorded between the sort and the chain kernel

@@ -488,6 +488,9 @@ class PathSoA:
         seg = sum(int(a.shape[0]) * (1 + 4 * w) for a, w in zip(self.segments, _abi.SEGMENT_FLOATS))
         return 8 * self.n_paths + 24 * stroked + seg
 
+    def any_stroked(self) -> bool:
+        return bool(((self.stroke_options["flags"] & _abi.CR_STROKE_FLAG_STROKED) != 0).any())
+
     def arrays(self):
         return [self.start, self.segment_begin, self.segment_types, self.type_begin, *self.segments, self.stroke_options]
 
@@ -501,6 +504,8 @@ class PathSoA:
             for a in self.arrays():
                 assert a.flags["C_CONTIGUOUS"]
             pointers = [a.ctypes.data for a in self.arrays()]
+            if not self.any_stroked():
+                pointers[9] = None   # `stroke_options: None` for every Path: nothing to send
         (c.start, c.segment_begin, c.segment_types, c.type_begin, c.line_segments, c.integral_quadratic, c.integral_cubic,
          c.rational_quadratic, c.rational_cubic, c.stroke_options) = pointers
         return c

@@ -128,7 +128,7 @@ typedef struct cr_path_soa {
     const float* integral_cubic;           /* [n_ic][6]                   control_points[0..3] */
     const float* rational_quadratic;       /* [n_rq][5]                   weight, control_points[0..2] */
     const float* rational_cubic;           /* [n_rc][10]                  weights[0..4], control_points[0..3] */
-    const cr_stroke_options* stroke_options; /* [n_paths]; flags & STROKED == 0 means a filled Path */
+    const cr_stroke_options* stroke_options; /* [n_paths]; flags & STROKED == 0 means a filled Path; NULL = every Path is filled */
 } cr_path_soa;
 
 /* --------------------------------------------------------------------------------------------- renderer setup */
@@ -282,7 +282,11 @@ typedef struct cr_stats {
     float last_tess_ms;                    /* CUDA-event duration of the emit kernels (0 if timing disabled) */
     float last_raster_ms;                  /* CUDA-event duration of the tile raster kernel */
     float last_bin_ms;
+    float last_hull_sort_ms;               /* CUDA-event duration of hull_sort_kernel / hull_chain_kernel of the last from_paths */
+    float last_hull_chain_ms;
     float _reserved;
+    uint64_t proto_hull_points;            /* points that went through convex_hull::andrew in the last from_paths, over all shapes */
+    uint64_t hull_vertices;                /* hull vertices it produced */
 } cr_stats;
 int cr_renderer_get_stats(cr_renderer* renderer, cr_stats* out);
 int cr_renderer_enable_timing(cr_renderer* renderer, uint32_t enabled);
