@@ -26,6 +26,7 @@
 namespace {
 
 #define RCHUNK 128            // primitives staged in shared memory at a time
+#define PIXEL_RUN_MAX 12u     // runs of at most this many primitives execute in pixel mode (see K3)
 #define BIG_TILE_BOX 8        // candidates touching more tiles than this are binned by the whole warp
 
 struct Descriptor {   // DynamicStrokeDescriptor, src/renderer.rs:18-27 (48 B)
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
     __shared__ int acc[2][CR_TILE * CR_TILE * S];   // per-sample result of a stencil run; double buffered so that one barrier per run suffices
     __shared__ uint32_t run_mask[RCHUNK / 32];
     __shared__ uint8_t run_start[RCHUNK + 1];
-    __shared__ unsigned long long cov[CR_TILE][CR_TILE];   // row coverage masks (bit x * S + k) of the cover primitives of one sweep
+    __shared__ unsigned long long cov[2][CR_TILE][CR_TILE];   // row coverage masks (bit x * S + k) of the cover primitives of one sweep; double buffered: one barrier per sweep
     const uint32_t tile = blockIdx.x;
     const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];
     if (begin == end) return;
@@ -488,6 +489,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
     int pending = -1;            // accumulator buffer of the pending run, or -1
     uint32_t pending_kind = 0, pending_ref = 0;
     int cur = 0;                 // buffer the next stencil run accumulates into
+    int cb = 0;                  // row-mask buffer the next cover sweep writes
     auto apply_pending = [&]() {
         if (pending < 0) return;
 #pragma unroll
@@ -500,6 +502,53 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
             }
         }
         pending = -1;
+    };
+
+    // One cover primitive on the samples `hit` of this thread's pixel: stencil test / op and blend of its pipeline.
+    auto cover_apply = [&](const TilePrim& ps, uint32_t hit) {
+        const uint32_t pipe = ps.meta & 15u, ref = ps.ref;
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            if (!((hit >> q) & 1u)) continue;
+            if (pipe == P_COLOR) {                                                                   // src/renderer.rs:736-754
+                if ((ref & M) < (s[q] & M)) {
+                    const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
+                    const float sa = ic.w;
+                    const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
+                    if (tg.blending == CR_BLEND_PREMULTIPLIED_OVER) {
+                        const float kk = 1.0f - sa;
+                        col[q].x = sr + col[q].x * kk; col[q].y = sg + col[q].y * kk; col[q].z = sb + col[q].z * kk; col[q].w = sa + col[q].w * kk;
+                    } else { col[q].x = sr; col[q].y = sg; col[q].z = sb; col[q].w = sa; }
+                    covered += 1;
+                }
+                s[q] = s[q] & ~W;
+            } else if (pipe == P_CLIP) {                                                             // src/renderer.rs:692-710
+                if ((ref & W) != (s[q] & W)) s[q] = (s[q] & ~M) | (ref & M);
+            } else if (pipe == P_UNCLIP) {                                                           // src/renderer.rs:711-729
+                if ((ref & C) < (s[q] & C)) s[q] = (s[q] & ~M) | (ref & M);
+            } else if ((ref & M) <= (s[q] & M)) {   // the three alpha-context covers share one stencil state (src/renderer.rs:761-766)
+                if (pipe == P_SAVE_ALPHA) {
+                    tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix + q] = col[q].w;
+                } else if (pipe == P_SCALE_ALPHA) {
+                    const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
+                    col[q].w = sa + col[q].w * (1.0f - sa);
+                } else {
+                    const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix + q];
+                    const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
+                    col[q].w = col[q].w - sa;
+                }
+            }
+        }
+    };
+    // PIXEL MODE for short runs: every thread walks the run's primitives for its own pixel — no shared accumulator, no
+    // barrier, all 256 threads busy however few primitives the run has. Returns false if the pixel is outside the
+    // primitive's box; else E[] = the biased edge values at the pixel's evaluation origin.
+    auto pixel_edges = [&](const TilePrim& ps, long long* E) -> bool {
+        const uint32_t bbox = ps.bbox;
+        if (lx < (int)(bbox & 255u) || lx > (int)((bbox >> 16) & 255u) || ly < (int)((bbox >> 8) & 255u) || ly > (int)(bbox >> 24)) return false;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) E[e] = ps.e0[e] + (long long)ps.A[e] * (ly * 256) - (long long)ps.B[e] * (lx * 256);
+        return true;
     };
 
     for (uint32_t chunk = begin; chunk < end; chunk += RCHUNK) {
@@ -545,7 +594,37 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
             if (first == b) continue;
             const uint32_t kind = run_kind(sh[first].meta & 15u);
             apply_pending();
-            if (kind < 2u) {
+            if (kind < 2u && b - a <= PIXEL_RUN_MAX) {
+                // short stencil run, pixel mode: the run's net effect on this pixel's samples, applied at once
+                int net[S];
+#pragma unroll
+                for (int q = 0; q < S; ++q) net[q] = 0;
+                for (uint32_t k = a; k < b; ++k) {
+                    const TilePrim& ps = sh[k];
+                    const uint32_t meta = ps.meta;
+                    if (!(meta & META_VALID)) continue;
+                    long long E[3];
+                    if (!pixel_edges(ps, E)) continue;
+                    const uint32_t pipe = meta & 15u;
+                    const int delta = kind == 0u ? 1 : ((meta & META_FRONT) ? 1 : -1);
+#pragma unroll
+                    for (int q = 0; q < S; ++q) {
+                        long long Es[3];
+#pragma unroll
+                        for (int e = 0; e < 3; ++e)
+                            Es[e] = S == 1 ? E[e] : E[e] + (long long)ps.A[e] * sample_y<S>(q) - (long long)ps.B[e] * sample_x<S>(q);
+                        if ((Es[0] | Es[1] | Es[2]) >= 0 && (pipe == P_FILL_SOLID || fragment_keep(sc, ps, pipe, Es))) net[q] = kind == 0u ? 1 : net[q] + delta;
+                    }
+                }
+                const uint32_t ref = sh[first].ref;
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    if (net[q] != 0) {
+                        if (kind == 0u) { if ((ref & M) == (s[q] & M)) s[q] = (s[q] & ~W) | ((s[q] + 1u) & W); }                  // src/renderer.rs:571-576
+                        else if ((ref & M) <= (s[q] & M)) s[q] = (s[q] & ~W) | ((s[q] + (uint32_t)net[q]) & W);                      // src/renderer.rs:577-582
+                    }
+                }
+            } else if (kind < 2u) {
                 // stencil run: (primitive, row) work items, 16 primitives x 16 rows per sweep
                 int* const out = acc[cur];
                 for (uint32_t base = a; base < b; base += CR_TILE) {
@@ -588,6 +667,28 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
                 pending_kind = kind;
                 pending_ref = sh[first].ref;
                 cur ^= 1;
+            } else if (b - a <= PIXEL_RUN_MAX) {
+                // short cover run (the usual hull of a few triangles), pixel mode: in draw order, this thread's pixel only
+                for (uint32_t k = a; k < b; ++k) {
+                    const TilePrim& ps = sh[k];
+                    const uint32_t meta = ps.meta;
+                    if (!(meta & META_VALID)) continue;
+                    long long E[3];
+                    if (!pixel_edges(ps, E)) continue;
+                    uint32_t hit = (1u << S) - 1u;
+                    if (!(meta & META_FULL)) {
+                        hit = 0;
+#pragma unroll
+                        for (int q = 0; q < S; ++q) {
+                            long long any = 0;
+#pragma unroll
+                            for (int e = 0; e < 3; ++e)
+                                any |= S == 1 ? E[e] : E[e] + (long long)ps.A[e] * sample_y<S>(q) - (long long)ps.B[e] * sample_x<S>(q);
+                            if (any >= 0) hit |= 1u << q;
+                        }
+                    }
+                    if (hit) cover_apply(ps, hit);
+                }
             } else {
                 // cover run: one (command, instance) hull draw. Order dependent, so the stencil / blend ops run one thread per
                 // pixel, but coverage is found first by (primitive, row) work items as row masks, 16 primitives a sweep.
@@ -624,49 +725,15 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
                                 }
                             }
                         }
-                        cov[threadIdx.x >> 4][threadIdx.x & 15u] = mask;
+                        cov[cb][threadIdx.x >> 4][threadIdx.x & 15u] = mask;
                     }
                     __syncthreads();
                     const uint32_t count = min((uint32_t)CR_TILE, b - base);
                     for (uint32_t j = 0; j < count; ++j) {
-                        const uint32_t hit = (uint32_t)(cov[j][ly] >> (lx * S)) & ((1u << S) - 1u);
-                        if (!hit) continue;
-                        const TilePrim& ps = sh[base + j];
-                        const uint32_t pipe = ps.meta & 15u, ref = ps.ref;
-#pragma unroll
-                        for (int q = 0; q < S; ++q) {
-                            if (!((hit >> q) & 1u)) continue;
-                            if (pipe == P_COLOR) {                                                                   // src/renderer.rs:736-754
-                                if ((ref & M) < (s[q] & M)) {
-                                    const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
-                                    const float sa = ic.w;
-                                    const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
-                                    if (tg.blending == CR_BLEND_PREMULTIPLIED_OVER) {
-                                        const float kk = 1.0f - sa;
-                                        col[q].x = sr + col[q].x * kk; col[q].y = sg + col[q].y * kk; col[q].z = sb + col[q].z * kk; col[q].w = sa + col[q].w * kk;
-                                    } else { col[q].x = sr; col[q].y = sg; col[q].z = sb; col[q].w = sa; }
-                                    covered += 1;
-                                }
-                                s[q] = s[q] & ~W;
-                            } else if (pipe == P_CLIP) {                                                             // src/renderer.rs:692-710
-                                if ((ref & W) != (s[q] & W)) s[q] = (s[q] & ~M) | (ref & M);
-                            } else if (pipe == P_UNCLIP) {                                                           // src/renderer.rs:711-729
-                                if ((ref & C) < (s[q] & C)) s[q] = (s[q] & ~M) | (ref & M);
-                            } else if ((ref & M) <= (s[q] & M)) {   // the three alpha-context covers share one stencil state (src/renderer.rs:761-766)
-                                if (pipe == P_SAVE_ALPHA) {
-                                    tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix + q] = col[q].w;
-                                } else if (pipe == P_SCALE_ALPHA) {
-                                    const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
-                                    col[q].w = sa + col[q].w * (1.0f - sa);
-                                } else {
-                                    const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix + q];
-                                    const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
-                                    col[q].w = col[q].w - sa;
-                                }
-                            }
-                        }
+                        const uint32_t hit = (uint32_t)(cov[cb][j][ly] >> (lx * S)) & ((1u << S) - 1u);
+                        if (hit) cover_apply(sh[base + j], hit);
                     }
-                    __syncthreads();   // the next sweep overwrites the row masks
+                    cb ^= 1;   // the next sweep writes the other buffer; this one is rewritten only after that sweep's barrier
                 }
             }
         }
