@@ -52,13 +52,26 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms 10` in the background. It needs ~0.1 s to come up, longer than a short timed region, so it is started
+    before the warm-up and the samples are selected by their timestamps: those taken inside the timed window [mark_begin(),
+    mark_end()]; only if the window is too short to hold one are the (identically loaded) warm-up samples used, and the
+    result says so in "window"."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index: int):
         self.device_index = device_index
         self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
+
+    def mark_end(self):
+        import datetime
+        self.t_end = datetime.datetime.now()
 
     def start(self):
         try:
@@ -78,23 +91,26 @@ class ClockSampler:
             self.proc.kill()
         self.file.flush()
         self.file.seek(0)
-        sm, smax, reasons = [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.file.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
+                stamp = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((stamp, float(parts[1]), float(parts[2]), [n for n, v in zip(names, parts[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.file.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if self.t_begin is not None and self.t_end is not None and self.t_begin <= r[0] <= self.t_end]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed region (the timed region is shorter than one sampling period)"
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted({n for r in inside for n in r[3]}), samples=len(inside), window=window)
         return out
 
 
@@ -277,17 +293,23 @@ def main():
         return ms, covered, kernel_ms
 
     # warm-up (both arms), then the two timed regions
-    for _ in range(max(3, args.warmup)):
-        step(True)
-    step(False)
-    torch.cuda.synchronize(dev)
-    launches0 = int(rnd.stats().kernel_launches)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    import time
+    t_warm = time.time()
+    for _ in range(max(3, args.warmup)):
+        step(True)
+    step(False)
+    while rank == 0 and time.time() - t_warm < 0.5:   # untimed: gives nvidia-smi time to come up, under the benchmark's own load
+        step(True)
+    torch.cuda.synchronize(dev)
+    launches0 = int(rnd.stats().kernel_launches)
+    sampler.mark_begin()
     ms_dev, covered, kernel_ms = timed(True, args.steps, collect=True)
     launches = int(rnd.stats().kernel_launches) - launches0
     ms_e2e, covered_e2e, _ = timed(False, args.steps, collect=False)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     st = rnd.stats()
 

@@ -802,6 +802,10 @@ static int submit(cr_pass* p) {
     tg.cmask = ((1u << r->config.clip_nesting_counter_bits) - 1u) << r->config.winding_counter_bits;
     tg.blending = r->config.blending;
     tg.cull_mode = r->config.cull_mode;
+    {
+        static const int env_run = getenv("CR_PIXEL_RUN_MAX") ? atoi(getenv("CR_PIXEL_RUN_MAX")) : -1;   // tuning knob for experiments
+        tg.pixel_run_max = env_run >= 0 ? (uint32_t)env_run : 12u;
+    }
     tg.shard_world = r->shard_world;
     tg.shard_rank = r->shard_rank;
     for (int i = 0; i < CR_MAX_PEERS; ++i) { tg.peer_color[i] = static_cast<float4*>(r->peer_color[i]); tg.peer_stencil[i] = static_cast<uint8_t*>(r->peer_stencil[i]); }

@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
             if (first == b) continue;
             const uint32_t kind = run_kind(sh[first].meta & 15u);
             apply_pending();
-            if (kind < 2u && b - a <= PIXEL_RUN_MAX) {
+            if (kind < 2u && b - a <= tg.pixel_run_max) {
                 // short stencil run, pixel mode: the run's net effect on this pixel's samples, applied at once
                 int net[S];
 #pragma unroll
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
                 pending_kind = kind;
                 pending_ref = sh[first].ref;
                 cur ^= 1;
-            } else if (b - a <= PIXEL_RUN_MAX) {
+            } else if (b - a <= tg.pixel_run_max) {
                 // short cover run (the usual hull of a few triangles), pixel mode: in draw order, this thread's pixel only
                 for (uint32_t k = a; k < b; ++k) {
                     const TilePrim& ps = sh[k];
