@@ -368,11 +368,20 @@ def text_glyphs(n_glyphs: int = 100000, seed: int = SEED0 + 3, extent: Tuple[int
 def dashed_rational_strokes(n_paths: int = 1000000, seed: int = SEED0 + 5, extent: Tuple[int, int] = (7680, 4320), paths_per_shape: int = 1000,
                             angle_step: float = 0.2, pixels_per_unit: float = 10.0) -> Scene:
     """BASELINE config 5: open paths of 2 rational cubics (weights U[0.5,2]), width U[1,4], round joins and caps,
-    two-interval dash pattern, UniformTangentAngle(0.2)."""
+    two-interval dash pattern, UniformTangentAngle(0.2). A Shape is the `paths_per_shape` paths of one cell of a grid over
+    the target, in LOCAL coordinates around the cell centre, placed by its instance translation (MODEL UNITS, top of this
+    file): with absolute coordinates of hundreds of units the reference's hull tolerance drowns in f32 noise and every
+    Shape's "hull" keeps ~1500 vertices in overlapping slivers (measured: 13 (tile, primitive) pairs per tile per cover)."""
     rng = np.random.default_rng(seed)
     ppu = float(pixels_per_unit)
     seg_counts = np.full(n_paths, 2, np.int64)
-    p0 = np.stack([rng.uniform(0, extent[0], n_paths), rng.uniform(0, extent[1], n_paths)], 1) / ppu
+    n_cells = (n_paths + paths_per_shape - 1) // paths_per_shape
+    gx = max(1, int(round(np.sqrt(n_cells * extent[0] / extent[1]))))
+    gy = (n_cells + gx - 1) // gx
+    cell_w, cell_h = extent[0] / gx, extent[1] / gy
+    cell = np.arange(n_cells)
+    origins = np.stack([(cell % gx + 0.5) * cell_w, (cell // gx + 0.5) * cell_h], 1) / ppu
+    p0 = np.stack([rng.uniform(-0.5 * cell_w, 0.5 * cell_w, n_paths), rng.uniform(-0.5 * cell_h, 0.5 * cell_h, n_paths)], 1) / ppu
     step = rng.uniform(8.0, 30.0, (n_paths, 1)) / ppu
     direction = rng.uniform(0, 2 * np.pi, n_paths)
     d = np.stack([np.cos(direction), np.sin(direction)], 1)
@@ -403,7 +412,7 @@ def dashed_rational_strokes(n_paths: int = 1000000, seed: int = SEED0 + 5, exten
     colors = np.concatenate([rng.uniform(0, 1, (n_shapes, 3)), np.full((n_shapes, 1), 0.8)], 1).astype(np.float32)
     dso = DynamicStrokeOptions.Dashed(Join.Round, [DashInterval(2.0, 3.0, Cap.Round, Cap.Round), DashInterval(5.0, 5.5, Cap.Round, Cap.Round)],
                                       float(rng.uniform(0, 6)))
-    return Scene(soa, begin, [dso], extent[0], extent[1], colors, "dashed_rational_strokes", ppu)
+    return Scene(soa, begin, [dso], extent[0], extent[1], colors, "dashed_rational_strokes", ppu, origins[:n_shapes])
 
 
 def stencil_cover_commands(n_shapes: int) -> np.ndarray:
