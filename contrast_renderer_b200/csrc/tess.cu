@@ -1144,7 +1144,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
                 pn = lds_f2(k + 1 < k1 ? src : src - 8u);   // next point: independent of the stack, overlaps the tests below
                 // pop while (a v b) v p <= margin (src/convex_hull.rs:16-19); a, b are the two top entries
                 const float t1 = hull_side(lab, p), t2 = hull_side(lca, p);
-                const HullLine lbp = hull_line(b, p), lap = hull_line(a, p);
                 const bool keep = !(t1 <= CR_ERROR_MARGIN);                        // keep b:  .. c a b  ->  .. a b p
                 if (keep || top == floor2 || !(t2 <= CR_ERROR_MARGIN)) {           // else pop b only (a is the last entry, or a stays):  .. c a b  ->  .. c a p
                     const uint32_t at = keep ? top : top - 8u;                     // the two common outcomes, branch free
@@ -1153,8 +1152,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
                     c.x = keep ? a.x : c.x; c.y = keep ? a.y : c.y;
                     a.x = keep ? b.x : a.x; a.y = keep ? b.y : a.y;
                     lca.l0 = keep ? lab.l0 : lca.l0; lca.l1 = keep ? lab.l1 : lca.l1; lca.l2 = keep ? lab.l2 : lca.l2;
-                    lab.l0 = keep ? lbp.l0 : lap.l0; lab.l1 = keep ? lbp.l1 : lap.l1; lab.l2 = keep ? lbp.l2 : lap.l2;
                     b = p;
+                    lab = hull_line(a, b);                                         // one line from the selected entry (fewer instructions than both candidates + selects)
                 } else {                                                           // b and a are popped: continue on the shared stack, which now ends with c
                     top -= 16;
                     b = c;
