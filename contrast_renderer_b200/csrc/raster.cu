@@ -45,6 +45,7 @@ enum Pipe : uint32_t {
 #define META_FRONT 16u
 #define META_SWAPPED 32u
 #define META_VALID 64u
+#define META_E32 4096u    // (tile-local) the edge functions fit 32-bit integers everywhere in the tile
 #define META_FULL 2048u   // (tile-local) every pixel centre of the tile is inside the primitive
 
 __device__ __forceinline__ const float* vertex_ptr(const DeviceBatch& b, uint32_t cat, uint32_t v) {
@@ -352,7 +353,8 @@ __device__ bool stroke_dashed(const Descriptor& d, float tx, float ty) {   // sr
 
 // Fragment stage of the stencil pipelines (src/shaders.wgsl:233-300): perspective-correct attributes at the sample and
 // the sample_mask predicate. E[] are the biased edge values at the sample.
-__device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TilePrim& ps, uint32_t pipe, const long long* E) {
+template <typename EdgeT>   // long long, or int for primitives whose edge values fit 32 bits over the whole tile (META_E32)
+__device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TilePrim& ps, uint32_t pipe, const EdgeT* E) {
     const float e0 = (float)(E[1] - ps.bias[1]) * ps.invw[0], e1 = (float)(E[2] - ps.bias[2]) * ps.invw[1], e2 = (float)(E[0] - ps.bias[0]) * ps.invw[2];
     const float den = (e0 + e1) + e2;
     float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -386,6 +388,74 @@ __device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TileP
 // Sample positions inside a pixel in 1/256 px: the centre for 1x, the WebGPU standard pattern for 4x (same table as the oracle).
 template <int S> __device__ __forceinline__ int sample_x(int k) { return S == 1 ? 128 : (k == 0 ? 96 : (k == 1 ? 224 : (k == 2 ? 32 : 160))); }
 template <int S> __device__ __forceinline__ int sample_y(int k) { return S == 1 ? 128 : (k == 0 ? 32 : (k == 1 ? 96 : (k == 2 ? 160 : 224))); }
+
+// Edge values of primitive `ps` at pixel (lx, ly) of the tile (evaluation origin of stage_primitive), in EdgeT arithmetic.
+template <typename EdgeT> __device__ __forceinline__ EdgeT edge_origin(const TilePrim& ps, int e) {
+    return sizeof(EdgeT) == 8 ? (EdgeT)ps.e0[e] : (EdgeT)reinterpret_cast<const int*>(&ps.e0[e])[0];   // the low word IS the value when it fits
+}
+// Samples of pixel (lx, ly) inside the triangle (bit q), optionally also passing the pipeline's fragment predicate.
+template <int S, typename EdgeT>
+__device__ __forceinline__ uint32_t pixel_hits(const RasterScene& sc, const TilePrim& ps, uint32_t pipe, bool predicate, int lx, int ly) {
+    EdgeT E[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) E[e] = edge_origin<EdgeT>(ps, e) + (EdgeT)ps.A[e] * (EdgeT)(ly * 256) - (EdgeT)ps.B[e] * (EdgeT)(lx * 256);
+    uint32_t hit = 0;
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+        EdgeT Es[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) Es[e] = S == 1 ? E[e] : E[e] + (EdgeT)ps.A[e] * (EdgeT)sample_y<S>(q) - (EdgeT)ps.B[e] * (EdgeT)sample_x<S>(q);
+        if ((Es[0] | Es[1] | Es[2]) >= 0 && (!predicate || fragment_keep(sc, ps, pipe, Es))) hit |= 1u << q;
+    }
+    return hit;
+}
+// One (primitive, row) item of a stencil run in row mode: accumulate into `out` for the pixels x0..x1 of row y.
+template <int S, typename EdgeT>
+__device__ __forceinline__ void stencil_row(const RasterScene& sc, const TilePrim& ps, uint32_t pipe, uint32_t kind, int delta, int y, int x0, int x1, int* out) {
+    EdgeT E[3], step[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        step[e] = (EdgeT)ps.B[e] * (EdgeT)256;
+        E[e] = edge_origin<EdgeT>(ps, e) + (EdgeT)ps.A[e] * (EdgeT)(y * 256) - step[e] * (EdgeT)x0;
+    }
+    for (int x = x0; x <= x1; ++x) {
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            EdgeT Es[3];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) Es[e] = S == 1 ? E[e] : E[e] + (EdgeT)ps.A[e] * (EdgeT)sample_y<S>(q) - (EdgeT)ps.B[e] * (EdgeT)sample_x<S>(q);
+            if ((Es[0] | Es[1] | Es[2]) >= 0) {
+                if (pipe == P_FILL_SOLID || fragment_keep(sc, ps, pipe, Es)) {
+                    if (kind == 0u) atomicOr(&out[(y * CR_TILE + x) * S + q], 1);
+                    else atomicAdd(&out[(y * CR_TILE + x) * S + q], delta);
+                }
+            }
+        }
+        E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
+    }
+}
+// Coverage mask (bit x * S + q) of row y of a cover primitive, pixels x0..x1.
+template <int S, typename EdgeT>
+__device__ __forceinline__ unsigned long long cover_row_mask(const TilePrim& ps, int y, int x0, int x1) {
+    EdgeT E[3], step[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        step[e] = (EdgeT)ps.B[e] * (EdgeT)256;
+        E[e] = edge_origin<EdgeT>(ps, e) + (EdgeT)ps.A[e] * (EdgeT)(y * 256) - step[e] * (EdgeT)x0;
+    }
+    unsigned long long mask = 0;
+    for (int x = x0; x <= x1; ++x) {
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            EdgeT any = 0;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) any |= S == 1 ? E[e] : E[e] + (EdgeT)ps.A[e] * (EdgeT)sample_y<S>(q) - (EdgeT)ps.B[e] * (EdgeT)sample_x<S>(q);
+            if (any >= 0) mask |= 1ull << (x * S + q);
+        }
+        E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
+    }
+    return mask;
+}
 
 // Stage one primitive of this tile into shared memory (one thread per primitive). The edge functions are evaluated at the
 // centre of the tile's pixel (0, 0) for 1x and at its top-left corner for 4x (sample offsets are added per sample).
@@ -441,7 +511,15 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
             }
         }
     }
-    ps.meta = rec.meta | (full ? META_FULL : 0u);
+    // 32-bit edge arithmetic is exact for this tile if every edge value at every sample position of the tile (and +-1 for the
+    // bias that fragment_keep removes again) stays inside int range
+    bool fits = true;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const long long reach = ((long long)abs(t.A[e]) + (long long)abs(t.B[e])) * (15 * 256 + 256) + 2;
+        if (ps.e0[e] > 0x7fffffffLL - reach || ps.e0[e] < -0x7fffffffLL + reach) fits = false;
+    }
+    ps.meta = rec.meta | (full ? META_FULL : 0u) | (fits ? META_E32 : 0u);
 }
 
 // Run kinds: primitives of one run commute (see the file header).
@@ -541,14 +619,10 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
         }
     };
     // PIXEL MODE for short runs: every thread walks the run's primitives for its own pixel — no shared accumulator, no
-    // barrier, all 256 threads busy however few primitives the run has. Returns false if the pixel is outside the
-    // primitive's box; else E[] = the biased edge values at the pixel's evaluation origin.
-    auto pixel_edges = [&](const TilePrim& ps, long long* E) -> bool {
+    // barrier, all 256 threads busy however few primitives the run has.
+    auto pixel_in_box = [&](const TilePrim& ps) -> bool {
         const uint32_t bbox = ps.bbox;
-        if (lx < (int)(bbox & 255u) || lx > (int)((bbox >> 16) & 255u) || ly < (int)((bbox >> 8) & 255u) || ly > (int)(bbox >> 24)) return false;
-#pragma unroll
-        for (int e = 0; e < 3; ++e) E[e] = ps.e0[e] + (long long)ps.A[e] * (ly * 256) - (long long)ps.B[e] * (lx * 256);
-        return true;
+        return lx >= (int)(bbox & 255u) && lx <= (int)((bbox >> 16) & 255u) && ly >= (int)((bbox >> 8) & 255u) && ly <= (int)(bbox >> 24);
     };
 
     for (uint32_t chunk = begin; chunk < end; chunk += RCHUNK) {
@@ -603,18 +677,14 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
                     const TilePrim& ps = sh[k];
                     const uint32_t meta = ps.meta;
                     if (!(meta & META_VALID)) continue;
-                    long long E[3];
-                    if (!pixel_edges(ps, E)) continue;
+                    if (!pixel_in_box(ps)) continue;
                     const uint32_t pipe = meta & 15u;
                     const int delta = kind == 0u ? 1 : ((meta & META_FRONT) ? 1 : -1);
+                    const uint32_t hit = (meta & META_E32) ? pixel_hits<S, int>(sc, ps, pipe, pipe != P_FILL_SOLID, lx, ly)
+                                                           : pixel_hits<S, long long>(sc, ps, pipe, pipe != P_FILL_SOLID, lx, ly);
 #pragma unroll
-                    for (int q = 0; q < S; ++q) {
-                        long long Es[3];
-#pragma unroll
-                        for (int e = 0; e < 3; ++e)
-                            Es[e] = S == 1 ? E[e] : E[e] + (long long)ps.A[e] * sample_y<S>(q) - (long long)ps.B[e] * sample_x<S>(q);
-                        if ((Es[0] | Es[1] | Es[2]) >= 0 && (pipe == P_FILL_SOLID || fragment_keep(sc, ps, pipe, Es))) net[q] = kind == 0u ? 1 : net[q] + delta;
-                    }
+                    for (int q = 0; q < S; ++q)
+                        if ((hit >> q) & 1u) net[q] = kind == 0u ? 1 : net[q] + delta;
                 }
                 const uint32_t ref = sh[first].ref;
 #pragma unroll
@@ -638,29 +708,9 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
                     if (y > (int)(bbox >> 24)) continue;
                     const int x0 = (int)(bbox & 255u), x1 = (int)((bbox >> 16) & 255u);
                     const uint32_t pipe = meta & 15u;
-                    long long E[3], step[3];
-#pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                        step[e] = (long long)ps.B[e] * 256;
-                        E[e] = ps.e0[e] + (long long)ps.A[e] * (y * 256) - step[e] * x0;
-                    }
                     const int delta = kind == 0u ? 1 : ((meta & META_FRONT) ? 1 : -1);
-                    for (int x = x0; x <= x1; ++x) {
-#pragma unroll
-                        for (int q = 0; q < S; ++q) {
-                            long long Es[3];
-#pragma unroll
-                            for (int e = 0; e < 3; ++e)
-                                Es[e] = S == 1 ? E[e] : E[e] + (long long)ps.A[e] * sample_y<S>(q) - (long long)ps.B[e] * sample_x<S>(q);
-                            if ((Es[0] | Es[1] | Es[2]) >= 0) {
-                                if (pipe == P_FILL_SOLID || fragment_keep(sc, ps, pipe, Es)) {
-                                    if (kind == 0u) atomicOr(&out[(y * CR_TILE + x) * S + q], 1);
-                                    else atomicAdd(&out[(y * CR_TILE + x) * S + q], delta);
-                                }
-                            }
-                        }
-                        E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
-                    }
+                    if (meta & META_E32) stencil_row<S, int>(sc, ps, pipe, kind, delta, y, x0, x1, out);
+                    else stencil_row<S, long long>(sc, ps, pipe, kind, delta, y, x0, x1, out);
                 }
                 __syncthreads();
                 pending = cur;
@@ -673,20 +723,10 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
                     const TilePrim& ps = sh[k];
                     const uint32_t meta = ps.meta;
                     if (!(meta & META_VALID)) continue;
-                    long long E[3];
-                    if (!pixel_edges(ps, E)) continue;
+                    if (!pixel_in_box(ps)) continue;
                     uint32_t hit = (1u << S) - 1u;
-                    if (!(meta & META_FULL)) {
-                        hit = 0;
-#pragma unroll
-                        for (int q = 0; q < S; ++q) {
-                            long long any = 0;
-#pragma unroll
-                            for (int e = 0; e < 3; ++e)
-                                any |= S == 1 ? E[e] : E[e] + (long long)ps.A[e] * sample_y<S>(q) - (long long)ps.B[e] * sample_x<S>(q);
-                            if (any >= 0) hit |= 1u << q;
-                        }
-                    }
+                    if (!(meta & META_FULL))
+                        hit = (meta & META_E32) ? pixel_hits<S, int>(sc, ps, 0u, false, lx, ly) : pixel_hits<S, long long>(sc, ps, 0u, false, lx, ly);
                     if (hit) cover_apply(ps, hit);
                 }
             } else {
@@ -704,25 +744,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
                             if ((meta & META_VALID) && y >= (int)((bbox >> 8) & 255u) && y <= (int)(bbox >> 24)) {
                                 const int x0 = (int)(bbox & 255u), x1 = (int)((bbox >> 16) & 255u);
                                 if (meta & META_FULL) mask = (x1 * S + S >= 64 ? ~0ull : ((1ull << (x1 * S + S)) - 1ull)) & ~((1ull << (x0 * S)) - 1ull);
-                                else {
-                                    long long E[3], step[3];
-#pragma unroll
-                                    for (int e = 0; e < 3; ++e) {
-                                        step[e] = (long long)ps.B[e] * 256;
-                                        E[e] = ps.e0[e] + (long long)ps.A[e] * (y * 256) - step[e] * x0;
-                                    }
-                                    for (int x = x0; x <= x1; ++x) {
-#pragma unroll
-                                        for (int q = 0; q < S; ++q) {
-                                            long long any = 0;
-#pragma unroll
-                                            for (int e = 0; e < 3; ++e)
-                                                any |= S == 1 ? E[e] : E[e] + (long long)ps.A[e] * sample_y<S>(q) - (long long)ps.B[e] * sample_x<S>(q);
-                                            if (any >= 0) mask |= 1ull << (x * S + q);
-                                        }
-                                        E[0] -= step[0]; E[1] -= step[1]; E[2] -= step[2];
-                                    }
-                                }
+                                else mask = (meta & META_E32) ? cover_row_mask<S, int>(ps, y, x0, x1) : cover_row_mask<S, long long>(ps, y, x0, x1);
                             }
                         }
                         cov[cb][threadIdx.x >> 4][threadIdx.x & 15u] = mask;
