@@ -992,6 +992,42 @@ __device__ __forceinline__ void sort_store16(float2* sm, uint32_t n, uint32_t i0
         for (int m = 0; m < 16; ++m) if (i0 + m * s < n) sm[p0 + m * ps] = v[m];
     }
 }
+// Half-cleaner stages lj = top_lj .. 0 of the network on sm[0, n), four at a time: group g holds lj = 4g .. 4g+3.
+__device__ void shared_half_cleaners(float2* sm, uint32_t n, int top_lj) {
+    for (int g = top_lj >> 2; g >= 0; --g) {
+        const int top_q = min(3, top_lj - 4 * g);
+        const uint32_t s = 1u << (4 * g), ps = g == 0 ? 1u : s + (s >> 4);
+        const uint32_t count = ((n + 16u * s - 1u) / (16u * s)) * s;
+        for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) {
+            const uint32_t i0 = ((t >> (4 * g)) << (4 * g + 4)) + (t & (s - 1u));
+            if (i0 >= n) continue;
+            float2 v[16];
+            sort_load16(sm, n, i0, s, ps, v);
+            if (top_q >= 3) reg_stage<3>(v);
+            if (top_q >= 2) reg_stage<2>(v);
+            if (top_q >= 1) reg_stage<1>(v);
+            reg_stage<0>(v);
+            sort_store16(sm, n, i0, s, ps, v);
+        }
+        __syncthreads();
+    }
+}
+// One stage of the network directly on global memory (shapes larger than the shared-memory capacity): comparator distance
+// 2^lj, `flip` = first stage of a merge. Same comparators as block_sort_points.
+__device__ void global_sort_stage(float2* pts, uint32_t n, uint32_t lj, bool flip) {
+    const uint32_t blocks = (n + (2u << lj) - 1) >> (lj + 1);
+    const uint32_t count = blocks << lj;
+    for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) {
+        const uint32_t block = t >> lj, off = t & ((1u << lj) - 1u);
+        const uint32_t lo = (block << (lj + 1)) + off;
+        const uint32_t hi = flip ? (block << (lj + 1)) + (2u << lj) - 1u - off : lo + (1u << lj);
+        if (hi < n) {
+            const float2 a = pts[lo], b = pts[hi];
+            if (lex_less(b, a)) { pts[lo] = b; pts[hi] = a; }
+        }
+    }
+    __syncthreads();
+}
 __device__ void block_sort_points_shared(float2* sm, uint32_t n) {
     uint32_t log_n2 = 4;
     while ((1u << log_n2) < n) ++log_n2;
@@ -1020,23 +1056,7 @@ __device__ void block_sort_points_shared(float2* sm, uint32_t n) {
             }
             __syncthreads();
         }
-        for (int g = (int)(lk - 2) >> 2; g >= 0; --g) {   // half-cleaners lj = lk-2 .. 0, four at a time: group g holds lj = 4g .. 4g+3
-            const int top_q = min(3, (int)lk - 2 - 4 * g);
-            const uint32_t s = 1u << (4 * g), ps = g == 0 ? 1u : s + (s >> 4);
-            const uint32_t count = ((n + 16u * s - 1u) / (16u * s)) * s;
-            for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) {
-                const uint32_t i0 = ((t >> (4 * g)) << (4 * g + 4)) + (t & (s - 1u));
-                if (i0 >= n) continue;
-                float2 v[16];
-                sort_load16(sm, n, i0, s, ps, v);
-                if (top_q >= 3) reg_stage<3>(v);
-                if (top_q >= 2) reg_stage<2>(v);
-                if (top_q >= 1) reg_stage<1>(v);
-                reg_stage<0>(v);
-                sort_store16(sm, n, i0, s, ps, v);
-            }
-            __syncthreads();
-        }
+        shared_half_cleaners(sm, n, (int)lk - 2);
     }
 }
 
@@ -1052,7 +1072,34 @@ __global__ void __launch_bounds__(512) hull_sort_kernel(float2* __restrict__ pro
         block_sort_points_shared(hull_smem, n);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) proto[begin + i] = hull_smem[SORT_SLOT(i)];
     } else {
-        block_sort_points(proto + begin, n);
+        // Larger than shared memory: the same network, with every stage whose comparator distance is below the chunk size C
+        // done chunk by chunk in shared memory. Chunks are sorted first (merge levels up to C); each further level is its
+        // flip stage and its half-cleaners of distance >= C on global memory (L2 resident), then one shared-memory pass
+        // per chunk for the half-cleaners below C.
+        float2* const g = proto + begin;
+        const uint32_t log_c = 31u - (uint32_t)__clz((int)cap), C = 1u << log_c, n_chunks = (n + C - 1u) / C;
+        uint32_t log_n2 = log_c;
+        while ((1u << log_n2) < n) ++log_n2;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t len = min(C, n - c * C);
+            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) hull_smem[SORT_SLOT(i)] = g[c * C + i];
+            __syncthreads();
+            block_sort_points_shared(hull_smem, len);
+            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) g[c * C + i] = hull_smem[SORT_SLOT(i)];
+            __syncthreads();
+        }
+        for (uint32_t lk = log_c + 1u; lk <= log_n2; ++lk) {
+            global_sort_stage(g, n, lk - 1u, true);
+            for (uint32_t lj = lk - 2u; lj >= log_c; --lj) global_sort_stage(g, n, lj, false);
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                const uint32_t len = min(C, n - c * C);
+                for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) hull_smem[SORT_SLOT(i)] = g[c * C + i];
+                __syncthreads();
+                shared_half_cleaners(hull_smem, len, (int)log_c - 1);
+                for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) g[c * C + i] = hull_smem[SORT_SLOT(i)];
+                __syncthreads();
+            }
+        }
     }
 }
 
