@@ -160,6 +160,7 @@ struct cr_pass {
     std::vector<InstanceSet> instance_sets;
     uint32_t instance_total = 0;
     uint32_t clip_depth = 0, save_layer = 0, restore_layer = 0;
+    bool clear_color = false, clear_stencil = false;   // LoadOp::Clear of the attachments, executed at submit (fused into the tile kernel)
 };
 
 namespace {
@@ -641,12 +642,14 @@ int cr_pass_begin(cr_renderer* r, uint32_t clear_color, uint32_t clear_stencil, 
     *out = nullptr;
     if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
     CR_GUARD(r);
-    const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
-    if (clear_color) CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * 16, r->stream));
-    if (clear_stencil) CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
     cr_pass* p = new (std::nothrow) cr_pass();
     if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "out of host memory");
     p->renderer = r;
+    // Like a wgpu render pass, the clear belongs to the pass and happens when the pass executes (cr_pass_submit): the tile
+    // kernel starts cleared tiles from zero instead of loading them and writes every tile, so the attachments are neither
+    // memset nor read. A pass that is dropped without submit clears nothing.
+    p->clear_color = clear_color != 0;
+    p->clear_stencil = clear_stencil != 0;
     ++r->live_objects;
     *out = p;
     return CR_OK;
@@ -735,11 +738,19 @@ int cr_pass_render_batch(cr_pass* p, cr_shape_batch* b, const cr_draw_command* c
     return CR_OK;
 }
 
+// The pass's clear without a tile kernel (nothing to draw): plain memsets.
+static int clear_attachments(cr_pass* p) {
+    cr_renderer* r = p->renderer;
+    const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
+    if (p->clear_color) CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * 16, r->stream));
+    if (p->clear_stencil) CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
+    return CR_OK;
+}
 static int submit(cr_pass* p) {
     cr_renderer* r = p->renderer;
     cudaStream_t st = r->stream;
     const uint32_t n_cmds = (uint32_t)p->commands.size();
-    if (n_cmds == 0) return CR_OK;
+    if (n_cmds == 0) return clear_attachments(p);
     // ---- instance slots
     const float* transforms = nullptr;
     const float* colors = nullptr;
@@ -779,7 +790,7 @@ static int submit(cr_pass* p) {
     }
     cand_begin[n_cmds] = (uint32_t)total;
     const uint32_t n_cands = (uint32_t)total;
-    if (n_cands == 0) return CR_OK;
+    if (n_cands == 0) return clear_attachments(p);
     CR_TRY(r->cmd_cands.reserve(st, (size_t)(n_cmds + 1) * 4));
     CR_CUDA_TRY(cudaMemcpyAsync(r->cmd_cands.p, cand_begin.data(), (size_t)(n_cmds + 1) * 4, cudaMemcpyHostToDevice, st));
 
@@ -806,6 +817,8 @@ static int submit(cr_pass* p) {
         static const int env_run = getenv("CR_PIXEL_RUN_MAX") ? atoi(getenv("CR_PIXEL_RUN_MAX")) : -1;   // tuning knob for experiments
         tg.pixel_run_max = env_run >= 0 ? (uint32_t)env_run : 12u;
     }
+    tg.clear_color = p->clear_color ? 1u : 0u;
+    tg.clear_stencil = p->clear_stencil ? 1u : 0u;
     tg.shard_world = r->shard_world;
     tg.shard_rank = r->shard_rank;
     for (int i = 0; i < CR_MAX_PEERS; ++i) { tg.peer_color[i] = static_cast<float4*>(r->peer_color[i]); tg.peer_stencil[i] = static_cast<uint8_t*>(r->peer_stencil[i]); }
@@ -843,6 +856,8 @@ static int submit(cr_pass* p) {
         if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[3], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[4], st)); }
         CR_TRY(cr_raster_tiles(st, sc, tg, r->records.as<PrimRecord>(), r->tile_begin.as<uint32_t>(), sorted_cand, r->covered_dev.as<unsigned long long>()));
         if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }
+    } else {
+        CR_TRY(clear_attachments(p));
     }
     return CR_OK;
 }

@@ -537,7 +537,8 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
     __shared__ unsigned long long cov[2][CR_TILE][CR_TILE];   // row coverage masks (bit x * S + k) of the cover primitives of one sweep; double buffered: one barrier per sweep
     const uint32_t tile = blockIdx.x;
     const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];
-    if (begin == end) return;
+    const bool clears = tg.clear_color != 0u || tg.clear_stencil != 0u;
+    if (begin == end && (!clears || !cr_tile_owned(tg, (int)(tile % tg.tiles_x), (int)(tile / tg.tiles_x)))) return;   // nothing drawn here and nothing to clear (or not ours to clear)
     const int tile_px = (int)(tile % tg.tiles_x) * CR_TILE, tile_py = (int)(tile / tg.tiles_x) * CR_TILE;
     const int lx = threadIdx.x & (CR_TILE - 1), ly = threadIdx.x / CR_TILE;
     const int px = tile_px + lx, py = tile_py + ly;
@@ -547,15 +548,19 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? 5 : 3) raster_tile
     float4 col[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) { s[k] = 0; col[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
-    if (in_fb) {
-        if (S == 1) s[0] = tg.stencil[pix];
-        else {
-            const uint32_t packed = *reinterpret_cast<const uint32_t*>(tg.stencil + pix);   // 4 samples = 4 bytes, 4-byte aligned
+    if (in_fb) {   // LoadOp::Load reads the attachment, LoadOp::Clear starts from zero (and the tile is written in any case)
+        if (tg.clear_stencil == 0u) {
+            if (S == 1) s[0] = tg.stencil[pix];
+            else {
+                const uint32_t packed = *reinterpret_cast<const uint32_t*>(tg.stencil + pix);   // 4 samples = 4 bytes, 4-byte aligned
 #pragma unroll
-            for (int k = 0; k < S; ++k) s[k] = (packed >> (8 * k)) & 255u;
+                for (int k = 0; k < S; ++k) s[k] = (packed >> (8 * k)) & 255u;
+            }
         }
+        if (tg.clear_color == 0u) {
 #pragma unroll
-        for (int k = 0; k < S; ++k) col[k] = tg.color[pix + k];
+            for (int k = 0; k < S; ++k) col[k] = tg.color[pix + k];
+        }
     }
     const uint32_t W = tg.wmask, C = tg.cmask, M = W | C;
     uint32_t covered = 0;

@@ -62,6 +62,7 @@ struct RasterTarget {
     uint32_t wmask, cmask;        // winding_counter_mask / clip_nesting_counter_mask (src/renderer.rs:565-566)
     uint32_t blending, cull_mode;
     uint32_t pixel_run_max;       // runs of at most this many primitives execute in K3's pixel mode
+    uint32_t clear_color, clear_stencil;   // the pass clears the attachment: K3 starts from zero instead of loading, and writes EVERY tile
     // One render target spanning several GPUs (tile sharding): tile (tx, ty) is owned by rank (tx + ty) % world.
     // A rank bins and rasterises only the tiles it owns and K3 stores every finished tile into its own attachments AND,
     // over NVLink, into the peer-mapped attachments of the other ranks, so each rank ends up with the complete frame.
