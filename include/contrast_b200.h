@@ -209,7 +209,9 @@ int cr_shape_read_stroke_buffer(cr_shape* shape, void* dst, size_t capacity);
 /* ------------------------------------------------------------------------------------------------- render pass */
 
 /* wgpu begin_render_pass with LoadOp::Clear / LoadOp::Load (examples/showcase/main.rs:211-234): clear colour is
- * transparent black, clear stencil is 0. */
+ * transparent black, clear stencil is 0. As in wgpu the clear is part of the pass and executes with it at cr_pass_submit
+ * (the tile kernel starts cleared tiles from zero and writes every tile: no memset, no read of the old contents); a pass
+ * that is aborted clears nothing. */
 int cr_pass_begin(cr_renderer* renderer, uint32_t clear_color, uint32_t clear_stencil, cr_pass** out);
 /* Vertex buffer slot 0 (instance mat4: four vec4 that become the matrix COLUMNS, src/shaders.wgsl:13-27,
  * src/renderer.rs:462-466; 64 B each) and the instance colour slot (16 B each, src/renderer.rs:502-506).
@@ -259,7 +261,8 @@ int cr_renderer_get_attachments(cr_renderer* renderer, void** color_dev, void** 
  * and the tile kernel stores each finished tile into its own attachments and, with P2P stores over NVLink, into the
  * imported attachments of every other rank: after all ranks have submitted (and a barrier), each rank holds the
  * complete colour and stencil attachments. Alpha layers and cr_stats.covered_samples stay per-owner.
- * The caller orders the ranks: a barrier between cr_pass_begin (which clears) and cr_pass_submit, and one after
+ * The caller orders the ranks: a barrier before cr_pass_submit (no rank may still be reading or clearing the previous
+ * frame when another rank's tiles arrive), and one after
  * cr_pass_submit (contrast_renderer_b200/sharding.py does both with stream-ordered NCCL collectives).
  * cr_renderer_set_tile_sharding(r, 1, 0) returns to a single-GPU target and closes the imported handles. */
 #define CR_IPC_HANDLE_BYTES 64
