@@ -125,6 +125,12 @@ struct cr_renderer {
     bool timing = false;
     cudaEvent_t ev[9] = {};   // tess begin/end, bin begin/end, raster begin/end, hull begin / after sort / end
     bool ev_valid[3] = {false, false, false};
+    // Draw commands are recorded straight into a pinned, grow-only arena (one recording pass at a time; a second concurrent
+    // pass falls back to a heap vector), so that cr_pass_submit uploads them with a truly asynchronous copy.
+    DeviceCommand* cmd_arena = nullptr;
+    size_t cmd_arena_cap = 0;
+    bool cmd_arena_busy = false, cmd_copy_pending = false;
+    cudaEvent_t cmd_copy_done = nullptr;
     uint32_t shard_world = 1, shard_rank = 0;              // tile sharding of one target across GPUs
     void* peer_color[CR_MAX_PEERS] = {};                   // peer-mapped attachments of the other ranks, slot = rank - (rank > shard_rank)
     void* peer_stencil[CR_MAX_PEERS] = {};
@@ -155,7 +161,9 @@ struct InstanceSet {
 };
 struct cr_pass {
     cr_renderer* renderer;
-    std::vector<DeviceCommand> commands;
+    std::vector<DeviceCommand> commands;   // heap fallback; the usual home of the commands is the renderer's pinned arena
+    bool arena = false;
+    size_t n_arena = 0;
     std::vector<cr_shape_batch*> batches;
     std::vector<InstanceSet> instance_sets;
     uint32_t instance_total = 0;
@@ -422,6 +430,8 @@ static void renderer_free(cr_renderer* r) {
     cudaStreamSynchronize(st);
     for (auto& e : r->ev) if (e) cudaEventDestroy(e);
     if (r->pinned) cudaFreeHost(r->pinned);
+    if (r->cmd_arena) cudaFreeHost(r->cmd_arena);
+    if (r->cmd_copy_done) cudaEventDestroy(r->cmd_copy_done);
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
     delete r;
 }
@@ -650,6 +660,11 @@ int cr_pass_begin(cr_renderer* r, uint32_t clear_color, uint32_t clear_stencil, 
     // memset nor read. A pass that is dropped without submit clears nothing.
     p->clear_color = clear_color != 0;
     p->clear_stencil = clear_stencil != 0;
+    if (!r->cmd_arena_busy) {
+        if (r->cmd_copy_pending) { cudaEventSynchronize(r->cmd_copy_done); r->cmd_copy_pending = false; }   // the previous pass's upload has long finished
+        if (!r->cmd_copy_done && cudaEventCreateWithFlags(&r->cmd_copy_done, cudaEventDisableTiming) != cudaSuccess) r->cmd_copy_done = nullptr;
+        if (r->cmd_copy_done) { p->arena = true; r->cmd_arena_busy = true; }
+    }
     ++r->live_objects;
     *out = p;
     return CR_OK;
@@ -721,7 +736,18 @@ static int record(cr_pass* p, cr_shape_batch* b, uint32_t shape, uint32_t instan
         c.vbase[cat] = cb[(cat < 7 ? cat : (int)CNT_PROTO) * stride + shape];
         if (cat < 3) c.ibase[cat] = cb[(CNT_LINE_IDX + cat) * stride + shape];
     }
-    p->commands.push_back(c);
+    if (!p->arena) { p->commands.push_back(c); return CR_OK; }
+    cr_renderer* r = p->renderer;
+    if (p->n_arena == r->cmd_arena_cap) {
+        const size_t cap = std::max<size_t>(4096, 2 * r->cmd_arena_cap);
+        DeviceCommand* grown = nullptr;
+        CR_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&grown), cap * sizeof(DeviceCommand), cudaHostAllocDefault));
+        if (p->n_arena) memcpy(grown, r->cmd_arena, p->n_arena * sizeof(DeviceCommand));
+        if (r->cmd_arena) cudaFreeHost(r->cmd_arena);
+        r->cmd_arena = grown;
+        r->cmd_arena_cap = cap;
+    }
+    r->cmd_arena[p->n_arena++] = c;
     return CR_OK;
 }
 
@@ -732,7 +758,7 @@ int cr_shape_render(cr_pass* p, cr_shape* s, uint32_t instance_begin, uint32_t i
 }
 int cr_pass_render_batch(cr_pass* p, cr_shape_batch* b, const cr_draw_command* commands, size_t count) {
     if (!p || !b || (count && !commands)) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
-    p->commands.reserve(p->commands.size() + count);
+    if (!p->arena) p->commands.reserve(p->commands.size() + count);
     for (size_t i = 0; i < count; ++i)
         CR_TRY(record(p, b, commands[i].shape_index, commands[i].instance_begin, commands[i].instance_end, commands[i].render_operation));
     return CR_OK;
@@ -749,7 +775,8 @@ static int clear_attachments(cr_pass* p) {
 static int submit(cr_pass* p) {
     cr_renderer* r = p->renderer;
     cudaStream_t st = r->stream;
-    const uint32_t n_cmds = (uint32_t)p->commands.size();
+    const DeviceCommand* const cmds = p->arena ? r->cmd_arena : p->commands.data();
+    const uint32_t n_cmds = (uint32_t)(p->arena ? p->n_arena : p->commands.size());
     if (n_cmds == 0) return clear_attachments(p);
     // ---- instance slots
     const float* transforms = nullptr;
@@ -779,13 +806,14 @@ static int submit(cr_pass* p) {
     for (size_t i = 0; i < p->batches.size(); ++i)
         CR_CUDA_TRY(cudaMemcpyAsync(r->batches_dev.as<DeviceBatch>() + i, p->batches[i]->desc_dev.p, sizeof(DeviceBatch), cudaMemcpyDeviceToDevice, st));
     CR_TRY(r->cmds_dev.reserve(st, (size_t)n_cmds * sizeof(DeviceCommand)));
-    CR_CUDA_TRY(cudaMemcpyAsync(r->cmds_dev.p, p->commands.data(), (size_t)n_cmds * sizeof(DeviceCommand), cudaMemcpyHostToDevice, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(r->cmds_dev.p, cmds, (size_t)n_cmds * sizeof(DeviceCommand), cudaMemcpyHostToDevice, st));
+    if (p->arena) { CR_CUDA_TRY(cudaEventRecord(r->cmd_copy_done, st)); r->cmd_copy_pending = true; }
     // candidates per command are known on the host (slice tables are mirrored), so the candidate scan needs no device pass
     std::vector<uint32_t> cand_begin(n_cmds + 1);
     uint64_t total = 0;
     for (uint32_t c = 0; c < n_cmds; ++c) {
         cand_begin[c] = (uint32_t)total;
-        total += p->commands[c].cat_end[7];
+        total += cmds[c].cat_end[7];
         if (total >= 0xFFFFFFFFull) return fail(CR_ERR_INVALID_ARGUMENT, "more than 2^32 candidate primitives in one pass; submit in several passes");
     }
     cand_begin[n_cmds] = (uint32_t)total;
@@ -871,6 +899,7 @@ int cr_pass_submit(cr_pass* p) {
         st = guard.ok ? submit(p) : fail(CR_ERR_CUDA, "cannot select CUDA device");
     }
     cr_renderer* r = p->renderer;
+    if (p->arena) r->cmd_arena_busy = false;
     delete p;
     renderer_release_child(r);
     return st;
@@ -879,6 +908,7 @@ int cr_pass_submit(cr_pass* p) {
 void cr_pass_abort(cr_pass* p) {
     if (!p) return;
     cr_renderer* r = p->renderer;
+    if (p->arena) r->cmd_arena_busy = false;
     delete p;
     renderer_release_child(r);
 }

@@ -7,6 +7,8 @@ sc = scenes.tiger_like(n, extent=ext, instance_px=(60.0, 260.0))
 rnd = R.Renderer(R.Configuration(alpha_layer_count=2)); rnd.resize_internal_buffers(sc.width, sc.height); rnd.enable_timing(True)
 batch = R.ShapeBatch(rnd, [], sc.paths, sc.shape_path_begin)
 for it in range(3):
-    rp = rnd.begin_render_pass(); rp.set_instances(sc.transforms, sc.colors); sc.record(rp, batch); rp.submit()
+    import time
+    rp = rnd.begin_render_pass(); rp.set_instances(sc.transforms, sc.colors); sc.record(rp, batch)
+    rnd.synchronize(); t0 = time.perf_counter(); rp.submit(); t1 = time.perf_counter(); rnd.synchronize(); t2 = time.perf_counter()
     st = rnd.stats()
-    print(f"tiger_like({n}) {ext}: bin {st.last_bin_ms:.3f} ms raster {st.last_raster_ms:.3f} ms pairs {st.tile_pairs} prims {st.primitives} covered {st.covered_samples}")
+    print(f"tiger_like({n}) {ext}: submit call {1e3*(t1-t0):.3f} ms, until done {1e3*(t2-t0):.3f} ms (host clock); bin {st.last_bin_ms:.3f} ms raster {st.last_raster_ms:.3f} ms pairs {st.tile_pairs} prims {st.primitives} covered {st.covered_samples}")
