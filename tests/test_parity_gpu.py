@@ -578,6 +578,41 @@ def test_load_op_keeps_previous_pass(cr, oracle):
     rnd.close()
 
 
+def test_clear_belongs_to_the_pass(cr, oracle):
+    """LoadOp::Clear executes with the pass (wgpu semantics): a pass dropped without submit clears nothing; an empty pass that
+    is submitted clears; a pass with draws clears every tile it does not touch as well (the tile kernel writes them)."""
+    scene = scenes.mixed_fills(12, extent=(200, 120), size=(10.0, 40.0), seed=3)
+    cmds = scenes.stencil_cover_commands(scene.n_shapes)
+    rnd = cr.Renderer()
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+
+    def draw(commands, **clear):
+        rp = rnd.begin_render_pass(**clear)
+        rp.set_instances(scene.transforms(), scene.colors)
+        rp.render_batch(batch, commands)
+        rp.submit()
+        return rnd.read_color(), rnd.read_stencil()
+
+    full_color, full_stencil = draw(cmds)
+    assert np.abs(full_color).sum() > 0
+    rp = rnd.begin_render_pass()          # clear requested ...
+    rp.close()                            # ... but the pass is dropped: nothing happens
+    assert np.array_equal(rnd.read_color().view(np.uint32), full_color.view(np.uint32))
+    first_color, first_stencil = draw(cmds[:2])            # one shape only, with clear: the other shapes' tiles are cleared too
+    rp = rnd.begin_render_pass()
+    rp.submit()                                            # empty pass, submitted: clears
+    assert not rnd.read_color().any() and not rnd.read_stencil().any()
+    again_color, again_stencil = draw(cmds[:2])
+    assert np.array_equal(again_color.view(np.uint32), first_color.view(np.uint32)) and np.array_equal(again_stencil, first_stencil)
+    refs = oracle_shapes(oracle, scene)
+    ref_color, ref_stencil, _, _ = oracle.render(rnd.config.to_c(), scene.width, scene.height, refs, [(0, 0, 1, 0, 0, 0, 0), (0, 0, 1, 3, 0, 0, 0)],
+                                                 scene.transforms(), scene.colors)
+    assert np.array_equal(first_color.view(np.uint32), ref_color.view(np.uint32)) and np.array_equal(first_stencil, ref_stencil)
+    batch.close()
+    rnd.close()
+
+
 # -------------------------------------------------------------------- size-independent properties at full size
 def test_full_size_config3_text_matches_oracle(cr, oracle):
     """BASELINE config 3 at full size through the text front-end (the benchmark workload): 100k OpenSans glyph instances,
