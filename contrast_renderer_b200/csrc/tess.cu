@@ -1104,8 +1104,8 @@ __global__ void __launch_bounds__(512) hull_sort_kernel(float2* __restrict__ pro
 }
 
 // ---- the two monotone chains
-// One warp per chain (the stack machine is strictly sequential, see hull_chain: all lanes execute it redundantly); the
-// lanes stream the sorted points into a double-buffered shared-memory window ahead of it. The three top stack entries (c, a, b;
+// One warp per chain, executed by lane 0 (the stack machine is strictly sequential, see hull_chain); the other lanes
+// stream the sorted points into a double-buffered shared-memory window ahead of it. The three top stack entries (c, a, b;
 // b on top) and the lines through (a, b) and (c, a) live in registers, and every point is tested against BOTH lines at
 // once, together with the two lines a push would create. The common outcomes — "keep b" and "pop b once" — then cost one
 // dependent test + select with no memory access on the critical path; only a point that pops two or more entries reloads
@@ -1169,7 +1169,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
     float2 a = make_float2(0.f, 0.f), b = a, c = a;
     HullLine lab = {0.f, 0.f, 0.f}, lca = lab;
     bool overflow = false;
-    {
+    if (lane == 0) {
         const uint32_t w0 = (uint32_t)__cvta_generic_to_shared(&window[warp][0][0]);
         a = lds_f2(w0); b = lds_f2(w0 + 8);
         sts_f2(stack0, a); sts_f2(stack0 + 8, b);
@@ -1179,8 +1179,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
     for (uint32_t w = 0; w < n_windows; ++w) {
         if (w + 1 < n_windows) fetch(w + 1);
         // The stack grows by at most one entry per point: one capacity check per window keeps it out of the loop.
-        if (!overflow && top + CHAIN_WINDOW * 8u > limit) overflow = true;
-        if (!overflow) {   // every lane runs the machine redundantly on the same data: uniform control flow (3 % faster than lane 0 alone)
+        if (lane == 0 && !overflow && top + CHAIN_WINDOW * 8u > limit) overflow = true;
+        if (lane == 0 && !overflow) {
             uint32_t src = (uint32_t)__cvta_generic_to_shared(&window[warp][w & 1u][0]);
             const uint32_t k0 = w == 0 ? 2u : 0u, k1 = min((uint32_t)CHAIN_WINDOW, n - w * CHAIN_WINDOW);
             src += k0 * 8u;
