@@ -23,11 +23,12 @@ struct TessOutput {
     uint32_t* idx[3];    // line, joint, solid: (shape-relative vertex index << 1) | strip parity, CR_RESTART between strips
 };
 
-int cr_tess_count(cudaStream_t stream, const DevicePaths& paths, uint32_t n_groups, uint32_t* counts, uint32_t* err_flag);
+// has_cubics: the batch holds integral or rational cubic segments (false selects the kernels without the cubic fill builder)
+int cr_tess_count(cudaStream_t stream, const DevicePaths& paths, uint32_t n_groups, uint32_t* counts, uint32_t* err_flag, bool has_cubics = true);
 // Also stores max over shapes of the proto-hull point count into *max_proto (device word, zeroed by the caller).
 int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t n_paths, const uint32_t* shape_path_begin, uint32_t n_shapes,
                          uint32_t* cat_begin, uint32_t* max_proto);
 int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* offsets, const uint32_t* shape_path_begin, uint32_t n_shapes,
-                 const TessOutput& out, uint32_t* err_flag);
+                 const TessOutput& out, uint32_t* err_flag, bool has_cubics = true);
 int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
                  float2* hull_out, uint32_t* hull_count, uint32_t max_points, cudaEvent_t after_sort = nullptr);   // after_sort: optional event recorded between the sort and the chain kernel
