@@ -23,6 +23,8 @@ from . import _abi
 from .path import DynamicStrokeOptions, Path, PathSoA, dynamic_stroke_options_array
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcontrast_b200.so")
+if os.environ.get("CONTRAST_B200_LIB"):   # experiments only: an alternative build of the same library
+    _LIB_PATH = os.environ["CONTRAST_B200_LIB"]
 _lib = None
 
 
