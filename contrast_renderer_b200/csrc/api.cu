@@ -767,13 +767,51 @@ int cr_pass_render_batch(cr_pass* p, cr_shape_batch* b, const cr_draw_command* c
     return CR_OK;
 }
 
-// The pass's clear without a tile kernel (nothing to draw): plain memsets.
+// The pass's view of the attachments and of the renderer's configuration.
+static RasterTarget make_target(const cr_pass* p) {
+    const cr_renderer* r = p->renderer;
+    RasterTarget tg{};
+    tg.color = r->color.as<float4>();
+    tg.stencil = r->stencil.as<uint8_t>();
+    tg.alpha_layers = r->alpha_layers.as<float>();
+    tg.width = r->width; tg.height = r->height; tg.tiles_x = r->tiles_x; tg.tiles_y = r->tiles_y;
+    tg.samples = r->config.msaa_sample_count;
+    tg.sample_lo = tg.samples == 4 ? 32 : 128;
+    tg.sample_hi = tg.samples == 4 ? 224 : 128;
+    tg.wmask = (1u << r->config.winding_counter_bits) - 1u;
+    tg.cmask = ((1u << r->config.clip_nesting_counter_bits) - 1u) << r->config.winding_counter_bits;
+    tg.blending = r->config.blending;
+    tg.cull_mode = r->config.cull_mode;
+    {
+        static const int env_run = getenv("CR_PIXEL_RUN_MAX") ? atoi(getenv("CR_PIXEL_RUN_MAX")) : -1;   // tuning knob for experiments
+        tg.pixel_run_max = env_run >= 0 ? (uint32_t)env_run : 12u;
+    }
+    tg.clear_color = p->clear_color ? 1u : 0u;
+    tg.clear_stencil = p->clear_stencil ? 1u : 0u;
+    tg.shard_world = r->shard_world;
+    tg.shard_rank = r->shard_rank;
+    for (int i = 0; i < CR_MAX_PEERS; ++i) { tg.peer_color[i] = static_cast<float4*>(r->peer_color[i]); tg.peer_stencil[i] = static_cast<uint8_t*>(r->peer_stencil[i]); }
+    return tg;
+}
+
+// The pass's clear when there is nothing to rasterise. Single GPU: plain memsets. Tile-sharded target: a rank may only touch
+// the tiles it owns (the others arrive from their owners, possibly before this call), so the tile kernel runs on an empty
+// tile table: every owned tile is cleared in all ranks' attachments.
 static int clear_attachments(cr_pass* p) {
     cr_renderer* r = p->renderer;
-    const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
-    if (p->clear_color) CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * 16, r->stream));
-    if (p->clear_stencil) CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
-    return CR_OK;
+    if (!p->clear_color && !p->clear_stencil) return CR_OK;
+    if (r->shard_world <= 1) {
+        const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
+        if (p->clear_color) CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * 16, r->stream));
+        if (p->clear_stencil) CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
+        return CR_OK;
+    }
+    const uint32_t n_tiles = r->tiles_x * r->tiles_y;
+    CR_TRY(r->tile_begin.reserve(r->stream, (size_t)(n_tiles + 1) * 4));
+    CR_CUDA_TRY(cudaMemsetAsync(r->tile_begin.p, 0, (size_t)(n_tiles + 1) * 4, r->stream));
+    CR_CUDA_TRY(cudaMemsetAsync(r->covered_dev.p, 0, 8, r->stream));
+    RasterScene none{};
+    return cr_raster_tiles(r->stream, none, make_target(p), nullptr, r->tile_begin.as<uint32_t>(), nullptr, r->covered_dev.as<unsigned long long>());
 }
 static int submit(cr_pass* p) {
     cr_renderer* r = p->renderer;
@@ -832,27 +870,7 @@ static int submit(cr_pass* p) {
     sc.n_commands = n_cmds;
     sc.transforms = transforms;
     sc.colors = colors;
-    RasterTarget tg{};
-    tg.color = r->color.as<float4>();
-    tg.stencil = r->stencil.as<uint8_t>();
-    tg.alpha_layers = r->alpha_layers.as<float>();
-    tg.width = r->width; tg.height = r->height; tg.tiles_x = r->tiles_x; tg.tiles_y = r->tiles_y;
-    tg.samples = r->config.msaa_sample_count;
-    tg.sample_lo = tg.samples == 4 ? 32 : 128;
-    tg.sample_hi = tg.samples == 4 ? 224 : 128;
-    tg.wmask = (1u << r->config.winding_counter_bits) - 1u;
-    tg.cmask = ((1u << r->config.clip_nesting_counter_bits) - 1u) << r->config.winding_counter_bits;
-    tg.blending = r->config.blending;
-    tg.cull_mode = r->config.cull_mode;
-    {
-        static const int env_run = getenv("CR_PIXEL_RUN_MAX") ? atoi(getenv("CR_PIXEL_RUN_MAX")) : -1;   // tuning knob for experiments
-        tg.pixel_run_max = env_run >= 0 ? (uint32_t)env_run : 12u;
-    }
-    tg.clear_color = p->clear_color ? 1u : 0u;
-    tg.clear_stencil = p->clear_stencil ? 1u : 0u;
-    tg.shard_world = r->shard_world;
-    tg.shard_rank = r->shard_rank;
-    for (int i = 0; i < CR_MAX_PEERS; ++i) { tg.peer_color[i] = static_cast<float4*>(r->peer_color[i]); tg.peer_stencil[i] = static_cast<uint8_t*>(r->peer_stencil[i]); }
+    const RasterTarget tg = make_target(p);
 
     // ---- bin: count, scan, emit, sort by tile (stable => draw order survives inside every tile)
     if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[2], st));

@@ -25,6 +25,7 @@ def main() -> int:
     config = R.Configuration(device=local, alpha_layer_count=2)
 
     kernel_ms = {}
+    cleared = [False]
 
     def render(sharded: bool, repeats: int = 1):
         rnd = R.Renderer(config)
@@ -58,6 +59,11 @@ def main() -> int:
         frame = (rnd.read_color(), rnd.read_stencil(), int(st.covered_samples), int(st.tile_pairs))
         kernel_ms[sharded] = (round(float(st.last_bin_ms), 3), round(float(st.last_raster_ms), 3))
         if sharded:
+            # an empty pass with LoadOp::Clear: every rank may only clear the tiles it owns, in all ranks' attachments
+            rp = target.begin_render_pass()
+            target.submit(rp)
+            rnd.synchronize()
+            cleared[0] = bool(not rnd.read_color().any() and not rnd.read_stencil().any())
             target.close()
         batch.close()
         rnd.close()
@@ -66,14 +72,14 @@ def main() -> int:
     (color1, stencil1, covered1, pairs1), ms_single = render(False, 3)
     (colorN, stencilN, coveredN, pairsN), ms_sharded = render(True, 3)
     same = bool(np.array_equal(color1.view(np.uint32), colorN.view(np.uint32)) and np.array_equal(stencil1, stencilN))
-    stats = torch.tensor([coveredN, pairsN, int(same)], dtype=torch.int64, device=f"cuda:{local}")
+    stats = torch.tensor([coveredN, pairsN, int(same and cleared[0])], dtype=torch.int64, device=f"cuda:{local}")
     total = stats.clone()
     dist.all_reduce(total)
     t = torch.tensor([ms_sharded], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = int(total[2].item()) == world and int(total[0].item()) == covered1 and int(total[1].item()) == pairs1
     if rank == 0:
-        print(json.dumps({"check": "tile_sharded_target", "n_gpus": world, "identical_on_every_rank": int(total[2].item()) == world,
+        print(json.dumps({"check": "tile_sharded_target", "n_gpus": world, "identical_and_empty_pass_cleared_on_every_rank": int(total[2].item()) == world,
                           "covered_samples_single": covered1, "covered_samples_sum_over_ranks": int(total[0].item()),
                           "tile_pairs_single": pairs1, "tile_pairs_sum_over_ranks": int(total[1].item()),
                           "submit_ms_single_gpu": round(ms_single, 3), "submit_ms_sharded_max_over_ranks": round(float(t.item()), 3),

@@ -696,4 +696,4 @@ def test_tile_sharded_target_matches_single_gpu():
     lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
     assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
     result = json.loads(lines[-1])
-    assert result["ok"] and result["identical_on_every_rank"] and result["n_gpus"] == n
+    assert result["ok"] and result["identical_and_empty_pass_cleared_on_every_rank"] and result["n_gpus"] == n
