@@ -29,6 +29,9 @@ namespace {
 #ifndef K3_MIN_BLOCKS
 #define K3_MIN_BLOCKS 6   // resident K3 CTAs per SM asked of the compiler (40 registers per thread): 6 measured best of 4..8 on configs 3, 4 and 5
 #endif
+#ifndef K3_MIN_BLOCKS_MSAA
+#define K3_MIN_BLOCKS_MSAA 3
+#endif
 #define PIXEL_RUN_MAX 12u     // runs of at most this many primitives execute in pixel mode (see K3)
 #define BIG_TILE_BOX 8        // candidates touching more tiles than this are binned by the whole warp
 
@@ -532,7 +535,7 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
 __device__ __forceinline__ uint32_t run_kind(uint32_t pipe) { return pipe <= P_STROKE_JOINT ? 0u : (pipe <= P_FILL_RC ? 1u : 2u); }
 
 template <int S>
-__global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : 3) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
+__global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3_MIN_BLOCKS_MSAA) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
                                                                                          const uint32_t* __restrict__ tile_begin,
                                                                                          const uint32_t* __restrict__ pair_cand,
                                                                                          unsigned long long* __restrict__ covered_out) {

@@ -4,7 +4,8 @@ from contrast_renderer_b200 import renderer as R, scenes
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 ext = (3840, 2160) if len(sys.argv) > 2 and sys.argv[2] == "4k" else (1920, 1080)
 sc = scenes.tiger_like(n, extent=ext, instance_px=(60.0, 260.0))
-rnd = R.Renderer(R.Configuration(alpha_layer_count=2)); rnd.resize_internal_buffers(sc.width, sc.height); rnd.enable_timing(True)
+msaa = 4 if "msaa4" in sys.argv else 1
+rnd = R.Renderer(R.Configuration(alpha_layer_count=2, msaa_sample_count=msaa)); rnd.resize_internal_buffers(sc.width, sc.height); rnd.enable_timing(True)
 batch = R.ShapeBatch(rnd, [], sc.paths, sc.shape_path_begin)
 for it in range(3):
     import time
