@@ -17,6 +17,12 @@
 //   * stroke stencil (src/renderer.rs:571-576): passes only while the winding bits are still equal to the reference
 //     (zero), then sets them to one => the run's net effect is "any primitive covers".
 // Cover operations (colour, clip, alpha contexts) are order dependent and run one thread per pixel.
+// Runs of at most PIXEL_RUN_MAX primitives (the usual hull cover, small fans) skip the shared accumulator altogether: every
+// thread walks the run's primitives for its own pixel (no barrier, all threads busy). Edge functions are evaluated in 32-bit
+// integers whenever every value over the tile fits (exact), else in 64-bit. The pass's LoadOp::Clear is fused: cleared tiles
+// start from zero instead of being loaded and every tile is written (empty ones too), so the target is neither memset nor
+// read. With a tile-sharded target (several GPUs, one frame) a CTA only processes tiles its rank owns and stores the
+// finished tile into every rank's attachments (peer-mapped, P2P over NVLink).
 //
 // Rasterisation contract: see the header comment of oracle/raster.hpp (written independently, same rules).
 #include "device_common.cuh"
