@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_ke
         else if ((x.tx1 - x.tx0 + 1) * (x.ty1 - x.ty0 + 1) <= BIG_TILE_BOX) count = walk_tiles_small<false>(rec.X, rec.Y, x, tg, cand, 0, nullptr, nullptr);
         else { rec.meta |= META_BIG; big[1 + atomicAdd(big, 1u)] = cand; }   // counted by bin_big_kernel<false>
     }
-    store_record(records + cand, rec);
+    if (rec.meta & META_VALID) store_record(records + cand, rec);   // nobody reads the record of a candidate without tiles (more than half of them: restarts, degenerate and culled triangles)
     cand_tiles[cand] = count;
 }
 
