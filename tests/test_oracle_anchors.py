@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from contrast_renderer_b200 import _abi, scenes
-from contrast_renderer_b200.path import (Cap, CurveApproximation, DynamicStrokeOptions, Join, Path, PathSoA, RationalQuadraticCurveSegment,
+from contrast_renderer_b200.path import (Cap, CurveApproximation, DashInterval, DynamicStrokeOptions, Join, Path, PathSoA, RationalQuadraticCurveSegment,
                                          StrokeOptions)
 from contrast_renderer_b200.renderer import Configuration, orthographic_transform
 
@@ -292,6 +292,108 @@ def test_stencil_equals_winding_number(oracle, rational, mirror):
             assert np.all(((got != 0) == (want != 0))[far]), f"shape {s}: non-zero coverage"
         compared += int(far.sum())
     assert compared > 100000 and exact_shapes >= 1
+
+
+def _distance_to_polyline(poly: np.ndarray, width: int, height: int, ppu: float) -> np.ndarray:
+    """Distance (model units) from every pixel centre to an open polyline given in model units; the scene is mapped y-down."""
+    ys, xs = np.mgrid[0:height, 0:width]
+    c = np.stack([(xs + 0.5) / ppu, (ys + 0.5) / ppu], -1).astype(np.float64)
+    best = np.full((height, width), np.inf)
+    for a, b in zip(poly[:-1], poly[1:]):
+        ab = b - a
+        t = np.clip(((c - a) @ ab) / (ab @ ab), 0.0, 1.0)
+        best = np.minimum(best, np.linalg.norm(c - (a + t[..., None] * ab), axis=-1))
+    return best
+
+
+def _stroke_coverage(oracle, path, dynamic, width_px, height_px, ppu):
+    from contrast_renderer_b200.renderer import orthographic_transform
+    soa = PathSoA.from_paths([path])
+    shape = oracle.shape_from_paths([dynamic], soa)
+    m = orthographic_transform(width_px / ppu, height_px / ppu).reshape(1, 16)
+    _, stencil, _, _ = oracle.render(Configuration().to_c(), width_px, height_px, [shape], [(0, 0, 1, 0, 0, 0, 0)], m, None)
+    return stencil[..., 0] != 0
+
+
+@pytest.mark.parametrize("closed", [False, True], ids=["open_round_caps", "closed"])
+def test_round_stroke_is_the_offset_region(oracle, closed):
+    """Strokes end to end (rows a10-a15, R1, R8): with round joins and round caps the stroked region of a polyline is exactly
+    the set of points within width / 2 of it (Minkowski sum with a disc) - an independent ground truth for offset vertices,
+    join wedges, cap geometry, the `joint` / `cap` fragment predicates (src/shaders.wgsl:165-300) and the stroke stencil
+    state. Pixels whose centre is closer than 0.02 px to the region's boundary are not compared."""
+    ppu, w, h, width = 20.0, 240, 180, 0.9
+    pts = np.array([[1.5, 1.5], [6.0, 2.0], [3.0, 5.0], [9.5, 4.0], [8.0, 7.5], [2.0, 7.0]])
+    path = Path(pts[0], StrokeOptions(width=width, offset=0.0, miter_clip=1.0, closed=closed))
+    for q in pts[1:]:
+        path.push_line(q)
+    covered = _stroke_coverage(oracle, path, DynamicStrokeOptions.Solid(Join.Round, Cap.Round, Cap.Round), w, h, ppu)
+    poly = np.vstack([pts, pts[:1]]) if closed else pts
+    dist = _distance_to_polyline(poly, w, h, ppu)
+    want = dist <= width / 2
+    decided = np.abs(dist - width / 2) > 0.02 / ppu
+    assert want.sum() > 5000
+    wrong = (covered != want) & decided
+    assert not wrong.any(), f"{int(wrong.sum())} pixels differ from the offset region, e.g. {np.argwhere(wrong)[:4].tolist()}"
+
+
+def test_stroked_circle_is_an_annulus(oracle):
+    """Curved strokes (curve.rs uniform tangent angle + emit_curve_stroke!, src/stroke.rs:134-168): the closed stroke of a
+    circle built from four rational quadratics (src/path.rs:811-813) is the annulus |r - R| <= width / 2. The curve is
+    sampled every 0.1 rad, so the strip deviates from the circle by at most R (1 - cos 0.05) = 0.004 units = 0.08 px here:
+    pixels closer than 0.15 px to either rim are not compared."""
+    ppu, w, h, width, radius = 20.0, 200, 200, 0.8, 3.0
+    circle = Path.from_circle([5.0, 5.0], radius, StrokeOptions(width=width, offset=0.0, miter_clip=1.0, closed=True,
+                                                               curve_approximation=CurveApproximation.UniformTangentAngle(0.1)))
+    covered = _stroke_coverage(oracle, circle, DynamicStrokeOptions.Solid(Join.Round, Cap.Butt, Cap.Butt), w, h, ppu)
+    ys, xs = np.mgrid[0:h, 0:w]
+    r = np.hypot((xs + 0.5) / ppu - 5.0, (ys + 0.5) / ppu - 5.0)
+    want = np.abs(r - radius) <= width / 2
+    decided = np.abs(np.abs(r - radius) - width / 2) > 0.15 / ppu
+    wrong = (covered != want) & decided
+    assert want.sum() > 5500 and not wrong.any(), f"{int(wrong.sum())} pixels differ from the annulus, e.g. {np.argwhere(wrong)[:4].tolist()}"
+
+
+def test_miter_stroke_of_a_square_is_a_frame(oracle):
+    """Miter joins (src/stroke.rs:53-121): the closed stroke of an axis-aligned square is the outer square minus
+    the inner square, corners included, when miter_clip admits the full tip (distance w / sqrt 2 <= miter_clip * w)."""
+    ppu, w, h, width = 20.0, 200, 200, 1.0
+    path = Path([2.5, 2.5], StrokeOptions(width=width, offset=0.0, miter_clip=1.0, closed=True))
+    for q in ([7.5, 2.5], [7.5, 7.5], [2.5, 7.5]):
+        path.push_line(q)
+    covered = _stroke_coverage(oracle, path, DynamicStrokeOptions.Solid(Join.Miter, Cap.Butt, Cap.Butt), w, h, ppu)
+    ys, xs = np.mgrid[0:h, 0:w]
+    x, y = (xs + 0.5) / ppu, (ys + 0.5) / ppu
+    cheb = np.maximum(np.abs(x - 5.0), np.abs(y - 5.0))
+    want = (cheb <= 2.5 + width / 2) & (cheb >= 2.5 - width / 2)
+    decided = (np.abs(cheb - (2.5 + width / 2)) > 0.02 / ppu) & (np.abs(cheb - (2.5 - width / 2)) > 0.02 / ppu)
+    wrong = (covered != want) & decided
+    assert want.sum() > 7000 and not wrong.any(), f"{int(wrong.sum())} pixels differ from the frame, e.g. {np.argwhere(wrong)[:4].tolist()}"
+
+
+def test_dashed_butt_stroke_of_a_line(oracle):
+    """Dashes (src/shaders.wgsl:205-231, descriptor packing src/renderer.rs:29-60): along a straight stroke the arc length in
+    units of the stroke width, minus the phase, modulo the pattern length selects dash or gap; with Butt caps a dash is an
+    exact rectangle. Pattern [gap 1..1.5], [gap 3..4] (pattern length 4 widths), phase 0.25. A dashed stroke has no end-cap
+    test (src/shaders.wgsl:276-278 returns before it), so the pattern simply continues over the half-width cap extensions of
+    the strip at both ends (src/stroke.rs:270-293,443-462)."""
+    ppu, w, h, width = 20.0, 320, 80, 0.5
+    x0, x1, yc = 1.0, 15.0, 2.0
+    path = Path([x0, yc], StrokeOptions(width=width, offset=0.0, miter_clip=1.0, closed=False))
+    path.push_line([x1, yc])
+    dyn = DynamicStrokeOptions.Dashed(Join.Bevel, [DashInterval(1.0, 1.5, Cap.Butt, Cap.Butt), DashInterval(3.0, 4.0, Cap.Butt, Cap.Butt)], 0.25)
+    covered = _stroke_coverage(oracle, path, dyn, w, h, ppu)
+    ys, xs = np.mgrid[0:h, 0:w]
+    x, y = (xs + 0.5) / ppu, (ys + 0.5) / ppu
+    pos = np.mod((x - x0) / width - 0.25, 4.0)
+    in_gap = ((pos > 1.0) & (pos < 1.5)) | ((pos > 3.0) & (pos < 4.0))
+    lo, hi = x0 - width / 2, x1 + width / 2
+    want = (np.abs(y - yc) <= width / 2) & (x >= lo) & (x <= hi) & ~in_gap
+    edges = np.array([0.0, 1.0, 1.5, 3.0, 4.0])
+    near_edge = np.min(np.abs(pos[..., None] - edges), -1) < 0.03 / (ppu * width)
+    decided = (np.abs(np.abs(y - yc) - width / 2) > 0.02 / ppu) & (np.abs(x - lo) > 0.02 / ppu) & (np.abs(x - hi) > 0.02 / ppu) & ~near_edge
+    wrong = (covered != want) & decided
+    assert want.sum() > 1500 and (~want & (np.abs(y - yc) <= width / 2) & (x > x0) & (x < x1)).sum() > 500
+    assert not wrong.any(), f"{int(wrong.sum())} pixels differ from the dash pattern, e.g. {np.argwhere(wrong)[:4].tolist()}"
 
 
 def test_color_cover_leaves_no_winding_residue(oracle):
