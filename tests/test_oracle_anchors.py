@@ -410,6 +410,39 @@ def test_color_cover_leaves_no_winding_residue(oracle):
 
 
 # ------------------------------------------------------------------------------------------- convex_hull.rs
+def test_clip_is_an_intersection(oracle):
+    """Nested clipping (src/renderer.rs:253-266,692-754): Stencil + Clip to a circle, then Stencil + Color of a rectangle at
+    clip depth 1, then Stencil + UnClip: exactly the pixels inside BOTH shapes are coloured (geometric ground truth), a second
+    nested clip intersects once more, and all stencil bits are back to zero at the end."""
+    ppu, w, h = 20.0, 240, 200
+    circle = Path.from_circle([5.0, 5.0], 3.0)
+    rect = Path.from_rect([7.0, 5.5], [3.0, 1.5])
+    band = Path.from_rect([6.0, 5.0], [0.8, 4.0])
+    soa = PathSoA.from_paths([circle, rect, band])
+    shapes = [oracle.shape_from_paths([], soa, i, i + 1) for i in range(3)]
+    m = np.tile(orthographic_transform(w / ppu, h / ppu), (3, 1))
+    colors = np.array([[1, 0, 0, 1], [0, 1, 0, 1], [0, 0, 1, 1]], np.float32)
+    S, CLIP, UNCLIP, COLOR = 0, 1, 2, 3
+    ys, xs = np.mgrid[0:h, 0:w]
+    x, y = (xs + 0.5) / ppu, (ys + 0.5) / ppu
+    in_circle = (x - 5.0) ** 2 + (y - 5.0) ** 2 < 9.0
+    in_rect = (np.abs(x - 7.0) < 3.0) & (np.abs(y - 5.5) < 1.5)
+    in_band = (np.abs(x - 6.0) < 0.8) & (np.abs(y - 5.0) < 4.0)
+    near = (np.abs(np.hypot(x - 5.0, y - 5.0) - 3.0) < 0.03 / ppu)   # the conic outline is exact to rounding; lines are exact
+    # one clip level
+    cmds = [(0, 0, 1, S, 0, 0, 0), (0, 0, 1, CLIP, 1, 0, 0), (1, 1, 2, S, 1, 0, 0), (1, 1, 2, COLOR, 1, 0, 0), (0, 0, 1, S, 0, 0, 0), (0, 0, 1, UNCLIP, 0, 0, 0)]
+    color, stencil, _, covered = oracle.render(Configuration().to_c(), w, h, shapes, cmds, m, colors)
+    green = color.reshape(h, w, 4)[:, :, 1] > 0.5
+    assert not ((green != (in_circle & in_rect)) & ~near).any() and (stencil == 0).all() and covered == int(green.sum()) > 4000
+    # two nested clip levels: circle, then band; the rectangle is drawn at depth 2
+    cmds = [(0, 0, 1, S, 0, 0, 0), (0, 0, 1, CLIP, 1, 0, 0), (2, 2, 3, S, 1, 0, 0), (2, 2, 3, CLIP, 2, 0, 0),
+            (1, 1, 2, S, 2, 0, 0), (1, 1, 2, COLOR, 2, 0, 0),
+            (2, 2, 3, S, 1, 0, 0), (2, 2, 3, UNCLIP, 1, 0, 0), (0, 0, 1, S, 0, 0, 0), (0, 0, 1, UNCLIP, 0, 0, 0)]
+    color, stencil, _, _ = oracle.render(Configuration().to_c(), w, h, shapes, cmds, m, colors)
+    green = color.reshape(h, w, 4)[:, :, 1] > 0.5
+    assert not ((green != (in_circle & in_rect & in_band)) & ~near).any() and (stencil == 0).all() and int(green.sum()) > 800
+
+
 def test_andrew_hull_invariants(oracle):
     """§4 invariant 7: convex, clockwise (y up), no three collinear points within 1e-4, and it contains every input point."""
     rng = np.random.default_rng(2)
