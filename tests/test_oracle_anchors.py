@@ -443,6 +443,30 @@ def test_clip_is_an_intersection(oracle):
     assert not ((green != (in_circle & in_rect & in_band)) & ~near).any() and (stencil == 0).all() and int(green.sum()) > 800
 
 
+def test_msaa_samples_are_the_webgpu_pattern(oracle):
+    """4x MSAA: sample k of a pixel sits at the WebGPU standard offsets (6,2), (14,6), (2,10), (10,14) / 16 and is
+    covered iff that point is inside the shape - checked per sample against an analytic polygon test."""
+    ppu, w, h = 16.0, 96, 80
+    tri = np.array([[0.7, 0.6], [5.3, 1.9], [2.1, 4.4]])
+    path = Path.from_polygon(tri)
+    shape = oracle.shape_from_paths([], PathSoA.from_paths([path]))
+    m = orthographic_transform(w / ppu, h / ppu).reshape(1, 16)
+    _, stencil, _, _ = oracle.render(Configuration(msaa_sample_count=4).to_c(), w, h, [shape], [(0, 0, 1, 0, 0, 0, 0)], m, None)
+    assert stencil.shape == (h, w, 4)
+    offsets = np.array([[6, 2], [14, 6], [2, 10], [10, 14]]) / 16.0
+    ys, xs = np.mgrid[0:h, 0:w]
+    a, b, c = tri * ppu
+    for k, (ox, oy) in enumerate(offsets):
+        px, py = xs + ox, ys + oy
+        e = [(q[0] - p[0]) * (py - p[1]) - (q[1] - p[1]) * (px - p[0]) for p, q in ((a, b), (b, c), (c, a))]
+        inside = ((e[0] > 0) & (e[1] > 0) & (e[2] > 0)) | ((e[0] < 0) & (e[1] < 0) & (e[2] < 0))
+        margin = np.min(np.abs(np.array(e)), 0) > 1e-3
+        assert not (((stencil[:, :, k] != 0) != inside) & margin).any(), f"sample {k}"
+        assert inside.sum() > 1000
+    per_pixel = (stencil != 0).sum(-1)
+    assert set(np.unique(per_pixel)) == {0, 1, 2, 3, 4}, "edge pixels are partially covered"
+
+
 def test_andrew_hull_invariants(oracle):
     """§4 invariant 7: convex, clockwise (y up), no three collinear points within 1e-4, and it contains every input point."""
     rng = np.random.default_rng(2)
