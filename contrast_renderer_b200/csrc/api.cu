@@ -100,6 +100,7 @@ int convert_dynamic_stroke_options(const cr_dynamic_stroke_options& o, Descripto
 }
 
 int decode_device_error(uint32_t flags) {
+    if (flags & CR_DEVERR_BAD_TABLES) return fail(CR_ERR_INVALID_ARGUMENT, "cr_path_soa: segment_begin / type_begin / segment_types are inconsistent (not monotone, not covering [0, n_segments], a type code above 4, or per-type counts that disagree with the type stream)");
     if (flags & CR_DEVERR_GROUP_OOB) return fail(CR_ERR_DYNAMIC_STROKE_OPTIONS_INDEX_OUT_OF_BOUNDS, "a path references a dynamic stroke options group that does not exist");
     if (flags & CR_DEVERR_NON_FINITE) return fail(CR_ERR_NON_FINITE, "tessellation produced a non-finite hull point");
     if (flags & CR_DEVERR_STEPS) return fail(CR_ERR_CURVE_STEPS_CAPACITY, "more than %d tangent-angle steps in one curve interval", CR_MAX_STEPS_PER_INTERVAL);
@@ -241,6 +242,8 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
             for (int t = 0; t < 5; ++t) type_totals[t] = r->pinned[t];
         }
     }
+    if ((uint64_t)type_totals[0] + type_totals[1] + type_totals[2] + type_totals[3] + type_totals[4] != soa->n_segments)
+        return fail(CR_ERR_INVALID_ARGUMENT, "cr_path_soa: the per-type totals type_begin[t][n_paths] do not add up to n_segments");
     static const int kSegFloats[5] = {2, 4, 6, 5, 10};
     CR_TRY(stage(r, 0, soa->start, 2 * (size_t)n_paths, soa->memory_space, &P.start));
     CR_TRY(stage(r, 1, soa->segment_begin, n_paths ? stride : 0, soa->memory_space, &P.segment_begin));
@@ -467,7 +470,7 @@ int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
     CR_TRY(r->color.reserve(r->stream, samples * 16));
     CR_TRY(r->stencil.reserve(r->stream, samples));
     CR_TRY(r->alpha_layers.reserve(r->stream, samples * 4 * std::max<uint32_t>(1, r->config.alpha_layer_count)));
-    CR_TRY(r->covered_dev.reserve(r->stream, 8));
+    CR_TRY(r->covered_dev.reserve(r->stream, 16));   // [0] covered samples, [1] 64-bit pair total of the last submit
     r->width = width;
     r->height = height;
     r->tiles_x = (width + CR_TILE - 1) / CR_TILE;
@@ -878,10 +881,16 @@ static int submit(cr_pass* p) {
     CR_TRY(r->records.reserve(st, (size_t)n_cands * sizeof(PrimRecord)));
     CR_TRY(r->scan_scratch.reserve(st, (size_t)cr_scan_scratch_words(n_cands + 1, 1) * 4));
     CR_TRY(r->big_list.reserve(st, (size_t)(n_cands + 1) * 4));
-    CR_TRY(cr_raster_setup(st, sc, tg, n_cands, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>()));
+    CR_TRY(cr_raster_setup(st, sc, tg, n_cands, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(),
+                           r->covered_dev.as<unsigned long long>() + 1));
     CR_TRY(cr_scan_exclusive(st, r->cand_tiles.as<uint32_t>(), n_cands + 1, 1, r->scan_scratch.as<uint32_t>()));
     CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[0], r->cand_tiles.as<uint32_t>() + n_cands, 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[2], r->covered_dev.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, st));
     CR_CUDA_TRY(cudaStreamSynchronize(st));
+    unsigned long long pair_total = 0;
+    memcpy(&pair_total, &r->pinned[2], 8);
+    if (pair_total >= 0xFFFFFFFFull)
+        return fail(CR_ERR_INVALID_ARGUMENT, "%llu (tile, primitive) pairs in one pass exceed 2^32; submit in several passes", pair_total);
     const uint32_t n_pairs = r->pinned[0];
     const uint32_t n_tiles = r->tiles_x * r->tiles_y;
     r->stats.primitives = n_cands;

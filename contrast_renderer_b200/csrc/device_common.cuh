@@ -36,6 +36,8 @@ static const int kCategoryStride[8] = {20, 24, 8, 16, 20, 20, 24, 8};
 #define CR_DEVERR_NON_FINITE 2u
 #define CR_DEVERR_STEPS 4u
 #define CR_DEVERR_CUBIC 8u
+#define CR_DEVERR_BAD_TABLES 16u   // cr_path_soa cursor tables are inconsistent (checked before anything is indexed with them)
+#define CR_DEVERR_FATAL_MASK (CR_DEVERR_GROUP_OOB | CR_DEVERR_BAD_TABLES)   // set by the count pass: the emit pass must not run
 
 namespace crd {
 

@@ -268,7 +268,8 @@ __device__ __forceinline__ uint32_t walk_tiles_warp(const int* X, const int* Y, 
 #define META_BIG 128u
 // big[0] = number of big candidates, big[1 ...] = their candidate numbers
 __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_kernel(RasterScene sc, RasterTarget tg, uint32_t n, PrimRecord* __restrict__ records,
-                                                                   uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ big) {
+                                                                   uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ big,
+                                                                   unsigned long long* __restrict__ pair_total) {
     __shared__ uint32_t sh_begin[SETUP_CMD_CACHE + 1];
     const uint32_t* cmd_begin = sc.cmd_cand_begin;
     if (sc.n_commands <= SETUP_CMD_CACHE) {
@@ -277,17 +278,22 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_ke
         cmd_begin = sh_begin;
     }
     const uint32_t cand = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cand >= n) return;
-    PrimRecord rec;
     uint32_t count = 0;
-    if (build_record(sc, tg, cand, cmd_begin, rec)) {
-        const Extent x = extent_of(rec.X, rec.Y, tg);
-        if (x.empty) rec.meta = 0;
-        else if ((x.tx1 - x.tx0 + 1) * (x.ty1 - x.ty0 + 1) <= BIG_TILE_BOX) count = walk_tiles_small<false>(rec.X, rec.Y, x, tg, cand, 0, nullptr, nullptr);
-        else { rec.meta |= META_BIG; big[1 + atomicAdd(big, 1u)] = cand; }   // counted by bin_big_kernel<false>
+    if (cand < n) {
+        PrimRecord rec;
+        if (build_record(sc, tg, cand, cmd_begin, rec)) {
+            const Extent x = extent_of(rec.X, rec.Y, tg);
+            if (x.empty) rec.meta = 0;
+            else if ((x.tx1 - x.tx0 + 1) * (x.ty1 - x.ty0 + 1) <= BIG_TILE_BOX) count = walk_tiles_small<false>(rec.X, rec.Y, x, tg, cand, 0, nullptr, nullptr);
+            else { rec.meta |= META_BIG; big[1 + atomicAdd(big, 1u)] = cand; }   // counted by bin_big_kernel<false>
+        }
+        if (rec.meta & META_VALID) store_record(records + cand, rec);   // nobody reads the record of a candidate without tiles (more than half of them: restarts, degenerate and culled triangles)
+        cand_tiles[cand] = count;
     }
-    if (rec.meta & META_VALID) store_record(records + cand, rec);   // nobody reads the record of a candidate without tiles (more than half of them: restarts, degenerate and culled triangles)
-    cand_tiles[cand] = count;
+    // 64-bit total of the (tile, candidate) pairs: the scan that places them is 32-bit, so the host must see an overflow
+    // (33 k full-target hull covers at 8K wrap it) instead of sizing the pair arrays from a wrapped count
+    const uint32_t warp_pairs = __reduce_add_sync(0xffffffffu, count);
+    if ((threadIdx.x & 31u) == 0 && warp_pairs) atomicAdd(pair_total, (unsigned long long)warp_pairs);
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS) bin_emit_kernel(RasterTarget tg, uint32_t n, const PrimRecord* __restrict__ records,
@@ -305,7 +311,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) bin_emit_kernel(RasterTarget tg
 // One warp per big candidate (grid-stride over the list built by prim_setup_kernel).
 template <bool EMIT>
 __global__ void __launch_bounds__(128) bin_big_kernel(RasterTarget tg, const PrimRecord* __restrict__ records, const uint32_t* __restrict__ big,
-                                                      uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ pair_tile, uint32_t* __restrict__ pair_cand) {
+                                                      uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ pair_tile, uint32_t* __restrict__ pair_cand,
+                                                      unsigned long long* __restrict__ pair_total) {
     const uint32_t n_big = big[0];
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_big; i += warps) {
@@ -314,7 +321,7 @@ __global__ void __launch_bounds__(128) bin_big_kernel(RasterTarget tg, const Pri
         if (EMIT) walk_tiles_warp<true>(rec.X, rec.Y, tg, cand, cand_tiles[cand], pair_tile, pair_cand);   // cand_tiles now holds the exclusive scan
         else {
             const uint32_t count = walk_tiles_warp<false>(rec.X, rec.Y, tg, cand, 0, nullptr, nullptr);
-            if ((threadIdx.x & 31u) == 0) cand_tiles[cand] = count;
+            if ((threadIdx.x & 31u) == 0) { cand_tiles[cand] = count; if (count) atomicAdd(pair_total, (unsigned long long)count); }
         }
     }
 }
@@ -818,11 +825,12 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
 
 #define BIG_GRID (148 * 8)
 int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, PrimRecord* records, uint32_t* cand_tiles,
-                    uint32_t* big_list) {
+                    uint32_t* big_list, unsigned long long* pair_total) {
     if (n_candidates == 0) return CR_OK;
     CR_CUDA_TRY(cudaMemsetAsync(big_list, 0, 4, stream));
-    prim_setup_kernel<<<(n_candidates + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(scene, target, n_candidates, records, cand_tiles, big_list);
-    bin_big_kernel<false><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, cand_tiles, nullptr, nullptr);
+    CR_CUDA_TRY(cudaMemsetAsync(pair_total, 0, 8, stream));
+    prim_setup_kernel<<<(n_candidates + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(scene, target, n_candidates, records, cand_tiles, big_list, pair_total);
+    bin_big_kernel<false><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, cand_tiles, nullptr, nullptr, pair_total);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
@@ -831,7 +839,7 @@ int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t
                        const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand) {
     if (n_candidates == 0) return CR_OK;
     bin_emit_kernel<<<(n_candidates + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(target, n_candidates, records, cand_pair_begin, pair_tile, pair_cand);
-    bin_big_kernel<true><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, const_cast<uint32_t*>(cand_pair_begin), pair_tile, pair_cand);
+    bin_big_kernel<true><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, const_cast<uint32_t*>(cand_pair_begin), pair_tile, pair_cand, nullptr);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;

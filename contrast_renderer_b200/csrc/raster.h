@@ -85,8 +85,9 @@ struct RasterScene {
 
 // Vertex stage + tile counting: fills records[0..n) and cand_tiles[0..n). big_list: n + 1 words of scratch (candidates
 // whose tile box is large are listed there and binned one warp each).
+// *pair_total (device, zeroed here) receives the 64-bit number of (tile, candidate) pairs: the placing scan is 32-bit.
 int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, PrimRecord* records, uint32_t* cand_tiles,
-                    uint32_t* big_list);
+                    uint32_t* big_list, unsigned long long* pair_total);
 // (tile, candidate) pairs of every valid record, at cand_pair_begin[candidate].
 int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t n_candidates, const PrimRecord* records, const uint32_t* cand_pair_begin,
                        const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand);

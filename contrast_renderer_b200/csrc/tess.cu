@@ -812,6 +812,36 @@ __device__ __forceinline__ PathView load_path(const DevicePaths& P, uint32_t p) 
     return pv;
 }
 
+// The cursor tables of cr_path_soa come from the caller; everything below indexes with them. A Path of the reference cannot
+// be inconsistent (its vectors carry their own lengths, src/path.rs:213-230), a C caller's tables can: check, before any
+// segment is read, that the path's slice of the type stream lies inside [0, n_segments] and that its per-type cursor deltas
+// are exactly the number of segments of each type in that slice (so every per-type read stays inside the path's slice, and
+// the slices of consecutive paths tile the arrays). Any violation sets CR_DEVERR_BAD_TABLES and the path emits nothing.
+__device__ bool path_tables_valid(const DevicePaths& P, uint32_t p) {
+    const uint32_t sb = P.segment_begin[p], se = P.segment_begin[p + 1];
+    if (sb > se || se > P.n_segments) return false;
+    if (p == 0 && sb != 0) return false;
+    if (p + 1 == P.n_paths && se != P.n_segments) return false;
+    const size_t stride = (size_t)P.n_paths + 1;
+    uint32_t want[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+        const uint32_t tb = P.type_begin[t * stride + p], te = P.type_begin[t * stride + p + 1];
+        if (tb > te || (p == 0 && tb != 0)) return false;
+        want[t] = te - tb;
+    }
+    uint32_t have[5] = {0, 0, 0, 0, 0};
+    for (uint32_t i = sb; i < se; ++i) {
+        const uint32_t type = P.segment_types[i];
+        if (type > 4u) return false;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) have[t] += type == (uint32_t)t ? 1u : 0u;
+    }
+#pragma unroll
+    for (int t = 0; t < 5; ++t) if (have[t] != want[t]) return false;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------- kernels
 // Pass A: per-path output sizes. counts is [CNT_COUNT][n_paths + 1].
 // MODE 0: anything. MODE 1: the batch has no stroke options at all (cr_path_soa.stroke_options == NULL, every Path is filled): the
@@ -821,6 +851,13 @@ template <int MODE>
 __global__ void __launch_bounds__(128) tess_count_kernel(DevicePaths P, uint32_t n_groups, uint32_t* __restrict__ counts, uint32_t* __restrict__ err) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_paths) return;
+    const size_t stride = (size_t)P.n_paths + 1;
+    if (!path_tables_valid(P, p)) {
+#pragma unroll
+        for (int c = 0; c < CNT_COUNT; ++c) counts[c * stride + p] = 0;
+        atomicOr(err, CR_DEVERR_BAD_TABLES);
+        return;
+    }
     const PathView pv = load_path(P, p);
     Sink<false> s;
     s.init();
@@ -830,7 +867,6 @@ __global__ void __launch_bounds__(128) tess_count_kernel(DevicePaths P, uint32_t
     } else {
         fill_path<false, MODE != 2>(s, pv);
     }
-    const size_t stride = (size_t)P.n_paths + 1;
 #pragma unroll
     for (int c = 0; c < CNT_COUNT; ++c) counts[c * stride + p] = s.n[c];
     if (s.err) atomicOr(err, s.err);
@@ -842,6 +878,7 @@ __global__ void __launch_bounds__(128) tess_emit_kernel(DevicePaths P, const uin
                                                        uint32_t n_shapes, TessOutput out, uint32_t* __restrict__ err) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_paths) return;
+    if (*reinterpret_cast<volatile const uint32_t*>(err) & CR_DEVERR_FATAL_MASK) return;   // the count pass rejected the input (uniform): write nothing
     const PathView pv = load_path(P, p);
     const size_t stride = (size_t)P.n_paths + 1;
     Sink<true> s;

@@ -458,7 +458,6 @@ def calculate_aligned_positions(face: Face, layout: Layout, text: str):
         offset[1 - major_axis] = _div_trunc(face.x_height(), 2)
     else:
         offset[1 - major_axis] = -line_minor_extent
-    last_offset = list(offset)
     for _, positions in lines:
         lme = positions[-1][0][major_axis]
         off = list(offset)
@@ -472,8 +471,8 @@ def calculate_aligned_positions(face: Face, layout: Layout, text: str):
         for p, _ in positions:
             p[0] = sign_x * (p[0] + off[0])
             p[1] = sign_y * (p[1] + off[1])
-        last_offset = off
-    return extent, [sign_x * last_offset[0], sign_y * last_offset[1]], lines
+    # the macro's loop shadows `offset` (`let mut offset = offset;`, src/text.rs:216): the tuple returns the OUTER one
+    return extent, [sign_x * offset[0], sign_y * offset[1]], lines
 
 
 def _sat_overlap(a: np.ndarray, b: np.ndarray) -> bool:

@@ -187,6 +187,13 @@ void oracle_curve_eval(int kind, const float* cp, const float* w, float t, float
     out_normal[0] = d[1];
     out_normal[1] = d[2];
 }
+// ppga2d sign conventions, exposed so that tests can pin them against the reference's own GA-free statements
+// (src/utils.rs:80-101 "Expects the vertices to be ordered clockwise", src/stroke.rs:272-281 cap direction).
+float oracle_ga_triple(const float* a, const float* b, const float* c) { return triple(vec_to_point(a), vec_to_point(b), vec_to_point(c)); }
+void oracle_ga_join(const float* p, const float* q, float* out_plane) {
+    const Plane l = regressive(vec_to_point(p), vec_to_point(q));
+    out_plane[0] = l[0]; out_plane[1] = l[1]; out_plane[2] = l[2];
+}
 int oracle_andrew(const float* xy, uint32_t n, float* out_xy) {
     std::vector<Vertex0> pts(n);
     for (uint32_t i = 0; i < n; ++i) pts[i] = Vertex0{{cr::canon_zero(xy[2 * i]), cr::canon_zero(xy[2 * i + 1])}};

@@ -64,6 +64,10 @@ def lib():
         _lib.oracle_curve_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         _lib.oracle_curve_eval.restype = None
         _lib.oracle_andrew.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        _lib.oracle_ga_triple.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_ga_triple.restype = C.c_float
+        _lib.oracle_ga_join.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_ga_join.restype = None
     return _lib
 
 
@@ -229,6 +233,20 @@ def curve_eval(kind: int, control_points, weights, t: float):
     xy, normal = np.zeros(2, np.float32), np.zeros(2, np.float32)
     lib().oracle_curve_eval(kind, cp.ctypes.data, w.ctypes.data if w is not None else None, t, xy.ctypes.data, normal.ctypes.data)
     return xy, normal
+
+
+def ga_triple(a, b, c) -> float:
+    """(A v B) v C of three unweighted ppga2d points, as the oracle evaluates it."""
+    a, b, c = (np.ascontiguousarray(v, dtype=np.float32) for v in (a, b, c))
+    return float(lib().oracle_ga_triple(a.ctypes.data, b.ctypes.data, c.ctypes.data))
+
+
+def ga_join(p, q) -> np.ndarray:
+    """P v Q of two unweighted ppga2d points: the Plane (g0, g1, g2)."""
+    p, q = (np.ascontiguousarray(v, dtype=np.float32) for v in (p, q))
+    out = np.zeros(3, np.float32)
+    lib().oracle_ga_join(p.ctypes.data, q.ctypes.data, out.ctypes.data)
+    return out
 
 
 def andrew(points) -> np.ndarray:

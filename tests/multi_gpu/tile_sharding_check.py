@@ -2,7 +2,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/multi_gpu/tile_sharding_check.py
 Every rank renders the same scripted scene into ONE target spanning the ranks (own tiles only, finished tiles stored into
 all ranks' attachments by the tile kernel) and then checks that ITS copy of the complete frame is bit-identical to the
-frame a single-GPU renderer produces for the same scene. Prints one JSON line from rank 0; exit code 0 = identical."""
+frame the CPU ORACLE produces for the same scene (rank 0 runs the oracle and broadcasts the frame digests) and to the frame
+a single-GPU renderer produces. Prints one JSON line from rank 0; exit code 0 = identical."""
+import hashlib
 import json
 import os
 import sys
@@ -69,17 +71,35 @@ def main() -> int:
         rnd.close()
         return frame, min(ms)
 
+    def digest(a):
+        return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()
+
+    # the checker: the CPU oracle's frame of the same scene (test infrastructure; rank 0 only, digests broadcast)
+    reference = [None]
+    if rank == 0:
+        from oracle import oracle
+        oracle.build()
+        refs = [oracle.shape_from_paths([], scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1])) for i in range(scene.n_shapes)]
+        ref_color, ref_stencil, _, ref_covered = oracle.render(config.to_c(), scene.width, scene.height, refs, scene.oracle_commands(), scene.transforms,
+                                                               scene.colors, threads=oracle.max_threads())
+        reference[0] = (digest(ref_color), digest(ref_stencil), int(ref_covered))
+    dist.broadcast_object_list(reference, src=0)
+    ref_color_digest, ref_stencil_digest, ref_covered = reference[0]
+
     (color1, stencil1, covered1, pairs1), ms_single = render(False, 3)
     (colorN, stencilN, coveredN, pairsN), ms_sharded = render(True, 3)
-    same = bool(np.array_equal(color1.view(np.uint32), colorN.view(np.uint32)) and np.array_equal(stencil1, stencilN))
+    same_as_oracle = bool(digest(colorN) == ref_color_digest and digest(stencilN) == ref_stencil_digest)
+    same = bool(same_as_oracle and np.array_equal(color1.view(np.uint32), colorN.view(np.uint32)) and np.array_equal(stencil1, stencilN))
     stats = torch.tensor([coveredN, pairsN, int(same and cleared[0])], dtype=torch.int64, device=f"cuda:{local}")
     total = stats.clone()
     dist.all_reduce(total)
     t = torch.tensor([ms_sharded], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ok = int(total[2].item()) == world and int(total[0].item()) == covered1 and int(total[1].item()) == pairs1
+    ok = int(total[2].item()) == world and int(total[0].item()) == covered1 == ref_covered and int(total[1].item()) == pairs1
     if rank == 0:
         print(json.dumps({"check": "tile_sharded_target", "n_gpus": world, "identical_and_empty_pass_cleared_on_every_rank": int(total[2].item()) == world,
+                          "identical": int(total[2].item()) == world, "checked_against": "CPU oracle frame (sha256 of colour and stencil) and the single-GPU frame",
+                          "covered_samples_oracle": ref_covered,
                           "covered_samples_single": covered1, "covered_samples_sum_over_ranks": int(total[0].item()),
                           "tile_pairs_single": pairs1, "tile_pairs_sum_over_ranks": int(total[1].item()),
                           "submit_ms_single_gpu": round(ms_single, 3), "submit_ms_sharded_max_over_ranks": round(float(t.item()), 3),

@@ -100,9 +100,13 @@ def test_layout_arithmetic(fixture_face):
     assert [p for p, _ in lines[0][1]] == [[x0, y_shift], [x0 + adv["A"], y_shift], [x0 + width, y_shift]]
     assert [p for p, _ in lines[1][1]] == [[x0, -(2789 - y_shift)], [x0 + adv["i"], -(2789 - y_shift)]]
     assert [g for _, g in lines[1][1]] == [fixture_face.glyph_index("i"), 0]     # end-of-line marker carries glyph 0
+    # the second tuple element is the OUTER `offset` (the loop's `let mut offset = offset;` shadows it, src/text.rs:216-229):
+    # major component 0, minor component the alignment term alone (Baseline: 0), without the centring shift
+    assert offset == [0, 0]
     # Center / Center: each line centred on its own extent, minor offset x_height / 2
     lay = Layout(1.0, Orientation.LeftToRight, Alignment.Center, Alignment.Center)
-    _, _, lines = calculate_aligned_positions(fixture_face, lay, "AV")
+    _, offset, lines = calculate_aligned_positions(fixture_face, lay, "AV")
+    assert offset == [0, -(1096 // 2)]   # sign_y = -1 (src/text.rs:150-158) times x_height / 2
     assert lines[0][1][0][0] == [-(width // 2) if width % 2 == 0 else -((width - 1) // 2), -(1096 // 2)]
     # RightToLeft mirrors x
     lay = Layout(1.0, Orientation.RightToLeft, Alignment.Begin, Alignment.Baseline)
