@@ -22,6 +22,7 @@ CR_ERR_NOT_RESIZED = 106
 
 CR_SEG_LINE, CR_SEG_INTEGRAL_QUADRATIC, CR_SEG_INTEGRAL_CUBIC, CR_SEG_RATIONAL_QUADRATIC, CR_SEG_RATIONAL_CUBIC = range(5)
 CR_MEM_HOST, CR_MEM_DEVICE = 0, 1
+CR_FORMAT_RGBA32F, CR_FORMAT_RGBA8_UNORM, CR_FORMAT_BGRA8_UNORM = 0, 1, 2
 CR_STROKE_FLAG_STROKED, CR_STROKE_FLAG_CLOSED, CR_STROKE_FLAG_UNIFORM_TANGENT_ANGLE = 1, 2, 4
 SEGMENT_FLOATS = (2, 4, 6, 5, 10)  # floats per segment of each type
 
@@ -54,7 +55,7 @@ class PathSoAC(C.Structure):
 class ConfigC(C.Structure):
     _fields_ = [("msaa_sample_count", C.c_uint32), ("clip_nesting_counter_bits", C.c_uint32), ("winding_counter_bits", C.c_uint32),
                 ("alpha_layer_count", C.c_uint32), ("blending", C.c_uint32), ("cull_mode", C.c_uint32), ("device", C.c_int32),
-                ("_reserved", C.c_uint32)]
+                ("depth_compare", C.c_uint32), ("depth_write_enabled", C.c_uint32), ("color_format", C.c_uint32), ("_reserved", C.c_uint32 * 2)]
 
 
 class ShapeLayoutC(C.Structure):
@@ -84,7 +85,7 @@ EXPORTED_SYMBOLS = (
     "cr_renderer_synchronize", "cr_shape_from_paths", "cr_shape_destroy", "cr_shape_batch_from_paths", "cr_shape_batch_destroy",
     "cr_shape_batch_size", "cr_shape_batch_get", "cr_shape_set_dynamic_stroke_options", "cr_shape_batch_set_dynamic_stroke_options",
     "cr_shape_get_layout", "cr_shape_read_vertex_buffer", "cr_shape_read_index_buffer", "cr_shape_read_stroke_buffer",
-    "cr_pass_begin", "cr_pass_set_instances", "cr_pass_set_clip_depth", "cr_pass_save_alpha_context",
+    "cr_pass_begin", "cr_pass_begin_depth", "cr_renderer_read_depth", "cr_pass_set_instances", "cr_pass_set_clip_depth", "cr_pass_save_alpha_context",
     "cr_pass_restore_alpha_context", "cr_shape_render", "cr_pass_render_batch", "cr_pass_submit", "cr_pass_abort", "cr_renderer_read_color",
     "cr_renderer_read_stencil", "cr_renderer_read_alpha_layer", "cr_renderer_get_attachments", "cr_renderer_get_stats",
     "cr_renderer_enable_timing", "cr_renderer_set_tile_sharding", "cr_renderer_export_attachments", "cr_renderer_import_peer_attachments",

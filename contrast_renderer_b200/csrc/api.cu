@@ -116,7 +116,7 @@ struct cr_renderer {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint32_t width = 0, height = 0, tiles_x = 0, tiles_y = 0;
-    DevBuf color, stencil, alpha_layers;
+    DevBuf color, stencil, alpha_layers, depth;
     // scratch shared by every from_paths / submit of this renderer
     DevBuf staging[10], counts, scan_scratch, shape_begin_dev, err_flag, hull_scratch_a, hull_scratch_b;
     DevBuf cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, radix_scratch, tile_begin, inst_transforms, inst_colors,
@@ -169,7 +169,8 @@ struct cr_pass {
     std::vector<InstanceSet> instance_sets;
     uint32_t instance_total = 0;
     uint32_t clip_depth = 0, save_layer = 0, restore_layer = 0;
-    bool clear_color = false, clear_stencil = false;   // LoadOp::Clear of the attachments, executed at submit (fused into the tile kernel)
+    bool clear_color = false, clear_stencil = false, clear_depth = false;   // LoadOp::Clear of the attachments, executed at submit (fused into the tile kernel)
+    float depth_clear_value = 1.0f;
 };
 
 namespace {
@@ -359,7 +360,7 @@ uint32_t slots_of_host(const cr_shape_batch* b, uint32_t shape, int cat) {
 // ============================================================================================= exported C-ABI
 extern "C" {
 
-uint32_t cr_abi_version(void) { return 2; }
+uint32_t cr_abi_version(void) { return 3; }
 const char* cr_last_error_message(void) { return g_error_message; }
 const char* cr_status_string(int status) {
     switch (status) {
@@ -389,6 +390,8 @@ int cr_renderer_create(const cr_config* config, cr_renderer** out) {
                     config->clip_nesting_counter_bits);
     if (config->msaa_sample_count != 1 && config->msaa_sample_count != 4) return fail(CR_ERR_INVALID_ARGUMENT, "msaa_sample_count must be 1 or 4");
     if (config->blending > CR_BLEND_REPLACE || config->cull_mode > CR_CULL_BACK) return fail(CR_ERR_INVALID_ARGUMENT, "bad blending / cull_mode");
+    if (config->depth_compare > CR_COMPARE_ALWAYS || config->depth_write_enabled > 1u) return fail(CR_ERR_INVALID_ARGUMENT, "bad depth_compare / depth_write_enabled");
+    if (config->color_format > CR_FORMAT_BGRA8_UNORM) return fail(CR_ERR_INVALID_ARGUMENT, "bad color_format");
     int n_devices = 0;
     if (cudaGetDeviceCount(&n_devices) != cudaSuccess || n_devices == 0) {
         cudaGetLastError();
@@ -428,7 +431,7 @@ static void renderer_free(cr_renderer* r) {
     cudaStreamSynchronize(r->stream);
     close_peers(r);
     cudaStream_t st = r->stream;
-    DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
+    DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->depth, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
                      &r->hull_scratch_b, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand, &r->pair_tile_alt,
                      &r->pair_cand_alt, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->covered_dev};
     for (DevBuf* d : all) d->release(st);
@@ -459,6 +462,11 @@ int cr_renderer_get_config(const cr_renderer* r, cr_config* out) {
     return CR_OK;
 }
 
+static bool has_depth(const cr_renderer* r) {
+    const uint32_t f = r->config.depth_compare;
+    return (f != CR_COMPARE_DEFAULT_ALWAYS && f != CR_COMPARE_ALWAYS) || r->config.depth_write_enabled != 0u;
+}
+static size_t color_texel_bytes(const cr_renderer* r) { return r->config.color_format == CR_FORMAT_RGBA32F ? 16 : 4; }
 // Renderer::resize_internal_buffers (src/renderer.rs:892-929) + the caller-owned colour / depth-stencil textures.
 int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
@@ -467,17 +475,24 @@ int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
     const size_t samples = (size_t)width * height * r->config.msaa_sample_count;
     if (r->peer_color[0] || r->peer_stencil[0]) return fail(CR_ERR_INVALID_ARGUMENT, "resize while peer attachments are imported: call cr_renderer_set_tile_sharding(r, 1, 0) first");
     r->color.plain = r->stencil.plain = true;   // exportable to the other ranks of a tile-sharded target
-    CR_TRY(r->color.reserve(r->stream, samples * 16));
+    const size_t texel = color_texel_bytes(r), layer_texel = r->config.color_format == CR_FORMAT_RGBA32F ? 4 : 1;
+    CR_TRY(r->color.reserve(r->stream, samples * texel));
     CR_TRY(r->stencil.reserve(r->stream, samples));
-    CR_TRY(r->alpha_layers.reserve(r->stream, samples * 4 * std::max<uint32_t>(1, r->config.alpha_layer_count)));
+    CR_TRY(r->alpha_layers.reserve(r->stream, samples * layer_texel * std::max<uint32_t>(1, r->config.alpha_layer_count)));
+    if (has_depth(r)) {   // wgpu clears depth to 1.0 in the pass (LoadOp::Clear); a fresh attachment starts there too
+        CR_TRY(r->depth.reserve(r->stream, samples * 4));
+        std::vector<float> ones(samples, 1.0f);
+        CR_CUDA_TRY(cudaMemcpyAsync(r->depth.p, ones.data(), samples * 4, cudaMemcpyHostToDevice, r->stream));
+        CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    }
     CR_TRY(r->covered_dev.reserve(r->stream, 16));   // [0] covered samples, [1] 64-bit pair total of the last submit
     r->width = width;
     r->height = height;
     r->tiles_x = (width + CR_TILE - 1) / CR_TILE;
     r->tiles_y = (height + CR_TILE - 1) / CR_TILE;
-    CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * 16, r->stream));
+    CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * texel, r->stream));
     CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
-    CR_CUDA_TRY(cudaMemsetAsync(r->alpha_layers.p, 0, samples * 4 * std::max<uint32_t>(1, r->config.alpha_layer_count), r->stream));
+    CR_CUDA_TRY(cudaMemsetAsync(r->alpha_layers.p, 0, samples * layer_texel * std::max<uint32_t>(1, r->config.alpha_layer_count), r->stream));
     return CR_OK;
 }
 
@@ -654,6 +669,9 @@ int cr_shape_read_stroke_buffer(cr_shape* s, void* dst, size_t capacity) {
 
 // ------------------------------------------------------------------------------------------------- render pass
 int cr_pass_begin(cr_renderer* r, uint32_t clear_color, uint32_t clear_stencil, cr_pass** out) {
+    return cr_pass_begin_depth(r, clear_color, clear_stencil, clear_stencil, 1.0f, out);
+}
+int cr_pass_begin_depth(cr_renderer* r, uint32_t clear_color, uint32_t clear_stencil, uint32_t clear_depth, float depth_clear_value, cr_pass** out) {
     if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
@@ -666,6 +684,8 @@ int cr_pass_begin(cr_renderer* r, uint32_t clear_color, uint32_t clear_stencil, 
     // memset nor read. A pass that is dropped without submit clears nothing.
     p->clear_color = clear_color != 0;
     p->clear_stencil = clear_stencil != 0;
+    p->clear_depth = clear_depth != 0;
+    p->depth_clear_value = depth_clear_value;
     if (!r->cmd_arena_busy) {
         if (r->cmd_copy_pending) { cudaEventSynchronize(r->cmd_copy_done); r->cmd_copy_pending = false; }   // the previous pass's upload has long finished
         if (!r->cmd_copy_done && cudaEventCreateWithFlags(&r->cmd_copy_done, cudaEventDisableTiming) != cudaSuccess) r->cmd_copy_done = nullptr;
@@ -774,9 +794,15 @@ int cr_pass_render_batch(cr_pass* p, cr_shape_batch* b, const cr_draw_command* c
 static RasterTarget make_target(const cr_pass* p) {
     const cr_renderer* r = p->renderer;
     RasterTarget tg{};
-    tg.color = r->color.as<float4>();
+    tg.color = r->color.p;
     tg.stencil = r->stencil.as<uint8_t>();
-    tg.alpha_layers = r->alpha_layers.as<float>();
+    tg.alpha_layers = r->alpha_layers.p;
+    tg.depth = has_depth(r) ? r->depth.as<float>() : nullptr;
+    tg.depth_compare = r->config.depth_compare;
+    tg.depth_write = r->config.depth_write_enabled;
+    tg.clear_depth = p->clear_depth ? 1u : 0u;
+    tg.depth_clear_value = p->depth_clear_value;
+    tg.color_format = r->config.color_format;
     tg.width = r->width; tg.height = r->height; tg.tiles_x = r->tiles_x; tg.tiles_y = r->tiles_y;
     tg.samples = r->config.msaa_sample_count;
     tg.sample_lo = tg.samples == 4 ? 32 : 128;
@@ -793,7 +819,7 @@ static RasterTarget make_target(const cr_pass* p) {
     tg.clear_stencil = p->clear_stencil ? 1u : 0u;
     tg.shard_world = r->shard_world;
     tg.shard_rank = r->shard_rank;
-    for (int i = 0; i < CR_MAX_PEERS; ++i) { tg.peer_color[i] = static_cast<float4*>(r->peer_color[i]); tg.peer_stencil[i] = static_cast<uint8_t*>(r->peer_stencil[i]); }
+    for (int i = 0; i < CR_MAX_PEERS; ++i) { tg.peer_color[i] = r->peer_color[i]; tg.peer_stencil[i] = static_cast<uint8_t*>(r->peer_stencil[i]); }
     return tg;
 }
 
@@ -802,10 +828,11 @@ static RasterTarget make_target(const cr_pass* p) {
 // tile table: every owned tile is cleared in all ranks' attachments.
 static int clear_attachments(cr_pass* p) {
     cr_renderer* r = p->renderer;
-    if (!p->clear_color && !p->clear_stencil) return CR_OK;
-    if (r->shard_world <= 1) {
+    const bool depth_clear = p->clear_depth && has_depth(r);
+    if (!p->clear_color && !p->clear_stencil && !depth_clear) return CR_OK;
+    if (r->shard_world <= 1 && !depth_clear) {
         const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
-        if (p->clear_color) CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * 16, r->stream));
+        if (p->clear_color) CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * color_texel_bytes(r), r->stream));
         if (p->clear_stencil) CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
         return CR_OK;
     }
@@ -955,7 +982,23 @@ static int read_back(cr_renderer* r, const void* src, size_t bytes, void* dst, s
 }
 int cr_renderer_read_color(cr_renderer* r, float* dst, size_t capacity_bytes) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
-    return read_back(r, r->color.p, (size_t)r->width * r->height * r->config.msaa_sample_count * 16, dst, capacity_bytes);
+    const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
+    if (r->config.color_format == CR_FORMAT_RGBA32F) return read_back(r, r->color.p, samples * 16, dst, capacity_bytes);
+    if (capacity_bytes < samples * 16) return fail(CR_ERR_INVALID_ARGUMENT, "capacity %zu < %zu", capacity_bytes, samples * 16);
+    std::vector<uint32_t> texels(samples);   // unorm8 texels -> the floats a shader would read: c / 255, in RGBA order
+    CR_TRY(read_back(r, r->color.p, samples * 4, texels.data(), samples * 4));
+    const bool bgra = r->config.color_format == CR_FORMAT_BGRA8_UNORM;
+    for (size_t i = 0; i < samples; ++i) {
+        const uint32_t t = texels[i];
+        const float c0 = (float)(t & 255u) / 255.0f, c1 = (float)((t >> 8) & 255u) / 255.0f, c2 = (float)((t >> 16) & 255u) / 255.0f;
+        dst[4 * i + 0] = bgra ? c2 : c0; dst[4 * i + 1] = c1; dst[4 * i + 2] = bgra ? c0 : c2; dst[4 * i + 3] = (float)(t >> 24) / 255.0f;
+    }
+    return CR_OK;
+}
+int cr_renderer_read_depth(cr_renderer* r, float* dst, size_t capacity_bytes) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    if (!has_depth(r)) return fail(CR_ERR_INVALID_ARGUMENT, "this configuration has no depth attachment (depth_compare Always, depth_write_enabled 0)");
+    return read_back(r, r->depth.p, (size_t)r->width * r->height * r->config.msaa_sample_count * 4, dst, capacity_bytes);
 }
 int cr_renderer_read_stencil(cr_renderer* r, uint8_t* dst, size_t capacity_bytes) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
@@ -964,8 +1007,14 @@ int cr_renderer_read_stencil(cr_renderer* r, uint8_t* dst, size_t capacity_bytes
 int cr_renderer_read_alpha_layer(cr_renderer* r, uint32_t layer, float* dst, size_t capacity_bytes) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
     if (layer >= r->config.alpha_layer_count) return fail(CR_ERR_TOO_MANY_NESTED_OPACITY_GROUPS, "alpha layer %u", layer);
-    const size_t layer_bytes = (size_t)r->width * r->height * r->config.msaa_sample_count * 4;
-    return read_back(r, static_cast<const char*>(r->alpha_layers.p) + layer * layer_bytes, layer_bytes, dst, capacity_bytes);
+    const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
+    if (r->config.color_format == CR_FORMAT_RGBA32F)
+        return read_back(r, static_cast<const char*>(r->alpha_layers.p) + layer * samples * 4, samples * 4, dst, capacity_bytes);
+    if (capacity_bytes < samples * 4) return fail(CR_ERR_INVALID_ARGUMENT, "capacity %zu < %zu", capacity_bytes, samples * 4);
+    std::vector<uint8_t> texels(samples);   // R8Unorm layer (src/renderer.rs:898)
+    CR_TRY(read_back(r, static_cast<const char*>(r->alpha_layers.p) + layer * samples, samples, texels.data(), samples));
+    for (size_t i = 0; i < samples; ++i) dst[i] = (float)texels[i] / 255.0f;
+    return CR_OK;
 }
 int cr_renderer_get_attachments(cr_renderer* r, void** color_dev, void** stencil_dev) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");

@@ -76,6 +76,27 @@ __device__ __forceinline__ const float* vertex_ptr(const DeviceBatch& b, uint32_
 struct SnapVertex { int X, Y; bool ok; };
 // vertex shader + viewport transform + 1/256 px snapping (src/shaders.wgsl:66-74)
 __device__ __forceinline__ float clip_w(const float* __restrict__ m, float x, float y) { return (m[3] * x + m[7] * y) + m[15]; }
+__device__ __forceinline__ float clip_z(const float* __restrict__ m, float x, float y) { return (m[2] * x + m[6] * y) + m[14]; }
+// wgpu::CompareFunction of the depth test: does the fragment's depth `z` pass against the stored `d`?
+__device__ __forceinline__ bool depth_passes(uint32_t f, float z, float d) {
+    switch (f) {
+        case CR_COMPARE_NEVER: return false;
+        case CR_COMPARE_LESS: return z < d;
+        case CR_COMPARE_EQUAL: return z == d;
+        case CR_COMPARE_LESS_EQUAL: return z <= d;
+        case CR_COMPARE_GREATER: return z > d;
+        case CR_COMPARE_NOT_EQUAL: return z != d;
+        case CR_COMPARE_GREATER_EQUAL: return z >= d;
+        default: return true;
+    }
+}
+// Storing a blend result into an 8-bit unorm attachment and reading it back: clamp, x * 255 + 0.5, truncate; texel / 255.
+__device__ __forceinline__ float unorm8(float x) {
+    x = x > 0.0f ? x : 0.0f;   // NaN -> 0
+    x = x < 1.0f ? x : 1.0f;
+    return cr::floor_f(x * 255.0f + 0.5f) / 255.0f;
+}
+__device__ __forceinline__ uint32_t unorm8_bits(float q) { return (uint32_t)(q * 255.0f + 0.5f); }   // q is k / 255 exactly rounded: recovers k
 __device__ __forceinline__ SnapVertex snap_vertex(const float* __restrict__ m, float x, float y, uint32_t W, uint32_t H) {
     SnapVertex v;
     const float cx = (m[0] * x + m[4] * y) + m[12];
@@ -481,7 +502,7 @@ __device__ __forceinline__ unsigned long long cover_row_mask(const TilePrim& ps,
 
 // Stage one primitive of this tile into shared memory (one thread per primitive). The edge functions are evaluated at the
 // centre of the tile's pixel (0, 0) for 1x and at its top-left corner for 4x (sample offsets are added per sample).
-template <int S>
+template <int S, bool DEPTH>
 __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, const PrimRecord& rec, int tile_px, int tile_py, TilePrim& ps) {
     ps.meta = 0;
     if (!(rec.meta & META_VALID)) return;
@@ -533,6 +554,17 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
             }
         }
     }
+    if (DEPTH && pipe == P_COLOR) {   // the depth test of the colour cover needs z / w of the three hull vertices (src/shaders.wgsl:72)
+        const DeviceBatch& b = sc.batches[rec.batch];
+        const float* m = sc.transforms + 16 * (size_t)rec.instance;
+        const bool swapped = (rec.meta & META_SWAPPED) != 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int src = i == 0 ? 0 : (swapped ? 3 - i : i);
+            const float* p = vertex_ptr(b, 7, rec.v[src]);
+            ps.attr[i][0] = clip_z(m, p[0], p[1]) / clip_w(m, p[0], p[1]);
+        }
+    }
     // 32-bit edge arithmetic is exact for this tile if every edge value at every sample position of the tile (and +-1 for the
     // bias that fragment_keep removes again) stays inside int range
     bool fits = true;
@@ -547,8 +579,8 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
 // Run kinds: primitives of one run commute (see the file header).
 __device__ __forceinline__ uint32_t run_kind(uint32_t pipe) { return pipe <= P_STROKE_JOINT ? 0u : (pipe <= P_FILL_RC ? 1u : 2u); }
 
-template <int S>
-__global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3_MIN_BLOCKS_MSAA) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
+template <int S, bool DEPTH, bool U8>   // samples per pixel; depth test / write on the colour cover; 8-bit unorm colour + R8 alpha layers
+__global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ? K3_MIN_BLOCKS : K3_MIN_BLOCKS_MSAA) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
                                                                                          const uint32_t* __restrict__ tile_begin,
                                                                                          const uint32_t* __restrict__ pair_cand,
                                                                                          unsigned long long* __restrict__ covered_out) {
@@ -568,8 +600,13 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
     const size_t pix = ((size_t)py * tg.width + px) * S;   // first sample of this thread's pixel
     uint32_t s[S];
     float4 col[S];
+    float dep[DEPTH ? S : 1];
 #pragma unroll
     for (int k = 0; k < S; ++k) { s[k] = 0; col[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (DEPTH) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) dep[k] = (tg.clear_depth != 0u || !in_fb) ? tg.depth_clear_value : tg.depth[pix + k];
+    }
     if (in_fb) {   // LoadOp::Load reads the attachment, LoadOp::Clear starts from zero (and the tile is written in any case)
         if (tg.clear_stencil == 0u) {
             if (S == 1) s[0] = tg.stencil[pix];
@@ -581,7 +618,13 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
         }
         if (tg.clear_color == 0u) {
 #pragma unroll
-            for (int k = 0; k < S; ++k) col[k] = tg.color[pix + k];
+            for (int k = 0; k < S; ++k) {
+                if (U8) {
+                    const uint32_t t = reinterpret_cast<const uint32_t*>(tg.color)[pix + k];
+                    const float c0 = (float)(t & 255u) / 255.0f, c1 = (float)((t >> 8) & 255u) / 255.0f, c2 = (float)((t >> 16) & 255u) / 255.0f;
+                    col[k] = tg.color_format == CR_FORMAT_BGRA8_UNORM ? make_float4(c2, c1, c0, (float)(t >> 24) / 255.0f) : make_float4(c0, c1, c2, (float)(t >> 24) / 255.0f);
+                } else col[k] = reinterpret_cast<const float4*>(tg.color)[pix + k];
+            }
         }
     }
     const uint32_t W = tg.wmask, C = tg.cmask, M = W | C;
@@ -617,6 +660,19 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
             if (!((hit >> q) & 1u)) continue;
             if (pipe == P_COLOR) {                                                                   // src/renderer.rs:736-754
                 if ((ref & M) < (s[q] & M)) {
+                    if (DEPTH) {
+                        // depth of the fragment: z / w of the vertices interpolated linearly in screen space (the rasteriser's rule for
+                        // depth), weights = the unbiased edge values at the sample; a depth failure KEEPS the stencil value
+                        // (depth_fail_op, src/renderer.rs:442) and writes nothing
+                        long long E[3];
+#pragma unroll
+                        for (int e = 0; e < 3; ++e)
+                            E[e] = ps.e0[e] - ps.bias[e] + (long long)ps.A[e] * (ly * 256 + (S == 1 ? 0 : sample_y<S>(q))) - (long long)ps.B[e] * (lx * 256 + (S == 1 ? 0 : sample_x<S>(q)));
+                        const float b0 = (float)E[1], b1 = (float)E[2], b2 = (float)E[0];
+                        const float z = ((b0 * ps.attr[0][0] + b1 * ps.attr[1][0]) + b2 * ps.attr[2][0]) / ((b0 + b1) + b2);
+                        if (!depth_passes(tg.depth_compare, z, dep[q])) continue;
+                        if (tg.depth_write) dep[q] = z;
+                    }
                     const float4 ic = reinterpret_cast<const float4*>(sc.colors)[ps.instance];
                     const float sa = ic.w;
                     const float sr = ic.x * sa, sg = ic.y * sa, sb = ic.z * sa;
@@ -624,6 +680,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
                         const float kk = 1.0f - sa;
                         col[q].x = sr + col[q].x * kk; col[q].y = sg + col[q].y * kk; col[q].z = sb + col[q].z * kk; col[q].w = sa + col[q].w * kk;
                     } else { col[q].x = sr; col[q].y = sg; col[q].z = sb; col[q].w = sa; }
+                    if (U8) { col[q].x = unorm8(col[q].x); col[q].y = unorm8(col[q].y); col[q].z = unorm8(col[q].z); col[q].w = unorm8(col[q].w); }
                     covered += 1;
                 }
                 s[q] = s[q] & ~W;
@@ -632,15 +689,20 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
             } else if (pipe == P_UNCLIP) {                                                           // src/renderer.rs:711-729
                 if ((ref & C) < (s[q] & C)) s[q] = (s[q] & ~M) | (ref & M);
             } else if ((ref & M) <= (s[q] & M)) {   // the three alpha-context covers share one stencil state (src/renderer.rs:761-766)
-                if (pipe == P_SAVE_ALPHA) {
-                    tg.alpha_layers[(size_t)(ps.layers & 65535u) * layer_stride + pix + q] = col[q].w;
+                if (pipe == P_SAVE_ALPHA) {   // the frame's alpha into the layer: f32, or R8Unorm like the reference's (src/renderer.rs:783,898)
+                    const size_t at = (size_t)(ps.layers & 65535u) * layer_stride + pix + q;
+                    if (U8) reinterpret_cast<uint8_t*>(tg.alpha_layers)[at] = (uint8_t)unorm8_bits(unorm8(col[q].w));
+                    else reinterpret_cast<float*>(tg.alpha_layers)[at] = col[q].w;
                 } else if (pipe == P_SCALE_ALPHA) {
                     const float sa = 1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w;
                     col[q].w = sa + col[q].w * (1.0f - sa);
+                    if (U8) col[q].w = unorm8(col[q].w);
                 } else {
-                    const float saved = tg.alpha_layers[(size_t)(ps.layers >> 16) * layer_stride + pix + q];
+                    const size_t at = (size_t)(ps.layers >> 16) * layer_stride + pix + q;
+                    const float saved = U8 ? (float)reinterpret_cast<const uint8_t*>(tg.alpha_layers)[at] / 255.0f : reinterpret_cast<const float*>(tg.alpha_layers)[at];
                     const float sa = (1.0f - saved) * (1.0f - reinterpret_cast<const float4*>(sc.colors)[ps.instance].w);
                     col[q].w = col[q].w - sa;
+                    if (U8) col[q].w = unorm8(col[q].w);
                 }
             }
         }
@@ -659,7 +721,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
         bool boundary = false;
         if (threadIdx.x < n) {
             const PrimRecord rec = load_record<true>(records + pair_cand[chunk + threadIdx.x]);
-            stage_primitive<S>(sc, tg, rec, tile_px, tile_py, sh[threadIdx.x]);
+            stage_primitive<S, DEPTH>(sc, tg, rec, tile_px, tile_py, sh[threadIdx.x]);
         }
         __syncthreads();
         if (threadIdx.x < RCHUNK) {
@@ -796,11 +858,29 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
             for (int k = 0; k < S; ++k) packed |= (s[k] & 255u) << (8 * k);
             *reinterpret_cast<uint32_t*>(tg.stencil + pix) = packed;
         }
+        uint32_t texel[U8 ? S : 1];
+        if (U8) {
 #pragma unroll
-        for (int k = 0; k < S; ++k) tg.color[pix + k] = col[k];
+            for (int k = 0; k < S; ++k) {
+                const uint32_t r8 = unorm8_bits(col[k].x), g8 = unorm8_bits(col[k].y), b8 = unorm8_bits(col[k].z), a8 = unorm8_bits(col[k].w);
+                texel[k] = tg.color_format == CR_FORMAT_BGRA8_UNORM ? (b8 | (g8 << 8) | (r8 << 16) | (a8 << 24)) : (r8 | (g8 << 8) | (b8 << 16) | (a8 << 24));
+            }
+        }
+        auto store_color = [&](void* base) {
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                if (U8) reinterpret_cast<uint32_t*>(base)[pix + k] = texel[k];
+                else reinterpret_cast<float4*>(base)[pix + k] = col[k];
+            }
+        };
+        store_color(tg.color);
+        if (DEPTH) {
+#pragma unroll
+            for (int k = 0; k < S; ++k) tg.depth[pix + k] = dep[k];
+        }
         // tile sharding: the finished tile also goes to every other rank's attachments (P2P stores over NVLink)
         for (uint32_t peer = 0; peer + 1 < tg.shard_world; ++peer) {
-            float4* pc = tg.peer_color[peer];
+            void* pc = tg.peer_color[peer];
             uint8_t* ps = tg.peer_stencil[peer];
             if (pc == nullptr) continue;
             if (S == 1) ps[pix] = (uint8_t)s[0];
@@ -810,8 +890,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, S == 1 ? K3_MIN_BLOCKS : K3
                 for (int k = 0; k < S; ++k) packed |= (s[k] & 255u) << (8 * k);
                 *reinterpret_cast<uint32_t*>(ps + pix) = packed;
             }
-#pragma unroll
-            for (int k = 0; k < S; ++k) pc[pix + k] = col[k];
+            store_color(pc);
         }
         if (tg.shard_world > 1u) __threadfence_system();
     }
@@ -848,8 +927,16 @@ int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterT
                     const uint32_t* pair_cand, unsigned long long* covered_samples) {
     const uint32_t n_tiles = target.tiles_x * target.tiles_y;
     if (n_tiles == 0) return CR_OK;
-    if (target.samples == 4) raster_tiles_kernel<4><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, covered_samples);
-    else raster_tiles_kernel<1><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, covered_samples);
+    const bool depth = target.depth != nullptr, u8 = target.color_format != CR_FORMAT_RGBA32F;
+#define K3_LAUNCH(S, D, U) raster_tiles_kernel<S, D, U><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, covered_samples)
+    if (target.samples == 4) {
+        if (depth) { if (u8) K3_LAUNCH(4, true, true); else K3_LAUNCH(4, true, false); }
+        else { if (u8) K3_LAUNCH(4, false, true); else K3_LAUNCH(4, false, false); }
+    } else {
+        if (depth) { if (u8) K3_LAUNCH(1, true, true); else K3_LAUNCH(1, true, false); }
+        else { if (u8) K3_LAUNCH(1, false, true); else K3_LAUNCH(1, false, false); }
+    }
+#undef K3_LAUNCH
     g_cr_kernel_launches += 1;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;

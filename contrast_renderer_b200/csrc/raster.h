@@ -53,9 +53,15 @@ struct PrimRecord {
 static_assert(sizeof(PrimRecord) == 64, "PrimRecord layout");
 
 struct RasterTarget {
-    float4* color;                // [height][width][samples] premultiplied RGBA32F
+    void* color;                  // [height][width][samples] premultiplied: float4 (RGBA32F) or one packed unorm8 texel (u32) per sample
     uint8_t* stencil;             // [height][width][samples]
-    float* alpha_layers;          // [layer][height][width][samples]
+    void* alpha_layers;           // [layer][height][width][samples]: f32 (RGBA32F targets) or R8Unorm (8-bit targets, src/renderer.rs:783,898)
+    float* depth;                 // [height][width][samples] f32, or null when the configuration has no depth test / write
+    uint32_t depth_compare;       // cr_compare_function of the colour cover, 0 / 8 = always
+    uint32_t depth_write;
+    uint32_t clear_depth;         // the pass clears the depth aspect to depth_clear_value
+    float depth_clear_value;
+    uint32_t color_format;        // cr_color_format
     uint32_t width, height, tiles_x, tiles_y;
     uint32_t samples;             // 1 (pixel centre) or 4 (WebGPU standard pattern (6,2),(14,6),(2,10),(10,14) / 16)
     int sample_lo, sample_hi;     // smallest / largest sample offset inside a pixel in 1/256 px: 128,128 or 32,224
@@ -67,7 +73,7 @@ struct RasterTarget {
     // A rank bins and rasterises only the tiles it owns and K3 stores every finished tile into its own attachments AND,
     // over NVLink, into the peer-mapped attachments of the other ranks, so each rank ends up with the complete frame.
     uint32_t shard_world, shard_rank;             // world <= 1: not sharded
-    float4* peer_color[CR_MAX_PEERS];             // [world - 1] attachments of the other ranks (peer-mapped), or null
+    void* peer_color[CR_MAX_PEERS];               // [world - 1] attachments of the other ranks (peer-mapped), or null
     uint8_t* peer_stencil[CR_MAX_PEERS];
 };
 __host__ __device__ inline bool cr_tile_owned(const RasterTarget& tg, int tx, int ty) {

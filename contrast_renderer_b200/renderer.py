@@ -56,6 +56,8 @@ def lib():
             "cr_shape_read_index_buffer": [vp, vp, sz],
             "cr_shape_read_stroke_buffer": [vp, vp, sz],
             "cr_pass_begin": [vp, u32, u32, C.POINTER(vp)],
+            "cr_pass_begin_depth": [vp, u32, u32, u32, C.c_float, C.POINTER(vp)],
+            "cr_renderer_read_depth": [vp, vp, sz],
             "cr_pass_set_instances": [vp, vp, vp, u32, u32],
             "cr_pass_set_clip_depth": [vp, u32],
             "cr_pass_save_alpha_context": [vp, u32],
@@ -151,11 +153,33 @@ class CullMode(enum.IntEnum):
     Back = 2
 
 
+class CompareFunction(enum.IntEnum):   # wgpu::CompareFunction (Configuration::depth_compare, src/renderer.rs:388)
+    Never = 1
+    Less = 2
+    Equal = 3
+    LessEqual = 4
+    Greater = 5
+    NotEqual = 6
+    GreaterEqual = 7
+    Always = 8
+
+
+class ColorFormat(enum.IntEnum):       # Configuration::blending.format (src/renderer.rs:382)
+    Rgba32Float = 0                    # parity mode: no quantisation between blend operations
+    Rgba8Unorm = 1
+    Bgra8Unorm = 2                     # the demo's surface format (examples/application_framework.rs:175)
+
+
 class Configuration:
     """`struct Configuration` (src/renderer.rs:380-405) minus the wgpu-only fields."""
 
     def __init__(self, msaa_sample_count: int = 1, clip_nesting_counter_bits: int = 4, winding_counter_bits: int = 4, alpha_layer_count: int = 0,
-                 blending: Blending = Blending.PremultipliedOver, cull_mode: CullMode = CullMode.Off, device: int = -1):
+                 blending: Blending = Blending.PremultipliedOver, cull_mode: CullMode = CullMode.Off, device: int = -1,
+                 depth_compare: CompareFunction = CompareFunction.Always, depth_write_enabled: bool = False,
+                 color_format: ColorFormat = ColorFormat.Rgba32Float):
+        self.depth_compare = depth_compare
+        self.depth_write_enabled = depth_write_enabled
+        self.color_format = color_format
         self.msaa_sample_count = msaa_sample_count
         self.clip_nesting_counter_bits = clip_nesting_counter_bits
         self.winding_counter_bits = winding_counter_bits
@@ -166,7 +190,12 @@ class Configuration:
 
     def to_c(self) -> _abi.ConfigC:
         return _abi.ConfigC(self.msaa_sample_count, self.clip_nesting_counter_bits, self.winding_counter_bits, self.alpha_layer_count,
-                            int(self.blending), int(self.cull_mode), self.device, 0)
+                            int(self.blending), int(self.cull_mode), self.device, int(self.depth_compare), 1 if self.depth_write_enabled else 0,
+                            int(self.color_format))
+
+    @property
+    def has_depth(self) -> bool:
+        return self.depth_compare != CompareFunction.Always or bool(self.depth_write_enabled)
 
 
 def _as_soa(paths) -> PathSoA:
@@ -189,7 +218,7 @@ class Renderer:
         c = _abi.ConfigC()
         _check(lib().cr_renderer_get_config(self._h, C.byref(c)))
         return Configuration(c.msaa_sample_count, c.clip_nesting_counter_bits, c.winding_counter_bits, c.alpha_layer_count, Blending(c.blending),
-                             CullMode(c.cull_mode), c.device)
+                             CullMode(c.cull_mode), c.device, CompareFunction(c.depth_compare or 8), bool(c.depth_write_enabled), ColorFormat(c.color_format))
 
     # Renderer::resize_internal_buffers
     def resize_internal_buffers(self, width: int, height: int) -> None:
@@ -202,8 +231,10 @@ class Renderer:
     def synchronize(self) -> None:
         _check(lib().cr_renderer_synchronize(self._h))
 
-    def begin_render_pass(self, clear_color: bool = True, clear_stencil: bool = True) -> "RenderPass":
-        return RenderPass(self, clear_color, clear_stencil)
+    def begin_render_pass(self, clear_color: bool = True, clear_stencil: bool = True, clear_depth: Optional[bool] = None,
+                          depth_clear_value: float = 1.0) -> "RenderPass":
+        """`clear_depth=None`: the depth aspect follows the stencil aspect (one depth-stencil attachment, cleared to 1.0)."""
+        return RenderPass(self, clear_color, clear_stencil, clear_stencil if clear_depth is None else clear_depth, depth_clear_value)
 
     def enable_timing(self, enabled: bool = True) -> None:
         _check(lib().cr_renderer_enable_timing(self._h, 1 if enabled else 0))
@@ -242,6 +273,11 @@ class Renderer:
     def read_stencil(self) -> np.ndarray:
         out = np.empty((self.height, self.width, self.config.msaa_sample_count), np.uint8)
         _check(lib().cr_renderer_read_stencil(self._h, out.ctypes.data, out.nbytes))
+        return out
+
+    def read_depth(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, self.config.msaa_sample_count), np.float32)
+        _check(lib().cr_renderer_read_depth(self._h, out.ctypes.data, out.nbytes))
         return out
 
     def read_alpha_layer(self, layer: int) -> np.ndarray:
@@ -379,11 +415,14 @@ class RenderPass:
     """The `wgpu::RenderPass` of src/renderer.rs:267-355 plus the per-pass renderer state (`set_clip_depth`,
     `save_alpha_context`, `restore_alpha_context`). Records; `submit()` runs everything on the renderer's stream."""
 
-    def __init__(self, renderer: Renderer, clear_color: bool = True, clear_stencil: bool = True):
+    def __init__(self, renderer: Renderer, clear_color: bool = True, clear_stencil: bool = True, clear_depth: Optional[bool] = None,
+                 depth_clear_value: float = 1.0):
         self._renderer = renderer
         self._h = C.c_void_p()
         self._keep = []  # host arrays referenced by the pass until submit
-        _check(lib().cr_pass_begin(renderer._h, 1 if clear_color else 0, 1 if clear_stencil else 0, C.byref(self._h)))
+        clear_depth = clear_stencil if clear_depth is None else clear_depth
+        _check(lib().cr_pass_begin_depth(renderer._h, 1 if clear_color else 0, 1 if clear_stencil else 0, 1 if clear_depth else 0,
+                                         float(depth_clear_value), C.byref(self._h)))
         renderer._children.add(self)
 
     def set_instances(self, transforms, colors=None, count: Optional[int] = None, memory_space: int = _abi.CR_MEM_HOST) -> None:

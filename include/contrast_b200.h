@@ -68,6 +68,17 @@ typedef enum cr_render_operation {        /* enum RenderOperation, src/renderer.
 typedef enum cr_memory_space { CR_MEM_HOST = 0, CR_MEM_DEVICE = 1 } cr_memory_space;
 typedef enum cr_blending { CR_BLEND_PREMULTIPLIED_OVER = 0, CR_BLEND_REPLACE = 1 } cr_blending;
 typedef enum cr_cull_mode { CR_CULL_NONE = 0, CR_CULL_FRONT = 1, CR_CULL_BACK = 2 } cr_cull_mode;
+/* wgpu::CompareFunction with its own numbering (Configuration::depth_compare, src/renderer.rs:388); 0 reads as Always so that
+ * a zero-initialised cr_config has no depth test. */
+typedef enum cr_compare_function {
+    CR_COMPARE_DEFAULT_ALWAYS = 0, CR_COMPARE_NEVER = 1, CR_COMPARE_LESS = 2, CR_COMPARE_EQUAL = 3, CR_COMPARE_LESS_EQUAL = 4,
+    CR_COMPARE_GREATER = 5, CR_COMPARE_NOT_EQUAL = 6, CR_COMPARE_GREATER_EQUAL = 7, CR_COMPARE_ALWAYS = 8
+} cr_compare_function;
+/* Format of the colour attachment (Configuration::blending.format, src/renderer.rs:382; the demo's surface is Bgra8Unorm,
+ * examples/application_framework.rs:175). RGBA32F is the parity mode: no quantisation between blend operations. With an 8-bit
+ * format every blend result is stored as unorm8 (clamp, x * 255 + 0.5, truncate) and the alpha layers are R8Unorm like the
+ * reference's (src/renderer.rs:783,898). */
+typedef enum cr_color_format { CR_FORMAT_RGBA32F = 0, CR_FORMAT_RGBA8_UNORM = 1, CR_FORMAT_BGRA8_UNORM = 2 } cr_color_format;
 
 #define CR_MAX_DASH_INTERVALS 4           /* src/path.rs:121 */
 #define CR_DASH_PATTERN_CAPACITY 8        /* struct capacity; > CR_MAX_DASH_INTERVALS yields CR_ERR_TOO_MANY_DASH_INTERVALS */
@@ -133,8 +144,11 @@ typedef struct cr_path_soa {
 
 /* --------------------------------------------------------------------------------------------- renderer setup */
 
-/* struct Configuration, src/renderer.rs:380-405, minus the wgpu-only fields. Depth testing is not part of this
- * path (z is always 0 after `vec4(position, 0, 1)`, src/shaders.wgsl:72). */
+/* struct Configuration, src/renderer.rs:380-405, minus the wgpu-only fields. Depth: gl_Position = instance_transform *
+ * vec4(position, 0, 1) (src/shaders.wgsl:72), so clip z = col0.z * x + col1.z * y + col3.z; the colour cover is the only
+ * pipeline with a depth test and depth writes (src/renderer.rs:743-745; every other pipeline: Always / false), and a depth
+ * failure keeps the stencil value (depth_fail_op: Keep, src/renderer.rs:442). The depth attachment is 32-bit float per
+ * sample (a conforming Depth24Plus, examples/showcase/main.rs:46) and only exists when depth_compare / depth_write ask for it. */
 typedef struct cr_config {
     uint32_t msaa_sample_count;            /* 1 or 4 */
     uint32_t clip_nesting_counter_bits;
@@ -143,7 +157,10 @@ typedef struct cr_config {
     uint32_t blending;                     /* cr_blending of the colour cover */
     uint32_t cull_mode;                    /* cr_cull_mode of the colour cover */
     int32_t device;                        /* CUDA device ordinal; -1 = current */
-    uint32_t _reserved;
+    uint32_t depth_compare;                /* cr_compare_function of the colour cover (src/renderer.rs:744) */
+    uint32_t depth_write_enabled;          /* src/renderer.rs:745 */
+    uint32_t color_format;                 /* cr_color_format */
+    uint32_t _reserved[2];
 } cr_config;
 
 typedef struct cr_renderer cr_renderer;   /* struct Renderer, src/renderer.rs:408 (+ the colour / stencil attachments) */
@@ -213,6 +230,10 @@ int cr_shape_read_stroke_buffer(cr_shape* shape, void* dst, size_t capacity);
  * (the tile kernel starts cleared tiles from zero and writes every tile: no memset, no read of the old contents); a pass
  * that is aborted clears nothing. */
 int cr_pass_begin(cr_renderer* renderer, uint32_t clear_color, uint32_t clear_stencil, cr_pass** out);
+/* The same with the depth aspect's load operation spelled out (depth_ops: LoadOp::Clear(1.0) in the demo, main.rs:222-225).
+ * cr_pass_begin clears depth to 1.0 whenever it clears the stencil (one depth-stencil attachment). */
+int cr_pass_begin_depth(cr_renderer* renderer, uint32_t clear_color, uint32_t clear_stencil, uint32_t clear_depth,
+                        float depth_clear_value, cr_pass** out);
 /* Vertex buffer slot 0 (instance mat4: four vec4 that become the matrix COLUMNS, src/shaders.wgsl:13-27,
  * src/renderer.rs:462-466; 64 B each) and the instance colour slot (16 B each, src/renderer.rs:502-506).
  * `colors` may be NULL if no colour-consuming operation is recorded. */
@@ -251,6 +272,8 @@ void cr_pass_abort(cr_pass* pass);
 int cr_renderer_read_color(cr_renderer* renderer, float* dst, size_t capacity_bytes);
 int cr_renderer_read_stencil(cr_renderer* renderer, uint8_t* dst, size_t capacity_bytes);
 int cr_renderer_read_alpha_layer(cr_renderer* renderer, uint32_t layer, float* dst, size_t capacity_bytes);
+/* depth: [height][width][samples] f32; CR_ERR_INVALID_ARGUMENT if the configuration has no depth attachment. */
+int cr_renderer_read_depth(cr_renderer* renderer, float* dst, size_t capacity_bytes);
 /* Device pointers of the attachments (for zero-copy consumers and multi-GPU tile exchange). */
 int cr_renderer_get_attachments(cr_renderer* renderer, void** color_dev, void** stencil_dev);
 

@@ -87,7 +87,7 @@ int oracle_tessellate_batch(const cr_dynamic_stroke_options* groups, size_t n_gr
 
 int oracle_render(const cr_config* config, uint32_t width, uint32_t height, oracle_shape* const* shapes, uint32_t n_shapes,
                   const RenderCommand* cmds, size_t n_cmds, const float* transforms, const float* colors, float* color, uint8_t* stencil,
-                  float* alpha_layers, int threads, uint64_t* covered_samples) {
+                  float* alpha_layers, int threads, uint64_t* covered_samples, float* depth) {
     std::vector<RasterShape> rs(n_shapes);
     for (uint32_t i = 0; i < n_shapes; ++i) {
         const oracle_shape& s = *shapes[i];
@@ -103,7 +103,7 @@ int oracle_render(const cr_config* config, uint32_t width, uint32_t height, orac
     const int n_bands = ((int)height + band - 1) / band;
     std::vector<uint64_t> covered(n_threads, 0);
     parallel_for(n_bands, n_threads, 1, [&](int64_t b, int t) {
-        Framebuffer fb{width, height, config->msaa_sample_count, color, stencil, alpha_layers, 0};
+        Framebuffer fb{width, height, config->msaa_sample_count, color, stencil, alpha_layers, 0, depth};
         render_band(*config, fb, rs.data(), cmds, n_cmds, transforms, colors, (int)b * band, std::min<int>(((int)b + 1) * band, (int)height));
         covered[t] += fb.covered_samples;
     });

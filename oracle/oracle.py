@@ -48,7 +48,7 @@ def lib():
         _lib.oracle_tessellate_batch.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(_abi.PathSoAC), C.c_void_p, C.c_uint32, C.c_int,
                                                  C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         _lib.oracle_render.argtypes = [C.POINTER(_abi.ConfigC), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
-                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]
         _lib.oracle_atan2.argtypes = [C.c_float, C.c_float]
         _lib.oracle_atan2.restype = C.c_float
         _lib.oracle_acos.argtypes = [C.c_float]
@@ -181,9 +181,10 @@ def tessellate_batch(dynamic_stroke_options, soa: PathSoA, shape_path_begin: np.
 
 def render(config: _abi.ConfigC, width: int, height: int, shapes: Sequence[OracleShape], commands: np.ndarray, transforms: np.ndarray,
            colors: Optional[np.ndarray], color: Optional[np.ndarray] = None, stencil: Optional[np.ndarray] = None,
-           alpha_layers: Optional[np.ndarray] = None, threads: int = 1):
+           alpha_layers: Optional[np.ndarray] = None, threads: int = 1, depth: Optional[np.ndarray] = None):
     """commands: structured array / list of (shape, inst_begin, inst_end, op, clip_depth, save_layer, restore_layer).
-    Returns (color[h,w,s,4] f32, stencil[h,w,s] u8, alpha_layers[l,h,w,s] f32, covered_samples)."""
+    Returns (color[h,w,s,4] f32, stencil[h,w,s] u8, alpha_layers[l,h,w,s] f32, covered_samples). `depth`: the f32 depth
+    attachment [h,w,s], updated in place (pass np.ones(...) for a pass that clears depth to 1.0); None = no depth attachment."""
     s = int(config.msaa_sample_count)
     if color is None:
         color = np.zeros((height, width, s, 4), np.float32)
@@ -200,7 +201,7 @@ def render(config: _abi.ConfigC, width: int, height: int, shapes: Sequence[Oracl
     covered = C.c_uint64()
     st = lib().oracle_render(C.byref(config), width, height, handles, len(shapes), cmds, len(commands), transforms.ctypes.data,
                              colors_arr.ctypes.data if colors_arr is not None else None, color.ctypes.data, stencil.ctypes.data,
-                             alpha_layers.ctypes.data, threads, C.byref(covered))
+                             alpha_layers.ctypes.data, threads, C.byref(covered), depth.ctypes.data if depth is not None else None)
     if st:
         raise OracleError(st)
     return color, stencil, alpha_layers, int(covered.value)

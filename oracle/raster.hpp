@@ -4,8 +4,14 @@
 // src/shaders.wgsl. One sample at a time, one triangle at a time, in exact draw order.
 //
 // Rasterisation contract (shared, in words, with csrc/raster.cu — the code is written twice):
-//  * clip = col0*x + col1*y + col3 of the instance mat4 (src/shaders.wgsl:20-27,72); z is ignored; a primitive with
-//    any w <= 0 or a vertex further than 2^21 px from the origin is discarded (no frustum clipping).
+//  * clip = col0*x + col1*y + col3 of the instance mat4 (src/shaders.wgsl:20-27,72); a primitive with any w <= 0 or a vertex
+//    further than 2^21 px from the origin is discarded (no frustum clipping).
+//  * depth (colour cover only, src/renderer.rs:743-745): z / w of each vertex, interpolated linearly in screen space with
+//    the unbiased edge values as weights, f32 attachment, viewport depth range [0, 1]; order stencil test -> depth test;
+//    stencil fail -> fail_op (Zero), depth fail -> depth_fail_op (Keep, src/renderer.rs:442), both pass -> pass_op (Zero),
+//    colour write, depth write if enabled.
+//  * 8-bit colour formats: every blend result is stored as unorm8 (clamp, x*255 + 0.5, truncate) and read back as c / 255;
+//    the alpha layers are R8Unorm (src/renderer.rs:783,898). The float arrays below then hold exactly those c / 255 values.
 //  * framebuffer coordinates: fx = (ndc.x*0.5+0.5)*W, fy = (0.5-ndc.y*0.5)*H, snapped to 1/256 px
 //    (floor(v*256+0.5)); edge functions are exact 64-bit integers; top-left fill rule; zero-area => nothing.
 //  * front face = counter-clockwise in NDC (src/renderer.rs:477) = negative doubled area in y-down pixels; odd
@@ -43,6 +49,7 @@ struct Framebuffer {
     uint8_t* stencil;    // [h][w][s]
     float* alpha_layers; // [layer][h][w][s]
     uint64_t covered_samples;
+    float* depth = nullptr;   // [h][w][s], or null: no depth attachment
 };
 
 enum PipelineKind {
@@ -53,6 +60,7 @@ enum PipelineKind {
 struct RVertex {
     int64_t X, Y;
     float invw;
+    float z;   // clip z / clip w
     float attr[4];
     uint32_t flat_u;
     bool ok;
@@ -81,6 +89,7 @@ inline RVertex transform_vertex(const float* m, const float pos[2], uint32_t W, 
     v.ok = cw > 0.0f;
     if (!v.ok) return v;
     v.invw = 1.0f / cw;
+    v.z = ((m[2] * x + m[6] * y) + m[14]) / cw;
     const float fx = ((cx * v.invw) * 0.5f + 0.5f) * (float)W;
     const float fy = (0.5f - (cy * v.invw) * 0.5f) * (float)H;
     if (!(cr::fabs_f(fx) <= 2097152.0f) || !(cr::fabs_f(fy) <= 2097152.0f)) { v.ok = false; return v; }
@@ -160,9 +169,28 @@ inline bool fragment_keep(PipelineKind pipe, const DrawState& st, const float a[
     }
 }
 
-// Stencil test + stencil op + colour write for one covered sample (src/renderer.rs:571-861).
-inline void apply_sample(PipelineKind pipe, const DrawState& st, bool front, size_t sample_index) {
+inline bool depth_passes(uint32_t f, float z, float d) {   // wgpu::CompareFunction
+    switch (f) {
+        case CR_COMPARE_NEVER: return false;
+        case CR_COMPARE_LESS: return z < d;
+        case CR_COMPARE_EQUAL: return z == d;
+        case CR_COMPARE_LESS_EQUAL: return z <= d;
+        case CR_COMPARE_GREATER: return z > d;
+        case CR_COMPARE_NOT_EQUAL: return z != d;
+        case CR_COMPARE_GREATER_EQUAL: return z >= d;
+        default: return true;
+    }
+}
+inline float unorm8(float x) {
+    x = x > 0.0f ? x : 0.0f;
+    x = x < 1.0f ? x : 1.0f;
+    return cr::floor_f(x * 255.0f + 0.5f) / 255.0f;
+}
+
+// Stencil test + stencil op + colour write for one covered sample (src/renderer.rs:571-861). `z`: the fragment's depth.
+inline void apply_sample(PipelineKind pipe, const DrawState& st, bool front, size_t sample_index, float z) {
     Framebuffer& fb = *st.fb;
+    const bool u8 = st.config->color_format != CR_FORMAT_RGBA32F;
     const uint32_t W = st.wmask, C = st.cmask, M = W | C;
     uint32_t s = fb.stencil[sample_index];
     const uint32_t ref = st.ref;
@@ -183,6 +211,10 @@ inline void apply_sample(PipelineKind pipe, const DrawState& st, bool front, siz
             break;
         case PIPE_COLOR: {
             if ((ref & M) < (s & M)) {
+                if (fb.depth) {
+                    if (!depth_passes(st.config->depth_compare, z, fb.depth[sample_index])) break;   // depth_fail_op: Keep
+                    if (st.config->depth_write_enabled) fb.depth[sample_index] = z;
+                }
                 const float a = st.color[3];
                 const float src[4] = {st.color[0] * a, st.color[1] * a, st.color[2] * a, a};
                 if (st.config->blending == CR_BLEND_PREMULTIPLIED_OVER) {
@@ -191,17 +223,19 @@ inline void apply_sample(PipelineKind pipe, const DrawState& st, bool front, siz
                 } else {
                     for (int c = 0; c < 4; ++c) px[c] = src[c];
                 }
+                if (u8) for (int c = 0; c < 4; ++c) px[c] = unorm8(px[c]);
                 fb.covered_samples += 1;
             }
             s = s & ~W;  // pass_op = fail_op = Zero on write_mask W
         } break;
         case PIPE_SAVE_ALPHA:
-            if ((ref & M) <= (s & M)) fb.alpha_layers[(size_t)st.save_layer * fb.width * fb.height * fb.samples + sample_index] = px[3];
+            if ((ref & M) <= (s & M)) fb.alpha_layers[(size_t)st.save_layer * fb.width * fb.height * fb.samples + sample_index] = u8 ? unorm8(px[3]) : px[3];
             break;
         case PIPE_SCALE_ALPHA:
             if ((ref & M) <= (s & M)) {
                 const float sa = 1.0f - st.color[3];
                 px[3] = sa + px[3] * (1.0f - sa);
+                if (u8) px[3] = unorm8(px[3]);
             }
             break;
         case PIPE_RESTORE_ALPHA:
@@ -209,6 +243,7 @@ inline void apply_sample(PipelineKind pipe, const DrawState& st, bool front, siz
                 const float saved = fb.alpha_layers[(size_t)st.restore_layer * fb.width * fb.height * fb.samples + sample_index];
                 const float sa = (1.0f - saved) * (1.0f - st.color[3]);
                 px[3] = px[3] - sa;
+                if (u8) px[3] = unorm8(px[3]);
             }
             break;
     }
@@ -264,7 +299,12 @@ inline void rasterize_triangle(PipelineKind pipe, const DrawState& st, RVertex v
                 for (int k = 0; k < 4; ++k) a[k] = ((e0 * v0.attr[k] + e1 * v1.attr[k]) + e2 * v2.attr[k]) / den;
                 if (!fragment_keep(pipe, st, a, flat_u, flat_f)) continue;
                 const size_t sample_index = ((size_t)py * fb.width + (size_t)px) * fb.samples + sidx;
-                apply_sample(pipe, st, front, sample_index);
+                float z = 0.0f;
+                if (pipe == PIPE_COLOR && fb.depth) {
+                    const float b0 = (float)E[1], b1 = (float)E[2], b2 = (float)E[0];
+                    z = ((b0 * v0.z + b1 * v1.z) + b2 * v2.z) / ((b0 + b1) + b2);
+                }
+                apply_sample(pipe, st, front, sample_index, z);
             }
 }
 
