@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(cr):
     lib = C.CDLL(cr.library_path())
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} is declared in include/contrast_b200.h but not exported"
-    assert cr.lib().cr_abi_version() == 2
+    assert cr.lib().cr_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header():
