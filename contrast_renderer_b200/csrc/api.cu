@@ -111,6 +111,10 @@ int decode_device_error(uint32_t flags) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------- objects
+// Words of the renderer's pinned read-back area.
+enum { PIN_TESS = 0 /* 11 totals, err, max_proto, 5 type totals */, PIN_PASS = 24 /* PassCounters snapshot, 8 words */, PIN_MISC = 40 /* one 48-byte descriptor */, PIN_WORDS = 64 };
+
+struct cr_pass;
 struct cr_renderer {
     cr_config config;
     int device = 0;
@@ -119,19 +123,27 @@ struct cr_renderer {
     DevBuf color, stencil, alpha_layers, depth;
     // scratch shared by every from_paths / submit of this renderer
     DevBuf staging[10], counts, scan_scratch, shape_begin_dev, err_flag, hull_scratch_a, hull_scratch_b;
-    DevBuf cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, radix_scratch, tile_begin, inst_transforms, inst_colors,
-        covered_dev;
-    uint32_t* pinned = nullptr;   // small pinned read-back area
+    DevBuf compact_dev, cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, radix_scratch, tile_begin,
+        inst_transforms, inst_colors, pass_counters;
+    uint32_t* pinned = nullptr;   // PIN_WORDS words of pinned read-back area
     cr_stats stats{};
+    cr_shape_batch* stats_batch = nullptr;   // the batch of the last from_paths, for the hull-vertex statistic (its counts arrive later)
     bool timing = false;
     cudaEvent_t ev[9] = {};   // tess begin/end, bin begin/end, raster begin/end, hull begin / after sort / end
     bool ev_valid[3] = {false, false, false};
+    cudaEvent_t ev_sizes = nullptr;   // from_paths: the sizes of the build have reached the pinned area
+    cudaEvent_t ev_pass = nullptr;    // submit: the counters of the pass have reached the pinned area
+    cudaEvent_t ev_update = nullptr;  // set_dynamic_stroke_options: the 48-byte staging slot has been read
     // Draw commands are recorded straight into a pinned, grow-only arena (one recording pass at a time; a second concurrent
     // pass falls back to a heap vector), so that cr_pass_submit uploads them with a truly asynchronous copy.
-    DeviceCommand* cmd_arena = nullptr;
+    CompactCommand* cmd_arena = nullptr;
     size_t cmd_arena_cap = 0;
-    bool cmd_arena_busy = false, cmd_copy_pending = false;
-    cudaEvent_t cmd_copy_done = nullptr;
+    bool cmd_arena_busy = false;
+    // Capacities the next pass is sized with (candidates, (tile, candidate) pairs): what the last pass needed plus slack. 0: unknown.
+    uint32_t cand_cap = 0, pair_cap = 0;
+    cr_pass* inflight = nullptr;      // the last submitted pass until its device-side sizes have been checked (settle)
+    int deferred_status = CR_OK;      // an error found while settling, reported by the next entry point that can fail
+    char deferred_message[256] = "";
     uint32_t shard_world = 1, shard_rank = 0;              // tile sharding of one target across GPUs
     void* peer_color[CR_MAX_PEERS] = {};                   // peer-mapped attachments of the other ranks, slot = rank - (rank > shard_rank)
     void* peer_stencil[CR_MAX_PEERS] = {};
@@ -147,12 +159,21 @@ struct cr_shape {
 
 struct cr_shape_batch {
     cr_renderer* renderer = nullptr;
-    uint32_t n_shapes = 0, n_paths = 0, n_groups = 0;
+    uint32_t n_shapes = 0, n_paths = 0, n_groups = 0, n_segments = 0;
     DevBuf vtx[7], proto, hull, idx[3], cat_begin, hull_count, stroke, desc_dev;
-    std::vector<uint32_t> cat_begin_host;    // [CNT_COUNT][n_shapes + 1]
-    std::vector<uint32_t> hull_count_host;   // [n_shapes]
+    // Host mirrors of the slice tables ([CNT_COUNT][n_shapes + 1] cat_begin, then [n_shapes] hull_count, then the final error
+    // word), in pinned memory; they arrive asynchronously (ev_mirrors) and are only waited for by the layout / read-back calls.
+    uint32_t* mirrors = nullptr;
+    size_t mirrors_cap = 0;
+    cudaEvent_t ev_mirrors = nullptr;
+    bool mirrors_pending = false;
+    bool built = false;               // holds a finished build whose sizes can seed an optimistic rebuild
+    bool has_cubics = true;
+    uint32_t max_proto = 0;
     std::vector<cr_shape> views;
     uint64_t totals[CNT_COUNT] = {};
+    const uint32_t* cat_begin_host() const { return mirrors; }
+    const uint32_t* hull_count_host() const { return mirrors + (size_t)CNT_COUNT * (n_shapes + 1); }
 };
 
 struct InstanceSet {
@@ -162,7 +183,7 @@ struct InstanceSet {
 };
 struct cr_pass {
     cr_renderer* renderer;
-    std::vector<DeviceCommand> commands;   // heap fallback; the usual home of the commands is the renderer's pinned arena
+    std::vector<CompactCommand> commands;   // heap fallback; the usual home of the commands is the renderer's pinned arena
     bool arena = false;
     size_t n_arena = 0;
     std::vector<cr_shape_batch*> batches;
@@ -171,6 +192,7 @@ struct cr_pass {
     uint32_t clip_depth = 0, save_layer = 0, restore_layer = 0;
     bool clear_color = false, clear_stencil = false, clear_depth = false;   // LoadOp::Clear of the attachments, executed at submit (fused into the tile kernel)
     float depth_clear_value = 1.0f;
+    bool any_color = false;           // (after submit) the instance colour slot was bound
 };
 
 namespace {
@@ -188,11 +210,32 @@ struct DeviceGuard {
     DeviceGuard _guard((r)->device);                                                   \
     if (!_guard.ok) return fail(CR_ERR_CUDA, "cannot select CUDA device %d", (r)->device)
 
+int settle(cr_renderer* r);
+// An error found while settling an earlier pass is handed to the caller by the next entry point that returns a status.
+int take_deferred(cr_renderer* r) {
+    if (r->deferred_status == CR_OK) return CR_OK;
+    const int st = r->deferred_status;
+    r->deferred_status = CR_OK;
+    return fail(st, "%s", r->deferred_message);
+}
+
 void batch_release(cr_shape_batch* b) {
     cudaStream_t st = b->renderer->stream;
     for (auto& v : b->vtx) v.release(st);
     for (auto& v : b->idx) v.release(st);
     b->proto.release(st); b->hull.release(st); b->cat_begin.release(st); b->hull_count.release(st); b->stroke.release(st); b->desc_dev.release(st);
+    if (b->mirrors_pending && b->ev_mirrors) cudaEventSynchronize(b->ev_mirrors);
+    if (b->mirrors) cudaFreeHost(b->mirrors);
+    if (b->ev_mirrors) cudaEventDestroy(b->ev_mirrors);
+    b->mirrors = nullptr; b->mirrors_cap = 0; b->ev_mirrors = nullptr; b->mirrors_pending = false; b->built = false;
+}
+
+// The scan scratch carries ticket counters that must start at zero (prims.h): zero it whenever it is (re)allocated.
+int reserve_scan_scratch(cr_renderer* r, DevBuf& buf, size_t words) {
+    if (buf.p && words * 4 <= buf.cap) return CR_OK;
+    const size_t want = std::max<size_t>(words * 2, 4096);
+    CR_TRY(buf.reserve(r->stream, want * 4));
+    return cr_scan_prepare(r->stream, buf.as<uint32_t>(), buf.cap / 4);
 }
 
 // Bring one input array to the device: host memory is staged (cudaMemcpyAsync on the renderer's stream), device
@@ -208,6 +251,21 @@ int stage(cr_renderer* r, int slot, const T* src, size_t count, uint32_t space, 
     return CR_OK;
 }
 
+// The host mirrors of a batch's slice tables: wait for them (and for the build's final error word) if they are still in flight.
+int ensure_mirrors(cr_shape_batch* b) {
+    if (!b->mirrors_pending) return CR_OK;
+    CR_CUDA_TRY(cudaEventSynchronize(b->ev_mirrors));
+    b->mirrors_pending = false;
+    const uint32_t err = b->mirrors[(size_t)CNT_COUNT * (b->n_shapes + 1) + b->n_shapes];
+    return decode_device_error(err & ~CR_DEVERR_FATAL_MASK);   // an emit-pass error of an optimistic rebuild (non-finite vertex) surfaces here
+}
+
+// Shape::from_paths for many shapes. Two ways through:
+//  * cold (no previous build to go by): count, scan, bounds; the host waits for the sizes, allocates, then emit + hull;
+//  * optimistic (`b` holds a finished build of the same numbers of paths / shapes / segments): emit + hull are enqueued
+//    behind the count pass at once, writing into the previous build's arrays; shape_bounds_kernel checks on the device that
+//    they are large enough (else nothing is written and the host falls back to the cold order). The host only waits for
+//    the event after the size read-back, never for the stream: the GPU is already running the emit pass by then.
 int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t n_groups, const cr_path_soa* soa, const uint32_t* shape_path_begin,
                 uint32_t n_shapes, cr_shape_batch* b) {
     if (!soa) return fail(CR_ERR_INVALID_ARGUMENT, "paths is null");
@@ -221,95 +279,149 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     cudaStream_t st = r->stream;
     const uint32_t n_paths = soa->n_paths;
     const size_t stride = (size_t)n_paths + 1;
+    if (n_paths && !soa->type_begin) return fail(CR_ERR_INVALID_ARGUMENT, "type_begin is null");
 
     // descriptors first: TooManyDashIntervals is reported before any tessellation work (src/renderer.rs:210-215 runs
     // after the loop in the reference, but both are pure functions of the input and an error discards the Shape)
     std::vector<Descriptor48> descs(n_groups);
     for (size_t i = 0; i < n_groups; ++i) CR_TRY(convert_dynamic_stroke_options(groups[i], descs[i]));
 
+    // a pass that still reads the arrays of `b` must have been sized correctly before they are overwritten
+    CR_TRY(settle(r));
+    if (b->mirrors_pending) { CR_CUDA_TRY(cudaEventSynchronize(b->ev_mirrors)); b->mirrors_pending = false; }
+
+    const bool optimistic = b->built && b->n_paths == n_paths && b->n_shapes == n_shapes && b->n_segments == soa->n_segments && b->n_groups == n_groups;
+    b->built = false;
+
     if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[0], st));
     DevicePaths P{};
     P.n_paths = n_paths;
     P.n_segments = soa->n_segments;
+    // per-type segment totals: from the host table, or (device inputs) from the previous build of the same shape until the
+    // read-back below confirms them — they size the staging copies (host inputs only) and pick the kernel variant
     uint32_t type_totals[5] = {0, 0, 0, 0, 0};
-    if (n_paths) {
-        if (!soa->type_begin) return fail(CR_ERR_INVALID_ARGUMENT, "type_begin is null");
-        if (soa->memory_space == CR_MEM_HOST) {
-            for (int t = 0; t < 5; ++t) type_totals[t] = soa->type_begin[t * stride + n_paths];
-        } else {
-            for (int t = 0; t < 5; ++t)
-                CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[t], soa->type_begin + t * stride + n_paths, 4, cudaMemcpyDeviceToHost, st));
-            CR_CUDA_TRY(cudaStreamSynchronize(st));
-            for (int t = 0; t < 5; ++t) type_totals[t] = r->pinned[t];
-        }
+    bool totals_known = n_paths == 0;
+    if (n_paths && soa->memory_space == CR_MEM_HOST) {
+        for (int t = 0; t < 5; ++t) type_totals[t] = soa->type_begin[t * stride + n_paths];
+        totals_known = true;
+        if ((uint64_t)type_totals[0] + type_totals[1] + type_totals[2] + type_totals[3] + type_totals[4] != soa->n_segments)
+            return fail(CR_ERR_INVALID_ARGUMENT, "cr_path_soa: the per-type totals type_begin[t][n_paths] do not add up to n_segments");
     }
-    if ((uint64_t)type_totals[0] + type_totals[1] + type_totals[2] + type_totals[3] + type_totals[4] != soa->n_segments)
-        return fail(CR_ERR_INVALID_ARGUMENT, "cr_path_soa: the per-type totals type_begin[t][n_paths] do not add up to n_segments");
     static const int kSegFloats[5] = {2, 4, 6, 5, 10};
     CR_TRY(stage(r, 0, soa->start, 2 * (size_t)n_paths, soa->memory_space, &P.start));
     CR_TRY(stage(r, 1, soa->segment_begin, n_paths ? stride : 0, soa->memory_space, &P.segment_begin));
     CR_TRY(stage(r, 2, soa->segment_types, soa->n_segments, soa->memory_space, &P.segment_types));
     CR_TRY(stage(r, 3, soa->type_begin, n_paths ? 5 * stride : 0, soa->memory_space, &P.type_begin));
     const float* seg_src[5] = {soa->line_segments, soa->integral_quadratic, soa->integral_cubic, soa->rational_quadratic, soa->rational_cubic};
-    uint64_t input_bytes = 0;
     for (int t = 0; t < 5; ++t) {
-        CR_TRY(stage(r, 4 + t, seg_src[t], (size_t)type_totals[t] * kSegFloats[t], soa->memory_space, &P.seg[t]));
-        input_bytes += (uint64_t)type_totals[t] * (1 + 4 * kSegFloats[t]);
+        if (soa->memory_space == CR_MEM_DEVICE) P.seg[t] = seg_src[t];
+        else CR_TRY(stage(r, 4 + t, seg_src[t], (size_t)type_totals[t] * kSegFloats[t], soa->memory_space, &P.seg[t]));
     }
     // stroke_options == NULL: every Path has `stroke_options: None` (src/path.rs:215), i.e. all paths are filled
     if (soa->stroke_options) CR_TRY(stage(r, 9, soa->stroke_options, n_paths, soa->memory_space, &P.stroke_options));
     else P.stroke_options = nullptr;
-    input_bytes += 8ull * n_paths;
 
     // ---- pass A: count, scan, per-shape slice boundaries
     CR_TRY(r->counts.reserve(st, CNT_COUNT * stride * sizeof(uint32_t)));
-    CR_TRY(r->scan_scratch.reserve(st, (size_t)cr_scan_scratch_words((uint32_t)stride, CNT_COUNT) * 4));
+    CR_TRY(reserve_scan_scratch(r, r->scan_scratch, cr_scan_scratch_words((uint32_t)stride, CNT_COUNT)));
     CR_TRY(r->err_flag.reserve(st, 8));   // [0] error bits, [1] largest proto-hull slice of any shape
     CR_CUDA_TRY(cudaMemsetAsync(r->err_flag.p, 0, 8, st));
     CR_TRY(r->shape_begin_dev.reserve(st, (size_t)(n_shapes + 1) * 4));
     CR_CUDA_TRY(cudaMemcpyAsync(r->shape_begin_dev.p, shape_path_begin, (size_t)(n_shapes + 1) * 4, cudaMemcpyHostToDevice, st));
     CR_TRY(b->cat_begin.reserve(st, (size_t)CNT_COUNT * (n_shapes + 1) * 4));
+    CR_TRY(b->hull_count.reserve(st, (size_t)n_shapes * 4));
     uint32_t* counts = r->counts.as<uint32_t>();
-    const bool has_cubics = type_totals[CR_SEG_INTEGRAL_CUBIC] != 0 || type_totals[CR_SEG_RATIONAL_CUBIC] != 0;
-    CR_TRY(cr_tess_count(st, P, (uint32_t)n_groups, counts, r->err_flag.as<uint32_t>(), has_cubics));
-    CR_TRY(cr_scan_exclusive(st, counts, (uint32_t)stride, CNT_COUNT, r->scan_scratch.as<uint32_t>()));
-    CR_TRY(cr_tess_shape_bounds(st, counts, n_paths, r->shape_begin_dev.as<uint32_t>(), n_shapes, b->cat_begin.as<uint32_t>(), r->err_flag.as<uint32_t>() + 1));
-    for (int c = 0; c < CNT_COUNT; ++c)
-        CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[c], counts + c * stride + n_paths, 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[CNT_COUNT], r->err_flag.p, 8, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaStreamSynchronize(st));
-    CR_TRY(decode_device_error(r->pinned[CNT_COUNT]));
-    for (int c = 0; c < CNT_COUNT; ++c) b->totals[c] = r->pinned[c];
-    const uint32_t max_proto = r->pinned[CNT_COUNT + 1];
+    uint32_t* err = r->err_flag.as<uint32_t>();
 
-    // ---- allocate the outputs, pass B: emit, hull
+    auto run_sizes = [&](bool has_cubics, const TessCapacity& caps) -> int {
+        CR_TRY(cr_tess_count(st, P, (uint32_t)n_groups, counts, err, has_cubics));
+        CR_TRY(cr_scan_exclusive(st, counts, (uint32_t)stride, CNT_COUNT, r->scan_scratch.as<uint32_t>()));
+        CR_TRY(cr_tess_shape_bounds(st, counts, n_paths, r->shape_begin_dev.as<uint32_t>(), n_shapes, b->cat_begin.as<uint32_t>(), err + 1, caps, err));
+        for (int c = 0; c < CNT_COUNT; ++c)
+            CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_TESS + c], counts + c * stride + n_paths, 4, cudaMemcpyDeviceToHost, st));
+        CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_TESS + CNT_COUNT], err, 8, cudaMemcpyDeviceToHost, st));
+        if (n_paths && soa->memory_space == CR_MEM_DEVICE)
+            for (int t = 0; t < 5; ++t)
+                CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_TESS + CNT_COUNT + 2 + t], soa->type_begin + t * stride + n_paths, 4, cudaMemcpyDeviceToHost, st));
+        CR_CUDA_TRY(cudaEventRecord(r->ev_sizes, st));
+        return CR_OK;
+    };
+    auto reserve_outputs = [&](const uint64_t* totals) -> int {
+        for (int c = 0; c < 7; ++c) CR_TRY(b->vtx[c].reserve(st, totals[c] * (size_t)kCategoryStride[c]));
+        CR_TRY(b->proto.reserve(st, totals[CNT_PROTO] * 8));
+        CR_TRY(b->hull.reserve(st, totals[CNT_PROTO] * 8));
+        CR_TRY(r->hull_scratch_a.reserve(st, totals[CNT_PROTO] * 8));
+        CR_TRY(r->hull_scratch_b.reserve(st, totals[CNT_PROTO] * 8));
+        for (int k = 0; k < 3; ++k) CR_TRY(b->idx[k].reserve(st, totals[CNT_LINE_IDX + k] * 4));
+        return CR_OK;
+    };
+    auto run_emit = [&](uint32_t max_proto) -> int {
+        TessOutput out{};
+        for (int c = 0; c < 7; ++c) out.vtx[c] = b->vtx[c].p;
+        out.proto = b->proto.as<float2>();
+        for (int k = 0; k < 3; ++k) out.idx[k] = b->idx[k].as<uint32_t>();
+        // the emit pass is bound by its scattered stores: the lean kernel (3x the occupancy) measured 17 % SLOWER on the text scene, so
+        // only the count pass uses it (33 -> 7 us)
+        CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, err, true));
+        if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[6], st));
+        CR_TRY(cr_tess_hull(st, out.proto, r->hull_scratch_a.as<float2>(), r->hull_scratch_b.as<float2>(),
+                            b->cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, b->hull.as<float2>(), b->hull_count.as<uint32_t>(), max_proto, err,
+                            r->timing ? r->ev[7] : nullptr));
+        if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[8], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[1], st)); r->ev_valid[0] = true; }
+        return CR_OK;
+    };
+    TessCapacity unlimited;
+    for (int c = 0; c < CNT_COUNT; ++c) unlimited.v[c] = 0xFFFFFFFFu;
+
+    bool emitted = false;
+    if (optimistic) {
+        TessCapacity caps;
+        for (int c = 0; c < 7; ++c) caps.v[c] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, b->vtx[c].cap / kCategoryStride[c]);
+        caps.v[CNT_PROTO] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, std::min(std::min(b->proto.cap, b->hull.cap), std::min(r->hull_scratch_a.cap, r->hull_scratch_b.cap)) / 8);
+        for (int k = 0; k < 3; ++k) caps.v[CNT_LINE_IDX + k] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, b->idx[k].cap / 4);
+        CR_TRY(run_sizes(totals_known ? (type_totals[CR_SEG_INTEGRAL_CUBIC] != 0 || type_totals[CR_SEG_RATIONAL_CUBIC] != 0) : b->has_cubics, caps));
+        CR_TRY(run_emit(b->max_proto));   // the sort's shared-memory capacity is a launch parameter: larger shapes take its global-memory path
+        emitted = true;
+    } else {
+        // device inputs: the kernel variant without the cubic builder may only be used once the totals are known
+        CR_TRY(run_sizes(totals_known ? (type_totals[CR_SEG_INTEGRAL_CUBIC] != 0 || type_totals[CR_SEG_RATIONAL_CUBIC] != 0) : true, unlimited));
+    }
+    CR_CUDA_TRY(cudaEventSynchronize(r->ev_sizes));
+    uint32_t flags = r->pinned[PIN_TESS + CNT_COUNT];
+    if (n_paths && soa->memory_space == CR_MEM_DEVICE) {
+        for (int t = 0; t < 5; ++t) type_totals[t] = r->pinned[PIN_TESS + CNT_COUNT + 2 + t];
+        if ((uint64_t)type_totals[0] + type_totals[1] + type_totals[2] + type_totals[3] + type_totals[4] != soa->n_segments)
+            return fail(CR_ERR_INVALID_ARGUMENT, "cr_path_soa: the per-type totals type_begin[t][n_paths] do not add up to n_segments");
+    }
+    const bool has_cubics = type_totals[CR_SEG_INTEGRAL_CUBIC] != 0 || type_totals[CR_SEG_RATIONAL_CUBIC] != 0;
+    if (emitted && (flags & (CR_DEVERR_CAPACITY | CR_DEVERR_MODE))) {
+        // the optimistic launch did nothing (emit and hull return when they see these bits): redo in the cold order
+        CR_CUDA_TRY(cudaStreamSynchronize(st));
+        CR_CUDA_TRY(cudaMemsetAsync(r->err_flag.p, 0, 8, st));
+        CR_TRY(run_sizes(has_cubics, unlimited));
+        CR_CUDA_TRY(cudaEventSynchronize(r->ev_sizes));
+        flags = r->pinned[PIN_TESS + CNT_COUNT];
+        emitted = false;
+    }
+    CR_TRY(decode_device_error(flags));
+    for (int c = 0; c < CNT_COUNT; ++c) b->totals[c] = r->pinned[PIN_TESS + c];
+    const uint32_t max_proto = r->pinned[PIN_TESS + CNT_COUNT + 1];
+
     b->renderer = r;
     b->n_shapes = n_shapes;
     b->n_paths = n_paths;
     b->n_groups = (uint32_t)n_groups;
-    for (int c = 0; c < 7; ++c) CR_TRY(b->vtx[c].reserve(st, b->totals[c] * (size_t)kCategoryStride[c]));
-    CR_TRY(b->proto.reserve(st, b->totals[CNT_PROTO] * 8));
-    CR_TRY(b->hull.reserve(st, b->totals[CNT_PROTO] * 8));
-    CR_TRY(r->hull_scratch_a.reserve(st, b->totals[CNT_PROTO] * 8));
-    CR_TRY(r->hull_scratch_b.reserve(st, b->totals[CNT_PROTO] * 8));
-    for (int k = 0; k < 3; ++k) CR_TRY(b->idx[k].reserve(st, b->totals[CNT_LINE_IDX + k] * 4));
-    CR_TRY(b->hull_count.reserve(st, (size_t)n_shapes * 4));
+    b->n_segments = soa->n_segments;
+    b->has_cubics = has_cubics;
+    b->max_proto = max_proto;
+    if (!emitted) {
+        CR_TRY(reserve_outputs(b->totals));
+        CR_TRY(run_emit(max_proto));
+    }
     CR_TRY(b->stroke.reserve(st, n_groups * sizeof(Descriptor48)));
     if (n_groups) CR_CUDA_TRY(cudaMemcpyAsync(b->stroke.p, descs.data(), n_groups * sizeof(Descriptor48), cudaMemcpyHostToDevice, st));
-    TessOutput out{};
-    for (int c = 0; c < 7; ++c) out.vtx[c] = b->vtx[c].p;
-    out.proto = b->proto.as<float2>();
-    for (int k = 0; k < 3; ++k) out.idx[k] = b->idx[k].as<uint32_t>();
-    // the emit pass is bound by its scattered stores: the lean kernel (3x the occupancy) measured 17 % SLOWER on the text scene, so
-    // only the count pass uses it (33 -> 7 us)
-    CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, r->err_flag.as<uint32_t>(), true));
-    if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[6], st));
-    CR_TRY(cr_tess_hull(st, out.proto, r->hull_scratch_a.as<float2>(), r->hull_scratch_b.as<float2>(),
-                        b->cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, b->hull.as<float2>(), b->hull_count.as<uint32_t>(), max_proto,
-                        r->timing ? r->ev[7] : nullptr));
-    if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[8], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[1], st)); r->ev_valid[0] = true; }
 
-    // ---- the rasteriser's view of this batch + host mirrors of the slice tables
+    // ---- the rasteriser's view of this batch + host mirrors of the slice tables (asynchronous, pinned)
     DeviceBatch db{};
     for (int c = 0; c < 7; ++c) db.vtx[c] = b->vtx[c].p;
     db.hull = b->hull.as<float2>();
@@ -321,38 +433,38 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     db.n_groups = (uint32_t)n_groups;
     CR_TRY(b->desc_dev.reserve(st, sizeof(DeviceBatch)));
     CR_CUDA_TRY(cudaMemcpyAsync(b->desc_dev.p, &db, sizeof(db), cudaMemcpyHostToDevice, st));
-    b->cat_begin_host.resize((size_t)CNT_COUNT * (n_shapes + 1));
-    b->hull_count_host.resize(n_shapes);
-    CR_CUDA_TRY(cudaMemcpyAsync(b->cat_begin_host.data(), b->cat_begin.p, b->cat_begin_host.size() * 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaMemcpyAsync(b->hull_count_host.data(), b->hull_count.p, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[0], r->err_flag.p, 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaStreamSynchronize(st));
-    CR_TRY(decode_device_error(r->pinned[0]));
+    const size_t table_words = (size_t)CNT_COUNT * (n_shapes + 1), mirror_words = table_words + n_shapes + 2;
+    if (mirror_words > b->mirrors_cap) {
+        if (b->mirrors) cudaFreeHost(b->mirrors);
+        b->mirrors = nullptr;
+        CR_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&b->mirrors), mirror_words * 4, cudaHostAllocDefault));
+        b->mirrors_cap = mirror_words;
+    }
+    if (!b->ev_mirrors) CR_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_mirrors, cudaEventDisableTiming));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors, b->cat_begin.p, table_words * 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words, b->hull_count.p, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words + n_shapes, err, 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaEventRecord(b->ev_mirrors, st));
+    b->mirrors_pending = true;
     b->views.resize(n_shapes);
     for (uint32_t s = 0; s < n_shapes; ++s) b->views[s] = cr_shape{b, s, false};
+    b->built = true;
+    if (!optimistic) CR_TRY(ensure_mirrors(b));   // a first build reports every error of the emit pass (non-finite vertices) before it returns
 
+    uint64_t input_bytes = 8ull * n_paths;
+    for (int t = 0; t < 5; ++t) input_bytes += (uint64_t)type_totals[t] * (1 + 4 * kSegFloats[t]);
     uint64_t out_bytes = 0;
     for (int c = 0; c < 7; ++c) out_bytes += b->totals[c] * (uint64_t)kCategoryStride[c];
-    for (uint32_t s = 0; s < n_shapes; ++s) out_bytes += 8ull * b->hull_count_host[s];
     for (int k = 0; k < 3; ++k) out_bytes += 2ull * b->totals[CNT_LINE_IDX + k];
     // B_in of SURVEY §8d: 8 + 24 [stroked] per path; the stroked count is not known on the host for device inputs,
     // so the 24 B record is counted for every path that carries one (all of them in this ABI).
     r->stats.input_bytes = input_bytes + (soa->stroke_options ? 24ull * n_paths : 0ull);
-    r->stats.vertex_bytes = out_bytes;
+    r->stats.vertex_bytes = out_bytes;   // + 8 B per hull vertex, added by cr_renderer_get_stats once the hull counts have arrived
     r->stats.tessellated_paths = n_paths;
     r->stats.proto_hull_points = b->totals[CNT_PROTO];
     r->stats.hull_vertices = 0;
-    for (uint32_t s = 0; s < n_shapes; ++s) r->stats.hull_vertices += b->hull_count_host[s];
+    r->stats_batch = b;
     return CR_OK;
-}
-
-uint32_t slots_of_host(const cr_shape_batch* b, uint32_t shape, int cat) {
-    const size_t stride = (size_t)b->n_shapes + 1;
-    const uint32_t* cb = b->cat_begin_host.data();
-    if (cat <= 2) return cb[(CNT_LINE_IDX + cat) * stride + shape + 1] - cb[(CNT_LINE_IDX + cat) * stride + shape];
-    if (cat <= 6) return (cb[cat * stride + shape + 1] - cb[cat * stride + shape]) / 3u;
-    const uint32_t hc = b->hull_count_host[shape];
-    return hc >= 3 ? hc - 2 : 0u;
 }
 
 }  // namespace
@@ -413,8 +525,11 @@ int cr_renderer_create(const cr_config* config, cr_renderer** out) {
     CR_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = ~0ull;   // keep freed blocks cached: shape rebuilds every frame must not hit cudaMalloc
     CR_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-    CR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&r->pinned), 64 * sizeof(uint32_t)));
+    CR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&r->pinned), PIN_WORDS * sizeof(uint32_t)));
+    memset(r->pinned, 0, PIN_WORDS * sizeof(uint32_t));
     for (auto& e : r->ev) CR_CUDA_TRY(cudaEventCreate(&e));
+    CR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_sizes, cudaEventDisableTiming));
+    CR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_pass, cudaEventDisableTiming));
     *out = r.release();
     return CR_OK;
 }
@@ -426,21 +541,25 @@ static void close_peers(cr_renderer* r) {
         r->peer_color[i] = r->peer_stencil[i] = nullptr;
     }
 }
+static void pass_free(cr_pass* p);
 static void renderer_free(cr_renderer* r) {
     DeviceGuard guard(r->device);
     cudaStreamSynchronize(r->stream);
+    if (r->inflight) { pass_free(r->inflight); r->inflight = nullptr; }
     close_peers(r);
     cudaStream_t st = r->stream;
     DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->depth, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
-                     &r->hull_scratch_b, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand, &r->pair_tile_alt,
-                     &r->pair_cand_alt, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->covered_dev};
+                     &r->hull_scratch_b, &r->compact_dev, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand,
+                     &r->pair_tile_alt, &r->pair_cand_alt, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->pass_counters};
     for (DevBuf* d : all) d->release(st);
     for (auto& d : r->staging) d.release(st);
     cudaStreamSynchronize(st);
     for (auto& e : r->ev) if (e) cudaEventDestroy(e);
     if (r->pinned) cudaFreeHost(r->pinned);
     if (r->cmd_arena) cudaFreeHost(r->cmd_arena);
-    if (r->cmd_copy_done) cudaEventDestroy(r->cmd_copy_done);
+    if (r->ev_sizes) cudaEventDestroy(r->ev_sizes);
+    if (r->ev_pass) cudaEventDestroy(r->ev_pass);
+    if (r->ev_update) cudaEventDestroy(r->ev_update);
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
     delete r;
 }
@@ -452,6 +571,7 @@ static void renderer_release_child(cr_renderer* r) {
 }
 void cr_renderer_destroy(cr_renderer* r) {
     if (!r) return;
+    { DeviceGuard guard(r->device); settle(r); }   // the pass in flight is one of the live objects
     if (r->live_objects > 0) { r->destroy_requested = true; return; }
     renderer_free(r);
 }
@@ -472,6 +592,8 @@ int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
     if (width == 0 || height == 0 || width > 32768 || height > 32768) return fail(CR_ERR_INVALID_ARGUMENT, "bad extent %ux%u", width, height);
     CR_GUARD(r);
+    CR_TRY(settle(r));
+    r->cand_cap = r->pair_cap = 0;   // sized for another extent
     const size_t samples = (size_t)width * height * r->config.msaa_sample_count;
     if (r->peer_color[0] || r->peer_stencil[0]) return fail(CR_ERR_INVALID_ARGUMENT, "resize while peer attachments are imported: call cr_renderer_set_tile_sharding(r, 1, 0) first");
     r->color.plain = r->stencil.plain = true;   // exportable to the other ranks of a tile-sharded target
@@ -485,7 +607,6 @@ int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
         CR_CUDA_TRY(cudaMemcpyAsync(r->depth.p, ones.data(), samples * 4, cudaMemcpyHostToDevice, r->stream));
         CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     }
-    CR_TRY(r->covered_dev.reserve(r->stream, 16));   // [0] covered samples, [1] 64-bit pair total of the last submit
     r->width = width;
     r->height = height;
     r->tiles_x = (width + CR_TILE - 1) / CR_TILE;
@@ -499,6 +620,7 @@ int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
 int cr_renderer_set_stream(cr_renderer* r, void* cuda_stream) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
     CR_GUARD(r);
+    CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     r->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : r->own_stream;
     return CR_OK;
@@ -506,8 +628,9 @@ int cr_renderer_set_stream(cr_renderer* r, void* cuda_stream) {
 int cr_renderer_synchronize(cr_renderer* r) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
     CR_GUARD(r);
+    CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
-    return CR_OK;
+    return take_deferred(r);
 }
 
 // ---------------------------------------------------------------------------------------------- shape building
@@ -516,6 +639,8 @@ int cr_shape_batch_from_paths(cr_renderer* r, const cr_dynamic_stroke_options* g
     if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     CR_GUARD(r);
+    CR_TRY(settle(r));   // a pass in flight may still have to be re-submitted from the arrays this call is about to overwrite
+    CR_TRY(take_deferred(r));
     cr_shape_batch* b = existing;   // consumed: its allocations are reused in place when large enough (Buffer::update, src/renderer.rs:89-95)
     if (b && b->renderer != r) return fail(CR_ERR_INVALID_ARGUMENT, "existing batch belongs to another renderer");
     if (!b) {
@@ -526,6 +651,7 @@ int cr_shape_batch_from_paths(cr_renderer* r, const cr_dynamic_stroke_options* g
     }
     const int st = build_batch(r, groups, n_groups, paths, shape_path_begin, n_shapes, b);
     if (st != CR_OK) {
+        if (r->stats_batch == b) r->stats_batch = nullptr;
         batch_release(b);
         delete b;
         renderer_release_child(r);
@@ -539,6 +665,8 @@ void cr_shape_batch_destroy(cr_shape_batch* b) {
     cr_renderer* r = b->renderer;
     {
         DeviceGuard guard(r->device);
+        settle(r);   // a pass in flight may reference this batch
+        if (r->stats_batch == b) r->stats_batch = nullptr;
         batch_release(b);
     }
     delete b;
@@ -576,9 +704,16 @@ int cr_shape_batch_set_dynamic_stroke_options(cr_shape_batch* b, size_t index, c
     if (index >= b->n_groups) return fail(CR_ERR_DYNAMIC_STROKE_OPTIONS_INDEX_OUT_OF_BOUNDS, "group %zu of %u", index, b->n_groups);
     Descriptor48 d;
     CR_TRY(convert_dynamic_stroke_options(*options, d));
-    CR_GUARD(b->renderer);
-    CR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(b->stroke.p) + index * sizeof(d), &d, sizeof(d), cudaMemcpyHostToDevice, b->renderer->stream));
-    CR_CUDA_TRY(cudaStreamSynchronize(b->renderer->stream));   // `d` lives on this stack frame
+    cr_renderer* r = b->renderer;
+    CR_GUARD(r);
+    CR_TRY(settle(r));   // a pass in flight was recorded with the old descriptor
+    // staged through a slot of the pinned area (one 48-byte asynchronous copy, Buffer::update of src/renderer.rs:89-95); the slot
+    // is reused by the next update, which therefore waits for this copy — but not for the stream
+    if (!r->ev_update) CR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_update, cudaEventDisableTiming));
+    else CR_CUDA_TRY(cudaEventSynchronize(r->ev_update));
+    memcpy(&r->pinned[PIN_MISC], &d, sizeof(d));
+    CR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(b->stroke.p) + index * sizeof(d), &r->pinned[PIN_MISC], sizeof(d), cudaMemcpyHostToDevice, r->stream));
+    CR_CUDA_TRY(cudaEventRecord(r->ev_update, r->stream));
     return CR_OK;
 }
 int cr_shape_set_dynamic_stroke_options(cr_shape* s, size_t index, const cr_dynamic_stroke_options* options) {
@@ -588,15 +723,16 @@ int cr_shape_set_dynamic_stroke_options(cr_shape* s, size_t index, const cr_dyna
 
 int cr_shape_get_layout(cr_shape* s, cr_shape_layout* out) {
     if (!s || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
-    const cr_shape_batch* b = s->batch;
+    cr_shape_batch* b = s->batch;
+    CR_TRY(ensure_mirrors(b));
     const size_t stride = (size_t)b->n_shapes + 1;
-    const uint32_t* cb = b->cat_begin_host.data();
+    const uint32_t* cb = b->cat_begin_host();
     uint64_t acc = 0;
     for (int c = 0; c < 7; ++c) {
         acc += (uint64_t)(cb[c * stride + s->index + 1] - cb[c * stride + s->index]) * kCategoryStride[c];
         out->vertex_offsets[c] = acc;
     }
-    acc += 8ull * b->hull_count_host[s->index];
+    acc += 8ull * b->hull_count_host()[s->index];
     out->vertex_offsets[7] = acc;
     acc = 0;
     for (int k = 0; k < 3; ++k) {
@@ -617,7 +753,7 @@ int cr_shape_read_vertex_buffer(cr_shape* s, void* dst, size_t capacity) {
     CR_GUARD(b->renderer);
     cudaStream_t st = b->renderer->stream;
     const size_t stride = (size_t)b->n_shapes + 1;
-    const uint32_t* cb = b->cat_begin_host.data();
+    const uint32_t* cb = b->cat_begin_host();
     char* d = static_cast<char*>(dst);
     uint64_t at = 0;
     for (int c = 0; c < 8; ++c) {
@@ -642,7 +778,7 @@ int cr_shape_read_index_buffer(cr_shape* s, void* dst, size_t capacity) {
     CR_GUARD(b->renderer);
     cudaStream_t st = b->renderer->stream;
     const size_t stride = (size_t)b->n_shapes + 1;
-    const uint32_t* cb = b->cat_begin_host.data();
+    const uint32_t* cb = b->cat_begin_host();
     uint16_t* d = static_cast<uint16_t*>(dst);
     std::vector<uint32_t> wide;
     for (int k = 0; k < 3; ++k) {
@@ -668,6 +804,12 @@ int cr_shape_read_stroke_buffer(cr_shape* s, void* dst, size_t capacity) {
 }
 
 // ------------------------------------------------------------------------------------------------- render pass
+static void pass_free(cr_pass* p) {
+    cr_renderer* r = p->renderer;
+    if (p->arena) r->cmd_arena_busy = false;
+    delete p;
+}
+
 int cr_pass_begin(cr_renderer* r, uint32_t clear_color, uint32_t clear_stencil, cr_pass** out) {
     return cr_pass_begin_depth(r, clear_color, clear_stencil, clear_stencil, 1.0f, out);
 }
@@ -676,6 +818,8 @@ int cr_pass_begin_depth(cr_renderer* r, uint32_t clear_color, uint32_t clear_ste
     *out = nullptr;
     if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
     CR_GUARD(r);
+    CR_TRY(settle(r));   // the previous pass gives the command arena back (its device-side sizes have arrived long ago)
+    CR_TRY(take_deferred(r));
     cr_pass* p = new (std::nothrow) cr_pass();
     if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "out of host memory");
     p->renderer = r;
@@ -686,11 +830,7 @@ int cr_pass_begin_depth(cr_renderer* r, uint32_t clear_color, uint32_t clear_ste
     p->clear_stencil = clear_stencil != 0;
     p->clear_depth = clear_depth != 0;
     p->depth_clear_value = depth_clear_value;
-    if (!r->cmd_arena_busy) {
-        if (r->cmd_copy_pending) { cudaEventSynchronize(r->cmd_copy_done); r->cmd_copy_pending = false; }   // the previous pass's upload has long finished
-        if (!r->cmd_copy_done && cudaEventCreateWithFlags(&r->cmd_copy_done, cudaEventDisableTiming) != cudaSuccess) r->cmd_copy_done = nullptr;
-        if (r->cmd_copy_done) { p->arena = true; r->cmd_arena_busy = true; }
-    }
+    if (!r->cmd_arena_busy) { p->arena = true; r->cmd_arena_busy = true; }
     ++r->live_objects;
     *out = p;
     return CR_OK;
@@ -727,6 +867,8 @@ int cr_pass_restore_alpha_context(cr_pass* p, uint32_t alpha_layer) {
     return CR_OK;
 }
 
+// Records one draw: 32 bytes and no table look-up (the slice tables of the batch live on the device and may still be in
+// flight; the expansion into per-category candidate ranges happens on the device at submit).
 static int record(cr_pass* p, cr_shape_batch* b, uint32_t shape, uint32_t instance_begin, uint32_t instance_end, uint32_t op) {
     if (op > CR_OP_RESTORE_ALPHA_CONTEXT) return fail(CR_ERR_INVALID_ARGUMENT, "bad render operation %u", op);
     if (b->renderer != p->renderer) return fail(CR_ERR_INVALID_ARGUMENT, "shape belongs to another renderer");
@@ -742,33 +884,21 @@ static int record(cr_pass* p, cr_shape_batch* b, uint32_t shape, uint32_t instan
     uint32_t bi = 0;
     for (; bi < p->batches.size(); ++bi) if (p->batches[bi] == b) break;
     if (bi == p->batches.size()) p->batches.push_back(b);
-    DeviceCommand c{};
+    CompactCommand c{};
     c.batch = bi;
+    c.shape = shape;
     c.instance_begin = is.base + instance_begin;
     c.instance_count = instance_end - instance_begin;
     c.operation = op;
     c.ref = p->clip_depth << p->renderer->config.winding_counter_bits;
     c.layers = p->save_layer | (p->restore_layer << 16);
-    // candidates of this command, category by category in the draw order of src/renderer.rs:275-354
-    const size_t stride = (size_t)b->n_shapes + 1;
-    const uint32_t* cb = b->cat_begin_host.data();
-    uint64_t total = 0;
-    for (int cat = 0; cat < 8; ++cat) {
-        const bool drawn = op == CR_OP_STENCIL ? (cat < 7 && (cat >= 2 || b->n_groups > 0)) : cat == 7;
-        c.slots[cat] = drawn ? slots_of_host(b, shape, cat) : 0u;
-        total += (uint64_t)c.slots[cat] * c.instance_count;
-        if (total >= 0xFFFFFFFFull) return fail(CR_ERR_INVALID_ARGUMENT, "more than 2^32 candidate primitives in one draw");
-        c.cat_end[cat] = (uint32_t)total;
-        c.vbase[cat] = cb[(cat < 7 ? cat : (int)CNT_PROTO) * stride + shape];
-        if (cat < 3) c.ibase[cat] = cb[(CNT_LINE_IDX + cat) * stride + shape];
-    }
     if (!p->arena) { p->commands.push_back(c); return CR_OK; }
     cr_renderer* r = p->renderer;
     if (p->n_arena == r->cmd_arena_cap) {
         const size_t cap = std::max<size_t>(4096, 2 * r->cmd_arena_cap);
-        DeviceCommand* grown = nullptr;
-        CR_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&grown), cap * sizeof(DeviceCommand), cudaHostAllocDefault));
-        if (p->n_arena) memcpy(grown, r->cmd_arena, p->n_arena * sizeof(DeviceCommand));
+        CompactCommand* grown = nullptr;
+        CR_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&grown), cap * sizeof(CompactCommand), cudaHostAllocDefault));
+        if (p->n_arena) memcpy(grown, r->cmd_arena, p->n_arena * sizeof(CompactCommand));
         if (r->cmd_arena) cudaFreeHost(r->cmd_arena);
         r->cmd_arena = grown;
         r->cmd_arena_cap = cap;
@@ -825,7 +955,7 @@ static RasterTarget make_target(const cr_pass* p) {
 
 // The pass's clear when there is nothing to rasterise. Single GPU: plain memsets. Tile-sharded target: a rank may only touch
 // the tiles it owns (the others arrive from their owners, possibly before this call), so the tile kernel runs on an empty
-// tile table: every owned tile is cleared in all ranks' attachments.
+// tile table: every owned tile is cleared in all ranks' attachments. The depth aspect (cleared to a float) goes the same way.
 static int clear_attachments(cr_pass* p) {
     cr_renderer* r = p->renderer;
     const bool depth_clear = p->clear_depth && has_depth(r);
@@ -839,125 +969,185 @@ static int clear_attachments(cr_pass* p) {
     const uint32_t n_tiles = r->tiles_x * r->tiles_y;
     CR_TRY(r->tile_begin.reserve(r->stream, (size_t)(n_tiles + 1) * 4));
     CR_CUDA_TRY(cudaMemsetAsync(r->tile_begin.p, 0, (size_t)(n_tiles + 1) * 4, r->stream));
-    CR_CUDA_TRY(cudaMemsetAsync(r->covered_dev.p, 0, 8, r->stream));
     RasterScene none{};
-    return cr_raster_tiles(r->stream, none, make_target(p), nullptr, r->tile_begin.as<uint32_t>(), nullptr, r->covered_dev.as<unsigned long long>());
+    return cr_raster_tiles(r->stream, none, make_target(p), nullptr, r->tile_begin.as<uint32_t>(), nullptr, nullptr);
 }
-static int submit(cr_pass* p) {
+
+// Enqueues the whole pass. `sized` = false: OPTIMISTIC — buffers and grids are sized from the capacities the previous pass left
+// behind, nothing is read back before everything is enqueued; the kernels check the capacities on the device and the tile
+// kernel does not run when one did not suffice (settle() then re-submits). `sized` = true: the host waits for the candidate
+// and pair totals and sizes exactly (first pass of a renderer, tile-sharded targets, re-submission).
+static int enqueue_pass(cr_pass* p, bool sized) {
     cr_renderer* r = p->renderer;
     cudaStream_t st = r->stream;
-    const DeviceCommand* const cmds = p->arena ? r->cmd_arena : p->commands.data();
+    const CompactCommand* const cmds = p->arena ? r->cmd_arena : p->commands.data();
     const uint32_t n_cmds = (uint32_t)(p->arena ? p->n_arena : p->commands.size());
-    if (n_cmds == 0) return clear_attachments(p);
-    // ---- instance slots
-    const float* transforms = nullptr;
-    const float* colors = nullptr;
-    if (p->instance_sets.size() == 1 && p->instance_sets[0].space == CR_MEM_DEVICE) {
-        transforms = p->instance_sets[0].transforms;
-        colors = p->instance_sets[0].colors;
-    } else {
-        CR_TRY(r->inst_transforms.reserve(st, (size_t)p->instance_total * 64));
-        CR_TRY(r->inst_colors.reserve(st, (size_t)p->instance_total * 16));
-        bool any_color = false;
-        for (const InstanceSet& is : p->instance_sets) {
-            if (!is.count) continue;
-            const cudaMemcpyKind kind = is.space == CR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-            CR_CUDA_TRY(cudaMemcpyAsync(r->inst_transforms.as<float>() + 16 * (size_t)is.base, is.transforms, (size_t)is.count * 64, kind, st));
-            if (is.colors) {
-                CR_CUDA_TRY(cudaMemcpyAsync(r->inst_colors.as<float>() + 4 * (size_t)is.base, is.colors, (size_t)is.count * 16, kind, st));
-                any_color = true;
-            }
-        }
-        transforms = r->inst_transforms.as<float>();
-        colors = any_color ? r->inst_colors.as<float>() : nullptr;
-    }
-    // ---- scene description
-    std::vector<DeviceBatch> host_batches(p->batches.size());
-    CR_TRY(r->batches_dev.reserve(st, host_batches.size() * sizeof(DeviceBatch)));
+    CR_TRY(r->pass_counters.reserve(st, sizeof(PassCounters)));
+    PassCounters* counters = r->pass_counters.as<PassCounters>();
+    // ---- scene description: batches, commands (expanded on the device), candidate numbering
+    CR_TRY(r->batches_dev.reserve(st, p->batches.size() * sizeof(DeviceBatch)));
     for (size_t i = 0; i < p->batches.size(); ++i)
         CR_CUDA_TRY(cudaMemcpyAsync(r->batches_dev.as<DeviceBatch>() + i, p->batches[i]->desc_dev.p, sizeof(DeviceBatch), cudaMemcpyDeviceToDevice, st));
+    CR_TRY(r->compact_dev.reserve(st, (size_t)n_cmds * sizeof(CompactCommand)));
+    CR_CUDA_TRY(cudaMemcpyAsync(r->compact_dev.p, cmds, (size_t)n_cmds * sizeof(CompactCommand), cudaMemcpyHostToDevice, st));
     CR_TRY(r->cmds_dev.reserve(st, (size_t)n_cmds * sizeof(DeviceCommand)));
-    CR_CUDA_TRY(cudaMemcpyAsync(r->cmds_dev.p, cmds, (size_t)n_cmds * sizeof(DeviceCommand), cudaMemcpyHostToDevice, st));
-    if (p->arena) { CR_CUDA_TRY(cudaEventRecord(r->cmd_copy_done, st)); r->cmd_copy_pending = true; }
-    // candidates per command are known on the host (slice tables are mirrored), so the candidate scan needs no device pass
-    std::vector<uint32_t> cand_begin(n_cmds + 1);
-    uint64_t total = 0;
-    for (uint32_t c = 0; c < n_cmds; ++c) {
-        cand_begin[c] = (uint32_t)total;
-        total += cmds[c].cat_end[7];
-        if (total >= 0xFFFFFFFFull) return fail(CR_ERR_INVALID_ARGUMENT, "more than 2^32 candidate primitives in one pass; submit in several passes");
-    }
-    cand_begin[n_cmds] = (uint32_t)total;
-    const uint32_t n_cands = (uint32_t)total;
-    if (n_cands == 0) return clear_attachments(p);
     CR_TRY(r->cmd_cands.reserve(st, (size_t)(n_cmds + 1) * 4));
-    CR_CUDA_TRY(cudaMemcpyAsync(r->cmd_cands.p, cand_begin.data(), (size_t)(n_cmds + 1) * 4, cudaMemcpyHostToDevice, st));
+    CR_TRY(reserve_scan_scratch(r, r->scan_scratch, cr_scan_scratch_words(n_cmds + 1, 1)));
+    if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[2], st));
+    CR_TRY(cr_raster_expand(st, r->compact_dev.as<CompactCommand>(), n_cmds, r->batches_dev.as<DeviceBatch>(), r->cmds_dev.as<DeviceCommand>(), r->cmd_cands.as<uint32_t>(),
+                            counters, r->scan_scratch.as<uint32_t>()));
+    if (sized) {
+        CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_PASS], counters, 8, cudaMemcpyDeviceToHost, st));
+        CR_CUDA_TRY(cudaStreamSynchronize(st));
+        unsigned long long cand_total = 0;
+        memcpy(&cand_total, &r->pinned[PIN_PASS], 8);
+        if (cand_total >= 0xFFFFFFFFull) return fail(CR_ERR_INVALID_ARGUMENT, "%llu candidate primitives in one pass exceed 2^32; submit in several passes", cand_total);
+        r->cand_cap = std::max<uint32_t>(r->cand_cap, (uint32_t)cand_total);
+    }
+    const uint32_t cand_cap = r->cand_cap;
 
     RasterScene sc{};
     sc.batches = r->batches_dev.as<DeviceBatch>();
     sc.commands = r->cmds_dev.as<DeviceCommand>();
     sc.cmd_cand_begin = r->cmd_cands.as<uint32_t>();
     sc.n_commands = n_cmds;
-    sc.transforms = transforms;
-    sc.colors = colors;
+    sc.transforms = r->inst_transforms.as<float>();
+    sc.colors = p->any_color ? r->inst_colors.as<float>() : nullptr;
     const RasterTarget tg = make_target(p);
+    const uint32_t n_tiles = r->tiles_x * r->tiles_y;
 
     // ---- bin: count, scan, emit, sort by tile (stable => draw order survives inside every tile)
-    if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[2], st));
-    CR_TRY(r->cand_tiles.reserve(st, (size_t)(n_cands + 1) * 4));
-    CR_TRY(r->records.reserve(st, (size_t)n_cands * sizeof(PrimRecord)));
-    CR_TRY(r->scan_scratch.reserve(st, (size_t)cr_scan_scratch_words(n_cands + 1, 1) * 4));
-    CR_TRY(r->big_list.reserve(st, (size_t)(n_cands + 1) * 4));
-    CR_TRY(cr_raster_setup(st, sc, tg, n_cands, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(),
-                           r->covered_dev.as<unsigned long long>() + 1));
-    CR_TRY(cr_scan_exclusive(st, r->cand_tiles.as<uint32_t>(), n_cands + 1, 1, r->scan_scratch.as<uint32_t>()));
-    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[0], r->cand_tiles.as<uint32_t>() + n_cands, 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[2], r->covered_dev.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaStreamSynchronize(st));
-    unsigned long long pair_total = 0;
-    memcpy(&pair_total, &r->pinned[2], 8);
-    if (pair_total >= 0xFFFFFFFFull)
-        return fail(CR_ERR_INVALID_ARGUMENT, "%llu (tile, primitive) pairs in one pass exceed 2^32; submit in several passes", pair_total);
-    const uint32_t n_pairs = r->pinned[0];
-    const uint32_t n_tiles = r->tiles_x * r->tiles_y;
-    r->stats.primitives = n_cands;
-    r->stats.tile_pairs = n_pairs;
-    CR_CUDA_TRY(cudaMemsetAsync(r->covered_dev.p, 0, 8, st));
-    if (n_pairs) {
-        CR_TRY(r->pair_tile.reserve(st, (size_t)n_pairs * 4));
-        CR_TRY(r->pair_cand.reserve(st, (size_t)n_pairs * 4));
-        CR_TRY(r->pair_tile_alt.reserve(st, (size_t)n_pairs * 4));
-        CR_TRY(r->pair_cand_alt.reserve(st, (size_t)n_pairs * 4));
-        CR_TRY(r->radix_scratch.reserve(st, (size_t)cr_radix_scratch_words(n_pairs) * 4));
-        CR_TRY(r->tile_begin.reserve(st, (size_t)(n_tiles + 1) * 4));
-        CR_TRY(cr_raster_bin_emit(st, tg, n_cands, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), r->pair_tile.as<uint32_t>(),
-                                  r->pair_cand.as<uint32_t>()));
-        uint32_t key_bits = 1;
-        while ((1u << key_bits) < n_tiles) ++key_bits;
-        uint32_t *sorted_tile = nullptr, *sorted_cand = nullptr;
-        CR_TRY(cr_radix_sort_pairs(st, r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>(), r->pair_tile_alt.as<uint32_t>(), r->pair_cand_alt.as<uint32_t>(),
-                                   n_pairs, key_bits, r->radix_scratch.as<uint32_t>(), &sorted_tile, &sorted_cand));
-        CR_TRY(cr_lower_bounds(st, sorted_tile, n_pairs, r->tile_begin.as<uint32_t>(), n_tiles + 1));
-        if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[3], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[4], st)); }
-        CR_TRY(cr_raster_tiles(st, sc, tg, r->records.as<PrimRecord>(), r->tile_begin.as<uint32_t>(), sorted_cand, r->covered_dev.as<unsigned long long>()));
-        if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }
-    } else {
-        CR_TRY(clear_attachments(p));
+    CR_TRY(r->cand_tiles.reserve(st, (size_t)(cand_cap + 1) * 4));
+    CR_TRY(r->records.reserve(st, (size_t)std::max<uint32_t>(cand_cap, 1u) * sizeof(PrimRecord)));
+    CR_TRY(reserve_scan_scratch(r, r->scan_scratch, cr_scan_scratch_words(cand_cap + 1, 1)));
+    CR_TRY(r->big_list.reserve(st, (size_t)(cand_cap + 1) * 4));
+    CR_TRY(cr_raster_setup(st, sc, tg, cand_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), counters));
+    if (sized) {
+        CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_PASS + 2], &counters->pair_total, 8, cudaMemcpyDeviceToHost, st));
+        CR_CUDA_TRY(cudaStreamSynchronize(st));
+        unsigned long long pair_total = 0;
+        memcpy(&pair_total, &r->pinned[PIN_PASS + 2], 8);
+        if (pair_total >= 0xFFFFFFFFull)
+            return fail(CR_ERR_INVALID_ARGUMENT, "%llu (tile, primitive) pairs in one pass exceed 2^32; submit in several passes", pair_total);
+        r->pair_cap = std::max<uint32_t>(r->pair_cap, (uint32_t)pair_total);
+    }
+    const uint32_t pair_cap = r->pair_cap;
+    if (cand_cap) CR_TRY(cr_scan_exclusive(st, r->cand_tiles.as<uint32_t>(), cand_cap + 1, 1, r->scan_scratch.as<uint32_t>()));
+    CR_TRY(r->pair_tile.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
+    CR_TRY(r->pair_cand.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
+    CR_TRY(r->pair_tile_alt.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
+    CR_TRY(r->pair_cand_alt.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
+    CR_TRY(reserve_scan_scratch(r, r->radix_scratch, cr_radix_scratch_words(pair_cap)));
+    CR_TRY(r->tile_begin.reserve(st, (size_t)(n_tiles + 1) * 4));
+    CR_TRY(cr_raster_bin_emit(st, tg, cand_cap, pair_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), r->pair_tile.as<uint32_t>(),
+                              r->pair_cand.as<uint32_t>(), counters));
+    if (cand_cap == 0) {   // no candidates: bin_emit (which publishes the live pair count) did not run
+        CR_CUDA_TRY(cudaMemsetAsync(&counters->n_pairs_live, 0, 4, st));
+    }
+    uint32_t key_bits = 1;
+    while ((1u << key_bits) < n_tiles) ++key_bits;
+    uint32_t *sorted_tile = r->pair_tile.as<uint32_t>(), *sorted_cand = r->pair_cand.as<uint32_t>();
+    CR_TRY(cr_radix_sort_pairs(st, r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>(), r->pair_tile_alt.as<uint32_t>(), r->pair_cand_alt.as<uint32_t>(), pair_cap,
+                               &counters->n_pairs_live, key_bits, r->radix_scratch.as<uint32_t>(), &sorted_tile, &sorted_cand));
+    CR_TRY(cr_lower_bounds(st, sorted_tile, &counters->n_pairs_live, r->tile_begin.as<uint32_t>(), n_tiles + 1));
+    if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[3], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[4], st)); }
+    CR_TRY(cr_raster_tiles(st, sc, tg, r->records.as<PrimRecord>(), r->tile_begin.as<uint32_t>(), sorted_cand, counters));
+    if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }
+    CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_PASS], counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaEventRecord(r->ev_pass, st));
+    return CR_OK;
+}
+
+static int submit(cr_pass* p) {
+    cr_renderer* r = p->renderer;
+    cudaStream_t st = r->stream;
+    const uint32_t n_cmds = (uint32_t)(p->arena ? p->n_arena : p->commands.size());
+    if (n_cmds == 0) {
+        r->stats.primitives = r->stats.tile_pairs = r->stats.covered_samples = 0;
+        return clear_attachments(p);
+    }
+    // ---- instance slots: always copied, so that a re-submission (settle) reads what this call was given
+    CR_TRY(r->inst_transforms.reserve(st, (size_t)p->instance_total * 64));
+    CR_TRY(r->inst_colors.reserve(st, (size_t)p->instance_total * 16));
+    p->any_color = false;
+    for (const InstanceSet& is : p->instance_sets) {
+        if (!is.count) continue;
+        const cudaMemcpyKind kind = is.space == CR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CR_CUDA_TRY(cudaMemcpyAsync(r->inst_transforms.as<float>() + 16 * (size_t)is.base, is.transforms, (size_t)is.count * 64, kind, st));
+        if (is.colors) {
+            CR_CUDA_TRY(cudaMemcpyAsync(r->inst_colors.as<float>() + 4 * (size_t)is.base, is.colors, (size_t)is.count * 16, kind, st));
+            p->any_color = true;
+        }
+    }
+    // optimistic unless there is nothing to go by, or the target spans several GPUs (the other ranks wait for this rank's tiles)
+    const bool sized = r->cand_cap == 0 || r->pair_cap == 0 || r->shard_world > 1;
+    CR_TRY(enqueue_pass(p, sized));
+    if (sized) {   // leave slack for the next (optimistic) pass: scenes drift from frame to frame
+        r->cand_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFEull, (uint64_t)r->cand_cap + r->cand_cap / 8 + 4096);
+        r->pair_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFEull, (uint64_t)r->pair_cap + r->pair_cap / 8 + 4096);
     }
     return CR_OK;
 }
 
-// queue.submit(encoder.finish()) (examples/showcase/main.rs:252)
+extern "C++" {
+namespace {
+// The device-side sizes of the pass submitted last: wait for them (they have long arrived unless the caller comes straight
+// back), keep them as statistics and capacities, and re-submit the pass with exact sizes if a capacity did not suffice.
+int settle(cr_renderer* r) {
+    cr_pass* p = r->inflight;
+    if (!p) return CR_OK;
+    r->inflight = nullptr;
+    int status = CR_OK;
+    if (cudaEventSynchronize(r->ev_pass) != cudaSuccess) status = fail(CR_ERR_CUDA, "waiting for the pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+    PassCounters pc;
+    memcpy(&pc, &r->pinned[PIN_PASS], sizeof(pc));
+    if (status == CR_OK && pc.flags != 0u) {
+        if (pc.cand_total >= 0xFFFFFFFFull) status = fail(CR_ERR_INVALID_ARGUMENT, "%llu candidate primitives in one pass exceed 2^32; submit in several passes", pc.cand_total);
+        else {
+            r->cand_cap = std::max<uint32_t>(r->cand_cap, (uint32_t)pc.cand_total);
+            status = enqueue_pass(p, true);
+            if (status == CR_OK) {
+                if (cudaEventSynchronize(r->ev_pass) != cudaSuccess) status = fail(CR_ERR_CUDA, "waiting for the re-submitted pass failed");
+                memcpy(&pc, &r->pinned[PIN_PASS], sizeof(pc));
+            }
+        }
+    }
+    if (status == CR_OK) {
+        r->stats.primitives = pc.cand_total;
+        r->stats.tile_pairs = pc.pair_total;
+        r->stats.covered_samples = pc.covered;
+    } else if (r->deferred_status == CR_OK) {
+        r->deferred_status = status;
+        snprintf(r->deferred_message, sizeof(r->deferred_message), "(pass submitted earlier) %s", g_error_message);
+    }
+    pass_free(p);
+    renderer_release_child(r);
+    return CR_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+// queue.submit(encoder.finish()) (examples/showcase/main.rs:252). Returns once everything is enqueued. A pass whose sizes were
+// only estimated (see enqueue_pass) is checked by the next call on the renderer that needs its result or its resources;
+// an error found then (more than 2^32 primitives or pairs) is returned by that call.
 int cr_pass_submit(cr_pass* p) {
     if (!p) return fail(CR_ERR_INVALID_ARGUMENT, "null pass");
-    int st;
-    {
-        DeviceGuard guard(p->renderer->device);
-        st = guard.ok ? submit(p) : fail(CR_ERR_CUDA, "cannot select CUDA device");
-    }
     cr_renderer* r = p->renderer;
-    if (p->arena) r->cmd_arena_busy = false;
-    delete p;
+    int st;
+    bool keep = false;
+    {
+        DeviceGuard guard(r->device);
+        if (!guard.ok) st = fail(CR_ERR_CUDA, "cannot select CUDA device");
+        else {
+            st = settle(r);
+            if (st == CR_OK) st = take_deferred(r);
+            if (st == CR_OK) st = submit(p);
+            const uint32_t n_cmds = (uint32_t)(p->arena ? p->n_arena : p->commands.size());
+            keep = st == CR_OK && n_cmds != 0;
+        }
+    }
+    if (keep) { r->inflight = p; return CR_OK; }   // its commands, batches and instance copies stay until settle()
+    pass_free(p);
     renderer_release_child(r);
     return st;
 }
@@ -965,8 +1155,7 @@ int cr_pass_submit(cr_pass* p) {
 void cr_pass_abort(cr_pass* p) {
     if (!p) return;
     cr_renderer* r = p->renderer;
-    if (p->arena) r->cmd_arena_busy = false;
-    delete p;
+    pass_free(p);
     renderer_release_child(r);
 }
 
@@ -976,6 +1165,8 @@ static int read_back(cr_renderer* r, const void* src, size_t bytes, void* dst, s
     if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
     if (capacity < bytes) return fail(CR_ERR_INVALID_ARGUMENT, "capacity %zu < %zu", capacity, bytes);
     CR_GUARD(r);
+    CR_TRY(settle(r));
+    CR_TRY(take_deferred(r));
     CR_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, r->stream));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     return CR_OK;
@@ -1029,10 +1220,12 @@ int cr_renderer_set_tile_sharding(cr_renderer* r, uint32_t world, uint32_t rank)
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
     if (world == 0 || world > CR_MAX_PEERS + 1 || rank >= world) return fail(CR_ERR_INVALID_ARGUMENT, "bad tile sharding %u of %u (at most %d ranks)", rank, world, CR_MAX_PEERS + 1);
     CR_GUARD(r);
+    CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peers(r);
     r->shard_world = world;
     r->shard_rank = rank;
+    r->cand_cap = r->pair_cap = 0;   // the pair counts of a rank depend on the tiles it owns
     return CR_OK;
 }
 int cr_renderer_export_attachments(cr_renderer* r, uint8_t* color_handle, uint8_t* stencil_handle) {
@@ -1067,11 +1260,16 @@ int cr_renderer_enable_timing(cr_renderer* r, uint32_t enabled) {
 int cr_renderer_get_stats(cr_renderer* r, cr_stats* out) {
     if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
     CR_GUARD(r);
+    CR_TRY(settle(r));
+    CR_TRY(take_deferred(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
-    if (r->covered_dev.p) {
-        unsigned long long covered = 0;
-        CR_CUDA_TRY(cudaMemcpy(&covered, r->covered_dev.p, 8, cudaMemcpyDeviceToHost));
-        r->stats.covered_samples = covered;
+    if (r->stats_batch) {   // hull vertices of the last from_paths: its counts arrive with the batch's mirrors
+        cr_shape_batch* b = r->stats_batch;
+        CR_TRY(ensure_mirrors(b));
+        uint64_t hv = 0;
+        for (uint32_t s = 0; s < b->n_shapes; ++s) hv += b->hull_count_host()[s];
+        r->stats.vertex_bytes += 8ull * (hv - r->stats.hull_vertices);
+        r->stats.hull_vertices = hv;
     }
     r->stats.kernel_launches = g_cr_kernel_launches;
     float ms = 0.0f;

@@ -37,7 +37,9 @@ static const int kCategoryStride[8] = {20, 24, 8, 16, 20, 20, 24, 8};
 #define CR_DEVERR_STEPS 4u
 #define CR_DEVERR_CUBIC 8u
 #define CR_DEVERR_BAD_TABLES 16u   // cr_path_soa cursor tables are inconsistent (checked before anything is indexed with them)
-#define CR_DEVERR_FATAL_MASK (CR_DEVERR_GROUP_OOB | CR_DEVERR_BAD_TABLES)   // set by the count pass: the emit pass must not run
+#define CR_DEVERR_CAPACITY 32u     // (optimistic rebuild) an output array of the previous build is too small for this one: nothing is emitted, the host re-runs
+#define CR_DEVERR_MODE 64u         // (optimistic rebuild) the batch holds a cubic segment but the kernels without the cubic builder were launched
+#define CR_DEVERR_FATAL_MASK (CR_DEVERR_GROUP_OOB | CR_DEVERR_BAD_TABLES | CR_DEVERR_CAPACITY | CR_DEVERR_MODE)   // set before the emit pass, which then must not run
 
 namespace crd {
 

@@ -281,6 +281,107 @@ __device__ __forceinline__ uint32_t walk_tiles_warp(const int* X, const int* Y, 
     return running;
 }
 
+// ------------------------------------------------------------------------------------------ command expansion
+// Live sizes of the pass as every kernel derives them from the device counters and the host's capacities.
+__device__ __forceinline__ uint32_t live_candidates(const PassCounters* c, uint32_t cand_capacity) {
+    const unsigned long long t = c->cand_total;
+    return t <= (unsigned long long)cand_capacity ? (uint32_t)t : 0u;
+}
+__device__ __forceinline__ bool pairs_fit(const PassCounters* c, uint32_t pair_capacity) {
+    return c->pair_total <= (unsigned long long)pair_capacity && c->pair_total < 0xFFFFFFFFull;
+}
+
+// Candidates of one command, category by category in the draw order of src/renderer.rs:275-354, from the batch's slice tables.
+__device__ __forceinline__ unsigned long long expand_command(const CompactCommand& cc, const DeviceBatch* __restrict__ batches, DeviceCommand& c) {
+    const DeviceBatch& b = batches[cc.batch];
+    const size_t stride = (size_t)b.n_shapes + 1;
+    const uint32_t* cb = b.cat_begin;
+    const uint32_t shape = cc.shape;
+    c.batch = cc.batch;
+    c.instance_begin = cc.instance_begin;
+    c.instance_count = cc.instance_count;
+    c.operation = cc.operation;
+    c.ref = cc.ref;
+    c.layers = cc.layers;
+    c._pad[0] = c._pad[1] = c._pad[2] = 0;
+    unsigned long long total = 0;
+#pragma unroll
+    for (int cat = 0; cat < 8; ++cat) {
+        const bool drawn = cc.operation == CR_OP_STENCIL ? (cat < 7 && (cat >= 2 || b.n_groups > 0)) : cat == 7;
+        uint32_t slots = 0;
+        if (drawn) {
+            if (cat <= 2) slots = cb[(CNT_LINE_IDX + cat) * stride + shape + 1] - cb[(CNT_LINE_IDX + cat) * stride + shape];
+            else if (cat <= 6) slots = (cb[cat * stride + shape + 1] - cb[cat * stride + shape]) / 3u;
+            else { const uint32_t hc = b.hull_count[shape]; slots = hc >= 3 ? hc - 2 : 0u; }
+        }
+        c.slots[cat] = slots;
+        total += (unsigned long long)slots * cc.instance_count;
+        c.cat_end[cat] = (uint32_t)(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
+        c.vbase[cat] = cb[(cat < 7 ? cat : (int)CNT_PROTO) * stride + shape];
+        if (cat < 3) c.ibase[cat] = cb[(CNT_LINE_IDX + cat) * stride + shape];
+    }
+    return total;
+}
+// Up to CR_EXPAND_FUSED_MAX commands: one CTA expands them and scans their candidate counts (chunks of 1024 with a carry).
+__global__ void __launch_bounds__(1024) expand_scan_kernel(const CompactCommand* __restrict__ compact, uint32_t n_commands, const DeviceBatch* __restrict__ batches,
+                                                           DeviceCommand* __restrict__ commands, uint32_t* __restrict__ cmd_cand_begin, PassCounters* __restrict__ counters) {
+    __shared__ unsigned long long sh_warp[32];
+    __shared__ unsigned long long sh_carry;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sh_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_commands; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        unsigned long long count = 0;
+        if (i < n_commands) {
+            DeviceCommand c;
+            count = expand_command(compact[i], batches, c);
+            commands[i] = c;
+        }
+        unsigned long long incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += y; }
+        if (lane == 31) sh_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = sh_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += y; }
+            sh_warp[lane] = w;
+        }
+        __syncthreads();
+        const unsigned long long excl = sh_carry + (warp ? sh_warp[warp - 1] : 0ull) + (incl - count);
+        if (i < n_commands) cmd_cand_begin[i] = (uint32_t)(excl < 0xFFFFFFFFull ? excl : 0xFFFFFFFFull);
+        __syncthreads();
+        if (threadIdx.x == 1023) sh_carry = excl + count;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long total = sh_carry;
+        cmd_cand_begin[n_commands] = (uint32_t)(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
+        counters->cand_total = total;
+        counters->pair_total = 0;
+        counters->covered = 0;
+        counters->n_pairs_live = 0;
+        counters->flags = 0;
+    }
+}
+// More commands than that: one thread per command writes its count into cmd_cand_begin (scanned afterwards by cr_scan_exclusive).
+__global__ void __launch_bounds__(256) expand_kernel(const CompactCommand* __restrict__ compact, uint32_t n_commands, const DeviceBatch* __restrict__ batches,
+                                                     DeviceCommand* __restrict__ commands, uint32_t* __restrict__ cmd_cand_begin, PassCounters* __restrict__ counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long count = 0;
+    if (i < n_commands) {
+        DeviceCommand c;
+        count = expand_command(compact[i], batches, c);
+        commands[i] = c;
+        cmd_cand_begin[i] = (uint32_t)(count < 0xFFFFFFFFull ? count : 0xFFFFFFFFull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if ((threadIdx.x & 31u) == 0 && count) atomicAdd(&counters->cand_total, count);
+}
+
 #define SETUP_THREADS 256
 #ifndef SETUP_MIN_BLOCKS
 #define SETUP_MIN_BLOCKS 6   // 40 registers: bin stage 0.295 -> 0.283 ms on the text scene
@@ -288,9 +389,11 @@ __device__ __forceinline__ uint32_t walk_tiles_warp(const int* X, const int* Y, 
 #define SETUP_CMD_CACHE 2048
 #define META_BIG 128u
 // big[0] = number of big candidates, big[1 ...] = their candidate numbers
-__global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_kernel(RasterScene sc, RasterTarget tg, uint32_t n, PrimRecord* __restrict__ records,
+__global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_kernel(RasterScene sc, RasterTarget tg, uint32_t cand_capacity, PrimRecord* __restrict__ records,
                                                                    uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ big,
-                                                                   unsigned long long* __restrict__ pair_total) {
+                                                                   PassCounters* __restrict__ counters) {
+    const uint32_t n = live_candidates(counters, cand_capacity);   // 0 when the capacity does not suffice: nothing is produced, the host re-submits
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n == 0 && counters->cand_total != 0ull) atomicOr(&counters->flags, CR_PASS_OVERFLOW_CANDS);
     __shared__ uint32_t sh_begin[SETUP_CMD_CACHE + 1];
     const uint32_t* cmd_begin = sc.cmd_cand_begin;
     if (sc.n_commands <= SETUP_CMD_CACHE) {
@@ -309,17 +412,24 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_ke
             else { rec.meta |= META_BIG; big[1 + atomicAdd(big, 1u)] = cand; }   // counted by bin_big_kernel<false>
         }
         if (rec.meta & META_VALID) store_record(records + cand, rec);   // nobody reads the record of a candidate without tiles (more than half of them: restarts, degenerate and culled triangles)
-        cand_tiles[cand] = count;
     }
+    if (cand < cand_capacity) cand_tiles[cand] = count;   // zero beyond the live count: the scan runs over the capacity
     // 64-bit total of the (tile, candidate) pairs: the scan that places them is 32-bit, so the host must see an overflow
     // (33 k full-target hull covers at 8K wrap it) instead of sizing the pair arrays from a wrapped count
     const uint32_t warp_pairs = __reduce_add_sync(0xffffffffu, count);
-    if ((threadIdx.x & 31u) == 0 && warp_pairs) atomicAdd(pair_total, (unsigned long long)warp_pairs);
+    if ((threadIdx.x & 31u) == 0 && warp_pairs) atomicAdd(&counters->pair_total, (unsigned long long)warp_pairs);
 }
 
-__global__ void __launch_bounds__(SETUP_THREADS) bin_emit_kernel(RasterTarget tg, uint32_t n, const PrimRecord* __restrict__ records,
+__global__ void __launch_bounds__(SETUP_THREADS) bin_emit_kernel(RasterTarget tg, uint32_t cand_capacity, uint32_t pair_capacity, const PrimRecord* __restrict__ records,
                                                                  const uint32_t* __restrict__ begin, uint32_t* __restrict__ pair_tile,
-                                                                 uint32_t* __restrict__ pair_cand) {
+                                                                 uint32_t* __restrict__ pair_cand, PassCounters* __restrict__ counters) {
+    const uint32_t n = live_candidates(counters, cand_capacity);
+    const bool fit = pairs_fit(counters, pair_capacity);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // the later kernels of the pass (sort, range search, tile kernel) read these
+        counters->n_pairs_live = (fit && n != 0u) ? (uint32_t)counters->pair_total : 0u;
+        if (!fit) atomicOr(&counters->flags, CR_PASS_OVERFLOW_PAIRS);
+    }
+    if (!fit) return;
     const uint32_t cand = blockIdx.x * blockDim.x + threadIdx.x;
     if (cand >= n) return;
     const uint32_t at = begin[cand];
@@ -333,7 +443,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) bin_emit_kernel(RasterTarget tg
 template <bool EMIT>
 __global__ void __launch_bounds__(128) bin_big_kernel(RasterTarget tg, const PrimRecord* __restrict__ records, const uint32_t* __restrict__ big,
                                                       uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ pair_tile, uint32_t* __restrict__ pair_cand,
-                                                      unsigned long long* __restrict__ pair_total) {
+                                                      PassCounters* __restrict__ counters, uint32_t pair_capacity) {
+    if (EMIT && !pairs_fit(counters, pair_capacity)) return;
     const uint32_t n_big = big[0];
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_big; i += warps) {
@@ -342,7 +453,7 @@ __global__ void __launch_bounds__(128) bin_big_kernel(RasterTarget tg, const Pri
         if (EMIT) walk_tiles_warp<true>(rec.X, rec.Y, tg, cand, cand_tiles[cand], pair_tile, pair_cand);   // cand_tiles now holds the exclusive scan
         else {
             const uint32_t count = walk_tiles_warp<false>(rec.X, rec.Y, tg, cand, 0, nullptr, nullptr);
-            if ((threadIdx.x & 31u) == 0) { cand_tiles[cand] = count; if (count) atomicAdd(pair_total, (unsigned long long)count); }
+            if ((threadIdx.x & 31u) == 0) { cand_tiles[cand] = count; if (count) atomicAdd(&counters->pair_total, (unsigned long long)count); }
         }
     }
 }
@@ -583,12 +694,13 @@ template <int S, bool DEPTH, bool U8>   // samples per pixel; depth test / write
 __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ? K3_MIN_BLOCKS : K3_MIN_BLOCKS_MSAA) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
                                                                                          const uint32_t* __restrict__ tile_begin,
                                                                                          const uint32_t* __restrict__ pair_cand,
-                                                                                         unsigned long long* __restrict__ covered_out) {
+                                                                                         PassCounters* __restrict__ counters) {
     __shared__ TilePrim sh[RCHUNK];
     __shared__ int acc[2][CR_TILE * CR_TILE * S];   // per-sample result of a stencil run; double buffered so that one barrier per run suffices
     __shared__ uint32_t run_mask[RCHUNK / 32];
     __shared__ uint8_t run_start[RCHUNK + 1];
     __shared__ unsigned long long cov[2][CR_TILE][CR_TILE];   // row coverage masks (bit x * S + k) of the cover primitives of one sweep; double buffered: one barrier per sweep
+    if (counters != nullptr && counters->flags != 0u) return;   // a capacity did not suffice: leave the attachments untouched, the host re-submits
     const uint32_t tile = blockIdx.x;
     const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];
     const bool clears = tg.clear_color != 0u || tg.clear_stencil != 0u;
@@ -897,38 +1009,53 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
     // covered-sample statistic: warp reduce, one atomic per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xffffffffu, covered, o);
-    if (lane == 0 && covered) atomicAdd(covered_out, (unsigned long long)covered);
+    if (lane == 0 && covered && counters != nullptr) atomicAdd(&counters->covered, (unsigned long long)covered);
 }
 
 }  // namespace
 
 #define BIG_GRID (148 * 8)
-int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, PrimRecord* records, uint32_t* cand_tiles,
-                    uint32_t* big_list, unsigned long long* pair_total) {
-    if (n_candidates == 0) return CR_OK;
+int cr_raster_expand(cudaStream_t stream, const CompactCommand* compact, uint32_t n_commands, const DeviceBatch* batches, DeviceCommand* commands,
+                     uint32_t* cmd_cand_begin, PassCounters* counters, uint32_t* scan_scratch) {
+    if (n_commands <= CR_EXPAND_FUSED_MAX) {
+        expand_scan_kernel<<<1, 1024, 0, stream>>>(compact, n_commands, batches, commands, cmd_cand_begin, counters);
+        g_cr_kernel_launches += 1;
+    } else {
+        CR_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(PassCounters), stream));
+        expand_kernel<<<(n_commands + 255) / 256, 256, 0, stream>>>(compact, n_commands, batches, commands, cmd_cand_begin, counters);
+        g_cr_kernel_launches += 1;
+        const int st = cr_scan_exclusive(stream, cmd_cand_begin, n_commands + 1, 1, scan_scratch);   // wraps only when cand_total >= 2^32, which no capacity admits
+        if (st != CR_OK) return st;
+    }
+    CR_CUDA_TRY(cudaGetLastError());
+    return CR_OK;
+}
+int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t cand_capacity, PrimRecord* records, uint32_t* cand_tiles,
+                    uint32_t* big_list, PassCounters* counters) {
+    if (cand_capacity == 0) return CR_OK;
     CR_CUDA_TRY(cudaMemsetAsync(big_list, 0, 4, stream));
-    CR_CUDA_TRY(cudaMemsetAsync(pair_total, 0, 8, stream));
-    prim_setup_kernel<<<(n_candidates + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(scene, target, n_candidates, records, cand_tiles, big_list, pair_total);
-    bin_big_kernel<false><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, cand_tiles, nullptr, nullptr, pair_total);
+    prim_setup_kernel<<<(cand_capacity + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(scene, target, cand_capacity, records, cand_tiles, big_list, counters);
+    bin_big_kernel<false><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, cand_tiles, nullptr, nullptr, counters, 0u);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }
-int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t n_candidates, const PrimRecord* records, const uint32_t* cand_pair_begin,
-                       const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand) {
-    if (n_candidates == 0) return CR_OK;
-    bin_emit_kernel<<<(n_candidates + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(target, n_candidates, records, cand_pair_begin, pair_tile, pair_cand);
-    bin_big_kernel<true><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, const_cast<uint32_t*>(cand_pair_begin), pair_tile, pair_cand, nullptr);
+int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t cand_capacity, uint32_t pair_capacity, const PrimRecord* records,
+                       const uint32_t* cand_pair_begin, const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand, PassCounters* counters) {
+    if (cand_capacity == 0) return CR_OK;
+    bin_emit_kernel<<<(cand_capacity + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(target, cand_capacity, pair_capacity, records, cand_pair_begin, pair_tile,
+                                                                                                      pair_cand, counters);
+    bin_big_kernel<true><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, const_cast<uint32_t*>(cand_pair_begin), pair_tile, pair_cand, counters, pair_capacity);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }
 int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* tile_begin,
-                    const uint32_t* pair_cand, unsigned long long* covered_samples) {
+                    const uint32_t* pair_cand, PassCounters* counters) {
     const uint32_t n_tiles = target.tiles_x * target.tiles_y;
     if (n_tiles == 0) return CR_OK;
     const bool depth = target.depth != nullptr, u8 = target.color_format != CR_FORMAT_RGBA32F;
-#define K3_LAUNCH(S, D, U) raster_tiles_kernel<S, D, U><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, covered_samples)
+#define K3_LAUNCH(S, D, U) raster_tiles_kernel<S, D, U><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, counters)
     if (target.samples == 4) {
         if (depth) { if (u8) K3_LAUNCH(4, true, true); else K3_LAUNCH(4, true, false); }
         else { if (u8) K3_LAUNCH(4, false, true); else K3_LAUNCH(4, false, false); }

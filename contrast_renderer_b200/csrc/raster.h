@@ -19,8 +19,33 @@ struct DeviceBatch {
     uint32_t n_groups;
 };
 
-// One recorded Shape::render call (src/renderer.rs:267) with the pass state current at record time, expanded on the
-// host (the slice tables are mirrored there) so that device code needs no further table walks. A "candidate" is one
+// One recorded Shape::render call (src/renderer.rs:267) with the pass state current at record time, as the host records it:
+// 32 bytes, no table look-ups (the slice tables of a batch live on the device and may still be in flight).
+struct CompactCommand {
+    uint32_t batch, shape;
+    uint32_t instance_begin, instance_count;
+    uint32_t operation;           // cr_render_operation
+    uint32_t ref;                 // stencil reference = clip_depth << winding_counter_bits (src/renderer.rs:936)
+    uint32_t layers;              // save_layer | restore_layer << 16
+    uint32_t _pad;
+};
+static_assert(sizeof(CompactCommand) == 32, "CompactCommand layout");
+
+// Device-side sizes of one submitted pass. The host sizes grids and buffers from CAPACITIES (last frame's sizes plus slack) and
+// only reads these words back after the pass has been enqueued; when a capacity does not suffice the kernels that would overrun
+// it do nothing, the tile kernel does not run (the attachments stay untouched) and the host re-submits with larger buffers.
+#define CR_PASS_OVERFLOW_CANDS 1u
+#define CR_PASS_OVERFLOW_PAIRS 2u
+struct PassCounters {
+    unsigned long long cand_total;    // candidates of the pass, 64-bit (the numbering itself is 32-bit)
+    unsigned long long pair_total;    // (tile, candidate) pairs, 64-bit
+    unsigned long long covered;       // samples that passed the stencil test of a colour cover
+    uint32_t n_pairs_live;            // pair_total if it fits the pair capacity and 32 bits, else 0 (published by the bin-emit kernel)
+    uint32_t flags;                   // CR_PASS_OVERFLOW_*
+};
+
+// The expanded form of a command (built on the device by cr_raster_expand from the batch's slice tables), so that the
+// vertex stage needs no further table walks. A "candidate" is one
 // index slot of a strip, one triangle of a list, or one triangle of the hull strip, times the instance count; the
 // candidates of a command are numbered category by category in the draw order of src/renderer.rs:275-354.
 struct DeviceCommand {
@@ -89,13 +114,19 @@ struct RasterScene {
     const float* colors;              // [n_instances][4] or null
 };
 
-// Vertex stage + tile counting: fills records[0..n) and cand_tiles[0..n). big_list: n + 1 words of scratch (candidates
-// whose tile box is large are listed there and binned one warp each).
-// *pair_total (device, zeroed here) receives the 64-bit number of (tile, candidate) pairs: the placing scan is 32-bit.
-int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t n_candidates, PrimRecord* records, uint32_t* cand_tiles,
-                    uint32_t* big_list, unsigned long long* pair_total);
-// (tile, candidate) pairs of every valid record, at cand_pair_begin[candidate].
-int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t n_candidates, const PrimRecord* records, const uint32_t* cand_pair_begin,
-                       const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand);
+// Commands -> DeviceCommands + the exclusive scan of their candidate counts (cmd_cand_begin, n_commands + 1 words; one launch
+// for up to CR_EXPAND_FUSED_MAX commands, else expand + cr_scan_exclusive with `scan_scratch`). Zeroes *counters first.
+#define CR_EXPAND_FUSED_MAX 32768u
+int cr_raster_expand(cudaStream_t stream, const CompactCommand* compact, uint32_t n_commands, const DeviceBatch* batches, DeviceCommand* commands,
+                     uint32_t* cmd_cand_begin, PassCounters* counters, uint32_t* scan_scratch);
+// Vertex stage + tile counting over the candidate CAPACITY: fills records and cand_tiles[0..cand_capacity) (zero beyond the
+// live count). big_list: cand_capacity + 1 words of scratch (candidates whose tile box is large are listed there and binned
+// one warp each). counters->pair_total receives the 64-bit number of (tile, candidate) pairs: the placing scan is 32-bit.
+int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t cand_capacity, PrimRecord* records, uint32_t* cand_tiles,
+                    uint32_t* big_list, PassCounters* counters);
+// (tile, candidate) pairs of every valid record, at cand_pair_begin[candidate]; publishes counters->n_pairs_live / flags.
+int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t cand_capacity, uint32_t pair_capacity, const PrimRecord* records,
+                       const uint32_t* cand_pair_begin, const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand, PassCounters* counters);
+// counters may be null (clear-only launch on an empty tile table).
 int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* tile_begin,
-                    const uint32_t* pair_cand, unsigned long long* covered_samples);
+                    const uint32_t* pair_cand, PassCounters* counters);

@@ -769,7 +769,7 @@ __device__ void fill_path(Sink<EMIT>& s, const PathView& pv) {   // CUBICS == fa
             case CR_SEG_INTEGRAL_CUBIC: {
                 const float* d = pv.seg[2] + 6 * (size_t)cur[2]++;
                 const Pt cp[4] = {from_vec(last.x, last.y), from_vec(d[0], d[1]), from_vec(d[2], d[3]), from_vec(d[4], d[5])};
-                if (CUBICS) fill_cubic<EMIT, false>(s, cp);
+                if (CUBICS) fill_cubic<EMIT, false>(s, cp); else s.err |= CR_DEVERR_MODE;
                 last = to_vec(cp[3]);
             } break;
             case CR_SEG_RATIONAL_QUADRATIC: {
@@ -787,7 +787,7 @@ __device__ void fill_path(Sink<EMIT>& s, const PathView& pv) {   // CUBICS == fa
             default: {
                 const float* d = pv.seg[4] + 10 * (size_t)cur[4]++;
                 const Pt cp[4] = {from_wvec(d[0], last.x, last.y), from_wvec(d[1], d[4], d[5]), from_wvec(d[2], d[6], d[7]), from_wvec(d[3], d[8], d[9])};
-                if (CUBICS) fill_cubic<EMIT, true>(s, cp);
+                if (CUBICS) fill_cubic<EMIT, true>(s, cp); else s.err |= CR_DEVERR_MODE;
                 last = to_vec(cp[3]);
             } break;
         }
@@ -901,8 +901,13 @@ __global__ void __launch_bounds__(128) tess_emit_kernel(DevicePaths P, const uin
 
 // Per-shape slice boundaries: cat_begin[c][s] = offsets[c][shape_path_begin[s]], s in [0, n_shapes].
 __global__ void shape_bounds_kernel(const uint32_t* __restrict__ offsets, uint32_t n_paths, const uint32_t* __restrict__ shape_path_begin, uint32_t n_shapes,
-                                    uint32_t* __restrict__ cat_begin, uint32_t* __restrict__ max_proto) {
+                                    uint32_t* __restrict__ cat_begin, uint32_t* __restrict__ max_proto, TessCapacity caps, uint32_t* __restrict__ err) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) {   // optimistic rebuild: the emit pass is already enqueued behind this kernel and writes into the previous build's arrays
+        bool fits = true;
+        for (int c = 0; c < CNT_COUNT; ++c) if (offsets[(size_t)c * (n_paths + 1) + n_paths] > caps.v[c]) fits = false;
+        if (!fits) atomicOr(err, CR_DEVERR_CAPACITY);
+    }
     if (s > n_shapes) return;
     const uint32_t p = shape_path_begin[s];
     for (int c = 0; c < CNT_COUNT; ++c) cat_begin[(size_t)c * (n_shapes + 1) + s] = offsets[(size_t)c * (n_paths + 1) + p];
@@ -1103,8 +1108,9 @@ __device__ void block_sort_points_shared(float2* sm, uint32_t n) {
 }
 
 // Sort kernel: one CTA per shape; proto[begin, begin + n) is sorted in place (shared memory when it fits `cap` points).
-__global__ void __launch_bounds__(512) hull_sort_kernel(float2* __restrict__ proto, const uint32_t* __restrict__ proto_begin, uint32_t cap) {
+__global__ void __launch_bounds__(512) hull_sort_kernel(float2* __restrict__ proto, const uint32_t* __restrict__ proto_begin, uint32_t cap, const uint32_t* __restrict__ err) {
     extern __shared__ float2 hull_smem[];
+    if (*reinterpret_cast<volatile const uint32_t*>(err) & CR_DEVERR_FATAL_MASK) return;   // nothing was emitted
     const uint32_t s = blockIdx.x;
     const uint32_t begin = proto_begin[s], n = proto_begin[s + 1] - begin;
     if (n < 3) return;   // returned as-is, unsorted (src/convex_hull.rs:9-11)
@@ -1170,7 +1176,8 @@ __device__ __forceinline__ float hull_side(const HullLine& l, float2 p) { return
 #define CHAIN_THREADS (64 * CHAIN_SHAPES)
 __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2* __restrict__ sorted, float2* __restrict__ scratch_a, float2* __restrict__ scratch_b,
                                                                    const uint32_t* __restrict__ proto_begin, uint32_t n_shapes,
-                                                                   float2* __restrict__ hull_out, uint32_t* __restrict__ hull_count) {
+                                                                   float2* __restrict__ hull_out, uint32_t* __restrict__ hull_count, const uint32_t* __restrict__ err) {
+    if (*reinterpret_cast<volatile const uint32_t*>(err) & CR_DEVERR_FATAL_MASK) return;   // nothing was emitted
     __shared__ float2 window[2 * CHAIN_SHAPES][2][CHAIN_WINDOW];
     __shared__ float2 stacks[2 * CHAIN_SHAPES][HULL_STACK];
     __shared__ uint32_t sh_len[2 * CHAIN_SHAPES];
@@ -1296,8 +1303,8 @@ int cr_tess_count(cudaStream_t stream, const DevicePaths& paths, uint32_t n_grou
     return CR_OK;
 }
 int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t n_paths, const uint32_t* shape_path_begin, uint32_t n_shapes, uint32_t* cat_begin,
-                         uint32_t* max_proto) {
-    shape_bounds_kernel<<<(n_shapes + 1 + 127) / 128, 128, 0, stream>>>(offsets, n_paths, shape_path_begin, n_shapes, cat_begin, max_proto);
+                         uint32_t* max_proto, const TessCapacity& caps, uint32_t* err_flag) {
+    shape_bounds_kernel<<<(n_shapes + 1 + 127) / 128, 128, 0, stream>>>(offsets, n_paths, shape_path_begin, n_shapes, cat_begin, max_proto, caps, err_flag);
     g_cr_kernel_launches += 1;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
@@ -1314,7 +1321,7 @@ int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* 
     return CR_OK;
 }
 int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* scratch_b, const uint32_t* proto_begin, uint32_t n_shapes,
-                 float2* hull_out, uint32_t* hull_count, uint32_t max_points, cudaEvent_t after_sort) {
+                 float2* hull_out, uint32_t* hull_count, uint32_t max_points, const uint32_t* err_flag, cudaEvent_t after_sort) {
     if (n_shapes == 0) return CR_OK;
     // Sort: shared-memory capacity (in points) = the largest shape rounded up to 512 if that fits one SM's shared memory
     // (8.5 bytes per point with the bank padding), else the maximum — larger shapes sort in global memory.
@@ -1326,9 +1333,9 @@ int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* 
     }
     const uint32_t cap = std::min<uint32_t>(max_cap, std::max<uint32_t>(512u, (max_points + 511u) / 512u * 512u));
     const uint32_t threads = std::min<uint32_t>(512u, std::max<uint32_t>(64u, cap / 16u));   // one 16-element register tile per thread
-    hull_sort_kernel<<<n_shapes, threads, (size_t)SORT_SLOT(cap) * sizeof(float2), stream>>>(proto, proto_begin, cap);
+    hull_sort_kernel<<<n_shapes, threads, (size_t)SORT_SLOT(cap) * sizeof(float2), stream>>>(proto, proto_begin, cap, err_flag);
     if (after_sort) CR_CUDA_TRY(cudaEventRecord(after_sort, stream));
-    hull_chain_kernel<<<(n_shapes + CHAIN_SHAPES - 1) / CHAIN_SHAPES, CHAIN_THREADS, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out, hull_count);
+    hull_chain_kernel<<<(n_shapes + CHAIN_SHAPES - 1) / CHAIN_SHAPES, CHAIN_THREADS, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out, hull_count, err_flag);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;

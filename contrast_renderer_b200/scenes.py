@@ -136,7 +136,7 @@ def _rotate(v: np.ndarray, angle: np.ndarray) -> np.ndarray:
 
 
 def closed_cubic_strokes(n_paths: int = 1000, seed: int = SEED0 + 1, extent: Tuple[int, int] = (1920, 1080), paths_per_shape: int = 1,
-                         pixels_per_unit: float = 40.0) -> Scene:
+                         pixels_per_unit: float = 40.0, angle_step: float = 0.1) -> Scene:
     """BASELINE config 1: closed paths of 4 integral cubics, width U[1,8] px, miter clip 4, UniformTangentAngle(0.1).
     Handles are rotated off the blob tangent by U[-0.7, 0.7] rad, so most anchors are corners (miter joins)."""
     rng = np.random.default_rng(seed)
@@ -154,7 +154,7 @@ def closed_cubic_strokes(n_paths: int = 1000, seed: int = SEED0 + 1, extent: Tup
     cubic = np.concatenate([a + tang * h0, b - tang_b * h1, b], 1)
     types = np.full(len(a), _abi.CR_SEG_INTEGRAL_CUBIC, np.uint8)
     payload = [np.zeros((0, 2)), np.zeros((0, 4)), cubic, np.zeros((0, 5)), np.zeros((0, 10))]
-    stroke = _stroke_records(n_paths, (rng.uniform(1.0, 8.0, n_paths) / ppu).astype(np.float32))
+    stroke = _stroke_records(n_paths, (rng.uniform(1.0, 8.0, n_paths) / ppu).astype(np.float32), angle_step=angle_step)
     soa = _assemble(start, seg_counts, types, payload, stroke)
     n_shapes = len(begin) - 1
     colors = np.concatenate([rng.uniform(0, 1, (n_shapes, 3)), np.ones((n_shapes, 1))], 1).astype(np.float32)

@@ -75,3 +75,87 @@ def test_pair_count_beyond_32_bits_is_an_error(cr):
     assert int(rnd.stats().covered_samples) == 7680 * 4320
     shape.close()
     rnd.close()
+
+
+def _render_scene(cr, rnd, scene, batch=None, memory_space=None, pointers=None):
+    kwargs = {}
+    if memory_space is not None:
+        kwargs = dict(memory_space=memory_space, pointers=pointers)
+    batch = cr.ShapeBatch(rnd, scene.dynamic_stroke_options, scene.paths, scene.shape_path_begin, existing=batch, **kwargs)
+    rp = rnd.begin_render_pass()
+    rp.set_instances(scene.transforms(), scene.colors)
+    rp.render_batch(batch, scenes.stencil_cover_commands(scene.n_shapes))
+    rp.submit()
+    return batch
+
+
+def _oracle_frame(oracle, rnd, scene):
+    refs = [oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
+            for i in range(scene.n_shapes)]
+    cmds = [(int(c[0]), int(c[1]), int(c[2]), int(c[3]), 0, 0, 0) for c in scenes.stencil_cover_commands(scene.n_shapes)]
+    color, stencil, _, covered = oracle.render(rnd.config.to_c(), scene.width, scene.height, refs, cmds, scene.transforms(), scene.colors, threads=4)
+    return color, stencil, covered
+
+
+def test_optimistic_pass_is_resubmitted_when_a_capacity_is_exceeded(cr, oracle):
+    """cr_pass_submit sizes the second and later passes of a renderer from what the previous pass needed and only checks the
+    device-side totals afterwards. A pass that needs more candidates and more (tile, primitive) pairs than its predecessor must
+    still produce the right frame (the tile kernel does not run on the undersized attempt; the pass is submitted again)."""
+    small = scenes.mixed_fills(12, extent=(512, 384), size=(10.0, 40.0), seed=5)
+    large = scenes.mixed_fills(500, extent=(512, 384), size=(10.0, 120.0), rational=True, seed=6)
+    rnd = cr.Renderer()
+    rnd.resize_internal_buffers(512, 384)
+    for scene in (small, large, small, large):
+        batch = _render_scene(cr, rnd, scene)
+        color, stencil = rnd.read_color(), rnd.read_stencil()
+        ref_color, ref_stencil, ref_covered = _oracle_frame(oracle, rnd, scene)
+        assert np.array_equal(stencil, ref_stencil) and np.array_equal(color.view(np.uint32), ref_color.view(np.uint32))
+        assert int(rnd.stats().covered_samples) == ref_covered
+        batch.close()
+    # back-to-back passes without any read in between: each is settled by the next call on the renderer
+    batches = []
+    for scene in (small, large):
+        batches.append(_render_scene(cr, rnd, scene))
+    ref_color, ref_stencil, _ = _oracle_frame(oracle, rnd, large)
+    assert np.array_equal(rnd.read_stencil(), ref_stencil) and np.array_equal(rnd.read_color().view(np.uint32), ref_color.view(np.uint32))
+    for b in batches:
+        b.close()
+    rnd.close()
+
+
+def test_optimistic_rebuild_falls_back_when_the_outputs_grow_or_change_kind(cr, oracle):
+    """cr_shape_batch_from_paths with `existing`: the emit pass is enqueued into the previous build's arrays before the host
+    knows the new sizes. Same numbers of paths / shapes / segments, but (a) a finer curve approximation (more vertices than
+    the arrays hold) and (b) cubic segments where the previous build had none (device inputs: the kernels without the cubic
+    builder were launched) must both end in the right buffers."""
+    import torch
+    coarse = scenes.closed_cubic_strokes(60, extent=(512, 384), angle_step=0.4)
+    fine = scenes.closed_cubic_strokes(60, extent=(512, 384), angle_step=0.05)
+    assert coarse.paths.n_segments == fine.paths.n_segments
+    rnd = cr.Renderer()
+    rnd.resize_internal_buffers(512, 384)
+    batch = None
+    for scene in (coarse, fine, coarse):
+        batch = _render_scene(cr, rnd, scene, batch)
+        for i in range(0, scene.n_shapes, 7):
+            ref = oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
+            assert np.array_equal(batch[i].vertex_buffer(), ref.vertex_buffer) and np.array_equal(batch[i].index_buffer(), ref.index_buffer)
+        ref_color, ref_stencil, _ = _oracle_frame(oracle, rnd, scene)
+        assert np.array_equal(rnd.read_stencil(), ref_stencil) and np.array_equal(rnd.read_color().view(np.uint32), ref_color.view(np.uint32))
+    batch.close()
+    # (b) device-resident inputs: quadratics only, then the same segment count as cubics
+    quads = scenes.mixed_fills(80, extent=(512, 384), seed=9, types=(1,))
+    cubics = scenes.mixed_fills(80, extent=(512, 384), seed=9, types=(2,))
+    assert quads.paths.n_segments == cubics.paths.n_segments and quads.paths.n_paths == cubics.paths.n_paths
+    batch = None
+    for scene in (quads, cubics, quads):
+        arrays = scene.paths.arrays()
+        tensors = [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).cuda() for a in arrays]
+        ptrs = [t.data_ptr() if t.numel() else 0 for t in tensors]
+        ptrs[9] = 0
+        torch.cuda.synchronize()
+        batch = _render_scene(cr, rnd, scene, batch, memory_space=_abi.CR_MEM_DEVICE, pointers=ptrs)
+        ref_color, ref_stencil, _ = _oracle_frame(oracle, rnd, scene)
+        assert np.array_equal(rnd.read_stencil(), ref_stencil) and np.array_equal(rnd.read_color().view(np.uint32), ref_color.view(np.uint32))
+    batch.close()
+    rnd.close()
