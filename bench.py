@@ -1,22 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — paths/sec and covered-Mpixel/s of the tessellate -> stencil-then-cover hot path on the 100k-glyph 4K scene
-(BASELINE.json configs[2]), one process per GPU.
+"""bench.py — paths/sec and covered-Mpixel/s of the tessellate -> stencil-then-cover hot path, one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--impl reference]
 
+--config picks the BASELINE.json configuration (default 3, the 100k-glyph 4K scene the metric is quoted on):
+  1  1k closed cubic paths -> stroke tessellation to vertex buffers only          (a step = Shape::from_paths)
+  2  10k mixed line / quadratic / cubic fills, non-zero winding, 1920x1080
+  3  100k TTF glyph instances through the text front-end, 3840x2160
+  4  1000 placed copies of the 240-path group, nested clips + opacity groups, 3840x2160
+  5  1M dashed round-joined rational-cubic strokes, 7680x4320
 A "step" is one whole pass of the hot path over the scene: Shape::from_paths for every shape of the scene (one batched
-launch sequence) followed by one render pass (Stencil + Color per shape) into a cleared 3840x2160 target.
-  value : paths/s with the path arrays already resident in HBM when the timed region starts
-  e2e   : the same metric through the C-ABI with HOST (pinned) input arrays — host->device staging of every input inside
-          the timed region — and a device->host read of the pass result (the covered-sample counter) every step
-N > 1: path instances shard across GPUs by batch (north_star): each rank owns an independent scene of the same size
-(weak scaling, no data-path collective); value = all paths of all ranks / max-over-ranks time.
+launch sequence; config 4 re-tessellates its 24-Shape group) followed by one render pass into a cleared target.
+  value            : paths/s with the path arrays already resident in HBM when the timed region starts; K steps back to back,
+                     nothing read back in between (CUDA events on the renderer's stream)
+  e2e              : the same through the C-ABI with HOST (pinned) input arrays — host->device staging of every input inside the
+                     timed region — and a device->host read of the pass result (the counters) every step
+  e2e_with_frame   : e2e plus the device->host copy of the colour attachment (RGBA8 target: the frame a presenter consumes)
+N > 1: configs 1, 2, 3, 5 shard path instances across GPUs by batch (north_star): each rank owns an independent scene of the
+same size (weak scaling, no data-path collective); config 4 is ONE target tile-sharded over the ranks (strong scaling, K3
+stores finished tiles into every rank's attachments over NVLink). At N > 1 the default run also renders a config-4 frame
+tile-sharded over the N ranks and checks every rank's copy against the CPU oracle's frame (`tile_sharded_check`).
 `--impl reference`: the reference is a Rust crate with no toolchain in this image, so the reference arm is its CPU
-restatement (oracle/, `kind: "port"`) on all host threads, on a bounded sample of the same scene.
+restatement (oracle/, `kind: "port"`): tessellation on one thread like the reference's loop, raster on all host threads.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -29,18 +39,77 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = ("100k TTF glyph instances via the text front-end (paths_of_text layout, OpenSans outlines: 143.6k contour paths, 1.6M line + integral-quadratic "
-            "segments), 12 px glyphs, 3840x2160, one Shape (Stencil+Color) per 160-glyph run")
-N_GLYPHS = 100000
-EXTENT = (3840, 2160)
-RASTER_DRAM_BYTES_R01 = 218110976   # raster_tiles_kernel, one launch on this workload: 112.59 MB read + 105.52 MB written (ncu --set full, profiles/)
-CHAIN_DRAM_BYTES_R01 = 21055744     # hull_chain_kernel, one launch: 21.06 MB read + 0 written
-GLYPHS_PER_SHAPE = 160
 
+# ------------------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """One BASELINE configuration: the scene, the renderer configuration, how a pass is recorded, the oracle's commands."""
 
-def make_scene(rank: int, n_glyphs: int = N_GLYPHS):
-    from contrast_renderer_b200 import scenes
-    return scenes.text_glyphs(n_glyphs, seed=scenes.SEED0 + 3 + 1000 * rank, extent=EXTENT, glyphs_per_shape=GLYPHS_PER_SHAPE)
+    def __init__(self, index: int, rank: int, scale: float = 1.0):
+        from contrast_renderer_b200 import scenes
+        self.index = index
+        seed_shift = 1000 * rank
+        self.alpha_layers = 0
+        self.tess_only = False
+        self.scripted = False
+        if index == 1:
+            n = max(8, int(1000 * scale))
+            self.scene = scenes.closed_cubic_strokes(n, seed=scenes.SEED0 + 1 + seed_shift)
+            self.tess_only = True
+            self.name = f"{n} closed paths of 4 integral cubics, stroked (width 1-8 px, miter, UniformTangentAngle(0.1)): tessellation to vertex / index / hull buffers only"
+        elif index == 2:
+            n = max(8, int(10000 * scale))
+            self.scene = scenes.mixed_fills(n, seed=scenes.SEED0 + 2 + seed_shift)
+            self.name = f"{n} mixed line / quadratic / cubic filled paths, non-zero winding (4 bits), 1920x1080, one Shape (Stencil+Color) per path"
+        elif index == 3:
+            n = max(160, int(100000 * scale))
+            self.scene = scenes.text_glyphs(n, seed=scenes.SEED0 + 3 + seed_shift, extent=(3840, 2160), glyphs_per_shape=160)
+            self.name = (f"{n} TTF glyph instances via the text front-end (paths_of_text layout, OpenSans outlines), 12 px glyphs, 3840x2160, "
+                         "one Shape (Stencil+Color) per 160-glyph run")
+        elif index == 4:
+            n = max(2, int(1000 * scale))
+            self.scene = scenes.tiger_like(n, seed=scenes.SEED0 + 4)   # ONE target for all ranks: the same scene everywhere
+            self.alpha_layers = 2
+            self.scripted = True
+            self.name = (f"{n} placed copies of a 24-Shape / 240-path constructor-built group (rational conics and cubics), 3 nested clips and 2 nested "
+                         "opacity groups per copy, 3840x2160")
+        elif index == 5:
+            n = max(1000, int(1000000 * scale))
+            self.scene = scenes.dashed_rational_strokes(n, seed=scenes.SEED0 + 5 + seed_shift)
+            self.name = f"{n} dashed stroked open paths of 2 rational cubics, round joins and caps, UniformTangentAngle(0.2), 7680x4320, one Shape per 1000 paths"
+        else:
+            raise SystemExit(f"--config {index}: BASELINE.json has configurations 1..5")
+        s = self.scene
+        self.width, self.height = s.width, s.height
+        self.transforms = s.transforms if self.scripted else s.transforms()
+        self.colors = s.colors
+        self.commands = None if self.scripted or self.tess_only else scenes.stencil_cover_commands(s.n_shapes)
+        self.n_instances = len(self.transforms)
+        # path INSTANCES drawn per step: config 4 draws its 240 paths once per placed copy
+        self.paths_per_step = s.paths.n_paths * (n if index == 4 else 1)
+
+    def configuration(self, cr, device: int, color_format=None):
+        kw = dict(device=device, alpha_layer_count=self.alpha_layers)
+        if color_format is not None:
+            kw["color_format"] = color_format
+        return cr.Configuration(**kw)
+
+    def record(self, rp, batch) -> None:
+        if self.scripted:
+            self.scene.record(rp, batch)
+        else:
+            rp.render_batch(batch, self.commands)
+
+    def oracle_commands(self):
+        if self.scripted:
+            return self.scene.oracle_commands()
+        return [(int(c[0]), int(c[1]), int(c[2]), int(c[3]), 0, 0, 0) for c in self.commands]
+
+    def config_dict(self):
+        """Identical in the b200 and the reference arm."""
+        return {"workload": f"BASELINE config {self.index}: {self.name}", "baseline_config": self.index, "paths_per_gpu": self.scene.paths.n_paths,
+                "path_instances_per_step_per_gpu": self.paths_per_step, "segments_per_gpu": self.scene.paths.n_segments, "shapes_per_gpu": self.scene.n_shapes,
+                "width": self.width, "height": self.height, "msaa_sample_count": 1, "winding_counter_bits": 4, "clip_nesting_counter_bits": 4,
+                "color_format": "rgba32f"}
 
 
 def measured_peak_gbs():
@@ -50,6 +119,17 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except (OSError, KeyError, TypeError, ValueError):
         return 6650.0, "fallback"   # the recipe's stated fallback
+
+
+def measured_traffic(kernel: str, config_index: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` capture of this
+    command (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            table = json.load(f)
+        return table.get(f"config{config_index}", {}).get(kernel)
+    except (OSError, ValueError):
+        return None
 
 
 class ClockSampler:
@@ -115,39 +195,56 @@ class ClockSampler:
         return out
 
 
-def run_reference(args, rank: int, world: int):
-    """The reference arm: the CPU restatement of the reference on all host threads, bounded sample per step."""
+# -------------------------------------------------------------------------------------------------- CPU (oracle) legs
+def oracle_step(work: Workload, threads: int):
+    """One step of the CPU restatement: sequential tessellation like the reference's loop (src/renderer.rs:187), raster on
+    `threads` host threads. Returns (seconds tessellating, seconds rasterising, covered samples)."""
+    from oracle import oracle
+    from contrast_renderer_b200.renderer import Configuration
+    scene = work.scene
+    t0 = time.perf_counter()
+    shapes = [oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
+              for i in range(scene.n_shapes)]
+    t1 = time.perf_counter()
+    covered = 0
+    if not work.tess_only:
+        cfg = Configuration(alpha_layer_count=work.alpha_layers).to_c()
+        _, _, _, covered = oracle.render(cfg, work.width, work.height, shapes, work.oracle_commands(), work.transforms, work.colors, threads=threads)
+    return t1 - t0, time.perf_counter() - t1, covered
+
+
+def reference_scale(index: int) -> float:
+    """Fraction of the configuration one step of the CPU arm processes, so that 25 steps end within a few minutes."""
+    return {1: 1.0, 2: 1.0, 3: 1.0, 4: 0.2, 5: 0.02}[index]
+
+
+def run_reference(args, rank: int):
+    """The reference arm: the CPU restatement of the reference on the box's host cores."""
     if rank != 0:
         return
     from oracle import oracle
-    from contrast_renderer_b200 import scenes
-    from contrast_renderer_b200.renderer import Configuration
+    oracle.build()
     threads = oracle.max_threads()
-    n_glyphs = args.ref_glyphs
-    scene = make_scene(0, n_glyphs)
-    cfg = Configuration().to_c()
-    cmds = [(int(c[0]), int(c[1]), int(c[2]), int(c[3]), 0, 0, 0) for c in scenes.stencil_cover_commands(scene.n_shapes)]
-    transforms = scene.transforms()
-
-    def step():
-        shapes = [oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
-                  for i in range(scene.n_shapes)]
-        _, _, _, covered = oracle.render(cfg, scene.width, scene.height, shapes, cmds, transforms, scene.colors, threads=threads)
-        return covered
-
+    scale = args.scale if args.scale is not None else reference_scale(args.config)
+    full = Workload(args.config, 0, 1.0 if args.scale is None else args.scale)
+    work = full if scale == 1.0 or args.scale is not None else Workload(args.config, 0, scale)
     for _ in range(args.warmup):
-        step()
+        oracle_step(work, threads)
     t0 = time.perf_counter()
+    tess = raster = 0.0
     covered = 0
     for _ in range(args.steps):
-        covered = step()
+        a, b, covered = oracle_step(work, threads)
+        tess, raster = tess + a, raster + b
     dt = time.perf_counter() - t0
-    value = scene.paths.n_paths * args.steps / dt
-    sample = f"first {n_glyphs} glyphs ({scene.paths.n_paths} paths, {scene.n_shapes} shapes) of the workload, full 3840x2160 target; tessellation 1 thread (the reference loop is sequential, src/renderer.rs:187), raster {threads} threads"
+    value = work.paths_per_step * args.steps / dt
+    sample = (f"{'the whole configuration' if work is full else f'{scale:g} of the configuration'} per step ({work.scene.paths.n_paths} paths, {work.scene.n_shapes} shapes, "
+              f"{work.width}x{work.height}); tessellation on 1 thread {tess / args.steps:.3f} s per step (the reference loop is sequential, src/renderer.rs:187), "
+              f"raster on {threads} threads {raster / args.steps:.3f} s per step")
     line = {
         "impl": "reference", "metric": "paths/sec", "value": value, "unit": "paths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "width": EXTENT[0], "height": EXTENT[1], "msaa_sample_count": 1, "sample_glyphs": n_glyphs},
+        "config": full.config_dict(),
         "covered_mpixel_per_s": covered * args.steps / dt / 1e6,
         "cpu_baseline": {"value": value, "unit": "paths/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -156,37 +253,72 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(budget_s: float = 12.0):
-    """Oracle (the CPU port of the reference) on a bounded sample of the same workload: sequential tessellation like the
-    reference, raster on all host threads. Sample size is calibrated so the leg takes about `budget_s` seconds."""
+def cpu_baseline_leg(index: int, scale_arg, budget_s: float = 12.0):
+    """Oracle (the CPU port of the reference) on a bounded sample of the same workload, about `budget_s` seconds."""
     from oracle import oracle
-    from contrast_renderer_b200 import scenes
-    from contrast_renderer_b200.renderer import Configuration
     threads = oracle.max_threads()
-    cfg = Configuration().to_c()
+    scale = scale_arg if scale_arg is not None else reference_scale(index)
+    work = Workload(index, 0, scale)
+    reps, tess, raster = 0, 0.0, 0.0
+    while reps < 12 and tess + raster < budget_s:
+        a, b, _ = oracle_step(work, threads)
+        reps, tess, raster = reps + 1, tess + a, raster + b
+    return {"value": reps * work.paths_per_step / (tess + raster), "unit": "paths/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x {scale:g} of the configuration ({work.scene.paths.n_paths} paths, {work.width}x{work.height} target); tessellation on 1 thread "
+                      f"{tess / reps:.3f} s per pass (the reference loop is sequential, src/renderer.rs:187), raster on {threads} threads {raster / reps:.3f} s per pass"}
 
-    def run(n_glyphs):
-        scene = make_scene(0, n_glyphs)
-        cmds = [(int(c[0]), int(c[1]), int(c[2]), int(c[3]), 0, 0, 0) for c in scenes.stencil_cover_commands(scene.n_shapes)]
-        t0 = time.perf_counter()
-        shapes = [oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
-                  for i in range(scene.n_shapes)]
-        t1 = time.perf_counter()
-        oracle.render(cfg, scene.width, scene.height, shapes, cmds, scene.transforms(), scene.colors, threads=threads)
-        t2 = time.perf_counter()
-        return scene.paths.n_paths, t1 - t0, t2 - t1
 
-    n = 2000
-    paths, t_tess, t_raster = run(n)
-    per_glyph = (t_tess + t_raster) / n
-    n = int(min(N_GLYPHS, max(n, budget_s / max(per_glyph, 1e-9))))
-    reps, tot_paths, tot_tess, tot_raster = 0, 0, 0.0, 0.0
-    while reps < 12 and tot_tess + tot_raster < budget_s:   # the whole workload takes ~1.4 s on this host: repeat it to fill the budget
-        paths, t_tess, t_raster = run(n)
-        reps, tot_paths, tot_tess, tot_raster = reps + 1, tot_paths + paths, tot_tess + t_tess, tot_raster + t_raster
-    return {"value": tot_paths / (tot_tess + tot_raster), "unit": "paths/s", "cores": threads, "kind": "port",
-            "sample": f"{reps} x the first {n} glyphs ({paths} paths) of the workload into the full 3840x2160 target; tessellation on 1 thread "
-                      f"{tot_tess / reps:.2f} s per pass (the reference loop is sequential, src/renderer.rs:187), raster on {threads} threads {tot_raster / reps:.2f} s per pass"}
+# ------------------------------------------------------------------------------------------------------- GPU legs
+def digest(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()
+
+
+def tile_sharded_check(cr, dist, torch, rank: int, world: int, local_rank: int):
+    """A config-4 frame (200 placed copies, 1920x1080) as ONE target tile-sharded over the ranks: every rank's copy of the
+    complete frame against the CPU oracle's frame (rank 0 runs the oracle and broadcasts the digests), with the submit time."""
+    from contrast_renderer_b200 import scenes, sharding
+    scene = scenes.tiger_like(200, extent=(1920, 1080), instance_px=(60.0, 260.0))
+    config = cr.Configuration(device=local_rank, alpha_layer_count=2)
+    reference = [None]
+    if rank == 0:
+        from oracle import oracle
+        oracle.build()
+        refs = [oracle.shape_from_paths([], scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1])) for i in range(scene.n_shapes)]
+        c, s, _, cov = oracle.render(config.to_c(), scene.width, scene.height, refs, scene.oracle_commands(), scene.transforms, scene.colors, threads=oracle.max_threads())
+        reference[0] = (digest(c), digest(s), int(cov))
+    dist.broadcast_object_list(reference, src=0)
+    rnd = cr.Renderer(config)
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    stream = torch.cuda.Stream()
+    rnd.set_stream(stream.cuda_stream)
+    target = sharding.TileShardedTarget(rnd, stream=stream)
+    batch = cr.ShapeBatch(rnd, [], scene.paths, scene.shape_path_begin)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = None
+    for _ in range(3):
+        rp = target.begin_render_pass()
+        rp.set_instances(scene.transforms, scene.colors)
+        scene.record(rp, batch)
+        torch.cuda.synchronize()
+        dist.barrier()
+        start.record(stream)
+        target.submit(rp)
+        stop.record(stream)
+        rnd.synchronize()
+        torch.cuda.synchronize()
+        best = start.elapsed_time(stop) if best is None else min(best, start.elapsed_time(stop))
+    same = digest(rnd.read_color()) == reference[0][0] and digest(rnd.read_stencil()) == reference[0][1]
+    covered = int(rnd.stats().covered_samples)
+    t = torch.tensor([int(same), covered], dtype=torch.int64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t)
+    ms = torch.tensor([best], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    target.close()
+    batch.close()
+    rnd.close()
+    return {"scene": "BASELINE config 4 at 200 copies, 1920x1080, 12 000 draws, one target tile-sharded over the ranks",
+            "identical": int(t[0].item()) == world, "checked_against": "CPU oracle frame (sha256 of colour and stencil), every rank's copy",
+            "covered_samples_sum_over_ranks": int(t[1].item()), "covered_samples_oracle": reference[0][2], "submit_ms_max_over_ranks": float(ms.item()), "n_gpus": world}
 
 
 def main():
@@ -195,21 +327,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-glyphs", type=int, default=8000, help="sample size of one step of the reference arm")
-    ap.add_argument("--glyphs", type=int, default=N_GLYPHS, help="debug only: a smaller scene is not the benchmark workload")
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json configuration 1..5 (default 3: the one the metric is quoted on)")
+    ap.add_argument("--scale", type=float, default=None, help="debug only: a fraction of the configuration is not the benchmark workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded-check", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
     import torch.distributed as dist
-    from contrast_renderer_b200 import _abi, renderer as R, scenes
+    from contrast_renderer_b200 import _abi, renderer as R, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
@@ -219,21 +352,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    scene = make_scene(rank, args.glyphs)
-    soa = scene.paths
-    n_paths = soa.n_paths
-    cmds = scenes.stencil_cover_commands(scene.n_shapes)
-    transforms = scene.transforms()
+    work = Workload(args.config, rank, 1.0 if args.scale is None else args.scale)
+    scene, soa = work.scene, work.scene.paths
+    one_target = args.config == 4 and world > 1      # ONE render target spanning the ranks (tile sharding), else an independent scene per rank
 
-    rnd = R.Renderer(R.Configuration(device=local_rank))
-    # The renderer and the CUDA events that time it share ONE stream. It must not be the legacy default stream: its handle is
-    # 0, which cr_renderer_set_stream reads as "use your own stream".
-    stream = torch.cuda.Stream(dev)
-    assert stream.cuda_stream != 0
+    def make_renderer(color_format=None):
+        rnd = R.Renderer(work.configuration(R, local_rank, color_format))
+        stream = torch.cuda.Stream(dev)   # not the legacy default stream: its handle is 0, which cr_renderer_set_stream reads as "use your own stream"
+        assert stream.cuda_stream != 0
+        rnd.set_stream(stream.cuda_stream)
+        rnd.resize_internal_buffers(work.width, work.height)
+        return rnd, stream
+
+    rnd, stream = make_renderer()
     torch.cuda.set_stream(stream)
-    rnd.set_stream(stream.cuda_stream)
-    rnd.resize_internal_buffers(scene.width, scene.height)
-    rnd.enable_timing(True)
+    target = sharding.TileShardedTarget(rnd, stream=stream) if one_target else None
 
     # device-resident and pinned-host copies of every input array
     host_arrays = soa.arrays()
@@ -241,136 +374,187 @@ def main():
         host_arrays[9] = host_arrays[9][:0]   # all paths are filled: cr_path_soa.stroke_options = NULL, nothing to copy
     pinned = [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).pin_memory() for a in host_arrays]
     resident = [t.to(dev) for t in pinned]
-    inst_host = [torch.from_numpy(transforms.reshape(-1).copy()).pin_memory(), torch.from_numpy(scene.colors.reshape(-1).copy()).pin_memory()]
+    inst_host = [torch.from_numpy(np.ascontiguousarray(work.transforms, np.float32).reshape(-1).copy()).pin_memory(),
+                 torch.from_numpy(np.ascontiguousarray(work.colors, np.float32).reshape(-1).copy()).pin_memory()]
     inst_dev = [t.to(dev) for t in inst_host]
-    h2d_bytes = sum(t.numel() for t in pinned) + sum(t.numel() * 4 for t in inst_host) + cmds.nbytes + 4 * len(scene.shape_path_begin)
+    n_commands = 0 if work.tess_only else (len(scene.script) if work.scripted else len(work.commands))
+    h2d_bytes = sum(t.numel() for t in pinned) + 4 * len(scene.shape_path_begin)
+    if not work.tess_only:
+        h2d_bytes += sum(t.numel() * 4 for t in inst_host) + 32 * n_commands
 
-    state = {"batch": None}
+    state = {}
 
-    def step(device_resident: bool):
+    def step(r, device_resident: bool):
         if device_resident:
-            ptrs = [t.data_ptr() if t.numel() else 0 for t in resident]
-            space = _abi.CR_MEM_DEVICE
+            ptrs, space = [t.data_ptr() if t.numel() else 0 for t in resident], _abi.CR_MEM_DEVICE
         else:
-            ptrs = [t.data_ptr() if t.numel() else 0 for t in pinned]
-            space = _abi.CR_MEM_HOST
-        state["batch"] = R.ShapeBatch(rnd, scene.dynamic_stroke_options, soa, scene.shape_path_begin, existing=state["batch"], memory_space=space, pointers=ptrs)
-        rp = rnd.begin_render_pass()
+            ptrs, space = [t.data_ptr() if t.numel() else 0 for t in pinned], _abi.CR_MEM_HOST
+        state[r] = R.ShapeBatch(r, scene.dynamic_stroke_options, soa, scene.shape_path_begin, existing=state.get(r), memory_space=space, pointers=ptrs)
+        if work.tess_only:
+            return
+        rp = target.begin_render_pass() if (one_target and r is rnd) else r.begin_render_pass()
         if device_resident:
-            rp.set_instances(inst_dev[0].data_ptr(), inst_dev[1].data_ptr(), count=scene.n_shapes, memory_space=_abi.CR_MEM_DEVICE)
+            rp.set_instances(inst_dev[0].data_ptr(), inst_dev[1].data_ptr(), count=work.n_instances, memory_space=_abi.CR_MEM_DEVICE)
         else:
-            rp.set_instances(inst_host[0].data_ptr(), inst_host[1].data_ptr(), count=scene.n_shapes, memory_space=_abi.CR_MEM_HOST)
-        rp.render_batch(state["batch"], cmds)
-        rp.submit()
+            rp.set_instances(inst_host[0].data_ptr(), inst_host[1].data_ptr(), count=work.n_instances, memory_space=_abi.CR_MEM_HOST)
+        work.record(rp, state[r])
+        if one_target and r is rnd:
+            target.submit(rp)
+        else:
+            rp.submit()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(device_resident: bool, steps: int, collect: bool):
-        kernel_ms = {"tess": [], "bin": [], "raster": [], "hull_sort": [], "hull_chain": []}
-        covered = 0
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            step(device_resident)
-            if collect or not device_resident:
-                st = rnd.stats()   # device->host read of the pass result (covered-sample counter); synchronises the stream
-                covered = int(st.covered_samples)
-                kernel_ms["tess"].append(st.last_tess_ms)
-                kernel_ms["bin"].append(st.last_bin_ms)
-                kernel_ms["raster"].append(st.last_raster_ms)
-                kernel_ms["hull_sort"].append(st.last_hull_sort_ms)
-                kernel_ms["hull_chain"].append(st.last_hull_chain_ms)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def max_over_ranks(ms: float) -> float:
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, covered, kernel_ms
+            return float(t.item())
+        return ms
 
-    # warm-up (both arms), then the two timed regions
+    def timed(r, st, steps: int, device_resident: bool, per_step=None):
+        """K steps back to back on stream `st`, bracketed by a barrier + synchronize on both sides, CUDA-event time, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            step(r, device_resident)
+            if per_step is not None:
+                per_step()
+        e1.record(st)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- warm-up, then the timed regions
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    import time
     t_warm = time.time()
     for _ in range(max(3, args.warmup)):
-        step(True)
-    step(False)
-    while rank == 0 and time.time() - t_warm < 0.5:   # untimed: gives nvidia-smi time to come up, under the benchmark's own load
-        step(True)
+        step(rnd, True)
+    step(rnd, False)
+    step(rnd, True)
+    while rank == 0 and world == 1 and time.time() - t_warm < 0.5:   # untimed: gives nvidia-smi time to come up, under the benchmark's own load
+        step(rnd, True)
     torch.cuda.synchronize(dev)
     launches0 = int(rnd.stats().kernel_launches)
     sampler.mark_begin()
-    ms_dev, covered, kernel_ms = timed(True, args.steps, collect=True)
+    ms_dev = timed(rnd, stream, args.steps, True)
     launches = int(rnd.stats().kernel_launches) - launches0
-    ms_e2e, covered_e2e, _ = timed(False, args.steps, collect=False)
+
+    results = {}
+
+    def read_result():
+        results["stats"] = rnd.stats()   # device->host read of the pass result (counters); synchronises the stream
+
+    ms_e2e = timed(rnd, stream, args.steps, False, per_step=read_result)
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    st = rnd.stats()
+    d2h_result_bytes = 3 * 8 + 2 * 4   # PassCounters
 
-    total_paths, total_covered = n_paths, covered
+    # per-kernel times (CUDA events inside the library, read back every step): a separate, untimed-for-throughput run
+    rnd.enable_timing(True)
+    kernel_ms = {"tess": [], "bin": [], "raster": [], "hull_sort": [], "hull_chain": []}
+    for _ in range(5):
+        step(rnd, True)
+        st = rnd.stats()
+        for key, v in (("tess", st.last_tess_ms), ("bin", st.last_bin_ms), ("raster", st.last_raster_ms), ("hull_sort", st.last_hull_sort_ms),
+                       ("hull_chain", st.last_hull_chain_ms)):
+            kernel_ms[key].append(v)
+    rnd.enable_timing(False)
+    st = rnd.stats()
+    covered = int(st.covered_samples)
+
+    # e2e_with_frame: host inputs in, the finished RGBA8 frame out, every step
+    frame_line = None
+    if not work.tess_only and not one_target:
+        rnd8, stream8 = make_renderer(R.ColorFormat.Rgba8Unorm)
+        frame = torch.empty(work.width * work.height * 4, dtype=torch.uint8).pin_memory()
+
+        def read_frame():
+            rnd8.read_color_texels(frame.data_ptr(), frame.numel())
+
+        torch.cuda.set_stream(stream8)
+        for _ in range(3):
+            step(rnd8, False)
+            read_frame()
+        ms_frame = timed(rnd8, stream8, args.steps, False, per_step=read_frame)
+        torch.cuda.set_stream(stream)
+        frame_line = {"value": None, "unit": "paths/s", "ms_per_step": ms_frame / args.steps, "h2d_bytes_per_step": int(h2d_bytes),
+                      "d2h_bytes_per_step": int(frame.numel()), "color_format": "rgba8unorm"}
+        state.pop(rnd8).close()
+        rnd8.close()
+
+    total_paths, total_covered = work.paths_per_step, covered
     if world > 1:
-        t = torch.tensor([n_paths, covered], device=dev, dtype=torch.float64)
+        t = torch.tensor([work.paths_per_step, covered], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        total_paths, total_covered = int(t[0].item()), int(t[1].item())
+        total_covered = int(t[1].item())
+        total_paths = work.paths_per_step if one_target else int(t[0].item())   # one target: every rank submits the SAME scene; count it once
+
+    sharded = None
+    if world > 1 and not args.no_sharded_check:
+        sharded = tile_sharded_check(R, dist, torch, rank, world, local_rank)
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
-        layout_bytes = int(st.vertex_bytes)
-        fb_bytes = scene.width * scene.height * (1 + 16)
-        raster_alg = layout_bytes + 80 * scene.n_shapes + fb_bytes           # SURVEY §8d B_rast
-        tess_alg = int(st.input_bytes) + layout_bytes                         # SURVEY §8d B_tess
         mean = lambda xs: float(np.mean(xs)) if xs else 0.0
         k_ms = {k: mean(v) for k, v in kernel_ms.items()}
-        # Roofline of the DOMINANT single kernel, whichever of the two heavy ones took longer in this run (both are timed live
-        # with CUDA events on the renderer's stream; the committed ncu launch list profiles/launches_r01.csv shows the same
-        # shares): K3 raster_tiles_kernel with B_rast of SURVEY 8d, or hull_chain_kernel (convex_hull::andrew's chains) with
-        # 8 B per proto-hull point read + 8 B per hull vertex written. The other one is reported
-        # next to it as "roofline_other".
-        proto_points, hull_vertices = int(st.proto_hull_points), int(st.hull_vertices)
-        chain_alg = 8 * proto_points + 8 * hull_vertices
+        layout_bytes = int(st.vertex_bytes)
+        fb_bytes = work.width * work.height * (1 + 16)
+        raster_alg = layout_bytes + 80 * work.n_instances + fb_bytes          # SURVEY §8d B_rast
+        tess_alg = int(st.input_bytes) + layout_bytes                         # SURVEY §8d B_tess
+        chain_alg = 8 * int(st.proto_hull_points) + 8 * int(st.hull_vertices)
 
-        def roofline_of(name, alg, ms, formula, traffic):
+        def roofline_of(name, alg, ms, formula):
             ach = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak if peak else None,
-                    "algorithmic_bytes": alg, "algorithmic_bytes_formula": formula, "kernel_ms": ms, "traffic": traffic}
-        default_workload = args.glyphs == N_GLYPHS
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/ncu_full_r01_summary.csv)
-        rooflines = [roofline_of("raster_tiles_kernel", raster_alg, k_ms["raster"], "vertex+index bytes + 80 B x instances + W x H x (1 B stencil + 16 B rgba32f)",
-                                 RASTER_DRAM_BYTES_R01 if default_workload else None),
-                     roofline_of("hull_chain_kernel", chain_alg, k_ms["hull_chain"], "8 B x proto-hull points + 8 B x hull vertices (latency-bound sequential stack machines, DESIGN.md section 7)",
-                                 CHAIN_DRAM_BYTES_R01 if default_workload else None)]
+                    "algorithmic_bytes": alg, "algorithmic_bytes_formula": formula, "kernel_ms": ms,
+                    "traffic": measured_traffic(name, args.config) if args.scale is None else None}
+        # Roofline of the DOMINANT single kernel of the step, timed live with CUDA events on the renderer's stream: K3
+        # raster_tiles_kernel with B_rast of SURVEY 8d, or hull_chain_kernel (convex_hull::andrew's chains: 8 B per proto-hull
+        # point read + 8 B per hull vertex written), or — tessellation-only config 1 — the emit pass with B_tess.
+        tess_emit_ms = max(k_ms["tess"] - k_ms["hull_sort"] - k_ms["hull_chain"], 0.0)
+        rooflines = [roofline_of("hull_chain_kernel", chain_alg, k_ms["hull_chain"], "8 B x proto-hull points + 8 B x hull vertices (latency-bound sequential stack machines)"),
+                     roofline_of("tess_count+scan+emit", tess_alg, tess_emit_ms, "B_in + B_out of SURVEY 8d (path input + packed vertex / index output)")]
+        if not work.tess_only:
+            rooflines.append(roofline_of("raster_tiles_kernel", raster_alg, k_ms["raster"], "vertex+index bytes + 80 B x instances + W x H x (1 B stencil + 16 B rgba32f)"))
         rooflines.sort(key=lambda r: -r["kernel_ms"])
+        cfg = work.config_dict()
+        cfg.update({"sharding": ("ONE render target tile-sharded over the ranks (16x16 tiles, owner (tx + ty) % N), finished tiles stored into every rank's attachments over NVLink"
+                                 if one_target else "independent scene per rank, no data-path collective"),
+                    "l2": "working set per step (target + vertex / index / record / pair arrays) exceeds the 126 MB L2 for configs 3-5; the target is cleared and re-written every step"})
         line = {
             "metric": "paths/sec", "value": total_paths * args.steps / (ms_dev * 1e-3), "unit": "paths/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "paths_per_gpu": n_paths, "segments_per_gpu": soa.n_segments, "shapes_per_gpu": scene.n_shapes,
-                       "width": scene.width, "height": scene.height, "msaa_sample_count": 1, "winding_counter_bits": 4, "clip_nesting_counter_bits": 4,
-                       "color_format": "rgba32f", "sharding": "independent scene per rank, no collective",
-                       "l2": "working set per step (141 MB target + vertex/index/pair arrays) exceeds the 126 MB L2; the target is cleared and re-written every step"},
+            "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if one_target else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "covered_mpixel_per_s": total_covered * args.steps / (ms_dev * 1e-3) / 1e6,
             "covered_samples_per_step": total_covered,
-            "e2e": {"value": total_paths * args.steps / (ms_e2e * 1e-3), "unit": "paths/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 8 + 4 * 12 + 4,
+            "e2e": {"value": total_paths * args.steps / (ms_e2e * 1e-3), "unit": "paths/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_result_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "kernel_ms_per_step": k_ms,
+            "kernel_ms_sum_over_step": (k_ms["tess"] + k_ms["bin"] + k_ms["raster"]) / (ms_dev / args.steps) if ms_dev > 0 else None,
             "roofline": rooflines[0],
-            "roofline_other": rooflines[1],
+            "roofline_other": rooflines[1:],
             "stages": {"tessellation": {"ms": k_ms["tess"], "algorithmic_bytes": tess_alg, "achieved_gbs": tess_alg / (k_ms["tess"] * 1e-3) / 1e9 if k_ms["tess"] else 0.0},
                        "binning": {"ms": k_ms["bin"], "tile_pairs": int(st.tile_pairs), "primitives": int(st.primitives)},
                        "raster": {"ms": k_ms["raster"]}},
             "clocks": clocks,
         }
+        if frame_line is not None:
+            frame_line["value"] = total_paths * args.steps / (frame_line["ms_per_step"] * args.steps * 1e-3)
+            line["e2e_with_frame"] = frame_line
+        if sharded is not None:
+            line["tile_sharded_check"] = sharded
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_leg()
+            line["cpu_baseline"] = cpu_baseline_leg(args.config, args.scale)
         print(json.dumps(line), flush=True)
+    if target is not None:
+        target.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1186,6 +1186,10 @@ int cr_renderer_read_color(cr_renderer* r, float* dst, size_t capacity_bytes) {
     }
     return CR_OK;
 }
+int cr_renderer_read_color_texels(cr_renderer* r, void* dst, size_t capacity_bytes) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    return read_back(r, r->color.p, (size_t)r->width * r->height * r->config.msaa_sample_count * color_texel_bytes(r), dst, capacity_bytes);
+}
 int cr_renderer_read_depth(cr_renderer* r, float* dst, size_t capacity_bytes) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
     if (!has_depth(r)) return fail(CR_ERR_INVALID_ARGUMENT, "this configuration has no depth attachment (depth_compare Always, depth_write_enabled 0)");

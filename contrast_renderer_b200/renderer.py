@@ -58,6 +58,7 @@ def lib():
             "cr_pass_begin": [vp, u32, u32, C.POINTER(vp)],
             "cr_pass_begin_depth": [vp, u32, u32, u32, C.c_float, C.POINTER(vp)],
             "cr_renderer_read_depth": [vp, vp, sz],
+            "cr_renderer_read_color_texels": [vp, vp, sz],
             "cr_pass_set_instances": [vp, vp, vp, u32, u32],
             "cr_pass_set_clip_depth": [vp, u32],
             "cr_pass_save_alpha_context": [vp, u32],
@@ -274,6 +275,10 @@ class Renderer:
         out = np.empty((self.height, self.width, self.config.msaa_sample_count), np.uint8)
         _check(lib().cr_renderer_read_stencil(self._h, out.ctypes.data, out.nbytes))
         return out
+
+    def read_color_texels(self, dst_address: int, capacity_bytes: int) -> None:
+        """The colour attachment as stored (16 B per sample, or one unorm8 texel), into caller memory (pinned for PCIe speed)."""
+        _check(lib().cr_renderer_read_color_texels(self._h, dst_address, capacity_bytes))
 
     def read_depth(self) -> np.ndarray:
         out = np.empty((self.height, self.width, self.config.msaa_sample_count), np.float32)

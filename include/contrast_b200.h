@@ -270,6 +270,9 @@ void cr_pass_abort(cr_pass* pass);
  * stencil: [height][width][samples] u8 (clip bits << winding bits | winding bits);
  * alpha layer: [height][width][samples] f32. These synchronise the stream. */
 int cr_renderer_read_color(cr_renderer* renderer, float* dst, size_t capacity_bytes);
+/* The colour attachment as stored: 16 bytes per sample (RGBA32F) or one packed unorm8 texel per sample (RGBA8 / BGRA8). This
+ * is the frame a presenter consumes; `dst` should be pinned host memory for the copy to run at PCIe speed. */
+int cr_renderer_read_color_texels(cr_renderer* renderer, void* dst, size_t capacity_bytes);
 int cr_renderer_read_stencil(cr_renderer* renderer, uint8_t* dst, size_t capacity_bytes);
 int cr_renderer_read_alpha_layer(cr_renderer* renderer, uint32_t layer, float* dst, size_t capacity_bytes);
 /* depth: [height][width][samples] f32; CR_ERR_INVALID_ARGUMENT if the configuration has no depth attachment. */
