@@ -920,6 +920,19 @@ int cr_pass_render_batch(cr_pass* p, cr_shape_batch* b, const cr_draw_command* c
     return CR_OK;
 }
 
+int cr_pass_render_script(cr_pass* p, cr_shape_batch* b, const cr_scripted_draw* draws, size_t count) {
+    if (!p || !b || (count && !draws)) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!p->arena) p->commands.reserve(p->commands.size() + count);
+    for (size_t i = 0; i < count; ++i) {
+        const cr_scripted_draw& d = draws[i];
+        if (d.clip_depth != p->clip_depth) CR_TRY(cr_pass_set_clip_depth(p, d.clip_depth));
+        if (d.save_alpha_layer != p->save_layer) CR_TRY(cr_pass_save_alpha_context(p, d.save_alpha_layer));
+        if (d.restore_alpha_layer != p->restore_layer) CR_TRY(cr_pass_restore_alpha_context(p, d.restore_alpha_layer));
+        CR_TRY(record(p, b, d.shape_index, d.instance_begin, d.instance_end, d.render_operation));
+    }
+    return CR_OK;
+}
+
 // The pass's view of the attachments and of the renderer's configuration.
 static RasterTarget make_target(const cr_pass* p) {
     const cr_renderer* r = p->renderer;

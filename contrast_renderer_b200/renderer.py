@@ -65,6 +65,7 @@ def lib():
             "cr_pass_restore_alpha_context": [vp, u32],
             "cr_shape_render": [vp, vp, u32, u32, u32],
             "cr_pass_render_batch": [vp, vp, vp, sz],
+            "cr_pass_render_script": [vp, vp, vp, sz],
             "cr_pass_submit": [vp],
             "cr_renderer_read_color": [vp, vp, sz],
             "cr_renderer_read_stencil": [vp, vp, sz],
@@ -454,6 +455,12 @@ class RenderPass:
         """commands: [n, 4] u32 rows of (shape_index, instance_begin, instance_end, render_operation)."""
         cmds = np.ascontiguousarray(commands, dtype=np.uint32).reshape(-1, 4)
         _check(lib().cr_pass_render_batch(self._h, batch._h, cmds.ctypes.data, len(cmds)))
+
+    def render_script(self, batch: ShapeBatch, script: np.ndarray) -> None:
+        """script: [n, 7] u32 rows of (shape_index, instance_begin, instance_end, render_operation, clip_depth, save_alpha_layer,
+        restore_alpha_layer): `cr_pass_render_script`, i.e. the state calls (where the state changes) and the draw, per row."""
+        rows = np.ascontiguousarray(script, dtype=np.uint32).reshape(-1, 7)
+        _check(lib().cr_pass_render_script(self._h, batch._h, rows.ctypes.data, len(rows)))
 
     def submit(self) -> None:
         h, self._h = self._h, None

@@ -451,8 +451,12 @@ class ScriptedScene:
     def oracle_commands(self):
         return [tuple(int(v) for v in row) for row in self.script]
 
-    def record(self, render_pass, batch) -> None:
-        """Replays the script into a RenderPass: state calls where the state changes, bulk recording in between."""
+    def record(self, render_pass, batch, one_call: bool = True) -> None:
+        """Replays the script into a RenderPass: one bulk call (`cr_pass_render_script`), or — one_call=False — the individual
+        state calls where the state changes with bulk recording in between (the two are equivalent by definition)."""
+        if one_call:
+            render_pass.render_script(batch, self.script)
+            return
         script = self.script
         state = (None, None, None)
         run_start = 0

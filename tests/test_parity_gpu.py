@@ -497,7 +497,7 @@ def test_config4_tiger_like_nested_clips_and_opacity_groups(cr, oracle, samples)
         assert_shape_equal(oracle, batch[i], ref, f"group shape {i}")
     rp = rnd.begin_render_pass()
     rp.set_instances(scene.transforms, scene.colors)
-    scene.record(rp, batch)
+    scene.record(rp, batch, one_call=(samples == 4))   # 1x: the individual state calls; 4x: cr_pass_render_script
     rp.submit()
     color, stencil, covered = rnd.read_color(), rnd.read_stencil(), int(rnd.stats().covered_samples)
     layers = [rnd.read_alpha_layer(k) for k in range(2)]
