@@ -331,6 +331,7 @@ def main():
     ap.add_argument("--scale", type=float, default=None, help="debug only: a fraction of the configuration is not the benchmark workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded-check", action="store_true")
+    ap.add_argument("--no-pipelining", action="store_true", help="keep every step on one stream (no overlap of consecutive steps)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -362,6 +363,8 @@ def main():
         assert stream.cuda_stream != 0
         rnd.set_stream(stream.cuda_stream)
         rnd.resize_internal_buffers(work.width, work.height)
+        if not args.no_pipelining:
+            rnd.set_pipelining(True)   # the rebuild of frame N + 1 overlaps the raster of frame N (inputs are complete before every call here)
         return rnd, stream
 
     rnd, stream = make_renderer()
@@ -451,6 +454,8 @@ def main():
         results["stats"] = rnd.stats()   # device->host read of the pass result (counters); synchronises the stream
 
     ms_e2e = timed(rnd, stream, args.steps, False, per_step=read_result)
+    # one step at a time (the host waits for each step before starting the next): the latency of a step, no overlap of steps
+    ms_serial = timed(rnd, stream, min(args.steps, 10), True, per_step=rnd.synchronize) / min(args.steps, 10)
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     d2h_result_bytes = 3 * 8 + 2 * 4   # PassCounters
@@ -526,10 +531,11 @@ def main():
         cfg = work.config_dict()
         cfg.update({"sharding": ("ONE render target tile-sharded over the ranks (16x16 tiles, owner (tx + ty) % N), finished tiles stored into every rank's attachments over NVLink"
                                  if one_target else "independent scene per rank, no data-path collective"),
+                    "frame_pipelining": (not args.no_pipelining),
                     "l2": "working set per step (target + vertex / index / record / pair arrays) exceeds the 126 MB L2 for configs 3-5; the target is cleared and re-written every step"})
         line = {
             "metric": "paths/sec", "value": total_paths * args.steps / (ms_dev * 1e-3), "unit": "paths/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if one_target else "weak", "vs_baseline": None,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "ms_per_step_one_at_a_time": ms_serial, "higher_is_better": True, "scaling": "strong" if one_target else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "covered_mpixel_per_s": total_covered * args.steps / (ms_dev * 1e-3) / 1e6,
             "covered_samples_per_step": total_covered,

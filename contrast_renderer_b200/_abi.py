@@ -82,7 +82,7 @@ CR_TILE = 16
 # Every symbol include/contrast_b200.h declares (checked against the built library by tests/test_abi.py).
 EXPORTED_SYMBOLS = (
     "cr_renderer_create", "cr_renderer_destroy", "cr_renderer_get_config", "cr_renderer_resize", "cr_renderer_set_stream",
-    "cr_renderer_synchronize", "cr_shape_from_paths", "cr_shape_destroy", "cr_shape_batch_from_paths", "cr_shape_batch_destroy",
+    "cr_renderer_synchronize", "cr_renderer_set_pipelining", "cr_shape_from_paths", "cr_shape_destroy", "cr_shape_batch_from_paths", "cr_shape_batch_destroy",
     "cr_shape_batch_size", "cr_shape_batch_get", "cr_shape_set_dynamic_stroke_options", "cr_shape_batch_set_dynamic_stroke_options",
     "cr_shape_get_layout", "cr_shape_read_vertex_buffer", "cr_shape_read_index_buffer", "cr_shape_read_stroke_buffer",
     "cr_pass_begin", "cr_pass_begin_depth", "cr_renderer_read_depth", "cr_renderer_read_color_texels", "cr_pass_set_instances", "cr_pass_set_clip_depth", "cr_pass_save_alpha_context",

@@ -119,10 +119,13 @@ struct cr_renderer {
     cr_config config;
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t tess = nullptr;      // frame pipelining: Shape::from_paths work runs here (high priority), concurrently with the passes on `stream`
+    bool pipelined = false;
+    cudaStream_t tstream() const { return pipelined ? tess : stream; }
     uint32_t width = 0, height = 0, tiles_x = 0, tiles_y = 0;
     DevBuf color, stencil, alpha_layers, depth;
     // scratch shared by every from_paths / submit of this renderer
-    DevBuf staging[10], counts, scan_scratch, shape_begin_dev, err_flag, hull_scratch_a, hull_scratch_b;
+    DevBuf staging[10], counts, scan_scratch_tess, scan_scratch, shape_begin_dev, err_flag, hull_scratch_a, hull_scratch_b;
     DevBuf compact_dev, cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, radix_scratch, tile_begin,
         inst_transforms, inst_colors, pass_counters;
     uint32_t* pinned = nullptr;   // PIN_WORDS words of pinned read-back area
@@ -157,10 +160,21 @@ struct cr_shape {
     bool owns_batch;
 };
 
+// The device arrays of one build of a batch. A batch owns two of them: with frame pipelining (cr_renderer_set_pipelining) a
+// rebuild writes the set the last pass is NOT reading, so that tessellating frame N + 1 overlaps rasterising frame N.
+struct BatchStorage {
+    DevBuf vtx[7], proto, hull, idx[3], cat_begin, hull_count, stroke, desc_dev;
+    cudaEvent_t written = nullptr;     // recorded on the tessellation stream when the build (and its descriptor) is complete
+    cudaEvent_t last_read = nullptr;   // recorded on the renderer's stream behind the last pass that reads these arrays
+    bool was_read = false;
+};
 struct cr_shape_batch {
     cr_renderer* renderer = nullptr;
     uint32_t n_shapes = 0, n_paths = 0, n_groups = 0, n_segments = 0;
-    DevBuf vtx[7], proto, hull, idx[3], cat_begin, hull_count, stroke, desc_dev;
+    BatchStorage set[2];
+    int cur = 0;                      // the set holding the latest build
+    BatchStorage& store() { return set[cur]; }
+    const BatchStorage& store() const { return set[cur]; }
     // Host mirrors of the slice tables ([CNT_COUNT][n_shapes + 1] cat_begin, then [n_shapes] hull_count, then the final error
     // word), in pinned memory; they arrive asynchronously (ev_mirrors) and are only waited for by the layout / read-back calls.
     uint32_t* mirrors = nullptr;
@@ -187,6 +201,7 @@ struct cr_pass {
     bool arena = false;
     size_t n_arena = 0;
     std::vector<cr_shape_batch*> batches;
+    std::vector<BatchStorage*> sets;        // (after submit) the build of each batch this pass renders
     std::vector<InstanceSet> instance_sets;
     uint32_t instance_total = 0;
     uint32_t clip_depth = 0, save_layer = 0, restore_layer = 0;
@@ -220,10 +235,17 @@ int take_deferred(cr_renderer* r) {
 }
 
 void batch_release(cr_shape_batch* b) {
-    cudaStream_t st = b->renderer->stream;
-    for (auto& v : b->vtx) v.release(st);
-    for (auto& v : b->idx) v.release(st);
-    b->proto.release(st); b->hull.release(st); b->cat_begin.release(st); b->hull_count.release(st); b->stroke.release(st); b->desc_dev.release(st);
+    cudaStream_t st = b->renderer->tstream();
+    for (BatchStorage& B : b->set) {
+        if (B.was_read && B.last_read) cudaStreamWaitEvent(st, B.last_read, 0);   // freed behind the last pass that reads them
+        for (auto& v : B.vtx) v.release(st);
+        for (auto& v : B.idx) v.release(st);
+        B.proto.release(st); B.hull.release(st); B.cat_begin.release(st); B.hull_count.release(st); B.stroke.release(st); B.desc_dev.release(st);
+        if (B.written) cudaEventDestroy(B.written);
+        if (B.last_read) cudaEventDestroy(B.last_read);
+        B.written = B.last_read = nullptr;
+        B.was_read = false;
+    }
     if (b->mirrors_pending && b->ev_mirrors) cudaEventSynchronize(b->ev_mirrors);
     if (b->mirrors) cudaFreeHost(b->mirrors);
     if (b->ev_mirrors) cudaEventDestroy(b->ev_mirrors);
@@ -231,11 +253,12 @@ void batch_release(cr_shape_batch* b) {
 }
 
 // The scan scratch carries ticket counters that must start at zero (prims.h): zero it whenever it is (re)allocated.
-int reserve_scan_scratch(cr_renderer* r, DevBuf& buf, size_t words) {
+int reserve_scan_scratch(cr_renderer* r, cudaStream_t st, DevBuf& buf, size_t words) {
+    (void)r;
     if (buf.p && words * 4 <= buf.cap) return CR_OK;
     const size_t want = std::max<size_t>(words * 2, 4096);
-    CR_TRY(buf.reserve(r->stream, want * 4));
-    return cr_scan_prepare(r->stream, buf.as<uint32_t>(), buf.cap / 4);
+    CR_TRY(buf.reserve(st, want * 4));
+    return cr_scan_prepare(st, buf.as<uint32_t>(), buf.cap / 4);
 }
 
 // Bring one input array to the device: host memory is staged (cudaMemcpyAsync on the renderer's stream), device
@@ -245,8 +268,8 @@ int stage(cr_renderer* r, int slot, const T* src, size_t count, uint32_t space, 
     if (count == 0) { *out = nullptr; return CR_OK; }
     if (!src) return fail(CR_ERR_INVALID_ARGUMENT, "null input array (slot %d)", slot);
     if (space == CR_MEM_DEVICE) { *out = src; return CR_OK; }
-    CR_TRY(r->staging[slot].reserve(r->stream, count * sizeof(T)));
-    CR_CUDA_TRY(cudaMemcpyAsync(r->staging[slot].p, src, count * sizeof(T), cudaMemcpyHostToDevice, r->stream));
+    CR_TRY(r->staging[slot].reserve(r->tstream(), count * sizeof(T)));
+    CR_CUDA_TRY(cudaMemcpyAsync(r->staging[slot].p, src, count * sizeof(T), cudaMemcpyHostToDevice, r->tstream()));
     *out = r->staging[slot].as<T>();
     return CR_OK;
 }
@@ -276,7 +299,7 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     if (shape_path_begin[0] != 0 || shape_path_begin[n_shapes] != soa->n_paths) return fail(CR_ERR_INVALID_ARGUMENT, "shape_path_begin must cover [0, n_paths]");
     for (uint32_t s = 0; s < n_shapes; ++s)
         if (shape_path_begin[s] > shape_path_begin[s + 1]) return fail(CR_ERR_INVALID_ARGUMENT, "shape_path_begin must be non-decreasing");
-    cudaStream_t st = r->stream;
+    cudaStream_t st = r->tstream();
     const uint32_t n_paths = soa->n_paths;
     const size_t stride = (size_t)n_paths + 1;
     if (n_paths && !soa->type_begin) return fail(CR_ERR_INVALID_ARGUMENT, "type_begin is null");
@@ -286,11 +309,16 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     std::vector<Descriptor48> descs(n_groups);
     for (size_t i = 0; i < n_groups; ++i) CR_TRY(convert_dynamic_stroke_options(groups[i], descs[i]));
 
-    // a pass that still reads the arrays of `b` must have been sized correctly before they are overwritten
-    CR_TRY(settle(r));
+    // A pass in flight may still have to be re-submitted from the arrays of its batches (settle): in place they must not be
+    // overwritten before that is known; with frame pipelining this build goes to the batch's OTHER set of arrays instead, and
+    // the tessellation stream only waits (on the device) for the last pass that read that set.
+    if (!r->pipelined) CR_TRY(settle(r));
     if (b->mirrors_pending) { CR_CUDA_TRY(cudaEventSynchronize(b->ev_mirrors)); b->mirrors_pending = false; }
 
     const bool optimistic = b->built && b->n_paths == n_paths && b->n_shapes == n_shapes && b->n_segments == soa->n_segments && b->n_groups == n_groups;
+    const int target = (r->pipelined && b->built) ? 1 - b->cur : b->cur;
+    BatchStorage& B = b->set[target];
+    if (B.was_read) CR_CUDA_TRY(cudaStreamWaitEvent(st, B.last_read, 0));
     b->built = false;
 
     if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[0], st));
@@ -323,20 +351,20 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
 
     // ---- pass A: count, scan, per-shape slice boundaries
     CR_TRY(r->counts.reserve(st, CNT_COUNT * stride * sizeof(uint32_t)));
-    CR_TRY(reserve_scan_scratch(r, r->scan_scratch, cr_scan_scratch_words((uint32_t)stride, CNT_COUNT)));
+    CR_TRY(reserve_scan_scratch(r, st, r->scan_scratch_tess, cr_scan_scratch_words((uint32_t)stride, CNT_COUNT)));
     CR_TRY(r->err_flag.reserve(st, 8));   // [0] error bits, [1] largest proto-hull slice of any shape
     CR_CUDA_TRY(cudaMemsetAsync(r->err_flag.p, 0, 8, st));
     CR_TRY(r->shape_begin_dev.reserve(st, (size_t)(n_shapes + 1) * 4));
     CR_CUDA_TRY(cudaMemcpyAsync(r->shape_begin_dev.p, shape_path_begin, (size_t)(n_shapes + 1) * 4, cudaMemcpyHostToDevice, st));
-    CR_TRY(b->cat_begin.reserve(st, (size_t)CNT_COUNT * (n_shapes + 1) * 4));
-    CR_TRY(b->hull_count.reserve(st, (size_t)n_shapes * 4));
+    CR_TRY(B.cat_begin.reserve(st, (size_t)CNT_COUNT * (n_shapes + 1) * 4));
+    CR_TRY(B.hull_count.reserve(st, (size_t)n_shapes * 4));
     uint32_t* counts = r->counts.as<uint32_t>();
     uint32_t* err = r->err_flag.as<uint32_t>();
 
     auto run_sizes = [&](bool has_cubics, const TessCapacity& caps) -> int {
         CR_TRY(cr_tess_count(st, P, (uint32_t)n_groups, counts, err, has_cubics));
-        CR_TRY(cr_scan_exclusive(st, counts, (uint32_t)stride, CNT_COUNT, r->scan_scratch.as<uint32_t>()));
-        CR_TRY(cr_tess_shape_bounds(st, counts, n_paths, r->shape_begin_dev.as<uint32_t>(), n_shapes, b->cat_begin.as<uint32_t>(), err + 1, caps, err));
+        CR_TRY(cr_scan_exclusive(st, counts, (uint32_t)stride, CNT_COUNT, r->scan_scratch_tess.as<uint32_t>()));
+        CR_TRY(cr_tess_shape_bounds(st, counts, n_paths, r->shape_begin_dev.as<uint32_t>(), n_shapes, B.cat_begin.as<uint32_t>(), err + 1, caps, err));
         for (int c = 0; c < CNT_COUNT; ++c)
             CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_TESS + c], counts + c * stride + n_paths, 4, cudaMemcpyDeviceToHost, st));
         CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_TESS + CNT_COUNT], err, 8, cudaMemcpyDeviceToHost, st));
@@ -347,25 +375,25 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
         return CR_OK;
     };
     auto reserve_outputs = [&](const uint64_t* totals) -> int {
-        for (int c = 0; c < 7; ++c) CR_TRY(b->vtx[c].reserve(st, totals[c] * (size_t)kCategoryStride[c]));
-        CR_TRY(b->proto.reserve(st, totals[CNT_PROTO] * 8));
-        CR_TRY(b->hull.reserve(st, totals[CNT_PROTO] * 8));
+        for (int c = 0; c < 7; ++c) CR_TRY(B.vtx[c].reserve(st, totals[c] * (size_t)kCategoryStride[c]));
+        CR_TRY(B.proto.reserve(st, totals[CNT_PROTO] * 8));
+        CR_TRY(B.hull.reserve(st, totals[CNT_PROTO] * 8));
         CR_TRY(r->hull_scratch_a.reserve(st, totals[CNT_PROTO] * 8));
         CR_TRY(r->hull_scratch_b.reserve(st, totals[CNT_PROTO] * 8));
-        for (int k = 0; k < 3; ++k) CR_TRY(b->idx[k].reserve(st, totals[CNT_LINE_IDX + k] * 4));
+        for (int k = 0; k < 3; ++k) CR_TRY(B.idx[k].reserve(st, totals[CNT_LINE_IDX + k] * 4));
         return CR_OK;
     };
     auto run_emit = [&](uint32_t max_proto) -> int {
         TessOutput out{};
-        for (int c = 0; c < 7; ++c) out.vtx[c] = b->vtx[c].p;
-        out.proto = b->proto.as<float2>();
-        for (int k = 0; k < 3; ++k) out.idx[k] = b->idx[k].as<uint32_t>();
+        for (int c = 0; c < 7; ++c) out.vtx[c] = B.vtx[c].p;
+        out.proto = B.proto.as<float2>();
+        for (int k = 0; k < 3; ++k) out.idx[k] = B.idx[k].as<uint32_t>();
         // the emit pass is bound by its scattered stores: the lean kernel (3x the occupancy) measured 17 % SLOWER on the text scene, so
         // only the count pass uses it (33 -> 7 us)
         CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, err, true));
         if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[6], st));
         CR_TRY(cr_tess_hull(st, out.proto, r->hull_scratch_a.as<float2>(), r->hull_scratch_b.as<float2>(),
-                            b->cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, b->hull.as<float2>(), b->hull_count.as<uint32_t>(), max_proto, err,
+                            B.cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, B.hull.as<float2>(), B.hull_count.as<uint32_t>(), max_proto, err,
                             r->timing ? r->ev[7] : nullptr));
         if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[8], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[1], st)); r->ev_valid[0] = true; }
         return CR_OK;
@@ -376,9 +404,9 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     bool emitted = false;
     if (optimistic) {
         TessCapacity caps;
-        for (int c = 0; c < 7; ++c) caps.v[c] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, b->vtx[c].cap / kCategoryStride[c]);
-        caps.v[CNT_PROTO] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, std::min(std::min(b->proto.cap, b->hull.cap), std::min(r->hull_scratch_a.cap, r->hull_scratch_b.cap)) / 8);
-        for (int k = 0; k < 3; ++k) caps.v[CNT_LINE_IDX + k] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, b->idx[k].cap / 4);
+        for (int c = 0; c < 7; ++c) caps.v[c] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, B.vtx[c].cap / kCategoryStride[c]);
+        caps.v[CNT_PROTO] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, std::min(std::min(B.proto.cap, B.hull.cap), std::min(r->hull_scratch_a.cap, r->hull_scratch_b.cap)) / 8);
+        for (int k = 0; k < 3; ++k) caps.v[CNT_LINE_IDX + k] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, B.idx[k].cap / 4);
         CR_TRY(run_sizes(totals_known ? (type_totals[CR_SEG_INTEGRAL_CUBIC] != 0 || type_totals[CR_SEG_RATIONAL_CUBIC] != 0) : b->has_cubics, caps));
         CR_TRY(run_emit(b->max_proto));   // the sort's shared-memory capacity is a launch parameter: larger shapes take its global-memory path
         emitted = true;
@@ -418,21 +446,21 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
         CR_TRY(reserve_outputs(b->totals));
         CR_TRY(run_emit(max_proto));
     }
-    CR_TRY(b->stroke.reserve(st, n_groups * sizeof(Descriptor48)));
-    if (n_groups) CR_CUDA_TRY(cudaMemcpyAsync(b->stroke.p, descs.data(), n_groups * sizeof(Descriptor48), cudaMemcpyHostToDevice, st));
+    CR_TRY(B.stroke.reserve(st, n_groups * sizeof(Descriptor48)));
+    if (n_groups) CR_CUDA_TRY(cudaMemcpyAsync(B.stroke.p, descs.data(), n_groups * sizeof(Descriptor48), cudaMemcpyHostToDevice, st));
 
     // ---- the rasteriser's view of this batch + host mirrors of the slice tables (asynchronous, pinned)
     DeviceBatch db{};
-    for (int c = 0; c < 7; ++c) db.vtx[c] = b->vtx[c].p;
-    db.hull = b->hull.as<float2>();
-    for (int k = 0; k < 3; ++k) db.idx[k] = b->idx[k].as<uint32_t>();
-    db.cat_begin = b->cat_begin.as<uint32_t>();
-    db.hull_count = b->hull_count.as<uint32_t>();
-    db.stroke = b->stroke.p;
+    for (int c = 0; c < 7; ++c) db.vtx[c] = B.vtx[c].p;
+    db.hull = B.hull.as<float2>();
+    for (int k = 0; k < 3; ++k) db.idx[k] = B.idx[k].as<uint32_t>();
+    db.cat_begin = B.cat_begin.as<uint32_t>();
+    db.hull_count = B.hull_count.as<uint32_t>();
+    db.stroke = B.stroke.p;
     db.n_shapes = n_shapes;
     db.n_groups = (uint32_t)n_groups;
-    CR_TRY(b->desc_dev.reserve(st, sizeof(DeviceBatch)));
-    CR_CUDA_TRY(cudaMemcpyAsync(b->desc_dev.p, &db, sizeof(db), cudaMemcpyHostToDevice, st));
+    CR_TRY(B.desc_dev.reserve(st, sizeof(DeviceBatch)));
+    CR_CUDA_TRY(cudaMemcpyAsync(B.desc_dev.p, &db, sizeof(db), cudaMemcpyHostToDevice, st));
     const size_t table_words = (size_t)CNT_COUNT * (n_shapes + 1), mirror_words = table_words + n_shapes + 2;
     if (mirror_words > b->mirrors_cap) {
         if (b->mirrors) cudaFreeHost(b->mirrors);
@@ -441,11 +469,14 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
         b->mirrors_cap = mirror_words;
     }
     if (!b->ev_mirrors) CR_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_mirrors, cudaEventDisableTiming));
-    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors, b->cat_begin.p, table_words * 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words, b->hull_count.p, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors, B.cat_begin.p, table_words * 4, cudaMemcpyDeviceToHost, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words, B.hull_count.p, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost, st));
     CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words + n_shapes, err, 4, cudaMemcpyDeviceToHost, st));
     CR_CUDA_TRY(cudaEventRecord(b->ev_mirrors, st));
     b->mirrors_pending = true;
+    if (!B.written) CR_CUDA_TRY(cudaEventCreateWithFlags(&B.written, cudaEventDisableTiming));
+    CR_CUDA_TRY(cudaEventRecord(B.written, st));
+    b->cur = target;
     b->views.resize(n_shapes);
     for (uint32_t s = 0; s < n_shapes; ++s) b->views[s] = cr_shape{b, s, false};
     b->built = true;
@@ -545,11 +576,12 @@ static void pass_free(cr_pass* p);
 static void renderer_free(cr_renderer* r) {
     DeviceGuard guard(r->device);
     cudaStreamSynchronize(r->stream);
+    if (r->tess) cudaStreamSynchronize(r->tess);
     if (r->inflight) { pass_free(r->inflight); r->inflight = nullptr; }
     close_peers(r);
     cudaStream_t st = r->stream;
     DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->depth, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
-                     &r->hull_scratch_b, &r->compact_dev, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand,
+                     &r->hull_scratch_b, &r->scan_scratch_tess, &r->compact_dev, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand,
                      &r->pair_tile_alt, &r->pair_cand_alt, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->pass_counters};
     for (DevBuf* d : all) d->release(st);
     for (auto& d : r->staging) d.release(st);
@@ -560,6 +592,7 @@ static void renderer_free(cr_renderer* r) {
     if (r->ev_sizes) cudaEventDestroy(r->ev_sizes);
     if (r->ev_pass) cudaEventDestroy(r->ev_pass);
     if (r->ev_update) cudaEventDestroy(r->ev_update);
+    if (r->tess) cudaStreamDestroy(r->tess);
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
     delete r;
 }
@@ -622,6 +655,7 @@ int cr_renderer_set_stream(cr_renderer* r, void* cuda_stream) {
     CR_GUARD(r);
     CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->tess) CR_CUDA_TRY(cudaStreamSynchronize(r->tess));
     r->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : r->own_stream;
     return CR_OK;
 }
@@ -630,7 +664,28 @@ int cr_renderer_synchronize(cr_renderer* r) {
     CR_GUARD(r);
     CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->pipelined) CR_CUDA_TRY(cudaStreamSynchronize(r->tess));
     return take_deferred(r);
+}
+
+// Frame pipelining: Shape::from_paths work moves to a second, high-priority stream of the renderer and every rebuild of a
+// batch (`existing`) writes the set of arrays the last pass is not reading, so that tessellating frame N + 1 overlaps
+// rasterising frame N. Passes wait (on the device) for the builds of the batches they render; everything the caller observes
+// through this API is ordered as before. What changes for the caller: input arrays in DEVICE memory must be complete when
+// cr_shape_from_paths / cr_shape_batch_from_paths is called — work merely enqueued on the renderer's stream is not waited for.
+int cr_renderer_set_pipelining(cr_renderer* r, uint32_t enabled) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    CR_GUARD(r);
+    CR_TRY(settle(r));
+    CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->tess) CR_CUDA_TRY(cudaStreamSynchronize(r->tess));
+    if (enabled && !r->tess) {
+        int least = 0, greatest = 0;
+        CR_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CR_CUDA_TRY(cudaStreamCreateWithPriority(&r->tess, cudaStreamNonBlocking, greatest));
+    }
+    r->pipelined = enabled != 0;
+    return CR_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- shape building
@@ -639,8 +694,10 @@ int cr_shape_batch_from_paths(cr_renderer* r, const cr_dynamic_stroke_options* g
     if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     CR_GUARD(r);
-    CR_TRY(settle(r));   // a pass in flight may still have to be re-submitted from the arrays this call is about to overwrite
-    CR_TRY(take_deferred(r));
+    if (!r->pipelined) {   // a pass in flight may still have to be re-submitted from the arrays this call is about to overwrite
+        CR_TRY(settle(r));
+        CR_TRY(take_deferred(r));
+    }
     cr_shape_batch* b = existing;   // consumed: its allocations are reused in place when large enough (Buffer::update, src/renderer.rs:89-95)
     if (b && b->renderer != r) return fail(CR_ERR_INVALID_ARGUMENT, "existing batch belongs to another renderer");
     if (!b) {
@@ -651,6 +708,10 @@ int cr_shape_batch_from_paths(cr_renderer* r, const cr_dynamic_stroke_options* g
     }
     const int st = build_batch(r, groups, n_groups, paths, shape_path_begin, n_shapes, b);
     if (st != CR_OK) {
+        char message[sizeof(g_error_message)];
+        memcpy(message, g_error_message, sizeof(message));
+        settle(r);   // the batch is about to be released: a pass in flight that renders it must be complete
+        memcpy(g_error_message, message, sizeof(message));
         if (r->stats_batch == b) r->stats_batch = nullptr;
         batch_release(b);
         delete b;
@@ -712,7 +773,9 @@ int cr_shape_batch_set_dynamic_stroke_options(cr_shape_batch* b, size_t index, c
     if (!r->ev_update) CR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_update, cudaEventDisableTiming));
     else CR_CUDA_TRY(cudaEventSynchronize(r->ev_update));
     memcpy(&r->pinned[PIN_MISC], &d, sizeof(d));
-    CR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(b->stroke.p) + index * sizeof(d), &r->pinned[PIN_MISC], sizeof(d), cudaMemcpyHostToDevice, r->stream));
+    BatchStorage& B = b->store();
+    if (B.written) CR_CUDA_TRY(cudaStreamWaitEvent(r->stream, B.written, 0));   // ordered behind the build and between the passes on the renderer's stream
+    CR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(B.stroke.p) + index * sizeof(d), &r->pinned[PIN_MISC], sizeof(d), cudaMemcpyHostToDevice, r->stream));
     CR_CUDA_TRY(cudaEventRecord(r->ev_update, r->stream));
     return CR_OK;
 }
@@ -752,6 +815,8 @@ int cr_shape_read_vertex_buffer(cr_shape* s, void* dst, size_t capacity) {
     const cr_shape_batch* b = s->batch;
     CR_GUARD(b->renderer);
     cudaStream_t st = b->renderer->stream;
+    const BatchStorage& B = b->store();
+    if (B.written) CR_CUDA_TRY(cudaStreamWaitEvent(st, B.written, 0));
     const size_t stride = (size_t)b->n_shapes + 1;
     const uint32_t* cb = b->cat_begin_host();
     char* d = static_cast<char*>(dst);
@@ -759,8 +824,8 @@ int cr_shape_read_vertex_buffer(cr_shape* s, void* dst, size_t capacity) {
     for (int c = 0; c < 8; ++c) {
         const uint64_t bytes = layout.vertex_offsets[c] - at;
         if (bytes) {
-            const char* src = c < 7 ? static_cast<const char*>(b->vtx[c].p) + (size_t)cb[c * stride + s->index] * kCategoryStride[c]
-                                    : static_cast<const char*>(b->hull.p) + (size_t)cb[CNT_PROTO * stride + s->index] * 8;
+            const char* src = c < 7 ? static_cast<const char*>(B.vtx[c].p) + (size_t)cb[c * stride + s->index] * kCategoryStride[c]
+                                    : static_cast<const char*>(B.hull.p) + (size_t)cb[CNT_PROTO * stride + s->index] * 8;
             CR_CUDA_TRY(cudaMemcpyAsync(d + at, src, bytes, cudaMemcpyDeviceToHost, st));
         }
         at = layout.vertex_offsets[c];
@@ -777,6 +842,8 @@ int cr_shape_read_index_buffer(cr_shape* s, void* dst, size_t capacity) {
     const cr_shape_batch* b = s->batch;
     CR_GUARD(b->renderer);
     cudaStream_t st = b->renderer->stream;
+    const BatchStorage& B = b->store();
+    if (B.written) CR_CUDA_TRY(cudaStreamWaitEvent(st, B.written, 0));
     const size_t stride = (size_t)b->n_shapes + 1;
     const uint32_t* cb = b->cat_begin_host();
     uint16_t* d = static_cast<uint16_t*>(dst);
@@ -784,7 +851,7 @@ int cr_shape_read_index_buffer(cr_shape* s, void* dst, size_t capacity) {
     for (int k = 0; k < 3; ++k) {
         const uint32_t begin = cb[(CNT_LINE_IDX + k) * stride + s->index], n = cb[(CNT_LINE_IDX + k) * stride + s->index + 1] - begin;
         wide.resize(n);
-        if (n) CR_CUDA_TRY(cudaMemcpyAsync(wide.data(), b->idx[k].as<uint32_t>() + begin, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (n) CR_CUDA_TRY(cudaMemcpyAsync(wide.data(), B.idx[k].as<uint32_t>() + begin, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         CR_CUDA_TRY(cudaStreamSynchronize(st));
         // `start_index as u16` (src/stroke.rs:108,128, src/fill.rs:363): the reference's u16 indices wrap modulo 65536
         for (uint32_t i = 0; i < n; ++i) *d++ = wide[i] == CR_RESTART ? (uint16_t)0xFFFF : (uint16_t)(wide[i] >> 1);
@@ -798,7 +865,8 @@ int cr_shape_read_stroke_buffer(cr_shape* s, void* dst, size_t capacity) {
     const size_t bytes = (size_t)b->n_groups * sizeof(Descriptor48);
     if (capacity < bytes) return fail(CR_ERR_INVALID_ARGUMENT, "capacity too small");
     CR_GUARD(b->renderer);
-    if (bytes) CR_CUDA_TRY(cudaMemcpyAsync(dst, b->stroke.p, bytes, cudaMemcpyDeviceToHost, b->renderer->stream));
+    if (b->store().written) CR_CUDA_TRY(cudaStreamWaitEvent(b->renderer->stream, b->store().written, 0));
+    if (bytes) CR_CUDA_TRY(cudaMemcpyAsync(dst, b->store().stroke.p, bytes, cudaMemcpyDeviceToHost, b->renderer->stream));
     CR_CUDA_TRY(cudaStreamSynchronize(b->renderer->stream));
     return CR_OK;
 }
@@ -999,13 +1067,20 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     PassCounters* counters = r->pass_counters.as<PassCounters>();
     // ---- scene description: batches, commands (expanded on the device), candidate numbering
     CR_TRY(r->batches_dev.reserve(st, p->batches.size() * sizeof(DeviceBatch)));
-    for (size_t i = 0; i < p->batches.size(); ++i)
-        CR_CUDA_TRY(cudaMemcpyAsync(r->batches_dev.as<DeviceBatch>() + i, p->batches[i]->desc_dev.p, sizeof(DeviceBatch), cudaMemcpyDeviceToDevice, st));
+    if (p->sets.size() != p->batches.size()) {   // first enqueue of this pass: it renders the build each batch holds NOW (a re-submission keeps them)
+        p->sets.clear();
+        for (cr_shape_batch* b : p->batches) p->sets.push_back(&b->store());
+    }
+    for (size_t i = 0; i < p->batches.size(); ++i) {
+        BatchStorage* B = p->sets[i];
+        if (B->written) CR_CUDA_TRY(cudaStreamWaitEvent(st, B->written, 0));   // the build may still be running on the tessellation stream
+        CR_CUDA_TRY(cudaMemcpyAsync(r->batches_dev.as<DeviceBatch>() + i, B->desc_dev.p, sizeof(DeviceBatch), cudaMemcpyDeviceToDevice, st));
+    }
     CR_TRY(r->compact_dev.reserve(st, (size_t)n_cmds * sizeof(CompactCommand)));
     CR_CUDA_TRY(cudaMemcpyAsync(r->compact_dev.p, cmds, (size_t)n_cmds * sizeof(CompactCommand), cudaMemcpyHostToDevice, st));
     CR_TRY(r->cmds_dev.reserve(st, (size_t)n_cmds * sizeof(DeviceCommand)));
     CR_TRY(r->cmd_cands.reserve(st, (size_t)(n_cmds + 1) * 4));
-    CR_TRY(reserve_scan_scratch(r, r->scan_scratch, cr_scan_scratch_words(n_cmds + 1, 1)));
+    CR_TRY(reserve_scan_scratch(r, st, r->scan_scratch, cr_scan_scratch_words(n_cmds + 1, 1)));
     if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[2], st));
     CR_TRY(cr_raster_expand(st, r->compact_dev.as<CompactCommand>(), n_cmds, r->batches_dev.as<DeviceBatch>(), r->cmds_dev.as<DeviceCommand>(), r->cmd_cands.as<uint32_t>(),
                             counters, r->scan_scratch.as<uint32_t>()));
@@ -1032,7 +1107,7 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     // ---- bin: count, scan, emit, sort by tile (stable => draw order survives inside every tile)
     CR_TRY(r->cand_tiles.reserve(st, (size_t)(cand_cap + 1) * 4));
     CR_TRY(r->records.reserve(st, (size_t)std::max<uint32_t>(cand_cap, 1u) * sizeof(PrimRecord)));
-    CR_TRY(reserve_scan_scratch(r, r->scan_scratch, cr_scan_scratch_words(cand_cap + 1, 1)));
+    CR_TRY(reserve_scan_scratch(r, st, r->scan_scratch, cr_scan_scratch_words(cand_cap + 1, 1)));
     CR_TRY(r->big_list.reserve(st, (size_t)(cand_cap + 1) * 4));
     CR_TRY(cr_raster_setup(st, sc, tg, cand_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), counters));
     if (sized) {
@@ -1050,7 +1125,7 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     CR_TRY(r->pair_cand.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
     CR_TRY(r->pair_tile_alt.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
     CR_TRY(r->pair_cand_alt.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
-    CR_TRY(reserve_scan_scratch(r, r->radix_scratch, cr_radix_scratch_words(pair_cap)));
+    CR_TRY(reserve_scan_scratch(r, st, r->radix_scratch, cr_radix_scratch_words(pair_cap)));
     CR_TRY(r->tile_begin.reserve(st, (size_t)(n_tiles + 1) * 4));
     CR_TRY(cr_raster_bin_emit(st, tg, cand_cap, pair_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), r->pair_tile.as<uint32_t>(),
                               r->pair_cand.as<uint32_t>(), counters));
@@ -1068,6 +1143,11 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }
     CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_PASS], counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
     CR_CUDA_TRY(cudaEventRecord(r->ev_pass, st));
+    for (BatchStorage* B : p->sets) {   // a rebuild into these arrays (and their release) waits for this pass
+        if (!B->last_read) CR_CUDA_TRY(cudaEventCreateWithFlags(&B->last_read, cudaEventDisableTiming));
+        CR_CUDA_TRY(cudaEventRecord(B->last_read, st));
+        B->was_read = true;
+    }
     return CR_OK;
 }
 
@@ -1280,6 +1360,7 @@ int cr_renderer_get_stats(cr_renderer* r, cr_stats* out) {
     CR_TRY(settle(r));
     CR_TRY(take_deferred(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->pipelined) CR_CUDA_TRY(cudaStreamSynchronize(r->tess));
     if (r->stats_batch) {   // hull vertices of the last from_paths: its counts arrive with the batch's mirrors
         cr_shape_batch* b = r->stats_batch;
         CR_TRY(ensure_mirrors(b));

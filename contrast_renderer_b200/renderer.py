@@ -47,6 +47,7 @@ def lib():
             "cr_renderer_resize": [vp, u32, u32],
             "cr_renderer_set_stream": [vp, vp],
             "cr_renderer_synchronize": [vp],
+            "cr_renderer_set_pipelining": [vp, u32],
             "cr_shape_from_paths": [vp, vp, sz, C.POINTER(_abi.PathSoAC), vp, C.POINTER(vp)],
             "cr_shape_batch_from_paths": [vp, vp, sz, C.POINTER(_abi.PathSoAC), vp, u32, vp, C.POINTER(vp)],
             "cr_shape_set_dynamic_stroke_options": [vp, sz, vp],
@@ -232,6 +233,11 @@ class Renderer:
 
     def synchronize(self) -> None:
         _check(lib().cr_renderer_synchronize(self._h))
+
+    def set_pipelining(self, enabled: bool = True) -> None:
+        """Frame pipelining (`cr_renderer_set_pipelining`): rebuilding a batch for frame N + 1 overlaps rasterising frame N.
+        Device-memory inputs must then be complete when `ShapeBatch(...)` / `Shape.from_paths` is called."""
+        _check(lib().cr_renderer_set_pipelining(self._h, 1 if enabled else 0))
 
     def begin_render_pass(self, clear_color: bool = True, clear_stencil: bool = True, clear_depth: Optional[bool] = None,
                           depth_clear_value: float = 1.0) -> "RenderPass":

@@ -179,6 +179,12 @@ int cr_renderer_resize(cr_renderer* renderer, uint32_t width, uint32_t height);
 /* Adopt an existing cudaStream_t (passed as void*); NULL restores the renderer's own stream. */
 int cr_renderer_set_stream(cr_renderer* renderer, void* cuda_stream);
 int cr_renderer_synchronize(cr_renderer* renderer);
+/* Frame pipelining (no reference counterpart; wgpu pipelines frames by itself): Shape::from_paths work runs on a second stream
+ * of the renderer and a rebuild of a batch (`existing`) writes the set of arrays the last pass is NOT reading, so tessellating
+ * frame N + 1 overlaps rasterising frame N. Passes wait on the device for the builds they render; results observed through this
+ * API are ordered as before. The one difference for the caller: input arrays in DEVICE memory must be complete when
+ * cr_shape_from_paths / cr_shape_batch_from_paths is called (work merely enqueued on the renderer's stream is not waited for). */
+int cr_renderer_set_pipelining(cr_renderer* renderer, uint32_t enabled);
 
 /* ---------------------------------------------------------------------------------------------- shape building */
 

@@ -159,3 +159,35 @@ def test_optimistic_rebuild_falls_back_when_the_outputs_grow_or_change_kind(cr, 
         assert np.array_equal(rnd.read_stencil(), ref_stencil) and np.array_equal(rnd.read_color().view(np.uint32), ref_color.view(np.uint32))
     batch.close()
     rnd.close()
+
+
+def test_frame_pipelining_renders_the_same_frames(cr, oracle):
+    """cr_renderer_set_pipelining: rebuilds go to a second stream and to the batch's other set of arrays while the previous
+    pass is still being rasterised. A sequence of different frames rendered back to back (no read in between, then one read per
+    frame in a second round) must give the oracle's frames, including a frame whose sizes exceed every capacity."""
+    frames = [scenes.mixed_fills(60, extent=(512, 384), size=(10.0, 60.0), seed=21, types=(0, 1)),
+              scenes.mixed_fills(60, extent=(512, 384), size=(10.0, 60.0), seed=22, types=(0, 1)),
+              scenes.mixed_fills(60, extent=(512, 384), size=(20.0, 140.0), seed=23, types=(0, 1)),   # larger: more candidates and pairs
+              scenes.mixed_fills(60, extent=(512, 384), size=(10.0, 60.0), seed=24, types=(0, 1))]
+    rnd = cr.Renderer()
+    rnd.resize_internal_buffers(512, 384)
+    rnd.set_pipelining(True)
+    batch = None
+    for scene in frames:   # back to back: every rebuild alternates between the two sets of arrays
+        batch = _render_scene(cr, rnd, scene, batch)
+    ref_color, ref_stencil, ref_covered = _oracle_frame(oracle, rnd, frames[-1])
+    assert np.array_equal(rnd.read_stencil(), ref_stencil) and np.array_equal(rnd.read_color().view(np.uint32), ref_color.view(np.uint32))
+    assert int(rnd.stats().covered_samples) == ref_covered
+    for scene in frames:   # one frame at a time
+        batch = _render_scene(cr, rnd, scene, batch)
+        ref_color, ref_stencil, _ = _oracle_frame(oracle, rnd, scene)
+        assert np.array_equal(rnd.read_stencil(), ref_stencil) and np.array_equal(rnd.read_color().view(np.uint32), ref_color.view(np.uint32))
+        ref = oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[3]), int(scene.shape_path_begin[4]))
+        assert np.array_equal(batch[3].vertex_buffer(), ref.vertex_buffer) and np.array_equal(batch[3].index_buffer(), ref.index_buffer)
+    batch.close()
+    rnd.set_pipelining(False)
+    batch = _render_scene(cr, rnd, frames[0])
+    ref_color, ref_stencil, _ = _oracle_frame(oracle, rnd, frames[0])
+    assert np.array_equal(rnd.read_stencil(), ref_stencil) and np.array_equal(rnd.read_color().view(np.uint32), ref_color.view(np.uint32))
+    batch.close()
+    rnd.close()
