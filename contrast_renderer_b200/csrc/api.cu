@@ -1137,7 +1137,7 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     uint32_t *sorted_tile = r->pair_tile.as<uint32_t>(), *sorted_cand = r->pair_cand.as<uint32_t>();
     CR_TRY(cr_radix_sort_pairs(st, r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>(), r->pair_tile_alt.as<uint32_t>(), r->pair_cand_alt.as<uint32_t>(), pair_cap,
                                &counters->n_pairs_live, key_bits, r->radix_scratch.as<uint32_t>(), &sorted_tile, &sorted_cand));
-    CR_TRY(cr_lower_bounds(st, sorted_tile, &counters->n_pairs_live, r->tile_begin.as<uint32_t>(), n_tiles + 1));
+    CR_TRY(cr_lower_bounds(st, sorted_tile, pair_cap, &counters->n_pairs_live, r->tile_begin.as<uint32_t>(), n_tiles + 1));
     if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[3], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[4], st)); }
     CR_TRY(cr_raster_tiles(st, sc, tg, r->records.as<PrimRecord>(), r->tile_begin.as<uint32_t>(), sorted_cand, counters));
     if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }

@@ -4,6 +4,7 @@
 //
 // Every primitive is ONE launch and takes its element count either from the host or from a device word, so that the
 // render pass can be enqueued without the host ever learning the sizes (api.cu, "optimistic submit").
+#include <algorithm>
 #include <atomic>
 #include "device_common.cuh"
 #include "prims.h"
@@ -18,7 +19,7 @@ namespace {
 // it meets one that already carries an inclusive prefix. Status word: epoch (30 bits) | state (2 bits) | value (32 bits); the
 // epoch changes with every call, so the scratch array is never cleared.
 #define SCAN_THREADS 512
-#define SCAN_ITEMS 8
+#define SCAN_ITEMS 16
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
 #define SCAN_AGGREGATE 1ull
 #define SCAN_INCLUSIVE 2ull
@@ -173,13 +174,16 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
         __syncthreads();
     }
 }
-__global__ void lower_bounds_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ begin, uint32_t count) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
+// begin[t] = first i with keys[i] >= t: element i owns the keys in (keys[i - 1], keys[i]] (all keys up to keys[0] for i = 0) and
+// writes i there; the thread behind the last element owns the rest. One coalesced pass instead of a binary search per key.
+__global__ void __launch_bounds__(256) key_ranges_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ begin, uint32_t count) {
     const uint32_t n = *n_ptr;
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] < t) lo = mid + 1; else hi = mid; }
-    begin[t] = lo;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        const uint32_t lo = i == 0 ? 0u : min(keys[i - 1] + 1u, count);
+        const uint32_t hi = i == n ? count : min(keys[i] + 1u, count);
+        for (uint32_t t = lo; t < hi; ++t) begin[t] = i;
+    }
 }
 
 }  // namespace
@@ -232,8 +236,9 @@ int cr_radix_sort_pairs(cudaStream_t stream, uint32_t* keys, uint32_t* vals, uin
     *vals_out = src_v;
     return CR_OK;
 }
-int cr_lower_bounds(cudaStream_t stream, const uint32_t* sorted_keys, const uint32_t* n_ptr, uint32_t* begin, uint32_t n_keys_plus_1) {
-    lower_bounds_kernel<<<(n_keys_plus_1 + 255) / 256, 256, 0, stream>>>(sorted_keys, n_ptr, begin, n_keys_plus_1);
+int cr_lower_bounds(cudaStream_t stream, const uint32_t* sorted_keys, uint32_t capacity, const uint32_t* n_ptr, uint32_t* begin, uint32_t n_keys_plus_1) {
+    const uint32_t blocks = std::min<uint32_t>(148u * 8u, capacity / 256u + 1u);
+    key_ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_keys, n_ptr, begin, n_keys_plus_1);
     g_cr_kernel_launches += 1;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;

@@ -19,7 +19,7 @@ int cr_radix_sort_pairs(cudaStream_t stream, uint32_t* keys, uint32_t* vals, uin
                         uint32_t key_bits, uint32_t* scratch, uint32_t** keys_out, uint32_t** vals_out);
 uint32_t cr_radix_scratch_words(uint32_t capacity);
 
-// begin[t] = first index i in [0, *n_ptr) with sorted_keys[i] >= t, for t in [0, n_keys_plus_1).
-int cr_lower_bounds(cudaStream_t stream, const uint32_t* sorted_keys, const uint32_t* n_ptr, uint32_t* begin, uint32_t n_keys_plus_1);
+// begin[t] = first index i in [0, *n_ptr] with i == *n_ptr or sorted_keys[i] >= t, for t in [0, n_keys_plus_1). `capacity` sizes the grid.
+int cr_lower_bounds(cudaStream_t stream, const uint32_t* sorted_keys, uint32_t capacity, const uint32_t* n_ptr, uint32_t* begin, uint32_t n_keys_plus_1);
 
 extern unsigned long long g_cr_kernel_launches;   // counted by every launcher of this library

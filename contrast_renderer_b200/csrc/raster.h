@@ -116,7 +116,7 @@ struct RasterScene {
 
 // Commands -> DeviceCommands + the exclusive scan of their candidate counts (cmd_cand_begin, n_commands + 1 words; one launch
 // for up to CR_EXPAND_FUSED_MAX commands, else expand + cr_scan_exclusive with `scan_scratch`). Zeroes *counters first.
-#define CR_EXPAND_FUSED_MAX 32768u
+#define CR_EXPAND_FUSED_MAX 1024u
 int cr_raster_expand(cudaStream_t stream, const CompactCommand* compact, uint32_t n_commands, const DeviceBatch* batches, DeviceCommand* commands,
                      uint32_t* cmd_cand_begin, PassCounters* counters, uint32_t* scan_scratch);
 // Vertex stage + tile counting over the candidate CAPACITY: fills records and cand_tiles[0..cand_capacity) (zero beyond the

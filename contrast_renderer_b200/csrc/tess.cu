@@ -440,8 +440,11 @@ struct PathView {
     const uint8_t* seg_types;
     uint32_t n_segments;
     const float* seg[5];   // per-type arrays positioned at this path's first segment of that type
+    uint32_t count[5];     // segments of each type in this path's slices (from the cursor tables): no read goes beyond them
     cr_stroke_options so;
 };
+// A segment of type T is about to be read with cursor `cur`: it must lie inside the path's slice of that type's array.
+#define CR_SEGMENT_IN_SLICE(pv, T, cur) ((cur) < (pv).count[T])
 
 // StrokeBuilder::add_path (src/stroke.rs:205-465)
 template <bool EMIT>
@@ -463,6 +466,11 @@ __device__ void stroke_path(Sink<EMIT>& s, const PathView& pv) {
         Pt next_cp;
         Ln st, et;
         const float* d = nullptr;
+        if (type > 4u || !((type == 0 && CR_SEGMENT_IN_SLICE(pv, 0, cur[0])) || (type == 1 && CR_SEGMENT_IN_SLICE(pv, 1, cur[1])) || (type == 2 && CR_SEGMENT_IN_SLICE(pv, 2, cur[2])) ||
+                           (type == 3 && CR_SEGMENT_IN_SLICE(pv, 3, cur[3])) || (type == 4 && CR_SEGMENT_IN_SLICE(pv, 4, cur[4])))) {
+            s.err |= CR_DEVERR_BAD_TABLES;   // the type stream and the per-type cursor tables disagree
+            break;
+        }
         switch (type) {
             case CR_SEG_LINE:
                 d = pv.seg[0] + 2 * (size_t)cur[0]++;
@@ -748,7 +756,13 @@ __device__ void fill_path(Sink<EMIT>& s, const PathView& pv) {   // CUBICS == fa
     s.proto(last);
     uint32_t cur[5] = {0, 0, 0, 0, 0};
     for (uint32_t si = 0; si < pv.n_segments; ++si) {
-        switch (pv.seg_types[si]) {
+        const uint32_t type = pv.seg_types[si];
+        if (type > 4u || !((type == 0 && CR_SEGMENT_IN_SLICE(pv, 0, cur[0])) || (type == 1 && CR_SEGMENT_IN_SLICE(pv, 1, cur[1])) || (type == 2 && CR_SEGMENT_IN_SLICE(pv, 2, cur[2])) ||
+                           (type == 3 && CR_SEGMENT_IN_SLICE(pv, 3, cur[3])) || (type == 4 && CR_SEGMENT_IN_SLICE(pv, 4, cur[4])))) {
+            s.err |= CR_DEVERR_BAD_TABLES;   // the type stream and the per-type cursor tables disagree
+            break;
+        }
+        switch (type) {
             case CR_SEG_LINE: {
                 const float* d = pv.seg[0] + 2 * (size_t)cur[0]++;
                 last = make_float2(d[0], d[1]);
@@ -792,6 +806,8 @@ __device__ void fill_path(Sink<EMIT>& s, const PathView& pv) {   // CUBICS == fa
             } break;
         }
     }
+    // a filled path consumes exactly its slices (a stroked one may not: degenerate curves leave their cursor where it is, quirk C.3)
+    if (cur[0] != pv.count[0] || cur[1] != pv.count[1] || cur[2] != pv.count[2] || cur[3] != pv.count[3] || cur[4] != pv.count[4]) s.err |= CR_DEVERR_BAD_TABLES;
     s.solid_indices();
 }
 
@@ -807,6 +823,8 @@ __device__ __forceinline__ PathView load_path(const DevicePaths& P, uint32_t p) 
     pv.seg[2] = P.seg[2] + 6 * (size_t)P.type_begin[2 * stride + p];
     pv.seg[3] = P.seg[3] + 5 * (size_t)P.type_begin[3 * stride + p];
     pv.seg[4] = P.seg[4] + 10 * (size_t)P.type_begin[4 * stride + p];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) pv.count[t] = P.type_begin[t * stride + p + 1] - P.type_begin[t * stride + p];
     if (P.stroke_options) pv.so = P.stroke_options[p];
     else pv.so = cr_stroke_options{};   // no stroke options: a filled Path
     return pv;
@@ -814,32 +832,25 @@ __device__ __forceinline__ PathView load_path(const DevicePaths& P, uint32_t p) 
 
 // The cursor tables of cr_path_soa come from the caller; everything below indexes with them. A Path of the reference cannot
 // be inconsistent (its vectors carry their own lengths, src/path.rs:213-230), a C caller's tables can: check, before any
-// segment is read, that the path's slice of the type stream lies inside [0, n_segments] and that its per-type cursor deltas
-// are exactly the number of segments of each type in that slice (so every per-type read stays inside the path's slice, and
-// the slices of consecutive paths tile the arrays). Any violation sets CR_DEVERR_BAD_TABLES and the path emits nothing.
+// segment is read, that the path's slice of the type stream lies inside [0, n_segments], that every per-type cursor runs
+// forwards and that the per-type slice lengths add up to the path's segment count. While the path is walked every segment
+// read is checked against its slice (CR_SEGMENT_IN_SLICE), so no read leaves the arrays even if the type stream disagrees
+// with the tables. Any violation sets CR_DEVERR_BAD_TABLES and nothing is emitted.
 __device__ bool path_tables_valid(const DevicePaths& P, uint32_t p) {
     const uint32_t sb = P.segment_begin[p], se = P.segment_begin[p + 1];
     if (sb > se || se > P.n_segments) return false;
     if (p == 0 && sb != 0) return false;
     if (p + 1 == P.n_paths && se != P.n_segments) return false;
     const size_t stride = (size_t)P.n_paths + 1;
-    uint32_t want[5];
+    uint32_t total = 0;
 #pragma unroll
     for (int t = 0; t < 5; ++t) {
         const uint32_t tb = P.type_begin[t * stride + p], te = P.type_begin[t * stride + p + 1];
         if (tb > te || (p == 0 && tb != 0)) return false;
-        want[t] = te - tb;
+        total += te - tb;
     }
-    uint32_t have[5] = {0, 0, 0, 0, 0};
-    for (uint32_t i = sb; i < se; ++i) {
-        const uint32_t type = P.segment_types[i];
-        if (type > 4u) return false;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) have[t] += type == (uint32_t)t ? 1u : 0u;
-    }
-#pragma unroll
-    for (int t = 0; t < 5; ++t) if (have[t] != want[t]) return false;
-    return true;
+    // the per-segment agreement of the type stream with these slices is checked where the segments are read (CR_SEGMENT_IN_SLICE)
+    return total == se - sb;
 }
 
 // ------------------------------------------------------------------------------------------------- kernels
