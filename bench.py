@@ -16,9 +16,9 @@ launch sequence; config 4 re-tessellates its 24-Shape group) followed by one ren
   e2e              : the same through the C-ABI with HOST (pinned) input arrays — host->device staging of every input inside the
                      timed region — and a device->host read of the pass result (the counters) every step
   e2e_with_frame   : e2e plus the device->host copy of the colour attachment (RGBA8 target: the frame a presenter consumes)
-N > 1: configs 1, 2, 3, 5 shard path instances across GPUs by batch (north_star): each rank owns an independent scene of the
-same size (weak scaling, no data-path collective); config 4 is ONE target tile-sharded over the ranks (strong scaling, K3
-stores finished tiles into every rank's attachments over NVLink). At N > 1 the default run also renders a config-4 frame
+N > 1: configs 1, 2, 3 shard path instances across GPUs by batch (north_star): each rank owns an independent scene of the same
+size (weak scaling, no data-path collective); config 4 is ONE target tile-sharded over the ranks and config 5 ONE target composed
+from the ranks' draw-order slices (both strong scaling: K3 stores tiles into the other ranks' attachments over NVLink). At N > 1 the default run also renders a config-4 frame
 tile-sharded over the N ranks and checks every rank's copy against the CPU oracle's frame (`tile_sharded_check`).
 `--impl reference`: the reference is a Rust crate with no toolchain in this image, so the reference arm is its CPU
 restatement (oracle/, `kind: "port"`): tessellation on one thread like the reference's loop, raster on all host threads.
@@ -44,10 +44,10 @@ sys.path.insert(0, ROOT)
 class Workload:
     """One BASELINE configuration: the scene, the renderer configuration, how a pass is recorded, the oracle's commands."""
 
-    def __init__(self, index: int, rank: int, scale: float = 1.0):
+    def __init__(self, index: int, rank: int, scale: float = 1.0, world: int = 1):
         from contrast_renderer_b200 import scenes
         self.index = index
-        seed_shift = 1000 * rank
+        seed_shift = 1000 * rank if index in (1, 2, 3) else 0   # configs 4 and 5 at N > 1: ONE scene, one target
         self.alpha_layers = 0
         self.tess_only = False
         self.scripted = False
@@ -78,6 +78,10 @@ class Workload:
             self.name = f"{n} dashed stroked open paths of 2 rational cubics, round joins and caps, UniformTangentAngle(0.2), 7680x4320, one Shape per 1000 paths"
         else:
             raise SystemExit(f"--config {index}: BASELINE.json has configurations 1..5")
+        self.total_paths = self.scene.paths.n_paths
+        if index == 5 and world > 1:   # this rank's contiguous slice of the draw order (the whole scene is composed into one target)
+            from contrast_renderer_b200 import sharding
+            self.scene = sharding.shard_scene(self.scene, world, rank)
         s = self.scene
         self.width, self.height = s.width, s.height
         self.transforms = s.transforms if self.scripted else s.transforms()
@@ -85,7 +89,7 @@ class Workload:
         self.commands = None if self.scripted or self.tess_only else scenes.stencil_cover_commands(s.n_shapes)
         self.n_instances = len(self.transforms)
         # path INSTANCES drawn per step: config 4 draws its 240 paths once per placed copy
-        self.paths_per_step = s.paths.n_paths * (n if index == 4 else 1)
+        self.paths_per_step = self.total_paths * (n if index == 4 else 1)   # of the whole scene (configs 4, 5 at N > 1: counted once, not per rank)
 
     def configuration(self, cr, device: int, color_format=None):
         kw = dict(device=device, alpha_layer_count=self.alpha_layers)
@@ -353,9 +357,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    work = Workload(args.config, rank, 1.0 if args.scale is None else args.scale)
+    work = Workload(args.config, rank, 1.0 if args.scale is None else args.scale, world)
     scene, soa = work.scene, work.scene.paths
-    one_target = args.config == 4 and world > 1      # ONE render target spanning the ranks (tile sharding), else an independent scene per rank
+    one_target = args.config in (4, 5) and world > 1   # ONE render target spanning the ranks (4: tile sharding, 5: draw-order slices), else an independent scene per rank
 
     def make_renderer(color_format=None):
         rnd = R.Renderer(work.configuration(R, local_rank, color_format))
@@ -369,7 +373,10 @@ def main():
 
     rnd, stream = make_renderer()
     torch.cuda.set_stream(stream)
-    target = sharding.TileShardedTarget(rnd, stream=stream) if one_target else None
+    target = None
+    if one_target:
+        rnd.set_pipelining(False)   # the ranks hand tiles to each other inside the pass: one stream, barriers around every submit
+        target = sharding.TileShardedTarget(rnd, stream=stream) if args.config == 4 else sharding.OrderShardedTarget(rnd, stream=stream)
 
     # device-resident and pinned-host copies of every input array
     host_arrays = soa.arrays()
@@ -498,7 +505,10 @@ def main():
         t = torch.tensor([work.paths_per_step, covered], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         total_covered = int(t[1].item())
-        total_paths = work.paths_per_step if one_target else int(t[0].item())   # one target: every rank submits the SAME scene; count it once
+        total_paths = work.paths_per_step if one_target else int(t[0].item())   # one target: one scene for all ranks; count it once
+        if one_target and args.config == 4:
+            total_covered = covered   # tile sharding: every rank's counter... is per owner; the sum over ranks is the frame's
+            total_covered = int(t[1].item())
 
     sharded = None
     if world > 1 and not args.no_sharded_check:
@@ -529,7 +539,10 @@ def main():
             rooflines.append(roofline_of("raster_tiles_kernel", raster_alg, k_ms["raster"], "vertex+index bytes + 80 B x instances + W x H x (1 B stencil + 16 B rgba32f)"))
         rooflines.sort(key=lambda r: -r["kernel_ms"])
         cfg = work.config_dict()
-        cfg.update({"sharding": ("ONE render target tile-sharded over the ranks (16x16 tiles, owner (tx + ty) % N), finished tiles stored into every rank's attachments over NVLink"
+        cfg.update({"sharding": (("ONE render target tile-sharded over the ranks (16x16 tiles, owner (tx + ty) % N), finished tiles stored into every rank's attachments over NVLink"
+                                  if args.config == 4 else
+                                  "ONE render target composed from the ranks' contiguous draw-order slices: per tile the touching ranks hand the tile state from rank to rank over NVLink "
+                                  "(same operations in the same order as one GPU), the last one stores the finished tile into every rank's attachments")
                                  if one_target else "independent scene per rank, no data-path collective"),
                     "frame_pipelining": (not args.no_pipelining),
                     "l2": "working set per step (target + vertex / index / record / pair arrays) exceeds the 126 MB L2 for configs 3-5; the target is cleared and re-written every step"})

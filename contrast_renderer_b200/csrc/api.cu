@@ -150,6 +150,9 @@ struct cr_renderer {
     uint32_t shard_world = 1, shard_rank = 0;              // tile sharding of one target across GPUs
     void* peer_color[CR_MAX_PEERS] = {};                   // peer-mapped attachments of the other ranks, slot = rank - (rank > shard_rank)
     void* peer_stencil[CR_MAX_PEERS] = {};
+    uint32_t order_world = 1, order_rank = 0, order_epoch = 0;   // draw-order sharding into one target (batch sharding composed)
+    DevBuf exchange;                                       // touched-tile bitmaps and flags (raster.h), exported to the other ranks
+    void* peer_exchange[CR_MAX_PEERS] = {};
     uint64_t live_objects = 0;        // shape batches and passes that still point at this renderer
     bool destroy_requested = false;   // cr_renderer_destroy was called while live_objects > 0: the last child frees it
 };
@@ -569,7 +572,8 @@ static void close_peers(cr_renderer* r) {
     for (int i = 0; i < CR_MAX_PEERS; ++i) {
         if (r->peer_color[i]) cudaIpcCloseMemHandle(r->peer_color[i]);
         if (r->peer_stencil[i]) cudaIpcCloseMemHandle(r->peer_stencil[i]);
-        r->peer_color[i] = r->peer_stencil[i] = nullptr;
+        if (r->peer_exchange[i]) cudaIpcCloseMemHandle(r->peer_exchange[i]);
+        r->peer_color[i] = r->peer_stencil[i] = r->peer_exchange[i] = nullptr;
     }
 }
 static void pass_free(cr_pass* p);
@@ -580,7 +584,7 @@ static void renderer_free(cr_renderer* r) {
     if (r->inflight) { pass_free(r->inflight); r->inflight = nullptr; }
     close_peers(r);
     cudaStream_t st = r->stream;
-    DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->depth, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
+    DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->depth, &r->exchange, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
                      &r->hull_scratch_b, &r->scan_scratch_tess, &r->compact_dev, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand,
                      &r->pair_tile_alt, &r->pair_cand_alt, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->pass_counters};
     for (DevBuf* d : all) d->release(st);
@@ -628,6 +632,7 @@ int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
     CR_TRY(settle(r));
     r->cand_cap = r->pair_cap = 0;   // sized for another extent
     const size_t samples = (size_t)width * height * r->config.msaa_sample_count;
+    if (r->order_world > 1) return fail(CR_ERR_INVALID_ARGUMENT, "resize of an order-sharded target: call cr_renderer_set_order_sharding(r, 1, 0) first");
     if (r->peer_color[0] || r->peer_stencil[0]) return fail(CR_ERR_INVALID_ARGUMENT, "resize while peer attachments are imported: call cr_renderer_set_tile_sharding(r, 1, 0) first");
     r->color.plain = r->stencil.plain = true;   // exportable to the other ranks of a tile-sharded target
     const size_t texel = color_texel_bytes(r), layer_texel = r->config.color_format == CR_FORMAT_RGBA32F ? 4 : 1;
@@ -1031,6 +1036,12 @@ static RasterTarget make_target(const cr_pass* p) {
     tg.shard_world = r->shard_world;
     tg.shard_rank = r->shard_rank;
     for (int i = 0; i < CR_MAX_PEERS; ++i) { tg.peer_color[i] = r->peer_color[i]; tg.peer_stencil[i] = static_cast<uint8_t*>(r->peer_stencil[i]); }
+    tg.order_world = r->order_world;
+    tg.order_rank = r->order_rank;
+    tg.order_epoch = r->order_epoch;
+    tg.order_mask_words = (r->tiles_x * r->tiles_y + 31) / 32;
+    tg.exchange = r->exchange.as<uint32_t>();
+    for (int i = 0; i < CR_MAX_PEERS; ++i) tg.peer_exchange[i] = static_cast<uint32_t*>(r->peer_exchange[i]);
     return tg;
 }
 
@@ -1040,8 +1051,8 @@ static RasterTarget make_target(const cr_pass* p) {
 static int clear_attachments(cr_pass* p) {
     cr_renderer* r = p->renderer;
     const bool depth_clear = p->clear_depth && has_depth(r);
-    if (!p->clear_color && !p->clear_stencil && !depth_clear) return CR_OK;
-    if (r->shard_world <= 1 && !depth_clear) {
+    if (r->order_world <= 1 && !p->clear_color && !p->clear_stencil && !depth_clear) return CR_OK;
+    if (r->shard_world <= 1 && r->order_world <= 1 && !depth_clear) {
         const size_t samples = (size_t)r->width * r->height * r->config.msaa_sample_count;
         if (p->clear_color) CR_CUDA_TRY(cudaMemsetAsync(r->color.p, 0, samples * color_texel_bytes(r), r->stream));
         if (p->clear_stencil) CR_CUDA_TRY(cudaMemsetAsync(r->stencil.p, 0, samples, r->stream));
@@ -1051,6 +1062,10 @@ static int clear_attachments(cr_pass* p) {
     CR_TRY(r->tile_begin.reserve(r->stream, (size_t)(n_tiles + 1) * 4));
     CR_CUDA_TRY(cudaMemsetAsync(r->tile_begin.p, 0, (size_t)(n_tiles + 1) * 4, r->stream));
     RasterScene none{};
+    if (r->order_world > 1) {   // a rank whose slice draws nothing still tells the others so, in this pass's epoch
+        r->order_epoch += 1;
+        CR_TRY(cr_raster_publish_touched_tiles(r->stream, make_target(p), r->tile_begin.as<uint32_t>()));
+    }
     return cr_raster_tiles(r->stream, none, make_target(p), nullptr, r->tile_begin.as<uint32_t>(), nullptr, nullptr);
 }
 
@@ -1065,6 +1080,7 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     const uint32_t n_cmds = (uint32_t)(p->arena ? p->n_arena : p->commands.size());
     CR_TRY(r->pass_counters.reserve(st, sizeof(PassCounters)));
     PassCounters* counters = r->pass_counters.as<PassCounters>();
+    if (r->order_world > 1) r->order_epoch += 1;   // every rank submits the same number of passes: the epoch names this one on all of them
     // ---- scene description: batches, commands (expanded on the device), candidate numbering
     CR_TRY(r->batches_dev.reserve(st, p->batches.size() * sizeof(DeviceBatch)));
     if (p->sets.size() != p->batches.size()) {   // first enqueue of this pass: it renders the build each batch holds NOW (a re-submission keeps them)
@@ -1138,6 +1154,7 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     CR_TRY(cr_radix_sort_pairs(st, r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>(), r->pair_tile_alt.as<uint32_t>(), r->pair_cand_alt.as<uint32_t>(), pair_cap,
                                &counters->n_pairs_live, key_bits, r->radix_scratch.as<uint32_t>(), &sorted_tile, &sorted_cand));
     CR_TRY(cr_lower_bounds(st, sorted_tile, pair_cap, &counters->n_pairs_live, r->tile_begin.as<uint32_t>(), n_tiles + 1));
+    if (r->order_world > 1) CR_TRY(cr_raster_publish_touched_tiles(st, tg, r->tile_begin.as<uint32_t>()));
     if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[3], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[4], st)); }
     CR_TRY(cr_raster_tiles(st, sc, tg, r->records.as<PrimRecord>(), r->tile_begin.as<uint32_t>(), sorted_cand, counters));
     if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }
@@ -1173,7 +1190,7 @@ static int submit(cr_pass* p) {
         }
     }
     // optimistic unless there is nothing to go by, or the target spans several GPUs (the other ranks wait for this rank's tiles)
-    const bool sized = r->cand_cap == 0 || r->pair_cap == 0 || r->shard_world > 1;
+    const bool sized = r->cand_cap == 0 || r->pair_cap == 0 || r->shard_world > 1 || r->order_world > 1;
     CR_TRY(enqueue_pass(p, sized));
     if (sized) {   // leave slack for the next (optimistic) pass: scenes drift from frame to frame
         r->cand_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFEull, (uint64_t)r->cand_cap + r->cand_cap / 8 + 4096);
@@ -1320,6 +1337,7 @@ int cr_renderer_set_tile_sharding(cr_renderer* r, uint32_t world, uint32_t rank)
     CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peers(r);
+    r->order_world = 1; r->order_rank = 0;
     r->shard_world = world;
     r->shard_rank = rank;
     r->cand_cap = r->pair_cap = 0;   // the pair counts of a rank depend on the tiles it owns
@@ -1336,15 +1354,60 @@ int cr_renderer_export_attachments(cr_renderer* r, uint8_t* color_handle, uint8_
 }
 int cr_renderer_import_peer_attachments(cr_renderer* r, uint32_t peer_rank, const uint8_t* color_handle, const uint8_t* stencil_handle) {
     if (!r || !color_handle || !stencil_handle) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
-    if (peer_rank >= r->shard_world || peer_rank == r->shard_rank) return fail(CR_ERR_INVALID_ARGUMENT, "peer rank %u is not another rank of a %u-rank target", peer_rank, r->shard_world);
+    const uint32_t world = std::max(r->shard_world, r->order_world), rank = r->order_world > 1 ? r->order_rank : r->shard_rank;
+    if (peer_rank >= world || peer_rank == rank) return fail(CR_ERR_INVALID_ARGUMENT, "peer rank %u is not another rank of a %u-rank target", peer_rank, world);
     CR_GUARD(r);
-    const uint32_t slot = peer_rank - (peer_rank > r->shard_rank ? 1u : 0u);
+    const uint32_t slot = peer_rank - (peer_rank > rank ? 1u : 0u);
     if (r->peer_color[slot] || r->peer_stencil[slot]) return fail(CR_ERR_INVALID_ARGUMENT, "peer rank %u is already imported", peer_rank);
     cudaIpcMemHandle_t hc, hs;
     memcpy(&hc, color_handle, sizeof(hc));
     memcpy(&hs, stencil_handle, sizeof(hs));
     CR_CUDA_TRY(cudaIpcOpenMemHandle(&r->peer_color[slot], hc, cudaIpcMemLazyEnablePeerAccess));
     CR_CUDA_TRY(cudaIpcOpenMemHandle(&r->peer_stencil[slot], hs, cudaIpcMemLazyEnablePeerAccess));
+    return CR_OK;
+}
+
+// ---- one render target composed from draw-order slices (batch sharding into one target)
+int cr_renderer_set_order_sharding(cr_renderer* r, uint32_t world, uint32_t rank) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    if (world == 0 || world > CR_MAX_PEERS + 1 || rank >= world) return fail(CR_ERR_INVALID_ARGUMENT, "bad order sharding %u of %u (at most %d ranks)", rank, world, CR_MAX_PEERS + 1);
+    if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
+    if (world > 1 && (has_depth(r) || r->config.alpha_layer_count != 0))
+        return fail(CR_ERR_INVALID_ARGUMENT, "draw-order sharding hands colour and stencil from rank to rank; depth and alpha layers are not exchanged");
+    CR_GUARD(r);
+    CR_TRY(settle(r));
+    CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    close_peers(r);
+    r->shard_world = 1; r->shard_rank = 0;
+    r->order_world = world;
+    r->order_rank = rank;
+    r->order_epoch = 0;
+    r->cand_cap = r->pair_cap = 0;
+    if (world > 1) {
+        const size_t words = cr_exchange_words(r->tiles_x * r->tiles_y);
+        r->exchange.plain = true;   // exportable with cudaIpcGetMemHandle
+        CR_TRY(r->exchange.reserve(r->stream, words * 4));
+        CR_CUDA_TRY(cudaMemsetAsync(r->exchange.p, 0, words * 4, r->stream));   // epoch 0 is never live
+        CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
+    }
+    return CR_OK;
+}
+int cr_renderer_export_exchange(cr_renderer* r, uint8_t* handle) {
+    if (!r || !handle) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    if (r->order_world <= 1 || !r->exchange.p) return fail(CR_ERR_INVALID_ARGUMENT, "cr_renderer_set_order_sharding has not been called");
+    CR_GUARD(r);
+    CR_CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle), r->exchange.p));
+    return CR_OK;
+}
+int cr_renderer_import_peer_exchange(cr_renderer* r, uint32_t peer_rank, const uint8_t* handle) {
+    if (!r || !handle) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    if (peer_rank >= r->order_world || peer_rank == r->order_rank) return fail(CR_ERR_INVALID_ARGUMENT, "peer rank %u is not another rank of a %u-rank target", peer_rank, r->order_world);
+    CR_GUARD(r);
+    const uint32_t slot = peer_rank - (peer_rank > r->order_rank ? 1u : 0u);
+    if (r->peer_exchange[slot]) return fail(CR_ERR_INVALID_ARGUMENT, "peer rank %u is already imported", peer_rank);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CR_CUDA_TRY(cudaIpcOpenMemHandle(&r->peer_exchange[slot], h, cudaIpcMemLazyEnablePeerAccess));
     return CR_OK;
 }
 

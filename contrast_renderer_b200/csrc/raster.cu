@@ -458,6 +458,36 @@ __global__ void __launch_bounds__(128) bin_big_kernel(RasterTarget tg, const Pri
     }
 }
 
+// ------------------------------------------------------------------------------ draw-order sharding: exchange
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t order_slot(const RasterTarget& tg, uint32_t rank) { return rank - (rank > tg.order_rank ? 1u : 0u); }
+
+// One thread per bitmap word: bit t = this rank's slice has primitives in tile 32 w + t. Written into every rank's table.
+__global__ void touched_tiles_kernel(RasterTarget tg, const uint32_t* __restrict__ tile_begin) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= tg.order_mask_words) return;
+    const uint32_t n_tiles = tg.tiles_x * tg.tiles_y;
+    uint32_t bits = 0;
+    for (uint32_t t = 0; t < 32u; ++t) {
+        const uint32_t tile = 32u * w + t;
+        if (tile < n_tiles && tile_begin[tile + 1] > tile_begin[tile]) bits |= 1u << t;
+    }
+    const size_t at = cr_exchange_mask_offset(n_tiles) + (size_t)tg.order_rank * tg.order_mask_words + w;
+    tg.exchange[at] = bits;
+    for (uint32_t peer = 0; peer + 1 < tg.order_world; ++peer) tg.peer_exchange[peer][at] = bits;
+}
+// Runs after touched_tiles_kernel has completed: the bitmap of this rank is in place everywhere, say so (release, system scope).
+__global__ void touched_ready_kernel(RasterTarget tg) {
+    __threadfence_system();
+    if (threadIdx.x == 0) st_release_sys(&tg.exchange[tg.order_rank], tg.order_epoch);
+    else if (threadIdx.x < tg.order_world) st_release_sys(&tg.peer_exchange[threadIdx.x - 1][tg.order_rank], tg.order_epoch);
+}
+
 // ------------------------------------------------------------------------------------------- K3: tile raster
 struct TilePrim {
     long long e0[3];        // edge functions, top-left bias folded in, at the centre of the tile's pixel (0, 0)
@@ -704,7 +734,36 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
     const uint32_t tile = blockIdx.x;
     const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];
     const bool clears = tg.clear_color != 0u || tg.clear_stencil != 0u;
-    if (begin == end && (!clears || !cr_tile_owned(tg, (int)(tile % tg.tiles_x), (int)(tile / tg.tiles_x)))) return;   // nothing drawn here and nothing to clear (or not ours to clear)
+    // ---- draw-order sharding: where is this rank in the tile's chain?
+    __shared__ uint32_t sh_chain[3];     // predecessor rank + 1 (0: none), successor rank + 1 (0: none), some rank touches the tile
+    bool continue_chain = false;         // start from the predecessor's tile state (in our attachments) instead of the pass's load / clear
+    uint32_t successor = 0;              // rank + 1 the finished tile state goes to; 0: this rank finishes the tile
+    if (tg.order_world > 1u) {
+        if (threadIdx.x == 0) {
+            for (uint32_t r = 0; r < tg.order_world; ++r)
+                while (ld_acquire_sys(&tg.exchange[r]) != tg.order_epoch) { }   // every rank's bitmap of this pass has arrived
+            const uint32_t n_tiles = tg.tiles_x * tg.tiles_y;
+            const uint32_t* masks = tg.exchange + cr_exchange_mask_offset(n_tiles);
+            uint32_t pred = 0, succ = 0, any = 0;
+            for (uint32_t r = 0; r < tg.order_world; ++r) {
+                const uint32_t touched = (__ldcg(&masks[(size_t)r * tg.order_mask_words + (tile >> 5)]) >> (tile & 31u)) & 1u;
+                if (!touched) continue;
+                any = 1u;
+                if (r < tg.order_rank) pred = r + 1u;
+                if (r > tg.order_rank && succ == 0u) succ = r + 1u;
+            }
+            if (begin != end && pred != 0u)
+                while (ld_acquire_sys(&tg.exchange[cr_exchange_flag_offset() + tile]) != tg.order_epoch) { }   // the predecessor has delivered the tile
+            sh_chain[0] = pred; sh_chain[1] = succ; sh_chain[2] = any;
+        }
+        __syncthreads();
+        if (begin == end) {
+            if (sh_chain[2] != 0u || !clears) return;   // another rank's slice draws here (the last one of the chain writes our copy too), or nothing to clear
+        } else {
+            continue_chain = sh_chain[0] != 0u;
+            successor = sh_chain[1];
+        }
+    } else if (begin == end && (!clears || !cr_tile_owned(tg, (int)(tile % tg.tiles_x), (int)(tile / tg.tiles_x)))) return;   // nothing drawn here and nothing to clear (or not ours to clear)
     const int tile_px = (int)(tile % tg.tiles_x) * CR_TILE, tile_py = (int)(tile / tg.tiles_x) * CR_TILE;
     const int lx = threadIdx.x & (CR_TILE - 1), ly = threadIdx.x / CR_TILE;
     const int px = tile_px + lx, py = tile_py + ly;
@@ -720,22 +779,22 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
         for (int k = 0; k < S; ++k) dep[k] = (tg.clear_depth != 0u || !in_fb) ? tg.depth_clear_value : tg.depth[pix + k];
     }
     if (in_fb) {   // LoadOp::Load reads the attachment, LoadOp::Clear starts from zero (and the tile is written in any case)
-        if (tg.clear_stencil == 0u) {
-            if (S == 1) s[0] = tg.stencil[pix];
+        if (tg.clear_stencil == 0u || continue_chain) {
+            if (S == 1) s[0] = __ldcg(tg.stencil + pix);
             else {
-                const uint32_t packed = *reinterpret_cast<const uint32_t*>(tg.stencil + pix);   // 4 samples = 4 bytes, 4-byte aligned
+                const uint32_t packed = __ldcg(reinterpret_cast<const uint32_t*>(tg.stencil + pix));   // 4 samples = 4 bytes, 4-byte aligned
 #pragma unroll
                 for (int k = 0; k < S; ++k) s[k] = (packed >> (8 * k)) & 255u;
             }
         }
-        if (tg.clear_color == 0u) {
+        if (tg.clear_color == 0u || continue_chain) {
 #pragma unroll
             for (int k = 0; k < S; ++k) {
                 if (U8) {
-                    const uint32_t t = reinterpret_cast<const uint32_t*>(tg.color)[pix + k];
+                    const uint32_t t = __ldcg(reinterpret_cast<const uint32_t*>(tg.color) + pix + k);
                     const float c0 = (float)(t & 255u) / 255.0f, c1 = (float)((t >> 8) & 255u) / 255.0f, c2 = (float)((t >> 16) & 255u) / 255.0f;
                     col[k] = tg.color_format == CR_FORMAT_BGRA8_UNORM ? make_float4(c2, c1, c0, (float)(t >> 24) / 255.0f) : make_float4(c0, c1, c2, (float)(t >> 24) / 255.0f);
-                } else col[k] = reinterpret_cast<const float4*>(tg.color)[pix + k];
+                } else col[k] = __ldcg(reinterpret_cast<const float4*>(tg.color) + pix + k);
             }
         }
     }
@@ -963,13 +1022,16 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
     }
     apply_pending();
     if (in_fb) {
-        if (S == 1) tg.stencil[pix] = (uint8_t)s[0];
-        else {
-            uint32_t packed = 0;
+        auto store_stencil = [&](uint8_t* base) {
+            if (S == 1) base[pix] = (uint8_t)s[0];
+            else {
+                uint32_t packed = 0;
 #pragma unroll
-            for (int k = 0; k < S; ++k) packed |= (s[k] & 255u) << (8 * k);
-            *reinterpret_cast<uint32_t*>(tg.stencil + pix) = packed;
-        }
+                for (int k = 0; k < S; ++k) packed |= (s[k] & 255u) << (8 * k);
+                *reinterpret_cast<uint32_t*>(base + pix) = packed;
+            }
+        };
+        if (successor == 0u) store_stencil(tg.stencil);
         uint32_t texel[U8 ? S : 1];
         if (U8) {
 #pragma unroll
@@ -985,26 +1047,32 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
                 else reinterpret_cast<float4*>(base)[pix + k] = col[k];
             }
         };
-        store_color(tg.color);
         if (DEPTH) {
 #pragma unroll
             for (int k = 0; k < S; ++k) tg.depth[pix + k] = dep[k];
         }
-        // tile sharding: the finished tile also goes to every other rank's attachments (P2P stores over NVLink)
-        for (uint32_t peer = 0; peer + 1 < tg.shard_world; ++peer) {
-            void* pc = tg.peer_color[peer];
-            uint8_t* ps = tg.peer_stencil[peer];
-            if (pc == nullptr) continue;
-            if (S == 1) ps[pix] = (uint8_t)s[0];
-            else {
-                uint32_t packed = 0;
-#pragma unroll
-                for (int k = 0; k < S; ++k) packed |= (s[k] & 255u) << (8 * k);
-                *reinterpret_cast<uint32_t*>(ps + pix) = packed;
+        if (successor != 0u) {
+            // draw-order sharding, not the last rank of the tile's chain: the tile state goes into the successor's attachments
+            const uint32_t slot = order_slot(tg, successor - 1u);
+            store_stencil(tg.peer_stencil[slot]);
+            store_color(tg.peer_color[slot]);
+        } else {
+            store_color(tg.color);
+            // tile sharding / last rank of a chain: the finished tile also goes to every other rank's attachments (P2P stores over NVLink)
+            const uint32_t peers = (tg.order_world > 1u && begin == end) ? 0u : max(tg.shard_world, tg.order_world);   // a tile no slice touches is cleared by every rank itself
+            for (uint32_t peer = 0; peer + 1 < peers; ++peer) {
+                void* pc = tg.peer_color[peer];
+                uint8_t* ps = tg.peer_stencil[peer];
+                if (pc == nullptr) continue;
+                store_stencil(ps);
+                store_color(pc);
             }
-            store_color(pc);
         }
-        if (tg.shard_world > 1u) __threadfence_system();
+        if (tg.shard_world > 1u || tg.order_world > 1u) __threadfence_system();
+    }
+    if (successor != 0u) {   // every thread's stores are fenced: tell the successor (release, system scope)
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(&tg.peer_exchange[order_slot(tg, successor - 1u)][cr_exchange_flag_offset() + tile], tg.order_epoch);
     }
     // covered-sample statistic: warp reduce, one atomic per warp
 #pragma unroll
@@ -1046,6 +1114,14 @@ int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t
     bin_emit_kernel<<<(cand_capacity + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(target, cand_capacity, pair_capacity, records, cand_pair_begin, pair_tile,
                                                                                                       pair_cand, counters);
     bin_big_kernel<true><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, const_cast<uint32_t*>(cand_pair_begin), pair_tile, pair_cand, counters, pair_capacity);
+    g_cr_kernel_launches += 2;
+    CR_CUDA_TRY(cudaGetLastError());
+    return CR_OK;
+}
+int cr_raster_publish_touched_tiles(cudaStream_t stream, const RasterTarget& target, const uint32_t* tile_begin) {
+    if (target.order_world <= 1u) return CR_OK;
+    touched_tiles_kernel<<<(target.order_mask_words + 255) / 256, 256, 0, stream>>>(target, tile_begin);
+    touched_ready_kernel<<<1, 32, 0, stream>>>(target);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;

@@ -100,7 +100,21 @@ struct RasterTarget {
     uint32_t shard_world, shard_rank;             // world <= 1: not sharded
     void* peer_color[CR_MAX_PEERS];               // [world - 1] attachments of the other ranks (peer-mapped), or null
     uint8_t* peer_stencil[CR_MAX_PEERS];
+    // One render target composed from DRAW-ORDER slices (batch sharding into one target): rank r tessellates and bins
+    // only its contiguous slice of the draw order. Per tile, the ranks whose slices touch it form a chain in rank order; a rank
+    // waits for its predecessor's tile state (colour + stencil, stored into ITS attachments over NVLink), continues rasterising
+    // on top of it — the same operations in the same order as one GPU would execute — and hands the tile to its successor; the
+    // last rank of the chain stores the finished tile into every rank's attachments. Which ranks touch which tile is exchanged
+    // as bitmaps through the peer-mapped `exchange` buffers; all flags carry the pass's epoch, so nothing is ever cleared.
+    uint32_t order_world, order_rank;             // world <= 1: off
+    uint32_t order_epoch;
+    uint32_t order_mask_words;                    // words per rank bitmap = ceil(n_tiles / 32)
+    uint32_t* exchange;                           // own: [CR_MAX_PEERS + 1 ready words][n_tiles tile flags][(CR_MAX_PEERS + 1) x mask_words bitmaps]
+    uint32_t* peer_exchange[CR_MAX_PEERS];        // the other ranks' (peer-mapped), slot = rank - (rank > order_rank)
 };
+__host__ __device__ inline uint32_t cr_exchange_flag_offset() { return CR_MAX_PEERS + 1; }
+__host__ __device__ inline uint32_t cr_exchange_mask_offset(uint32_t n_tiles) { return CR_MAX_PEERS + 1 + n_tiles; }
+__host__ __device__ inline size_t cr_exchange_words(uint32_t n_tiles) { return (size_t)CR_MAX_PEERS + 1 + n_tiles + (size_t)(CR_MAX_PEERS + 1) * ((n_tiles + 31) / 32); }
 __host__ __device__ inline bool cr_tile_owned(const RasterTarget& tg, int tx, int ty) {
     return tg.shard_world <= 1u || (uint32_t)(tx + ty) % tg.shard_world == tg.shard_rank;
 }
@@ -127,6 +141,8 @@ int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterT
 // (tile, candidate) pairs of every valid record, at cand_pair_begin[candidate]; publishes counters->n_pairs_live / flags.
 int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t cand_capacity, uint32_t pair_capacity, const PrimRecord* records,
                        const uint32_t* cand_pair_begin, const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand, PassCounters* counters);
+// Draw-order sharding: publishes which tiles this rank's slice touches (bitmap from tile_begin) to every rank, then the ready flag.
+int cr_raster_publish_touched_tiles(cudaStream_t stream, const RasterTarget& target, const uint32_t* tile_begin);
 // counters may be null (clear-only launch on an empty tile table).
 int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* tile_begin,
                     const uint32_t* pair_cand, PassCounters* counters);

@@ -75,6 +75,9 @@ def lib():
             "cr_renderer_get_stats": [vp, C.POINTER(_abi.StatsC)],
             "cr_renderer_enable_timing": [vp, u32],
             "cr_renderer_set_tile_sharding": [vp, u32, u32],
+            "cr_renderer_set_order_sharding": [vp, u32, u32],
+            "cr_renderer_export_exchange": [vp, vp],
+            "cr_renderer_import_peer_exchange": [vp, u32, vp],
             "cr_renderer_export_attachments": [vp, vp, vp],
             "cr_renderer_import_peer_attachments": [vp, u32, vp, vp],
         }
@@ -260,6 +263,19 @@ class Renderer:
     # ---- one target spanning several GPUs (include/contrast_b200.h, "tile sharding"); orchestration in sharding.py
     def set_tile_sharding(self, world: int, rank: int) -> None:
         _check(lib().cr_renderer_set_tile_sharding(self._h, world, rank))
+
+    # ---- one target composed from draw-order slices ("order sharding"); orchestration in sharding.py
+    def set_order_sharding(self, world: int, rank: int) -> None:
+        _check(lib().cr_renderer_set_order_sharding(self._h, world, rank))
+
+    def export_exchange(self) -> bytes:
+        handle = (C.c_uint8 * _abi.CR_IPC_HANDLE_BYTES)()
+        _check(lib().cr_renderer_export_exchange(self._h, handle))
+        return bytes(handle)
+
+    def import_peer_exchange(self, peer_rank: int, handle: bytes) -> None:
+        assert len(handle) == _abi.CR_IPC_HANDLE_BYTES
+        _check(lib().cr_renderer_import_peer_exchange(self._h, peer_rank, (C.c_uint8 * _abi.CR_IPC_HANDLE_BYTES).from_buffer_copy(handle)))
 
     def export_attachments(self) -> bytes:
         """The two 64-byte CUDA IPC handles (colour, stencil) of this renderer's attachments, concatenated."""

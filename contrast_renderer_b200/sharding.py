@@ -19,6 +19,7 @@ from typing import Tuple
 
 import numpy as np
 
+from . import _abi
 from .path import PathSoA
 from .scenes import Scene
 
@@ -138,3 +139,76 @@ class TileShardedTarget:
         self.barrier()
         self.renderer.synchronize()
         self.renderer.set_tile_sharding(1, 0)
+
+
+# ----------------------------------------------------------------------------------------------- order sharding
+class OrderShardedTarget:
+    """ONE render target composed from draw-order slices over the ranks of the default process group (BASELINE config 5:
+    "path instances shard across GPUs by batch", SURVEY 8e). Rank r tessellates and submits only `shard_scene(scene, world, r)`;
+    per tile the ranks whose slices touch it hand the tile state from rank to rank over NVLink (the tile kernel waits for its
+    predecessor, rasterises on top, stores into its successor's attachments) and the last one stores the finished tile into
+    every rank's attachments: the composed frame is what a single GPU produces for the whole scene, bit for bit. Usage,
+    identically on every rank:
+
+        target = OrderShardedTarget(renderer)           # after renderer.resize_internal_buffers(...)
+        rp = target.begin_render_pass()                 # barrier: nobody still reads the previous frame
+        ... record THIS rank's slice ...
+        target.submit(rp)                               # barrier: the frame is complete everywhere
+    """
+
+    def __init__(self, renderer, group=None, stream=None):
+        import torch
+        import torch.distributed as dist
+        self.renderer, self.group = renderer, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        device = torch.device(f"cuda:{renderer.config.device}")
+        self.stream = stream if stream is not None else torch.cuda.Stream(device)
+        assert self.stream.cuda_stream != 0, "the legacy default stream cannot be shared with the renderer"
+        self._token = torch.zeros(1, device=device)
+        renderer.set_stream(self.stream.cuda_stream)
+        renderer.set_order_sharding(self.world, self.rank)
+        handles = exchange_handles(renderer.export_attachments() + renderer.export_exchange(), group)
+        n = _abi.CR_IPC_HANDLE_BYTES
+        for peer, blob in enumerate(handles):
+            if peer != self.rank:
+                renderer.import_peer_attachments(peer, blob[:2 * n])
+                renderer.import_peer_exchange(peer, blob[2 * n:])
+        self.barrier()
+
+    def barrier(self) -> None:
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self._token, group=self.group)   # stream-ordered: completes once every rank's earlier work is done
+
+    def begin_render_pass(self, clear_color: bool = True, clear_stencil: bool = True):
+        rp = self.renderer.begin_render_pass(clear_color, clear_stencil)
+        self.barrier()
+        return rp
+
+    def submit(self, render_pass) -> None:
+        render_pass.submit()
+        self.barrier()
+
+    def close(self) -> None:
+        self.barrier()
+        self.renderer.synchronize()
+        self.renderer.set_order_sharding(1, 0)
+
+
+def tile_chains(touched: np.ndarray):
+    """The hand-off chains of an order-sharded target as the tile kernel derives them. `touched`: [world, n_tiles] bool.
+    Returns (predecessor, successor) int arrays [world, n_tiles]: the rank a rank receives the tile from / hands it to, -1 where
+    there is none (or where the rank does not touch the tile)."""
+    world, n_tiles = touched.shape
+    pred = np.full((world, n_tiles), -1, np.int64)
+    succ = np.full((world, n_tiles), -1, np.int64)
+    last = np.full(n_tiles, -1, np.int64)
+    for r in range(world):
+        pred[r] = np.where(touched[r], last, -1)
+        last = np.where(touched[r], r, last)
+    nxt = np.full(n_tiles, -1, np.int64)
+    for r in range(world - 1, -1, -1):
+        succ[r] = np.where(touched[r], nxt, -1)
+        nxt = np.where(touched[r], r, nxt)
+    return pred, succ

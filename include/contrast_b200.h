@@ -319,6 +319,21 @@ int cr_renderer_export_attachments(cr_renderer* renderer, uint8_t color_handle[C
 int cr_renderer_import_peer_attachments(cr_renderer* renderer, uint32_t peer_rank, const uint8_t color_handle[CR_IPC_HANDLE_BYTES],
                                         const uint8_t stencil_handle[CR_IPC_HANDLE_BYTES]);
 
+/* One render target composed from DRAW-ORDER slices ("path instances shard across GPUs by batch" into one target, BASELINE
+ * north_star; SURVEY 8e batch sharding). No reference counterpart. Rank r of `world` tessellates and submits only its contiguous
+ * slice of the draw order (slices must not cut through a clip or an opacity group). Per 16 x 16 tile the ranks whose slices
+ * touch it form a chain in rank order: each waits for its predecessor's tile state (colour + stencil, stored into ITS
+ * attachments over NVLink), rasterises its slice on top — the same operations in the same order as a single GPU would execute,
+ * so the composed frame is bit-identical to the single-GPU frame — and hands the tile on; the last rank of the chain stores
+ * the finished tile into every rank's attachments. Every rank submits the same number of passes; the caller puts a barrier
+ * before cr_pass_submit (nobody still reads the previous frame) and one after it (contrast_renderer_b200/sharding.py).
+ * Setup: cr_renderer_set_order_sharding, then exchange the handles of cr_renderer_export_attachments and
+ * cr_renderer_export_exchange and import them with cr_renderer_import_peer_attachments / cr_renderer_import_peer_exchange.
+ * cr_stats.covered_samples stays per rank (the sum over ranks is the frame's). (world, rank) = (1, 0) switches it off. */
+int cr_renderer_set_order_sharding(cr_renderer* renderer, uint32_t world, uint32_t rank);
+int cr_renderer_export_exchange(cr_renderer* renderer, uint8_t handle[CR_IPC_HANDLE_BYTES]);
+int cr_renderer_import_peer_exchange(cr_renderer* renderer, uint32_t peer_rank, const uint8_t handle[CR_IPC_HANDLE_BYTES]);
+
 /* Counters of the last submitted pass / last from_paths call (synchronises the stream). */
 typedef struct cr_stats {
     uint64_t covered_samples;              /* samples that passed the stencil test of a COLOR cover */

@@ -131,3 +131,34 @@ def test_two_rank_gloo_tile_sharded_frame(built):
         assert p.exitcode == 0
     assert handles == [bytes([0]) * 128, bytes([1]) * 128]   # blobs arrive indexed by rank
     assert same and energy > 0, "the owned tiles of the two ranks compose the whole frame"
+
+
+def test_tile_chains_of_an_order_sharded_target():
+    """Host-side restatement of the hand-off chains the tile kernel derives from the touched-tile bitmaps (raster.cu): per tile the
+    touching ranks in rank order; every touched tile has exactly one chain head (no predecessor) and one tail (no successor)."""
+    from contrast_renderer_b200 import sharding
+    rng = np.random.default_rng(4)
+    touched = rng.random((5, 300)) < 0.4
+    pred, succ = sharding.tile_chains(touched)
+    for t in range(touched.shape[1]):
+        ranks = [r for r in range(5) if touched[r, t]]
+        for i, r in enumerate(ranks):
+            assert pred[r, t] == (ranks[i - 1] if i else -1) and succ[r, t] == (ranks[i + 1] if i + 1 < len(ranks) else -1)
+        for r in range(5):
+            if not touched[r, t]:
+                assert pred[r, t] == -1 and succ[r, t] == -1
+    heads = ((pred == -1) & touched).sum(0)
+    tails = ((succ == -1) & touched).sum(0)
+    assert np.array_equal(heads, touched.any(0).astype(int)) and np.array_equal(tails, touched.any(0).astype(int))
+
+
+def test_draw_order_slices_cover_the_scene():
+    """shard_scene: the ranks' slices are contiguous, disjoint and complete in draw order (what order sharding relies on)."""
+    from contrast_renderer_b200 import scenes, sharding
+    scene = scenes.dashed_rational_strokes(5000, extent=(640, 360), paths_per_shape=250)
+    world = 3
+    parts = [sharding.shard_scene(scene, world, r) for r in range(world)]
+    assert sum(p.n_shapes for p in parts) == scene.n_shapes and sum(p.paths.n_paths for p in parts) == scene.paths.n_paths
+    assert np.array_equal(np.concatenate([p.colors for p in parts]), scene.colors)
+    assert np.array_equal(np.concatenate([p.paths.start for p in parts]), scene.paths.start)
+    assert np.array_equal(np.concatenate([p.transforms() for p in parts]), scene.transforms())
