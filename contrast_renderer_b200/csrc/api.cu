@@ -143,7 +143,7 @@ struct cr_renderer {
     size_t cmd_arena_cap = 0;
     bool cmd_arena_busy = false;
     // Capacities the next pass is sized with (candidates, (tile, candidate) pairs): what the last pass needed plus slack. 0: unknown.
-    uint32_t cand_cap = 0, pair_cap = 0;
+    uint32_t cand_cap = 0, pair_cap = 0, last_cands = 0, last_pairs = 0;
     cr_pass* inflight = nullptr;      // the last submitted pass until its device-side sizes have been checked (settle)
     int deferred_status = CR_OK;      // an error found while settling, reported by the next entry point that can fail
     char deferred_message[256] = "";
@@ -1106,6 +1106,7 @@ static int enqueue_pass(cr_pass* p, bool sized) {
         unsigned long long cand_total = 0;
         memcpy(&cand_total, &r->pinned[PIN_PASS], 8);
         if (cand_total >= 0xFFFFFFFFull) return fail(CR_ERR_INVALID_ARGUMENT, "%llu candidate primitives in one pass exceed 2^32; submit in several passes", cand_total);
+        r->last_cands = (uint32_t)cand_total;
         r->cand_cap = std::max<uint32_t>(r->cand_cap, (uint32_t)cand_total);
     }
     const uint32_t cand_cap = r->cand_cap;
@@ -1133,6 +1134,7 @@ static int enqueue_pass(cr_pass* p, bool sized) {
         memcpy(&pair_total, &r->pinned[PIN_PASS + 2], 8);
         if (pair_total >= 0xFFFFFFFFull)
             return fail(CR_ERR_INVALID_ARGUMENT, "%llu (tile, primitive) pairs in one pass exceed 2^32; submit in several passes", pair_total);
+        r->last_pairs = (uint32_t)pair_total;
         r->pair_cap = std::max<uint32_t>(r->pair_cap, (uint32_t)pair_total);
     }
     const uint32_t pair_cap = r->pair_cap;
@@ -1192,9 +1194,11 @@ static int submit(cr_pass* p) {
     // optimistic unless there is nothing to go by, or the target spans several GPUs (the other ranks wait for this rank's tiles)
     const bool sized = r->cand_cap == 0 || r->pair_cap == 0 || r->shard_world > 1 || r->order_world > 1;
     CR_TRY(enqueue_pass(p, sized));
-    if (sized) {   // leave slack for the next (optimistic) pass: scenes drift from frame to frame
-        r->cand_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFEull, (uint64_t)r->cand_cap + r->cand_cap / 8 + 4096);
-        r->pair_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFEull, (uint64_t)r->pair_cap + r->pair_cap / 8 + 4096);
+    if (sized && r->shard_world <= 1 && r->order_world <= 1) {
+        // leave slack for the next (optimistic) pass: scenes drift from frame to frame. Based on what THIS pass needed, so that
+        // a renderer whose passes are all sized never compounds it.
+        r->cand_cap = std::max<uint32_t>(r->cand_cap, (uint32_t)std::min<uint64_t>(0xFFFFFFFEull, (uint64_t)r->last_cands + r->last_cands / 8 + 4096));
+        r->pair_cap = std::max<uint32_t>(r->pair_cap, (uint32_t)std::min<uint64_t>(0xFFFFFFFEull, (uint64_t)r->last_pairs + r->last_pairs / 8 + 4096));
     }
     return CR_OK;
 }
