@@ -119,14 +119,22 @@ struct cr_renderer {
     cr_config config;
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t tess = nullptr;      // frame pipelining: Shape::from_paths work runs here (high priority), concurrently with the passes on `stream`
+    // Frame pipelining: a frame goes through four streams — host inputs are copied on `copy`, count / scan / emit run on `tess`,
+    // the convex hulls (sort + sequential chains: latency bound, few warps) on `hull`, the passes on `stream` — so that the copy
+    // of frame N + 2, the tessellation of frame N + 1... and the raster of frame N - 1 overlap. Events order the stages.
+    cudaStream_t tess = nullptr, copy = nullptr, hull = nullptr;
     bool pipelined = false;
     cudaStream_t tstream() const { return pipelined ? tess : stream; }
+    cudaStream_t cstream() const { return pipelined ? copy : stream; }
+    cudaStream_t hstream() const { return pipelined ? hull : stream; }
+    int staging_cur = 0;              // which of the two staging sets the build being enqueued copies into
+    cudaEvent_t staging_free[2] = {nullptr, nullptr};   // recorded on the tessellation stream behind the last kernel that reads the set
+    cudaEvent_t ev_copied = nullptr, ev_emitted = nullptr, ev_hull_idle = nullptr;
     uint32_t width = 0, height = 0, tiles_x = 0, tiles_y = 0;
     DevBuf color, stencil, alpha_layers, depth;
     // scratch shared by every from_paths / submit of this renderer
-    DevBuf staging[10], counts, scan_scratch_tess, scan_scratch, shape_begin_dev, err_flag, hull_scratch_a, hull_scratch_b;
-    DevBuf compact_dev, cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, radix_scratch, tile_begin,
+    DevBuf staging[2][10], counts, scan_scratch_tess, scan_scratch, shape_begin_dev, hull_scratch_a, hull_scratch_b;
+    DevBuf compact_dev, cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, tile_prims, radix_scratch, tile_begin,
         inst_transforms, inst_colors, pass_counters;
     uint32_t* pinned = nullptr;   // PIN_WORDS words of pinned read-back area
     cr_stats stats{};
@@ -163,10 +171,13 @@ struct cr_shape {
     bool owns_batch;
 };
 
-// The device arrays of one build of a batch. A batch owns two of them: with frame pipelining (cr_renderer_set_pipelining) a
-// rebuild writes the set the last pass is NOT reading, so that tessellating frame N + 1 overlaps rasterising frame N.
+// The device arrays of one build of a batch. A batch owns CR_BATCH_SETS of them: with frame pipelining
+// (cr_renderer_set_pipelining) a rebuild writes the set used least recently, so that tessellating frame N + 1 and building the
+// hulls of frame N overlap rasterising frame N - 1.
+#define CR_BATCH_SETS 3
 struct BatchStorage {
     DevBuf vtx[7], proto, hull, idx[3], cat_begin, hull_count, stroke, desc_dev;
+    DevBuf err;                        // [0] error bits of this build, [1] largest proto-hull slice of any shape
     cudaEvent_t written = nullptr;     // recorded on the tessellation stream when the build (and its descriptor) is complete
     cudaEvent_t last_read = nullptr;   // recorded on the renderer's stream behind the last pass that reads these arrays
     bool was_read = false;
@@ -174,7 +185,7 @@ struct BatchStorage {
 struct cr_shape_batch {
     cr_renderer* renderer = nullptr;
     uint32_t n_shapes = 0, n_paths = 0, n_groups = 0, n_segments = 0;
-    BatchStorage set[2];
+    BatchStorage set[CR_BATCH_SETS];
     int cur = 0;                      // the set holding the latest build
     BatchStorage& store() { return set[cur]; }
     const BatchStorage& store() const { return set[cur]; }
@@ -243,7 +254,8 @@ void batch_release(cr_shape_batch* b) {
         if (B.was_read && B.last_read) cudaStreamWaitEvent(st, B.last_read, 0);   // freed behind the last pass that reads them
         for (auto& v : B.vtx) v.release(st);
         for (auto& v : B.idx) v.release(st);
-        B.proto.release(st); B.hull.release(st); B.cat_begin.release(st); B.hull_count.release(st); B.stroke.release(st); B.desc_dev.release(st);
+        if (B.written) cudaStreamWaitEvent(st, B.written, 0);                     // ... and behind the build itself (the hull stream records it)
+        B.proto.release(st); B.hull.release(st); B.cat_begin.release(st); B.hull_count.release(st); B.stroke.release(st); B.desc_dev.release(st); B.err.release(st);
         if (B.written) cudaEventDestroy(B.written);
         if (B.last_read) cudaEventDestroy(B.last_read);
         B.written = B.last_read = nullptr;
@@ -271,9 +283,10 @@ int stage(cr_renderer* r, int slot, const T* src, size_t count, uint32_t space, 
     if (count == 0) { *out = nullptr; return CR_OK; }
     if (!src) return fail(CR_ERR_INVALID_ARGUMENT, "null input array (slot %d)", slot);
     if (space == CR_MEM_DEVICE) { *out = src; return CR_OK; }
-    CR_TRY(r->staging[slot].reserve(r->tstream(), count * sizeof(T)));
-    CR_CUDA_TRY(cudaMemcpyAsync(r->staging[slot].p, src, count * sizeof(T), cudaMemcpyHostToDevice, r->tstream()));
-    *out = r->staging[slot].as<T>();
+    DevBuf& buf = r->staging[r->staging_cur][slot];
+    CR_TRY(buf.reserve(r->cstream(), count * sizeof(T)));
+    CR_CUDA_TRY(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, r->cstream()));
+    *out = buf.as<T>();
     return CR_OK;
 }
 
@@ -302,7 +315,7 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     if (shape_path_begin[0] != 0 || shape_path_begin[n_shapes] != soa->n_paths) return fail(CR_ERR_INVALID_ARGUMENT, "shape_path_begin must cover [0, n_paths]");
     for (uint32_t s = 0; s < n_shapes; ++s)
         if (shape_path_begin[s] > shape_path_begin[s + 1]) return fail(CR_ERR_INVALID_ARGUMENT, "shape_path_begin must be non-decreasing");
-    cudaStream_t st = r->tstream();
+    cudaStream_t st = r->tstream(), hs = r->hstream();
     const uint32_t n_paths = soa->n_paths;
     const size_t stride = (size_t)n_paths + 1;
     if (n_paths && !soa->type_begin) return fail(CR_ERR_INVALID_ARGUMENT, "type_begin is null");
@@ -319,10 +332,16 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     if (b->mirrors_pending) { CR_CUDA_TRY(cudaEventSynchronize(b->ev_mirrors)); b->mirrors_pending = false; }
 
     const bool optimistic = b->built && b->n_paths == n_paths && b->n_shapes == n_shapes && b->n_segments == soa->n_segments && b->n_groups == n_groups;
-    const int target = (r->pipelined && b->built) ? 1 - b->cur : b->cur;
+    const int target = (r->pipelined && b->built) ? (b->cur + 1) % CR_BATCH_SETS : b->cur;
     BatchStorage& B = b->set[target];
     if (B.was_read) CR_CUDA_TRY(cudaStreamWaitEvent(st, B.last_read, 0));
+    if (r->pipelined && B.written) CR_CUDA_TRY(cudaStreamWaitEvent(st, B.written, 0));   // the set's previous build (its hulls run on another stream) is complete
     b->built = false;
+    const bool host_inputs = soa->memory_space == CR_MEM_HOST;
+    if (r->pipelined && host_inputs) {   // the other staging set; the copies wait for the kernels that read its previous contents
+        r->staging_cur ^= 1;
+        if (r->staging_free[r->staging_cur]) CR_CUDA_TRY(cudaStreamWaitEvent(r->copy, r->staging_free[r->staging_cur], 0));
+    }
 
     if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[0], st));
     DevicePaths P{};
@@ -351,18 +370,22 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     // stroke_options == NULL: every Path has `stroke_options: None` (src/path.rs:215), i.e. all paths are filled
     if (soa->stroke_options) CR_TRY(stage(r, 9, soa->stroke_options, n_paths, soa->memory_space, &P.stroke_options));
     else P.stroke_options = nullptr;
+    if (r->pipelined && host_inputs) {   // the tessellation kernels wait for the copies
+        CR_CUDA_TRY(cudaEventRecord(r->ev_copied, r->copy));
+        CR_CUDA_TRY(cudaStreamWaitEvent(st, r->ev_copied, 0));
+    }
 
     // ---- pass A: count, scan, per-shape slice boundaries
     CR_TRY(r->counts.reserve(st, CNT_COUNT * stride * sizeof(uint32_t)));
     CR_TRY(reserve_scan_scratch(r, st, r->scan_scratch_tess, cr_scan_scratch_words((uint32_t)stride, CNT_COUNT)));
-    CR_TRY(r->err_flag.reserve(st, 8));   // [0] error bits, [1] largest proto-hull slice of any shape
-    CR_CUDA_TRY(cudaMemsetAsync(r->err_flag.p, 0, 8, st));
+    CR_TRY(B.err.reserve(st, 8));
+    CR_CUDA_TRY(cudaMemsetAsync(B.err.p, 0, 8, st));
     CR_TRY(r->shape_begin_dev.reserve(st, (size_t)(n_shapes + 1) * 4));
     CR_CUDA_TRY(cudaMemcpyAsync(r->shape_begin_dev.p, shape_path_begin, (size_t)(n_shapes + 1) * 4, cudaMemcpyHostToDevice, st));
     CR_TRY(B.cat_begin.reserve(st, (size_t)CNT_COUNT * (n_shapes + 1) * 4));
     CR_TRY(B.hull_count.reserve(st, (size_t)n_shapes * 4));
     uint32_t* counts = r->counts.as<uint32_t>();
-    uint32_t* err = r->err_flag.as<uint32_t>();
+    uint32_t* err = B.err.as<uint32_t>();
 
     auto run_sizes = [&](bool has_cubics, const TessCapacity& caps) -> int {
         CR_TRY(cr_tess_count(st, P, (uint32_t)n_groups, counts, err, has_cubics));
@@ -394,11 +417,16 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
         // the emit pass is bound by its scattered stores: the lean kernel (3x the occupancy) measured 17 % SLOWER on the text scene, so
         // only the count pass uses it (33 -> 7 us)
         CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, err, true));
-        if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[6], st));
-        CR_TRY(cr_tess_hull(st, out.proto, r->hull_scratch_a.as<float2>(), r->hull_scratch_b.as<float2>(),
+        if (r->pipelined) {   // the input (staging) arrays are free again; the hulls continue on their own stream
+            if (host_inputs) CR_CUDA_TRY(cudaEventRecord(r->staging_free[r->staging_cur], st));
+            CR_CUDA_TRY(cudaEventRecord(r->ev_emitted, st));
+            CR_CUDA_TRY(cudaStreamWaitEvent(hs, r->ev_emitted, 0));
+        }
+        if (r->timing) CR_CUDA_TRY(cudaEventRecord(r->ev[6], hs));
+        CR_TRY(cr_tess_hull(hs, out.proto, r->hull_scratch_a.as<float2>(), r->hull_scratch_b.as<float2>(),
                             B.cat_begin.as<uint32_t>() + (size_t)CNT_PROTO * (n_shapes + 1), n_shapes, B.hull.as<float2>(), B.hull_count.as<uint32_t>(), max_proto, err,
                             r->timing ? r->ev[7] : nullptr));
-        if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[8], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[1], st)); r->ev_valid[0] = true; }
+        if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[8], hs)); CR_CUDA_TRY(cudaEventRecord(r->ev[1], hs)); r->ev_valid[0] = true; }
         return CR_OK;
     };
     TessCapacity unlimited;
@@ -428,7 +456,8 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     if (emitted && (flags & (CR_DEVERR_CAPACITY | CR_DEVERR_MODE))) {
         // the optimistic launch did nothing (emit and hull return when they see these bits): redo in the cold order
         CR_CUDA_TRY(cudaStreamSynchronize(st));
-        CR_CUDA_TRY(cudaMemsetAsync(r->err_flag.p, 0, 8, st));
+        if (r->pipelined) CR_CUDA_TRY(cudaStreamSynchronize(hs));
+        CR_CUDA_TRY(cudaMemsetAsync(B.err.p, 0, 8, st));
         CR_TRY(run_sizes(has_cubics, unlimited));
         CR_CUDA_TRY(cudaEventSynchronize(r->ev_sizes));
         flags = r->pinned[PIN_TESS + CNT_COUNT];
@@ -446,11 +475,18 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     b->has_cubics = has_cubics;
     b->max_proto = max_proto;
     if (!emitted) {
+        if (r->pipelined) {   // the hull scratch arrays may be re-allocated here (on the tessellation stream): the hulls of the previous build must be done with them
+            CR_CUDA_TRY(cudaEventRecord(r->ev_hull_idle, hs));
+            CR_CUDA_TRY(cudaStreamWaitEvent(st, r->ev_hull_idle, 0));
+        }
         CR_TRY(reserve_outputs(b->totals));
         CR_TRY(run_emit(max_proto));
     }
+    // everything below follows the hulls: it is enqueued on their stream, which is the build's last stage
     CR_TRY(B.stroke.reserve(st, n_groups * sizeof(Descriptor48)));
-    if (n_groups) CR_CUDA_TRY(cudaMemcpyAsync(B.stroke.p, descs.data(), n_groups * sizeof(Descriptor48), cudaMemcpyHostToDevice, st));
+    CR_TRY(B.desc_dev.reserve(st, sizeof(DeviceBatch)));
+    if (r->pipelined && !emitted) { CR_CUDA_TRY(cudaEventRecord(r->ev_emitted, st)); CR_CUDA_TRY(cudaStreamWaitEvent(hs, r->ev_emitted, 0)); }   // (re-)allocations above precede their use
+    if (n_groups) CR_CUDA_TRY(cudaMemcpyAsync(B.stroke.p, descs.data(), n_groups * sizeof(Descriptor48), cudaMemcpyHostToDevice, hs));
 
     // ---- the rasteriser's view of this batch + host mirrors of the slice tables (asynchronous, pinned)
     DeviceBatch db{};
@@ -462,8 +498,7 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     db.stroke = B.stroke.p;
     db.n_shapes = n_shapes;
     db.n_groups = (uint32_t)n_groups;
-    CR_TRY(B.desc_dev.reserve(st, sizeof(DeviceBatch)));
-    CR_CUDA_TRY(cudaMemcpyAsync(B.desc_dev.p, &db, sizeof(db), cudaMemcpyHostToDevice, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(B.desc_dev.p, &db, sizeof(db), cudaMemcpyHostToDevice, hs));
     const size_t table_words = (size_t)CNT_COUNT * (n_shapes + 1), mirror_words = table_words + n_shapes + 2;
     if (mirror_words > b->mirrors_cap) {
         if (b->mirrors) cudaFreeHost(b->mirrors);
@@ -472,13 +507,13 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
         b->mirrors_cap = mirror_words;
     }
     if (!b->ev_mirrors) CR_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_mirrors, cudaEventDisableTiming));
-    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors, B.cat_begin.p, table_words * 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words, B.hull_count.p, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words + n_shapes, err, 4, cudaMemcpyDeviceToHost, st));
-    CR_CUDA_TRY(cudaEventRecord(b->ev_mirrors, st));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors, B.cat_begin.p, table_words * 4, cudaMemcpyDeviceToHost, hs));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words, B.hull_count.p, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost, hs));
+    CR_CUDA_TRY(cudaMemcpyAsync(b->mirrors + table_words + n_shapes, err, 4, cudaMemcpyDeviceToHost, hs));
+    CR_CUDA_TRY(cudaEventRecord(b->ev_mirrors, hs));
     b->mirrors_pending = true;
     if (!B.written) CR_CUDA_TRY(cudaEventCreateWithFlags(&B.written, cudaEventDisableTiming));
-    CR_CUDA_TRY(cudaEventRecord(B.written, st));
+    CR_CUDA_TRY(cudaEventRecord(B.written, hs));
     b->cur = target;
     b->views.resize(n_shapes);
     for (uint32_t s = 0; s < n_shapes; ++s) b->views[s] = cr_shape{b, s, false};
@@ -580,15 +615,15 @@ static void pass_free(cr_pass* p);
 static void renderer_free(cr_renderer* r) {
     DeviceGuard guard(r->device);
     cudaStreamSynchronize(r->stream);
-    if (r->tess) cudaStreamSynchronize(r->tess);
+    for (cudaStream_t q : {r->tess, r->copy, r->hull}) if (q) cudaStreamSynchronize(q);
     if (r->inflight) { pass_free(r->inflight); r->inflight = nullptr; }
     close_peers(r);
     cudaStream_t st = r->stream;
-    DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->depth, &r->exchange, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->err_flag, &r->hull_scratch_a,
+    DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->depth, &r->exchange, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->hull_scratch_a,
                      &r->hull_scratch_b, &r->scan_scratch_tess, &r->compact_dev, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand,
-                     &r->pair_tile_alt, &r->pair_cand_alt, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->pass_counters};
+                     &r->pair_tile_alt, &r->pair_cand_alt, &r->tile_prims, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->pass_counters};
     for (DevBuf* d : all) d->release(st);
-    for (auto& d : r->staging) d.release(st);
+    for (auto& set : r->staging) for (auto& d : set) d.release(st);
     cudaStreamSynchronize(st);
     for (auto& e : r->ev) if (e) cudaEventDestroy(e);
     if (r->pinned) cudaFreeHost(r->pinned);
@@ -596,7 +631,8 @@ static void renderer_free(cr_renderer* r) {
     if (r->ev_sizes) cudaEventDestroy(r->ev_sizes);
     if (r->ev_pass) cudaEventDestroy(r->ev_pass);
     if (r->ev_update) cudaEventDestroy(r->ev_update);
-    if (r->tess) cudaStreamDestroy(r->tess);
+    for (cudaEvent_t e : {r->staging_free[0], r->staging_free[1], r->ev_copied, r->ev_emitted, r->ev_hull_idle}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t q : {r->tess, r->copy, r->hull}) if (q) cudaStreamDestroy(q);
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
     delete r;
 }
@@ -660,7 +696,7 @@ int cr_renderer_set_stream(cr_renderer* r, void* cuda_stream) {
     CR_GUARD(r);
     CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
-    if (r->tess) CR_CUDA_TRY(cudaStreamSynchronize(r->tess));
+    for (cudaStream_t q : {r->tess, r->copy, r->hull}) if (q) CR_CUDA_TRY(cudaStreamSynchronize(q));
     r->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : r->own_stream;
     return CR_OK;
 }
@@ -669,7 +705,7 @@ int cr_renderer_synchronize(cr_renderer* r) {
     CR_GUARD(r);
     CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
-    if (r->pipelined) CR_CUDA_TRY(cudaStreamSynchronize(r->tess));
+    if (r->pipelined) for (cudaStream_t q : {r->copy, r->tess, r->hull}) CR_CUDA_TRY(cudaStreamSynchronize(q));
     return take_deferred(r);
 }
 
@@ -683,11 +719,14 @@ int cr_renderer_set_pipelining(cr_renderer* r, uint32_t enabled) {
     CR_GUARD(r);
     CR_TRY(settle(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
-    if (r->tess) CR_CUDA_TRY(cudaStreamSynchronize(r->tess));
+    for (cudaStream_t q : {r->tess, r->copy, r->hull}) if (q) CR_CUDA_TRY(cudaStreamSynchronize(q));
     if (enabled && !r->tess) {
         int least = 0, greatest = 0;
         CR_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         CR_CUDA_TRY(cudaStreamCreateWithPriority(&r->tess, cudaStreamNonBlocking, greatest));
+        CR_CUDA_TRY(cudaStreamCreateWithPriority(&r->hull, cudaStreamNonBlocking, greatest));
+        CR_CUDA_TRY(cudaStreamCreateWithPriority(&r->copy, cudaStreamNonBlocking, greatest));
+        for (cudaEvent_t* e : {&r->staging_free[0], &r->staging_free[1], &r->ev_copied, &r->ev_emitted, &r->ev_hull_idle}) CR_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     r->pipelined = enabled != 0;
     return CR_OK;
@@ -1066,7 +1105,7 @@ static int clear_attachments(cr_pass* p) {
         r->order_epoch += 1;
         CR_TRY(cr_raster_publish_touched_tiles(r->stream, make_target(p), r->tile_begin.as<uint32_t>()));
     }
-    return cr_raster_tiles(r->stream, none, make_target(p), nullptr, r->tile_begin.as<uint32_t>(), nullptr, nullptr);
+    return cr_raster_tiles(r->stream, none, make_target(p), nullptr, r->tile_begin.as<uint32_t>(), nullptr);
 }
 
 // Enqueues the whole pass. `sized` = false: OPTIMISTIC — buffers and grids are sized from the capacities the previous pass left
@@ -1158,7 +1197,10 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     CR_TRY(cr_lower_bounds(st, sorted_tile, pair_cap, &counters->n_pairs_live, r->tile_begin.as<uint32_t>(), n_tiles + 1));
     if (r->order_world > 1) CR_TRY(cr_raster_publish_touched_tiles(st, tg, r->tile_begin.as<uint32_t>()));
     if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[3], st)); CR_CUDA_TRY(cudaEventRecord(r->ev[4], st)); }
-    CR_TRY(cr_raster_tiles(st, sc, tg, r->records.as<PrimRecord>(), r->tile_begin.as<uint32_t>(), sorted_cand, counters));
+    // tile-ordered primitive stream (set up per (tile, primitive) pair), then the tile kernel that bulk-loads it
+    CR_TRY(r->tile_prims.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * cr_tile_prim_bytes()));
+    CR_TRY(cr_raster_tile_prims(st, sc, tg, r->records.as<PrimRecord>(), sorted_tile, sorted_cand, pair_cap, r->tile_prims.p, counters));
+    CR_TRY(cr_raster_tiles(st, sc, tg, r->tile_prims.p, r->tile_begin.as<uint32_t>(), counters));
     if (r->timing) { CR_CUDA_TRY(cudaEventRecord(r->ev[5], st)); r->ev_valid[1] = r->ev_valid[2] = true; }
     CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_PASS], counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
     CR_CUDA_TRY(cudaEventRecord(r->ev_pass, st));
@@ -1421,13 +1463,22 @@ int cr_renderer_enable_timing(cr_renderer* r, uint32_t enabled) {
     r->ev_valid[0] = r->ev_valid[1] = r->ev_valid[2] = false;
     return CR_OK;
 }
+// The counters of the most recent pass that has been SETTLED (cr_pass_submit settles the pass before the one it submits), without
+// waiting for anything: with frame pipelining the host reads the result of frame N while frame N + 1 is running.
+int cr_renderer_get_settled_pass_stats(cr_renderer* r, cr_stats* out) {
+    if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    CR_TRY(take_deferred(r));
+    r->stats.kernel_launches = g_cr_kernel_launches;
+    *out = r->stats;
+    return CR_OK;
+}
 int cr_renderer_get_stats(cr_renderer* r, cr_stats* out) {
     if (!r || !out) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
     CR_GUARD(r);
     CR_TRY(settle(r));
     CR_TRY(take_deferred(r));
     CR_CUDA_TRY(cudaStreamSynchronize(r->stream));
-    if (r->pipelined) CR_CUDA_TRY(cudaStreamSynchronize(r->tess));
+    if (r->pipelined) for (cudaStream_t q : {r->copy, r->tess, r->hull}) CR_CUDA_TRY(cudaStreamSynchronize(q));
     if (r->stats_batch) {   // hull vertices of the last from_paths: its counts arrive with the batch's mirrors
         cr_shape_batch* b = r->stats_batch;
         CR_TRY(ensure_mirrors(b));

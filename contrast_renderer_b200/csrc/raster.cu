@@ -31,7 +31,7 @@
 
 namespace {
 
-#define RCHUNK 128            // primitives staged in shared memory at a time
+#define RCHUNK 64             // primitives of a tile in shared memory at a time (two buffers: the next chunk streams in while this one is rasterised)
 #ifndef K3_MIN_BLOCKS
 #define K3_MIN_BLOCKS 6   // resident K3 CTAs per SM asked of the compiler (40 registers per thread): 6 measured best of 4..8 on configs 3, 4 and 5
 #endif
@@ -59,6 +59,8 @@ enum Pipe : uint32_t {
 #define META_VALID 64u
 #define META_E32 4096u    // (tile-local) the edge functions fit 32-bit integers everywhere in the tile
 #define META_FULL 2048u   // (tile-local) every pixel centre of the tile is inside the primitive
+#define META_RUN_START 8192u   // (tile-local) this primitive does not commute with its predecessor in the tile: it opens a run
+#define META_BIAS_SHIFT 16     // (tile-local) bit 16 + e: edge e is neither a top nor a left edge (bias -1)
 
 __device__ __forceinline__ const float* vertex_ptr(const DeviceBatch& b, uint32_t cat, uint32_t v) {
     switch (cat) {
@@ -489,18 +491,21 @@ __global__ void touched_ready_kernel(RasterTarget tg) {
 }
 
 // ------------------------------------------------------------------------------------------- K3: tile raster
-struct TilePrim {
+struct TilePrim {          // 128 bytes: one primitive set up for one tile (a record of the tile-ordered stream K3 bulk-loads)
     long long e0[3];        // edge functions, top-left bias folded in, at the centre of the tile's pixel (0, 0)
     int A[3], B[3];         // per-pixel steps: +256 A per row, -256 B per column
-    int bias[3];
     float invw[3];
-    float attr[3][4];
-    uint32_t flat_u;
-    float flat_f;
-    uint32_t meta;          // PrimRecord::meta; META_VALID cleared if nothing of it can land in this tile
+    uint32_t meta;          // PrimRecord::meta + the tile-local flags; META_VALID cleared if nothing of it can land in this tile
+    float attr[3][4];       // attr[0][1] doubles as the flat float of stroke vertices, attr[0][3] holds their flat u32 (bits)
     uint32_t bbox;          // x0 | y0 << 8 | x1 << 16 | y1 << 24 in tile pixels
-    uint32_t ref, instance, batch, layers, cmd;
+    uint32_t ref_batch;     // stencil reference (8 bits) | batch << 8
+    uint32_t instance, layers;
 };
+static_assert(sizeof(TilePrim) == 128, "TilePrim streams are moved with 16-byte bulk copies");
+__device__ __forceinline__ int prim_bias(uint32_t meta, int e) { return -(int)((meta >> (META_BIAS_SHIFT + e)) & 1u); }   // top-left bias of edge e: 0 or -1
+__device__ __forceinline__ uint32_t prim_ref(const TilePrim& ps) { return ps.ref_batch & 255u; }
+__device__ __forceinline__ uint32_t prim_batch(const TilePrim& ps) { return ps.ref_batch >> 8; }
+__device__ __forceinline__ uint32_t prim_flat_u(const TilePrim& ps) { return __float_as_uint(ps.attr[0][3]); }
 
 __device__ __forceinline__ bool cap_test(float tx, float ty, uint32_t cap_type) {   // src/shaders.wgsl:165-189
     switch (cap_type & 15u) {
@@ -539,7 +544,8 @@ __device__ bool stroke_dashed(const Descriptor& d, float tx, float ty) {   // sr
 // the sample_mask predicate. E[] are the biased edge values at the sample.
 template <typename EdgeT>   // long long, or int for primitives whose edge values fit 32 bits over the whole tile (META_E32)
 __device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TilePrim& ps, uint32_t pipe, const EdgeT* E) {
-    const float e0 = (float)(E[1] - ps.bias[1]) * ps.invw[0], e1 = (float)(E[2] - ps.bias[2]) * ps.invw[1], e2 = (float)(E[0] - ps.bias[0]) * ps.invw[2];
+    const uint32_t meta = ps.meta;
+    const float e0 = (float)(E[1] - prim_bias(meta, 1)) * ps.invw[0], e1 = (float)(E[2] - prim_bias(meta, 2)) * ps.invw[1], e2 = (float)(E[0] - prim_bias(meta, 0)) * ps.invw[2];
     const float den = (e0 + e1) + e2;
     float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     const int needed = (pipe == P_FILL_IQ || pipe == P_STROKE_LINE) ? 2 : (pipe == P_FILL_RC ? 4 : 3);   // attributes the predicate reads
@@ -552,17 +558,19 @@ __device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TileP
         case P_FILL_RQ: return a[0] * a[0] - a[1] * a[2] <= 0.0f;
         case P_FILL_RC: return a[0] * a[0] * a[0] - a[1] * a[2] * a[3] <= 0.0f;
         case P_STROKE_LINE: {   // src/shaders.wgsl:268-285
-            const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[ps.batch].stroke)[ps.flat_u & 65535u];
+            const uint32_t flat_u = prim_flat_u(ps);
+            const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[prim_batch(ps)].stroke)[flat_u & 65535u];
             if ((d.count_dashed_join & 4u) != 0u) return stroke_dashed(d, a[0], a[1]);
-            if ((ps.flat_u & 65536u) != 0u) return cap_test(a[0], a[1] - ps.flat_f, d.caps >> 4u);
+            if ((flat_u & 65536u) != 0u) return cap_test(a[0], a[1] - ps.attr[0][1], d.caps >> 4u);
             if (a[1] < 0.0f) return cap_test(a[0], -a[1], d.caps);
             return true;
         }
         default: {              // P_STROKE_JOINT, src/shaders.wgsl:287-300
-            const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[ps.batch].stroke)[ps.flat_u & 65535u];
+            const uint32_t flat_u = prim_flat_u(ps);
+            const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[prim_batch(ps)].stroke)[flat_u & 65535u];
             const float radius = cr::sqrt_f(a[0] * a[0] + a[1] * a[1]);
             const uint32_t kind = d.count_dashed_join & 3u;
-            bool keep = kind == 1u ? (ps.flat_u & 65536u) != 0u : (kind == 2u ? radius <= 0.5f : true);
+            bool keep = kind == 1u ? (flat_u & 65536u) != 0u : (kind == 2u ? radius <= 0.5f : true);
             if (keep && (d.count_dashed_join & 4u) != 0u) keep = stroke_dashed(d, radius, a[2] + cr::atan2_f(a[1], a[0]) / 6.28318548202514648438f);
             return keep;
         }
@@ -641,28 +649,44 @@ __device__ __forceinline__ unsigned long long cover_row_mask(const TilePrim& ps,
     return mask;
 }
 
-// Stage one primitive of this tile into shared memory (one thread per primitive). The edge functions are evaluated at the
-// centre of the tile's pixel (0, 0) for 1x and at its top-left corner for 4x (sample offsets are added per sample).
-template <int S, bool DEPTH>
-__device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, const PrimRecord& rec, int tile_px, int tile_py, TilePrim& ps) {
-    ps.meta = 0;
-    if (!(rec.meta & META_VALID)) return;
-    const uint32_t pipe = rec.meta & 15u, cat = (rec.meta >> 8) & 7u;
-    const Edges t = make_edges(rec.X, rec.Y);
-    const int PX = tile_px * 256 + (S == 1 ? 128 : 0), PY = tile_py * 256 + (S == 1 ? 128 : 0);
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {
-        ps.A[e] = t.A[e]; ps.B[e] = t.B[e]; ps.bias[e] = t.bias[e];
-        ps.e0[e] = (long long)t.A[e] * (PY - rec.Y[e]) - (long long)t.B[e] * (PX - rec.X[e]) + t.bias[e];
-    }
-    // pixel bounding box clipped to this tile and to the target
+// Pixel bounding box of a primitive clipped to the tile at (tile_px, tile_py) and to the target; false if it is empty.
+template <int S>
+__device__ __forceinline__ bool tile_bbox(const RasterTarget& tg, const PrimRecord& rec, int tile_px, int tile_py, uint32_t& bbox) {
     const int minX = min(rec.X[0], min(rec.X[1], rec.X[2])), maxX = max(rec.X[0], max(rec.X[1], rec.X[2]));
     const int minY = min(rec.Y[0], min(rec.Y[1], rec.Y[2])), maxY = max(rec.Y[0], max(rec.Y[1], rec.Y[2]));
     const int slo = S == 1 ? 128 : 32, shi = S == 1 ? 128 : 224;   // sample offsets inside a pixel span [slo, shi]
     const int x0 = max(0, ((minX - shi + 255) >> 8) - tile_px), x1 = min(min(CR_TILE - 1, (int)tg.width - 1 - tile_px), ((maxX - slo) >> 8) - tile_px);
     const int y0 = max(0, ((minY - shi + 255) >> 8) - tile_py), y1 = min(min(CR_TILE - 1, (int)tg.height - 1 - tile_py), ((maxY - slo) >> 8) - tile_py);
-    if (x0 > x1 || y0 > y1) return;
-    ps.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+    bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+    return x0 <= x1 && y0 <= y1;
+}
+
+// Set one primitive up for one tile (one thread per (tile, primitive) pair). The edge functions are evaluated at the
+// centre of the tile's pixel (0, 0) for 1x and at its top-left corner for 4x (sample offsets are added per sample).
+template <int S, bool DEPTH>
+__device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, const PrimRecord& rec, int tile_px, int tile_py, TilePrim& ps) {
+    ps.meta = 0;
+    ps.bbox = 0; ps.ref_batch = 0; ps.instance = 0; ps.layers = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        ps.e0[i] = 0; ps.A[i] = 0; ps.B[i] = 0; ps.invw[i] = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ps.attr[i][a] = 0.0f;
+    }
+    if (!(rec.meta & META_VALID)) return;
+    uint32_t bbox;
+    if (!tile_bbox<S>(tg, rec, tile_px, tile_py, bbox)) return;
+    const uint32_t pipe = rec.meta & 15u, cat = (rec.meta >> 8) & 7u;
+    const Edges t = make_edges(rec.X, rec.Y);
+    const int PX = tile_px * 256 + (S == 1 ? 128 : 0), PY = tile_py * 256 + (S == 1 ? 128 : 0);
+    uint32_t bias_bits = 0;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        ps.A[e] = t.A[e]; ps.B[e] = t.B[e];
+        if (t.bias[e]) bias_bits |= 1u << (META_BIAS_SHIFT + e);
+        ps.e0[e] = (long long)t.A[e] * (PY - rec.Y[e]) - (long long)t.B[e] * (PX - rec.X[e]) + t.bias[e];
+    }
+    ps.bbox = bbox;
     bool full = true;   // minimum of every edge function over all sample positions of the tile is still inside
     const int far = (CR_TILE - 1) * 256 + (S == 1 ? 0 : 224), near = S == 1 ? 0 : 32;   // sample offsets from the evaluation origin
 #pragma unroll
@@ -670,13 +694,9 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
         const long long emin = ps.e0[e] + (long long)t.A[e] * (t.A[e] < 0 ? far : near) - (long long)t.B[e] * (t.B[e] > 0 ? far : near);
         if (emin < 0) full = false;
     }
-    ps.ref = rec.ref;
+    ps.ref_batch = (rec.ref & 255u) | (rec.batch << 8);
     ps.instance = rec.instance;
-    ps.batch = rec.batch;
     ps.layers = rec.layers;
-    ps.cmd = rec.cmd;
-    ps.flat_u = 0;
-    ps.flat_f = 0.0f;
     if (pipe <= P_FILL_RC && pipe != P_FILL_SOLID) {   // pipelines with a fragment predicate need the vertex attributes
         const DeviceBatch& b = sc.batches[rec.batch];
         const float* m = sc.transforms + 16 * (size_t)rec.instance;
@@ -689,10 +709,9 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
             ps.invw[i] = 1.0f / clip_w(m, p[0], p[1]);
 #pragma unroll
             for (int a = 0; a < 4; ++a) ps.attr[i][a] = a < n_attr ? p[2 + a] : 0.0f;
-            if (i == 0) {   // flat attributes come from the first (provoking) vertex
-                if (cat <= 1) ps.flat_u = __float_as_uint(p[2 + n_attr]);
-                ps.flat_f = n_attr > 1 ? p[3] : 0.0f;
-            }
+            // flat attributes come from the first (provoking) vertex: the flat float of a stroke vertex IS attr[0][1]; its flat
+            // u32 goes into attr[0][3], which no stroke predicate interpolates (2 and 3 attributes)
+            if (i == 0 && cat <= 1) ps.attr[0][3] = p[2 + n_attr];
         }
     }
     if (DEPTH && pipe == P_COLOR) {   // the depth test of the colour cover needs z / w of the three hull vertices (src/shaders.wgsl:72)
@@ -714,21 +733,106 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
         const long long reach = ((long long)abs(t.A[e]) + (long long)abs(t.B[e])) * (15 * 256 + 256) + 2;
         if (ps.e0[e] > 0x7fffffffLL - reach || ps.e0[e] < -0x7fffffffLL + reach) fits = false;
     }
-    ps.meta = rec.meta | (full ? META_FULL : 0u) | (fits ? META_E32 : 0u);
+    ps.meta = rec.meta | (full ? META_FULL : 0u) | (fits ? META_E32 : 0u) | bias_bits;
 }
 
 // Run kinds: primitives of one run commute (see the file header).
 __device__ __forceinline__ uint32_t run_kind(uint32_t pipe) { return pipe <= P_STROKE_JOINT ? 0u : (pipe <= P_FILL_RC ? 1u : 2u); }
 
+// ---- tile-ordered primitive streams
+// After the sort the (tile, candidate) pairs of a tile are contiguous and in draw order. One thread per PAIR does the whole
+// tile-local set-up of its primitive (edge functions at the tile origin, clipped bounding box, attribute fetch, the "covers the
+// whole tile" and "fits 32 bits" flags, and whether it opens a run) and writes the 128-byte TilePrim at the pair's position: the
+// tile kernel then reads each tile's primitives as ONE contiguous stream with bulk asynchronous copies (cp.async.bulk, the TMA
+// engine) into shared memory, double buffered, instead of gathering records and staging them itself.
+template <int S, bool DEPTH>
+__global__ void __launch_bounds__(256) tile_prims_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records, const uint32_t* __restrict__ pair_tile,
+                                                         const uint32_t* __restrict__ pair_cand, uint32_t pair_capacity, TilePrim* __restrict__ out,
+                                                         const PassCounters* __restrict__ counters) {
+    __shared__ uint4 sh_out[8][32 * 8];
+    if (counters->flags != 0u) return;   // a capacity did not suffice: the pairs are not there
+    const uint32_t n = min(counters->n_pairs_live, pair_capacity);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((i & ~31u) >= n) return;   // whole warps leave together (shuffles below)
+    const bool live = i < n;
+    TilePrim ps;
+    ps.meta = 0;
+    uint32_t tile = 0xFFFFFFFFu, ref = 0, cmd = 0;
+    if (live) {
+        tile = pair_tile[i];
+        const PrimRecord rec = load_record<true>(records + pair_cand[i]);
+        stage_primitive<S, DEPTH>(sc, tg, rec, (int)(tile % tg.tiles_x) * CR_TILE, (int)(tile / tg.tiles_x) * CR_TILE, ps);
+        ref = rec.ref; cmd = rec.cmd;
+    }
+    // does this primitive open a run? It needs its predecessor in the tile: the neighbouring lane's, or (lane 0) looked up here
+    uint32_t p_meta = __shfl_up_sync(0xffffffffu, ps.meta, 1), p_ref = __shfl_up_sync(0xffffffffu, ref, 1);
+    uint32_t p_cmd = __shfl_up_sync(0xffffffffu, cmd, 1), p_inst = __shfl_up_sync(0xffffffffu, ps.instance, 1), p_tile = __shfl_up_sync(0xffffffffu, tile, 1);
+    if (lane == 0) {
+        p_tile = 0xFFFFFFFEu;
+        if (live && i > 0 && pair_tile[i - 1] == tile) {
+            const PrimRecord prec = load_record<true>(records + pair_cand[i - 1]);
+            uint32_t bbox;
+            const bool valid = (prec.meta & META_VALID) != 0 && tile_bbox<S>(tg, prec, (int)(tile % tg.tiles_x) * CR_TILE, (int)(tile / tg.tiles_x) * CR_TILE, bbox);
+            p_tile = tile; p_meta = valid ? prec.meta : 0u; p_ref = prec.ref; p_cmd = prec.cmd; p_inst = prec.instance;
+        }
+    }
+    bool boundary = true;   // the first primitive of a tile
+    if (p_tile == tile) {
+        // staged-out primitives (meta == 0) join whatever run precedes them: they do nothing
+        const uint32_t kp = run_kind(p_meta & 15u), kq = run_kind(ps.meta & 15u);
+        const bool pv = (p_meta & META_VALID) != 0, qv = (ps.meta & META_VALID) != 0;
+        if (pv && qv) boundary = kp != kq || (kq < 2u ? p_ref != ref : (p_cmd != cmd || p_inst != ps.instance));
+        else boundary = qv;   // a valid primitive after a staged-out one conservatively opens a run
+    }
+    if (boundary) ps.meta |= META_RUN_START;
+    // The warp's 32 records leave through shared memory so that every store instruction writes 512 contiguous bytes (a record
+    // per thread would be 16 bytes every 128). Chunk k of lane l sits at slot 8 l + (k ^ (l & 7)): conflict free both ways.
+    uint4 q[8];
+    q[0] = make_uint4((uint32_t)ps.e0[0], (uint32_t)((unsigned long long)ps.e0[0] >> 32), (uint32_t)ps.e0[1], (uint32_t)((unsigned long long)ps.e0[1] >> 32));
+    q[1] = make_uint4((uint32_t)ps.e0[2], (uint32_t)((unsigned long long)ps.e0[2] >> 32), (uint32_t)ps.A[0], (uint32_t)ps.A[1]);
+    q[2] = make_uint4((uint32_t)ps.A[2], (uint32_t)ps.B[0], (uint32_t)ps.B[1], (uint32_t)ps.B[2]);
+    q[3] = make_uint4(__float_as_uint(ps.invw[0]), __float_as_uint(ps.invw[1]), __float_as_uint(ps.invw[2]), ps.meta);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) q[4 + k] = make_uint4(__float_as_uint(ps.attr[k][0]), __float_as_uint(ps.attr[k][1]), __float_as_uint(ps.attr[k][2]), __float_as_uint(ps.attr[k][3]));
+    q[7] = make_uint4(ps.bbox, ps.ref_batch, ps.instance, ps.layers);
+    uint4* const mine = sh_out[threadIdx.x >> 5];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mine[8u * lane + ((uint32_t)k ^ (lane & 7u))] = q[k];
+    __syncwarp();
+    const uint32_t warp_first = i - lane, n_out = min(32u, n - warp_first) * 8u;   // 16-byte pieces this warp owns
+    uint4* const dst = reinterpret_cast<uint4*>(out + warp_first);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t piece = (uint32_t)j * 32u + lane, rec = piece >> 3, chunk = piece & 7u;
+        if (piece < n_out) dst[piece] = mine[8u * rec + (chunk ^ (rec & 7u))];
+    }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// global -> shared bulk asynchronous copy (TMA engine, UBLKCP in SASS); completion is counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <int S, bool DEPTH, bool U8>   // samples per pixel; depth test / write on the colour cover; 8-bit unorm colour + R8 alpha layers
-__global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ? K3_MIN_BLOCKS : K3_MIN_BLOCKS_MSAA) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const PrimRecord* __restrict__ records,
+__global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ? K3_MIN_BLOCKS : K3_MIN_BLOCKS_MSAA) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const TilePrim* __restrict__ prims,
                                                                                          const uint32_t* __restrict__ tile_begin,
-                                                                                         const uint32_t* __restrict__ pair_cand,
                                                                                          PassCounters* __restrict__ counters) {
-    __shared__ TilePrim sh[RCHUNK];
+    __shared__ __align__(128) TilePrim sh_buf[2][RCHUNK];   // the tile's primitive stream, RCHUNK at a time: chunk c + 1 streams in (bulk copy) while chunk c is rasterised
+    __shared__ __align__(8) unsigned long long sh_bar[2];   // one mbarrier per buffer: completes when the chunk's bytes have landed
     __shared__ int acc[2][CR_TILE * CR_TILE * S];   // per-sample result of a stencil run; double buffered so that one barrier per run suffices
-    __shared__ uint32_t run_mask[RCHUNK / 32];
-    __shared__ uint8_t run_start[RCHUNK + 1];
     __shared__ unsigned long long cov[2][CR_TILE][CR_TILE];   // row coverage masks (bit x * S + k) of the cover primitives of one sweep; double buffered: one barrier per sweep
     if (counters != nullptr && counters->flags != 0u) return;   // a capacity did not suffice: leave the attachments untouched, the host re-submits
     const uint32_t tile = blockIdx.x;
@@ -764,6 +868,20 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
             successor = sh_chain[1];
         }
     } else if (begin == end && (!clears || !cr_tile_owned(tg, (int)(tile % tg.tiles_x), (int)(tile / tg.tiles_x)))) return;   // nothing drawn here and nothing to clear (or not ours to clear)
+    // ---- the primitive stream of this tile: prims[begin, end), RCHUNK per bulk copy; issue the first chunk now, it lands while the tile is loaded
+    const uint32_t n_chunks = (end - begin + RCHUNK - 1) / RCHUNK;
+    auto issue_chunk = [&](uint32_t c) {   // one thread
+        const uint32_t first = begin + c * RCHUNK, bytes = min((uint32_t)RCHUNK, end - first) * (uint32_t)sizeof(TilePrim);
+        mbar_expect_tx(&sh_bar[c & 1u], bytes);
+        bulk_copy_g2s(&sh_buf[c & 1u][0], prims + first, bytes, &sh_bar[c & 1u]);
+    };
+    if (threadIdx.x == 0 && n_chunks != 0u) {
+        mbar_init(&sh_bar[0], 1u);
+        mbar_init(&sh_bar[1], 1u);
+        fence_mbar_init();
+        issue_chunk(0u);
+        if (n_chunks > 1u) issue_chunk(1u);
+    }
     const int tile_px = (int)(tile % tg.tiles_x) * CR_TILE, tile_py = (int)(tile / tg.tiles_x) * CR_TILE;
     const int lx = threadIdx.x & (CR_TILE - 1), ly = threadIdx.x / CR_TILE;
     const int px = tile_px + lx, py = tile_py + ly;
@@ -825,7 +943,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
 
     // One cover primitive on the samples `hit` of this thread's pixel: stencil test / op and blend of its pipeline.
     auto cover_apply = [&](const TilePrim& ps, uint32_t hit) {
-        const uint32_t pipe = ps.meta & 15u, ref = ps.ref;
+        const uint32_t pipe = ps.meta & 15u, ref = prim_ref(ps);
 #pragma unroll
         for (int q = 0; q < S; ++q) {
             if (!((hit >> q) & 1u)) continue;
@@ -838,7 +956,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
                         long long E[3];
 #pragma unroll
                         for (int e = 0; e < 3; ++e)
-                            E[e] = ps.e0[e] - ps.bias[e] + (long long)ps.A[e] * (ly * 256 + (S == 1 ? 0 : sample_y<S>(q))) - (long long)ps.B[e] * (lx * 256 + (S == 1 ? 0 : sample_x<S>(q)));
+                            E[e] = ps.e0[e] - prim_bias(ps.meta, e) + (long long)ps.A[e] * (ly * 256 + (S == 1 ? 0 : sample_y<S>(q))) - (long long)ps.B[e] * (lx * 256 + (S == 1 ? 0 : sample_x<S>(q)));
                         const float b0 = (float)E[1], b1 = (float)E[2], b2 = (float)E[0];
                         const float z = ((b0 * ps.attr[0][0] + b1 * ps.attr[1][0]) + b2 * ps.attr[2][0]) / ((b0 + b1) + b2);
                         if (!depth_passes(tg.depth_compare, z, dep[q])) continue;
@@ -885,46 +1003,29 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
         return lx >= (int)(bbox & 255u) && lx <= (int)((bbox >> 16) & 255u) && ly >= (int)((bbox >> 8) & 255u) && ly <= (int)(bbox >> 24);
     };
 
-    for (uint32_t chunk = begin; chunk < end; chunk += RCHUNK) {
-        const uint32_t n = min((uint32_t)RCHUNK, end - chunk);
-        __syncthreads();   // everybody is done with the previous chunk's shared records
-        // ---- stage the chunk (one thread per primitive) and find the run boundaries
-        bool boundary = false;
-        if (threadIdx.x < n) {
-            const PrimRecord rec = load_record<true>(records + pair_cand[chunk + threadIdx.x]);
-            stage_primitive<S, DEPTH>(sc, tg, rec, tile_px, tile_py, sh[threadIdx.x]);
+    if (n_chunks != 0u) __syncthreads();   // the mbarriers are initialised before anybody waits on them
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint32_t n = min((uint32_t)RCHUNK, end - (begin + c * RCHUNK));
+        const TilePrim* const sh = sh_buf[c & 1u];
+        if (c >= 1u && c + 1u < n_chunks) {   // chunk c + 1 goes where chunk c - 1 was: everybody must be done with that one
+            __syncthreads();
+            if (threadIdx.x == 0) issue_chunk(c + 1u);
         }
-        __syncthreads();
-        if (threadIdx.x < RCHUNK) {
-            if (threadIdx.x < n) {
-                if (threadIdx.x == 0) boundary = true;
-                else {
-                    const TilePrim &p = sh[threadIdx.x - 1], &q = sh[threadIdx.x];
-                    // staged-out primitives (meta == 0) join whatever run precedes them: they do nothing
-                    const uint32_t kp = run_kind(p.meta & 15u), kq = run_kind(q.meta & 15u);
-                    const bool pv = (p.meta & META_VALID) != 0, qv = (q.meta & META_VALID) != 0;
-                    if (pv && qv) boundary = kp != kq || (kq < 2u ? p.ref != q.ref : (p.cmd != q.cmd || p.instance != q.instance));
-                    else boundary = qv;   // a valid primitive after a staged-out one conservatively opens a run
-                }
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, boundary);
-            if (lane == 0) run_mask[warp] = m;
-        }
-        __syncthreads();
-        uint32_t n_runs = 0;
-        {
-            uint32_t before = 0;
+        while (!mbar_try_wait(&sh_bar[c & 1u], (c >> 1) & 1u)) { }
+        // ---- run boundaries (found by tile_prims_kernel): every warp builds the chunk's bit mask of run starts for itself
+        unsigned long long starts = 1ull;   // the chunk's first primitive opens a run in any case
 #pragma unroll
-            for (int w = 0; w < RCHUNK / 32; ++w) { const uint32_t m = run_mask[w]; if ((uint32_t)w < warp) before += __popc(m); n_runs += __popc(m); }
-            if (boundary) run_start[before + __popc(run_mask[warp] & ((1u << lane) - 1u))] = (uint8_t)threadIdx.x;
-            if (threadIdx.x == 0) run_start[n_runs] = (uint8_t)n;   // n <= 128 fits
+        for (int w = 0; w < RCHUNK / 32; ++w) {
+            const uint32_t k = (uint32_t)w * 32u + lane;
+            starts |= (unsigned long long)__ballot_sync(0xffffffffu, k < n && (sh[k].meta & META_RUN_START) != 0u) << (32 * w);
         }
-        __syncthreads();
         // ---- execute the runs in draw order
-        for (uint32_t r = 0; r < n_runs; ++r) {
-            const uint32_t a = run_start[r], b = run_start[r + 1];
-            uint32_t first = a;   // only the chunk's first run can start with staged-out primitives (see `boundary`)
-            if (r == 0) { while (first < b && !(sh[first].meta & META_VALID)) ++first; }
+        while (starts != 0ull) {
+            const uint32_t a = (uint32_t)__ffsll((long long)starts) - 1u;
+            starts &= starts - 1ull;
+            const uint32_t b = starts != 0ull ? (uint32_t)__ffsll((long long)starts) - 1u : n;
+            uint32_t first = a;   // a run that starts with staged-out primitives (first of the tile / of the chunk) has nothing else
+            while (first < b && !(sh[first].meta & META_VALID)) ++first;
             if (first == b) continue;
             const uint32_t kind = run_kind(sh[first].meta & 15u);
             apply_pending();
@@ -946,7 +1047,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
                     for (int q = 0; q < S; ++q)
                         if ((hit >> q) & 1u) net[q] = kind == 0u ? 1 : net[q] + delta;
                 }
-                const uint32_t ref = sh[first].ref;
+                const uint32_t ref = prim_ref(sh[first]);
 #pragma unroll
                 for (int q = 0; q < S; ++q) {
                     if (net[q] != 0) {
@@ -975,7 +1076,7 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
                 __syncthreads();
                 pending = cur;
                 pending_kind = kind;
-                pending_ref = sh[first].ref;
+                pending_ref = prim_ref(sh[first]);
                 cur ^= 1;
             } else if (b - a <= tg.pixel_run_max) {
                 // short cover run (the usual hull of a few triangles), pixel mode: in draw order, this thread's pixel only
@@ -1126,12 +1227,30 @@ int cr_raster_publish_touched_tiles(cudaStream_t stream, const RasterTarget& tar
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }
-int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* tile_begin,
-                    const uint32_t* pair_cand, PassCounters* counters) {
+size_t cr_tile_prim_bytes() { return sizeof(TilePrim); }
+int cr_raster_tile_prims(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* pair_tile, const uint32_t* pair_cand,
+                         uint32_t pair_capacity, void* tile_prims, const PassCounters* counters) {
+    if (pair_capacity == 0) return CR_OK;
+    const uint32_t grid = (pair_capacity + 255u) / 256u;
+    TilePrim* out = static_cast<TilePrim*>(tile_prims);
+    const bool depth = target.depth != nullptr;
+    if (target.samples == 4) {
+        if (depth) tile_prims_kernel<4, true><<<grid, 256, 0, stream>>>(scene, target, records, pair_tile, pair_cand, pair_capacity, out, counters);
+        else tile_prims_kernel<4, false><<<grid, 256, 0, stream>>>(scene, target, records, pair_tile, pair_cand, pair_capacity, out, counters);
+    } else {
+        if (depth) tile_prims_kernel<1, true><<<grid, 256, 0, stream>>>(scene, target, records, pair_tile, pair_cand, pair_capacity, out, counters);
+        else tile_prims_kernel<1, false><<<grid, 256, 0, stream>>>(scene, target, records, pair_tile, pair_cand, pair_capacity, out, counters);
+    }
+    g_cr_kernel_launches += 1;
+    CR_CUDA_TRY(cudaGetLastError());
+    return CR_OK;
+}
+int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const void* tile_prims, const uint32_t* tile_begin, PassCounters* counters) {
     const uint32_t n_tiles = target.tiles_x * target.tiles_y;
     if (n_tiles == 0) return CR_OK;
+    const TilePrim* prims = static_cast<const TilePrim*>(tile_prims);
     const bool depth = target.depth != nullptr, u8 = target.color_format != CR_FORMAT_RGBA32F;
-#define K3_LAUNCH(S, D, U) raster_tiles_kernel<S, D, U><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, records, tile_begin, pair_cand, counters)
+#define K3_LAUNCH(S, D, U) raster_tiles_kernel<S, D, U><<<n_tiles, CR_TILE * CR_TILE, 0, stream>>>(scene, target, prims, tile_begin, counters)
     if (target.samples == 4) {
         if (depth) { if (u8) K3_LAUNCH(4, true, true); else K3_LAUNCH(4, true, false); }
         else { if (u8) K3_LAUNCH(4, false, true); else K3_LAUNCH(4, false, false); }

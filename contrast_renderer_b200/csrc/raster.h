@@ -144,5 +144,8 @@ int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t
 // Draw-order sharding: publishes which tiles this rank's slice touches (bitmap from tile_begin) to every rank, then the ready flag.
 int cr_raster_publish_touched_tiles(cudaStream_t stream, const RasterTarget& target, const uint32_t* tile_begin);
 // counters may be null (clear-only launch on an empty tile table).
-int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* tile_begin,
-                    const uint32_t* pair_cand, PassCounters* counters);
+// Tile-ordered primitive stream: one cr_tile_prim_bytes()-byte record per sorted (tile, candidate) pair, set up for its tile.
+size_t cr_tile_prim_bytes();
+int cr_raster_tile_prims(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const PrimRecord* records, const uint32_t* pair_tile, const uint32_t* pair_cand,
+                         uint32_t pair_capacity, void* tile_prims, const PassCounters* counters);
+int cr_raster_tiles(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, const void* tile_prims, const uint32_t* tile_begin, PassCounters* counters);

@@ -73,6 +73,7 @@ def lib():
             "cr_renderer_read_alpha_layer": [vp, u32, vp, sz],
             "cr_renderer_get_attachments": [vp, C.POINTER(vp), C.POINTER(vp)],
             "cr_renderer_get_stats": [vp, C.POINTER(_abi.StatsC)],
+            "cr_renderer_get_settled_pass_stats": [vp, C.POINTER(_abi.StatsC)],
             "cr_renderer_enable_timing": [vp, u32],
             "cr_renderer_set_tile_sharding": [vp, u32, u32],
             "cr_renderer_set_order_sharding": [vp, u32, u32],
@@ -253,6 +254,12 @@ class Renderer:
     def stats(self) -> _abi.StatsC:
         s = _abi.StatsC()
         _check(lib().cr_renderer_get_stats(self._h, C.byref(s)))
+        return s
+
+    def settled_pass_stats(self) -> _abi.StatsC:
+        """Counters of the last pass the renderer has settled (submit settles the pass before the one it submits); never waits."""
+        s = _abi.StatsC()
+        _check(lib().cr_renderer_get_settled_pass_stats(self._h, C.byref(s)))
         return s
 
     def attachments(self):

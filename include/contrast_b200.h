@@ -353,6 +353,9 @@ typedef struct cr_stats {
     uint64_t hull_vertices;                /* hull vertices it produced */
 } cr_stats;
 int cr_renderer_get_stats(cr_renderer* renderer, cr_stats* out);
+/* The same record as of the last pass the renderer has settled (cr_pass_submit settles the pass submitted before), without waiting:
+ * with frame pipelining the result of frame N is read while frame N + 1 runs (wgpu: mapping a buffer of an earlier submission). */
+int cr_renderer_get_settled_pass_stats(cr_renderer* renderer, cr_stats* out);
 int cr_renderer_enable_timing(cr_renderer* renderer, uint32_t enabled);
 
 const char* cr_status_string(int status);
