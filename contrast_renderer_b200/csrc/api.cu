@@ -409,14 +409,13 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
         for (int k = 0; k < 3; ++k) CR_TRY(B.idx[k].reserve(st, totals[CNT_LINE_IDX + k] * 4));
         return CR_OK;
     };
+    bool emit_has_cubics = true;   // false: the batch is known to hold no cubic segment (every filled path goes through the per-segment kernel)
     auto run_emit = [&](uint32_t max_proto) -> int {
         TessOutput out{};
         for (int c = 0; c < 7; ++c) out.vtx[c] = B.vtx[c].p;
         out.proto = B.proto.as<float2>();
         for (int k = 0; k < 3; ++k) out.idx[k] = B.idx[k].as<uint32_t>();
-        // the emit pass is bound by its scattered stores: the lean kernel (3x the occupancy) measured 17 % SLOWER on the text scene, so
-        // only the count pass uses it (33 -> 7 us)
-        CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, err, true));
+        CR_TRY(cr_tess_emit(st, P, counts, r->shape_begin_dev.as<uint32_t>(), n_shapes, out, err, emit_has_cubics));
         if (r->pipelined) {   // the input (staging) arrays are free again; the hulls continue on their own stream
             if (host_inputs) CR_CUDA_TRY(cudaEventRecord(r->staging_free[r->staging_cur], st));
             CR_CUDA_TRY(cudaEventRecord(r->ev_emitted, st));
@@ -438,7 +437,8 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
         for (int c = 0; c < 7; ++c) caps.v[c] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, B.vtx[c].cap / kCategoryStride[c]);
         caps.v[CNT_PROTO] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, std::min(std::min(B.proto.cap, B.hull.cap), std::min(r->hull_scratch_a.cap, r->hull_scratch_b.cap)) / 8);
         for (int k = 0; k < 3; ++k) caps.v[CNT_LINE_IDX + k] = (uint32_t)std::min<size_t>(0xFFFFFFFFu, B.idx[k].cap / 4);
-        CR_TRY(run_sizes(totals_known ? (type_totals[CR_SEG_INTEGRAL_CUBIC] != 0 || type_totals[CR_SEG_RATIONAL_CUBIC] != 0) : b->has_cubics, caps));
+        emit_has_cubics = totals_known ? (type_totals[CR_SEG_INTEGRAL_CUBIC] != 0 || type_totals[CR_SEG_RATIONAL_CUBIC] != 0) : b->has_cubics;
+        CR_TRY(run_sizes(emit_has_cubics, caps));
         CR_TRY(run_emit(b->max_proto));   // the sort's shared-memory capacity is a launch parameter: larger shapes take its global-memory path
         emitted = true;
     } else {
@@ -475,6 +475,7 @@ int build_batch(cr_renderer* r, const cr_dynamic_stroke_options* groups, size_t 
     b->has_cubics = has_cubics;
     b->max_proto = max_proto;
     if (!emitted) {
+        emit_has_cubics = has_cubics;
         if (r->pipelined) {   // the hull scratch arrays may be re-allocated here (on the tessellation stream): the hulls of the previous build must be done with them
             CR_CUDA_TRY(cudaEventRecord(r->ev_hull_idle, hs));
             CR_CUDA_TRY(cudaStreamWaitEvent(st, r->ev_hull_idle, 0));

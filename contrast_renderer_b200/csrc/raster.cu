@@ -32,6 +32,7 @@
 namespace {
 
 #define RCHUNK 64             // primitives of a tile in shared memory at a time (two buffers: the next chunk streams in while this one is rasterised)
+static_assert(RCHUNK == 64, "K3 scans a run's row counts two primitives per lane and keeps the run starts in one 64-bit mask");
 #ifndef K3_MIN_BLOCKS
 #define K3_MIN_BLOCKS 6   // resident K3 CTAs per SM asked of the compiler (40 registers per thread): 6 measured best of 4..8 on configs 3, 4 and 5
 #endif
@@ -39,6 +40,7 @@ namespace {
 #define K3_MIN_BLOCKS_MSAA 3
 #endif
 #define PIXEL_RUN_MAX 12u     // runs of at most this many primitives execute in pixel mode (see K3)
+#define ROW_SWEEP_MAX 32u     // stencil runs up to this length use the fixed 16 x 16 (primitive, row) grid, longer ones compact their rows (measured: text 8 % slower, dashed strokes 21 % faster with compaction everywhere)
 #define BIG_TILE_BOX 8        // candidates touching more tiles than this are binned by the whole warp
 
 struct Descriptor {   // DynamicStrokeDescriptor, src/renderer.rs:18-27 (48 B)
@@ -833,10 +835,11 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
     __shared__ __align__(128) TilePrim sh_buf[2][RCHUNK];   // the tile's primitive stream, RCHUNK at a time: chunk c + 1 streams in (bulk copy) while chunk c is rasterised
     __shared__ __align__(8) unsigned long long sh_bar[2];   // one mbarrier per buffer: completes when the chunk's bytes have landed
     __shared__ int acc[2][CR_TILE * CR_TILE * S];   // per-sample result of a stencil run; double buffered so that one barrier per run suffices
+    __shared__ uint32_t run_rows[CR_TILE * CR_TILE / 32][RCHUNK];   // per warp: prefix sums of the rows of a stencil run's primitives
     __shared__ unsigned long long cov[2][CR_TILE][CR_TILE];   // row coverage masks (bit x * S + k) of the cover primitives of one sweep; double buffered: one barrier per sweep
-    if (counters != nullptr && counters->flags != 0u) return;   // a capacity did not suffice: leave the attachments untouched, the host re-submits
     const uint32_t tile = blockIdx.x;
-    const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];
+    const uint32_t begin = tile_begin[tile], end = tile_begin[tile + 1];   // (three independent loads: one round trip)
+    if (counters != nullptr && counters->flags != 0u) return;   // a capacity did not suffice: leave the attachments untouched, the host re-submits
     const bool clears = tg.clear_color != 0u || tg.clear_stencil != 0u;
     // ---- draw-order sharding: where is this rank in the tile's chain?
     __shared__ uint32_t sh_chain[3];     // predecessor rank + 1 (0: none), successor rank + 1 (0: none), some rank touches the tile
@@ -1013,13 +1016,13 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
         }
         while (!mbar_try_wait(&sh_bar[c & 1u], (c >> 1) & 1u)) { }
         // ---- run boundaries (found by tile_prims_kernel): every warp builds the chunk's bit mask of run starts for itself
+        // ---- execute the runs in draw order (one 64-bit mask of run starts: two 32-bit halves cost registers this kernel does not have, measured 28 % slower)
         unsigned long long starts = 1ull;   // the chunk's first primitive opens a run in any case
 #pragma unroll
         for (int w = 0; w < RCHUNK / 32; ++w) {
             const uint32_t k = (uint32_t)w * 32u + lane;
             starts |= (unsigned long long)__ballot_sync(0xffffffffu, k < n && (sh[k].meta & META_RUN_START) != 0u) << (32 * w);
         }
-        // ---- execute the runs in draw order
         while (starts != 0ull) {
             const uint32_t a = (uint32_t)__ffsll((long long)starts) - 1u;
             starts &= starts - 1ull;
@@ -1056,16 +1059,55 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ?
                     }
                 }
             } else if (kind < 2u) {
-                // stencil run: (primitive, row) work items, 16 primitives x 16 rows per sweep
+                // stencil run: one work item per (primitive, row). Runs of up to ROW_SWEEP_MAX primitives lay the items out on a fixed
+                // grid, 16 primitives x 16 rows per sweep (no set-up; rows outside a primitive's bounding box idle). Longer runs COMPACT
+                // them: every warp scans the run's row counts for itself (two primitives per lane), item i belongs to the primitive
+                // whose prefix range holds i, so that small primitives keep the threads busy instead of idling through 16-row slots.
                 int* const out = acc[cur];
-                for (uint32_t base = a; base < b; base += CR_TILE) {
-                    const uint32_t k = base + (threadIdx.x >> 4);
-                    if (k >= b) continue;
+                uint32_t* const pre = run_rows[warp];   // inclusive prefix sums of the row counts of primitives a .. a + 63
+                const bool compact = b - a > ROW_SWEEP_MAX;
+                uint32_t total_items = ((b - a + CR_TILE - 1u) / CR_TILE) * (CR_TILE * CR_TILE);
+                if (compact) {
+                    uint32_t h[2];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t k = a + (uint32_t)half * 32u + lane;
+                        h[half] = 0;
+                        if (k < b) {
+                            const uint32_t meta = sh[k].meta, bbox = sh[k].bbox;
+                            if (meta & META_VALID) h[half] = (bbox >> 24) - ((bbox >> 8) & 255u) + 1u;
+                        }
+                    }
+                    uint32_t s0 = h[0], s1 = h[1];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y0 = __shfl_up_sync(0xffffffffu, s0, o), y1 = __shfl_up_sync(0xffffffffu, s1, o);
+                        if (lane >= (uint32_t)o) { s0 += y0; s1 += y1; }
+                    }
+                    s1 += __shfl_sync(0xffffffffu, s0, 31);
+                    total_items = __shfl_sync(0xffffffffu, s1, 31);
+                    pre[lane] = s0;
+                    pre[32u + lane] = s1;
+                    __syncwarp();
+                }
+                for (uint32_t i = threadIdx.x; i < total_items; i += CR_TILE * CR_TILE) {
+                    uint32_t k, row;
+                    if (compact) {
+                        uint32_t lo = 0;   // first slot whose inclusive prefix exceeds i
+#pragma unroll
+                        for (uint32_t step = 32u; step != 0u; step >>= 1)
+                            if (pre[lo + step - 1u] <= i) lo += step;
+                        k = a + lo;
+                        row = i - (lo ? pre[lo - 1u] : 0u);
+                    } else {
+                        k = a + (i >> 8) * CR_TILE + ((i & 255u) >> 4);
+                        row = i & 15u;
+                        if (k >= b) continue;
+                    }
                     const TilePrim& ps = sh[k];
-                    const uint32_t meta = ps.meta;
+                    const uint32_t meta = ps.meta, bbox = ps.bbox;
                     if (!(meta & META_VALID)) continue;
-                    const uint32_t bbox = ps.bbox;
-                    const int y = (int)((bbox >> 8) & 255u) + (int)(threadIdx.x & 15u);
+                    const int y = (int)((bbox >> 8) & 255u) + (int)row;
                     if (y > (int)(bbox >> 24)) continue;
                     const int x0 = (int)(bbox & 255u), x1 = (int)((bbox >> 16) & 255u);
                     const uint32_t pipe = meta & 15u;

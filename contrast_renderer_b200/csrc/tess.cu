@@ -883,13 +883,21 @@ __global__ void __launch_bounds__(128) tess_count_kernel(DevicePaths P, uint32_t
     if (s.err) atomicOr(err, s.err);
 }
 
+// A filled path without cubic segments: tessellated by fill_segments_kernel (one thread per segment, see below).
+__device__ __forceinline__ bool path_is_simple(const DevicePaths& P, uint32_t p) {
+    const size_t stride = (size_t)P.n_paths + 1;
+    if (P.stroke_options && (P.stroke_options[p].flags & CR_STROKE_FLAG_STROKED)) return false;
+    return P.type_begin[2 * stride + p + 1] == P.type_begin[2 * stride + p] && P.type_begin[4 * stride + p + 1] == P.type_begin[4 * stride + p];
+}
+
 // Pass B: write everything. offsets is the exclusive scan of counts ([CNT_COUNT][n_paths + 1], total in the last slot).
 template <int MODE>
 __global__ void __launch_bounds__(128) tess_emit_kernel(DevicePaths P, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ shape_path_begin,
-                                                       uint32_t n_shapes, TessOutput out, uint32_t* __restrict__ err) {
+                                                       uint32_t n_shapes, TessOutput out, uint32_t* __restrict__ err, uint32_t skip_simple) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_paths) return;
     if (*reinterpret_cast<volatile const uint32_t*>(err) & CR_DEVERR_FATAL_MASK) return;   // the count pass rejected the input (uniform): write nothing
+    if (skip_simple && path_is_simple(P, p)) return;                                       // fill_segments_kernel tessellates it
     const PathView pv = load_path(P, p);
     const size_t stride = (size_t)P.n_paths + 1;
     Sink<true> s;
@@ -908,6 +916,193 @@ __global__ void __launch_bounds__(128) tess_emit_kernel(DevicePaths P, const uin
     if (MODE == 0 && (pv.so.flags & CR_STROKE_FLAG_STROKED)) stroke_path<true>(s, pv);
     else fill_path<true, MODE != 2>(s, pv);
     if (s.err) atomicOr(err, s.err);
+}
+
+// ---------------------------------------------------------------------------------- fills, one thread per SEGMENT
+// FillBuilder::add_path (src/fill.rs:263-367) has no state that runs along the path except the solid-fan position and the
+// per-type cursors, and both are COUNTS: segment i of a path writes solid vertex i + 1, its curve triangle at 3 x (number of
+// earlier segments of its type), its proto-hull points behind 1 + lines + 2 x quadratics before it; the point it starts from is
+// the end point of segment i - 1. So filled paths without cubic segments ("simple" paths: the Loop-Blinn builder emits a
+// data-dependent number of vertices) are tessellated with one thread per segment: coalesced reads of the type stream and the
+// per-type segment arrays, ranks by warp ballots (plus one cooperative count for a path that began before the warp), and every
+// thread writes at its final address. The count pass, the scan and the layout are those of the per-path kernels; paths that are
+// stroked or hold cubics stay with tess_emit_kernel (which skips the simple ones when this kernel runs).
+__device__ __forceinline__ uint32_t shape_of_path(const uint32_t* __restrict__ shape_path_begin, uint32_t n_shapes, uint32_t p) {
+    uint32_t lo = 0, hi = n_shapes;   // last s with shape_path_begin[s] <= p
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (shape_path_begin[mid] <= p) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ void store_proto(float2* __restrict__ proto, uint32_t at, float2 p, uint32_t& err) {
+    if (!cr::is_finite(p.x) || !cr::is_finite(p.y)) err |= CR_DEVERR_NON_FINITE;
+    proto[at] = make_float2(cr::canon_zero(p.x), cr::canon_zero(p.y));
+}
+__device__ __forceinline__ uint32_t fan_to_strip_slot(uint32_t j, uint32_t total) { return (j < (total + 1) / 2) ? 2 * j : 2 * (total - 1 - j) + 1; }   // src/vertex.rs:28-35
+
+#define FS_THREADS 256
+// Last index i of a non-decreasing array with arr[i] <= key (arr[0] <= key), found by the whole warp: 32 probes per round,
+// so a table of a million entries takes 4 dependent loads instead of 20.
+__device__ __forceinline__ uint32_t warp_search_last_le(const uint32_t* __restrict__ arr, uint32_t n, uint32_t key, uint32_t lane) {
+    uint32_t lo = 0, len = n;
+    while (len > 1u) {
+        const uint32_t step = (len + 31u) / 32u, pos = lo + lane * step;
+        const bool le = pos < lo + len && arr[pos] <= key;
+        const uint32_t hit = __ballot_sync(0xffffffffu, le);          // monotone: lanes 0 .. j
+        const uint32_t j = 31u - (uint32_t)__clz((int)(hit | 1u));
+        const uint32_t end = lo + len;
+        lo += j * step;
+        len = min(step, end - lo);
+    }
+    return lo;
+}
+// Everything a segment thread needs to know about its path, loaded once per CTA into shared memory (a CTA's 256 consecutive
+// segments belong to a handful of consecutive paths).
+struct FillPathInfo {
+    uint32_t sb;                                   // segment_begin[p]
+    uint32_t solid, proto, iq, rq, solid_idx;      // the path's slices in the output arrays (scan of the count pass)
+    uint32_t tb0, tb1, tb3, te0, te1, te3;         // its slices of the line / integral quadratic / rational quadratic segment arrays
+    uint32_t rel;                                  // shape-relative number of its first solid vertex
+    uint32_t total_simple;                         // solid vertices (segments + 1) | simple << 31
+};
+// `shape_hint`: a shape at or before the path's (its own shape is found by walking forwards from there).
+__device__ __forceinline__ FillPathInfo load_fill_path_info(const DevicePaths& P, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ shape_path_begin,
+                                                            uint32_t n_shapes, uint32_t p, bool all_simple, uint32_t shape_hint) {
+    const size_t stride = (size_t)P.n_paths + 1;
+    FillPathInfo f;
+    f.sb = P.segment_begin[p];
+    f.solid = offsets[CAT_SOLID * stride + p]; f.proto = offsets[CNT_PROTO * stride + p]; f.iq = offsets[CAT_IQ * stride + p]; f.rq = offsets[CAT_RQ * stride + p];
+    f.solid_idx = offsets[CNT_SOLID_IDX * stride + p];
+    f.tb0 = P.type_begin[0 * stride + p]; f.te0 = P.type_begin[0 * stride + p + 1];
+    f.tb1 = P.type_begin[1 * stride + p]; f.te1 = P.type_begin[1 * stride + p + 1];
+    f.tb3 = P.type_begin[3 * stride + p]; f.te3 = P.type_begin[3 * stride + p + 1];
+    f.total_simple = (P.segment_begin[p + 1] - f.sb + 1u) | ((all_simple || path_is_simple(P, p)) ? 0x80000000u : 0u);
+    uint32_t sh = shape_hint;
+    while (sh + 1u < n_shapes && shape_path_begin[sh + 1u] <= p) ++sh;   // the CTA's paths lie in the hinted shape or the next few
+    f.rel = f.solid - offsets[CAT_SOLID * stride + shape_path_begin[sh]];
+    return f;
+}
+
+__global__ void __launch_bounds__(FS_THREADS) fill_segments_kernel(DevicePaths P, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ shape_path_begin,
+                                                                   uint32_t n_shapes, TessOutput out, uint32_t* __restrict__ err, uint32_t all_simple) {
+    if (*reinterpret_cast<volatile const uint32_t*>(err) & CR_DEVERR_FATAL_MASK) return;   // the count pass rejected the input (uniform): write nothing
+    __shared__ FillPathInfo sh_info[FS_THREADS];
+    __shared__ uint32_t sh_range[2];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    const uint32_t seg_threads = (P.n_segments + FS_THREADS - 1u) / FS_THREADS * FS_THREADS;   // whole CTAs of segment threads, then one thread per path for its start point
+    uint32_t e = 0;
+    if (tid >= seg_threads) {
+        // ---- the path's first point: solid vertex 0, proto-hull point 0, index entry 0 and the strip's restart (src/fill.rs:264-266,366)
+        const uint32_t p = tid - seg_threads, warp_p = min(p - lane, P.n_paths - 1u);
+        const uint32_t hint = warp_search_last_le(shape_path_begin, n_shapes, warp_p, lane);   // shape of the warp's first path
+        if (p >= P.n_paths) return;
+        const FillPathInfo f = load_fill_path_info(P, offsets, shape_path_begin, n_shapes, p, all_simple != 0u, hint);
+        if (!(f.total_simple >> 31)) return;
+        const float2 start = make_float2(P.start[2 * (size_t)p], P.start[2 * (size_t)p + 1]);
+        reinterpret_cast<float2*>(out.vtx[CAT_SOLID])[f.solid] = start;   // fan_to_strip_slot(0, total) == 0
+        store_proto(out.proto, f.proto, start, e);
+        uint32_t* idx = out.idx[2] + f.solid_idx;
+        idx[0] = f.rel << 1;
+        idx[f.total_simple & 0x7fffffffu] = CR_RESTART;
+        if (e) atomicOr(err, e);
+        return;
+    }
+    // ---- the CTA's paths: the first one (and its shape) by a warp-wide search, then everything about the next FS_THREADS paths into
+    // shared memory in one round of independent loads; the ones that begin beyond the CTA's last segment are not used
+    const uint32_t g = tid, g0 = blockIdx.x * FS_THREADS, g_last = min(g0 + FS_THREADS, P.n_segments) - 1u;
+    if (threadIdx.x < 32u) {
+        const uint32_t pf = warp_search_last_le(P.segment_begin, P.n_paths, g0, lane);   // segment_begin[n_paths] = n_segments > g0; empty paths share a value: the last one owns the segment
+        const uint32_t sf = warp_search_last_le(shape_path_begin, n_shapes, pf, lane);
+        if (lane == 0) { sh_range[0] = pf; sh_range[1] = sf; }
+    }
+    __syncthreads();
+    const uint32_t p_first = sh_range[0];
+    uint32_t mine_needed = 0;
+    if (p_first + threadIdx.x < P.n_paths) {
+        const FillPathInfo f = load_fill_path_info(P, offsets, shape_path_begin, n_shapes, p_first + threadIdx.x, all_simple != 0u, sh_range[1]);
+        sh_info[threadIdx.x] = f;
+        mine_needed = f.sb <= g_last ? 1u : 0u;
+    }
+    const uint32_t n_local = (uint32_t)__syncthreads_count((int)mine_needed);   // paths with sb <= g_last form a prefix (sb is non-decreasing)
+    const bool cached = n_local < FS_THREADS || p_first + FS_THREADS >= P.n_paths;   // else the CTA's last segment may belong to a path beyond the cached ones (runs of EMPTY paths)
+    const bool live = g < P.n_segments;
+    uint32_t p = 0xFFFFFFFFu, type = 255u;
+    FillPathInfo f{};
+    if (live) {
+        if (cached) {
+            uint32_t lo = 0, hi = n_local;   // last local path with sb <= g
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_info[mid].sb <= g) lo = mid; else hi = mid; }
+            p = p_first + lo;
+            f = sh_info[lo];
+        } else {
+            uint32_t lo = 0, hi = P.n_paths;
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.segment_begin[mid] <= g) lo = mid; else hi = mid; }
+            p = lo;
+            f = load_fill_path_info(P, offsets, shape_path_begin, n_shapes, p, all_simple != 0u, shape_of_path(shape_path_begin, n_shapes, p));
+        }
+        type = P.segment_types[g];
+    }
+    // ranks: how many segments of each type precede this one in its path. Inside the warp by ballots ...
+    const uint32_t same = __match_any_sync(0xffffffffu, p) & ((1u << lane) - 1u);
+    const uint32_t b0 = __ballot_sync(0xffffffffu, type == CR_SEG_LINE), b1 = __ballot_sync(0xffffffffu, type == CR_SEG_INTEGRAL_QUADRATIC),
+                   b3 = __ballot_sync(0xffffffffu, type == CR_SEG_RATIONAL_QUADRATIC);
+    uint32_t r0 = __popc(b0 & same), r1 = __popc(b1 & same), r3 = __popc(b3 & same);
+    // ... and, for the one path that began before this warp's first segment, by a cooperative count over [its begin, the warp's first segment)
+    const uint32_t g_warp = g - lane, p_lane0 = __shfl_sync(0xffffffffu, p, 0), sb_lane0 = __shfl_sync(0xffffffffu, f.sb, 0);
+    if (p_lane0 != 0xFFFFFFFFu && sb_lane0 < g_warp) {
+        uint32_t c0 = 0, c1 = 0, c3 = 0;
+        for (uint32_t k = sb_lane0 + lane; k < g_warp; k += 32u) {
+            const uint32_t t = P.segment_types[k];
+            c0 += t == CR_SEG_LINE; c1 += t == CR_SEG_INTEGRAL_QUADRATIC; c3 += t == CR_SEG_RATIONAL_QUADRATIC;
+        }
+        c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1); c3 = __reduce_add_sync(0xffffffffu, c3);
+        if (p == p_lane0) { r0 += c0; r1 += c1; r3 += c3; }
+    }
+    if (!live || !(f.total_simple >> 31)) return;
+    if (type != CR_SEG_LINE && type != CR_SEG_INTEGRAL_QUADRATIC && type != CR_SEG_RATIONAL_QUADRATIC) { atomicOr(err, CR_DEVERR_BAD_TABLES); return; }
+    {   // every read stays inside the path's slice of its type's array (the count pass has checked the tables; this keeps a disagreeing type stream harmless)
+        const uint32_t at = type == CR_SEG_LINE ? f.tb0 + r0 : (type == CR_SEG_INTEGRAL_QUADRATIC ? f.tb1 + r1 : f.tb3 + r3);
+        const uint32_t end = type == CR_SEG_LINE ? f.te0 : (type == CR_SEG_INTEGRAL_QUADRATIC ? f.te1 : f.te3);
+        if (at >= end) { atomicOr(err, CR_DEVERR_BAD_TABLES); return; }
+    }
+    const uint32_t si = g - f.sb, total = f.total_simple & 0x7fffffffu;
+    // the point this segment starts from: the path's start, or the end point of the previous segment
+    float2 last;
+    if (si == 0) last = make_float2(P.start[2 * (size_t)p], P.start[2 * (size_t)p + 1]);
+    else {
+        const uint32_t tp = P.segment_types[g - 1];
+        if (tp == CR_SEG_LINE) { const float* d = P.seg[0] + 2 * (size_t)(f.tb0 + r0 - 1u); last = make_float2(d[0], d[1]); }
+        else if (tp == CR_SEG_INTEGRAL_QUADRATIC) { const float* d = P.seg[1] + 4 * (size_t)(f.tb1 + r1 - 1u); last = make_float2(d[2], d[3]); }
+        else { const float* d = P.seg[3] + 5 * (size_t)(f.tb3 + r3 - 1u); last = make_float2(d[3], d[4]); }
+    }
+    const uint32_t proto_at = f.proto + 1u + r0 + 2u * (r1 + r3);
+    float2 end;
+    if (type == CR_SEG_LINE) {
+        const float* d = P.seg[0] + 2 * (size_t)(f.tb0 + r0);
+        end = make_float2(d[0], d[1]);
+        store_proto(out.proto, proto_at, end, e);
+    } else if (type == CR_SEG_INTEGRAL_QUADRATIC) {   // src/fill.rs:284-299
+        const float* dp = P.seg[1] + 4 * (size_t)(f.tb1 + r1);
+        const float4 d = (reinterpret_cast<uintptr_t>(P.seg[1]) & 15u) == 0 ? *reinterpret_cast<const float4*>(dp) : make_float4(dp[0], dp[1], dp[2], dp[3]);   // a caller's device array may be 4-byte aligned only
+        end = make_float2(d.z, d.w);
+        float4* v = reinterpret_cast<float4*>(out.vtx[CAT_IQ]) + (size_t)f.iq + 3u * (size_t)r1;
+        v[0] = make_float4(d.z, d.w, 1.0f, 1.0f);
+        v[1] = make_float4(d.x, d.y, 0.5f, 0.0f);
+        v[2] = make_float4(last.x, last.y, 0.0f, 0.0f);
+        store_proto(out.proto, proto_at, make_float2(d.x, d.y), e);
+        store_proto(out.proto, proto_at + 1u, end, e);
+    } else {                                          // src/fill.rs:320-335
+        const float* d = P.seg[3] + 5 * (size_t)(f.tb3 + r3);
+        const float weight = 1.0f / d[0];
+        end = make_float2(d[3], d[4]);
+        float* v = reinterpret_cast<float*>(out.vtx[CAT_RQ]) + ((size_t)f.rq + 3u * (size_t)r3) * 5;
+        v[0] = d[3]; v[1] = d[4]; v[2] = 1.0f; v[3] = 1.0f; v[4] = 1.0f;
+        v[5] = d[1]; v[6] = d[2]; v[7] = 0.5f * weight; v[8] = 0.0f; v[9] = weight;
+        v[10] = last.x; v[11] = last.y; v[12] = 0.0f; v[13] = 0.0f; v[14] = 1.0f;
+        store_proto(out.proto, proto_at, make_float2(d[1], d[2]), e);
+        store_proto(out.proto, proto_at + 1u, end, e);
+    }
+    reinterpret_cast<float2*>(out.vtx[CAT_SOLID])[f.solid + fan_to_strip_slot(si + 1u, total)] = end;
+    out.idx[2][f.solid_idx + si + 1u] = ((f.rel + si + 1u) << 1) | ((si + 1u) & 1u);
+    if (e) atomicOr(err, e);
 }
 
 // Per-shape slice boundaries: cat_begin[c][s] = offsets[c][shape_path_begin[s]], s in [0, n_shapes].
@@ -1323,11 +1518,17 @@ int cr_tess_shape_bounds(cudaStream_t stream, const uint32_t* offsets, uint32_t 
 int cr_tess_emit(cudaStream_t stream, const DevicePaths& paths, const uint32_t* offsets, const uint32_t* shape_path_begin, uint32_t n_shapes,
                  const TessOutput& out, uint32_t* err_flag, bool has_cubics) {
     if (paths.n_paths == 0) return CR_OK;
-    const uint32_t grid = (paths.n_paths + 127) / 128;
-    if (paths.stroke_options) tess_emit_kernel<0><<<grid, 128, 0, stream>>>(paths, offsets, shape_path_begin, n_shapes, out, err_flag);
-    else if (has_cubics) tess_emit_kernel<1><<<grid, 128, 0, stream>>>(paths, offsets, shape_path_begin, n_shapes, out, err_flag);
-    else tess_emit_kernel<2><<<grid, 128, 0, stream>>>(paths, offsets, shape_path_begin, n_shapes, out, err_flag);
+    // filled paths without cubics: one thread per segment (+ one per path); everything else: one thread per path
+    const bool all_simple = !paths.stroke_options && !has_cubics;
+    const uint32_t seg_threads = (paths.n_segments + 255u) / 256u * 256u + paths.n_paths;
+    fill_segments_kernel<<<(seg_threads + 255u) / 256u, 256, 0, stream>>>(paths, offsets, shape_path_begin, n_shapes, out, err_flag, all_simple ? 1u : 0u);
     g_cr_kernel_launches += 1;
+    if (!all_simple) {
+        const uint32_t grid = (paths.n_paths + 127) / 128;
+        if (paths.stroke_options) tess_emit_kernel<0><<<grid, 128, 0, stream>>>(paths, offsets, shape_path_begin, n_shapes, out, err_flag, 1u);
+        else tess_emit_kernel<1><<<grid, 128, 0, stream>>>(paths, offsets, shape_path_begin, n_shapes, out, err_flag, 1u);
+        g_cr_kernel_launches += 1;
+    }
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }

@@ -9,9 +9,13 @@ tests/test_path_constructors.py):
   * a Motor is (m0, m1, m2, m3); `rotate2d(a)` = (cos a/2, sin a/2, 0, 0) rotates counter-clockwise (y up),
     `translate2d(v)` = (1, 0, -v_y / 2, v_x / 2).
 
-The ppga3d camera motors of the demo (src/utils.rs:141-151,167-180) are out of scope; the
-perspective matrix, matrix product and colour-space helpers are here because instance matrices / colours are inputs
-of the hot path.
+The ppga3d camera motors of the demo (src/utils.rs:141-151,167-180: `rotate_around_axis`, `motor2d_to_motor3d`,
+`motor3d_to_mat4`, plus the `Translator` / `Motor` products examples/showcase/main.rs:163-201 builds its instance matrices
+with) are evaluated with a small generic geometric-product routine over the basis
+Motor = (1, e32, e13, e21, e0123, e01, e02, e03), Point = (e123, -e023, e013, -e012). The crate that defines the basis is
+not in the reference tree; the signs of e21, e01, e02 are FORCED by requiring `motor3d_to_mat4(motor2d_to_motor3d(m))` to
+move (x, y, 0, 1) exactly like `motor2d_to_mat3(m)` moves (x, y, 1) (tests/test_path_constructors.py), the remaining ones
+(e32, e13, e03, e0123) are the cyclic continuation. `save_png` writes a frame read back from the renderer.
 """
 from __future__ import annotations
 
@@ -177,6 +181,135 @@ def complex_powi(z, n: int) -> np.ndarray:
         x = complex_mul(x, x)
         n >>= 1
     return complex_mul(x, y)
+
+
+# ------------------------------------------------------------------------------------------------- ppga3d (demo camera)
+_METRIC = (0.0, 1.0, 1.0, 1.0)   # e0 is null
+
+
+def _blade_product(a: int, b: int):
+    """Geometric product of two basis blades given as bit masks over (e0, e1, e2, e3): (sign, blade)."""
+    sign = 1.0
+    for i in range(4):
+        if (b >> i) & 1:
+            if bin(a >> (i + 1)).count("1") & 1:
+                sign = -sign
+            if (a >> i) & 1:
+                sign *= _METRIC[i]
+                a ^= 1 << i
+            else:
+                a |= 1 << i
+    return sign, a
+
+
+def _blade(indices, sign=1.0):
+    mask = 0
+    for i in indices:
+        mask |= 1 << i
+    for i in range(len(indices)):
+        for j in range(i + 1, len(indices)):
+            if indices[i] > indices[j]:
+                sign = -sign
+    return mask, sign
+
+
+_MOTOR3 = [_blade(()), _blade((3, 2)), _blade((1, 3)), _blade((2, 1)), _blade((0, 1, 2, 3)), _blade((0, 1)), _blade((0, 2)), _blade((0, 3))]
+_POINT3 = [_blade((1, 2, 3)), _blade((0, 2, 3), -1.0), _blade((0, 1, 3)), _blade((0, 1, 2), -1.0)]
+
+
+def _to_multivector(basis, values):
+    out = {}
+    for (mask, sign), v in zip(basis, values):
+        out[mask] = out.get(mask, 0.0) + sign * float(v)
+    return out
+
+
+def _from_multivector(basis, x) -> np.ndarray:
+    return _v([x.get(mask, 0.0) * sign for mask, sign in basis])
+
+
+def _gp(x, y):
+    out = {}
+    for a, va in x.items():
+        for b, vb in y.items():
+            sign, c = _blade_product(a, b)
+            if sign:
+                out[c] = out.get(c, 0.0) + sign * va * vb
+    return out
+
+
+def _reverse(x):
+    return {a: v * (-1.0) ** (bin(a).count("1") * (bin(a).count("1") - 1) // 2) for a, v in x.items()}
+
+
+def rotate_around_axis(angle: float, axis) -> np.ndarray:
+    """src/utils.rs:143-146: ppga3d::Rotor (cos a/2, axis sin a/2)."""
+    sinus = math.sin(angle * 0.5)
+    return _v([math.cos(angle * 0.5), axis[0] * sinus, axis[1] * sinus, axis[2] * sinus])
+
+
+def translator3d(x: float, y: float, z: float) -> np.ndarray:
+    """ppga3d::Translator::new(1, x, y, z) as a Motor (examples/showcase/main.rs:171 passes -view_distance / 2 as z)."""
+    return _v([1.0, 0.0, 0.0, 0.0, 0.0, x, y, z])
+
+
+def rotor3d_to_motor3d(rotor) -> np.ndarray:
+    r = _v(rotor)
+    return _v([r[0], r[1], r[2], r[3], 0.0, 0.0, 0.0, 0.0])
+
+
+def motor3d_product(a, b) -> np.ndarray:
+    """`a.geometric_product(b)` of two ppga3d motors (8 components each)."""
+    return _from_multivector(_MOTOR3, _gp(_to_multivector(_MOTOR3, a), _to_multivector(_MOTOR3, b)))
+
+
+def motor2d_to_motor3d(motor) -> np.ndarray:
+    """src/utils.rs:149-151"""
+    m = _v(motor)
+    return _v([m[0], 0.0, 0.0, m[1], 0.0, -m[3], m[2], 0.0])
+
+
+def motor3d_transform_point(motor, point) -> np.ndarray:
+    """`motor.transformation(point)`: M P ~M on a ppga3d::Point (w, x, y, z)."""
+    m = _to_multivector(_MOTOR3, motor)
+    return _from_multivector(_POINT3, _gp(_gp(m, _to_multivector(_POINT3, point)), _reverse(m)))
+
+
+def motor3d_to_mat4(motor) -> np.ndarray:
+    """src/utils.rs:168-180: four column vectors (images of the x, y, z axes and of the origin), each as (x, y, z, w)."""
+    rows = []
+    for index in (1, 2, 3, 0):
+        point = np.zeros(4, np.float32)
+        point[index] = 1.0
+        r = motor3d_transform_point(motor, point)
+        rows.append([r[1], r[2], r[3], r[0]])
+    return _v(rows)
+
+
+# ------------------------------------------------------------------------------------------------- frame dump
+def save_png(path: str, rgba) -> None:
+    """Writes an [H, W, 4] frame as an 8-bit RGBA PNG. Float input is taken as the renderer's premultiplied linear colour
+    (`Renderer.read_color()`): un-premultiplied, converted with `linear_to_srgb`'s curve and quantised; uint8 input is
+    written as it is (`read_color_texels()` of an Rgba8Unorm target)."""
+    import struct
+    import zlib
+    a = np.asarray(rgba)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("save_png expects an [H, W, 4] array")
+    if a.dtype != np.uint8:
+        c = a.astype(np.float32)
+        alpha = c[..., 3:4]
+        rgb = np.where(alpha > 0, c[..., :3] / np.where(alpha > 0, alpha, 1), 0).clip(0, 1)
+        rgb = np.where(rgb > 0.0031308, 1.055 * np.power(rgb, 1.0 / 2.4) - 0.055, 12.92 * rgb)
+        a = (np.concatenate([rgb, alpha.clip(0, 1)], axis=2) * 255.0 + 0.5).astype(np.uint8)
+    h, w = a.shape[:2]
+    raw = b"".join(b"\x00" + a[y].tobytes() for y in range(h))
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
 
 # ------------------------------------------------------------------------------------------------- matrices, colours

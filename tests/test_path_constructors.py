@@ -219,3 +219,61 @@ def test_shape_constructors():
     assert 0.5 * float(np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y)) > 0   # regular polygon: counter-clockwise (increasing angle)
     rv = np.vstack([rect.start, np.array(rect.line_segments)])
     assert 0.5 * float(np.sum(rv[:, 0] * np.roll(rv[:, 1], -1) - np.roll(rv[:, 0], -1) * rv[:, 1])) < 0
+
+
+# ---------------------------------------------------------------------------------------------- demo helpers (f4)
+def test_motor3d_embedding_agrees_with_the_2d_motor():
+    """src/utils.rs:149-180: `motor3d_to_mat4(motor2d_to_motor3d(m))` moves (x, y, 0, 1) like `motor2d_to_mat3(m)` moves (x, y, 1)."""
+    rng = np.random.default_rng(7)
+    for _ in range(8):
+        m2 = U.motor_product(U.translate2d(rng.uniform(-2, 2, 2)), U.rotate2d(float(rng.uniform(-3, 3))))
+        m4, m3 = U.motor3d_to_mat4(U.motor2d_to_motor3d(m2)), U.motor2d_to_mat3(m2)
+        x, y = rng.uniform(-1, 1, 2).astype(np.float32)
+        p3 = m4[3] + x * m4[0] + y * m4[1]
+        p2 = m3[2] + x * m3[0] + y * m3[1]
+        assert np.allclose(p3[[0, 1, 3]], p2, atol=1e-5) and abs(p3[2]) < 1e-6
+
+
+def test_camera_motor_of_the_showcase():
+    """examples/showcase/main.rs:163-201: Translator(1, 0, 0, -d / 2) * view_rotation pushes the scene d along +z (the projection's
+    clip w is the view-space z, src/utils.rs:183-192), instance motors (.., tx, ty, tz) translate by -2 (tx, ty, tz)."""
+    view = U.motor3d_product(U.translator3d(0.0, 0.0, -0.5 * 10.0), U.rotor3d_to_motor3d(U.rotate_around_axis(0.0, [0, 1, 0])))
+    m = U.motor3d_to_mat4(view)
+    assert np.allclose(m[3], [0, 0, 10, 1], atol=1e-6) and np.allclose(m[:3, :3], np.eye(3), atol=1e-6)
+    # a quarter turn about z takes the x axis to the y axis (same sense as rotate2d)
+    q = U.motor3d_to_mat4(U.rotor3d_to_motor3d(U.rotate_around_axis(np.pi / 2, [0, 0, 1])))
+    assert np.allclose(q[0], [0, 1, 0, 0], atol=1e-6) and np.allclose(q[1], [-1, 0, 0, 0], atol=1e-6)
+    # rotations about x and y are proper rotations of the same handedness (cyclic continuation)
+    for axis, src, dst in (([1, 0, 0], 1, 2), ([0, 1, 0], 2, 0)):
+        r = U.motor3d_to_mat4(U.rotor3d_to_motor3d(U.rotate_around_axis(np.pi / 2, axis)))
+        expect = np.zeros(4, np.float32)
+        expect[dst] = 1.0
+        assert np.allclose(r[src], expect, atol=1e-6) and np.isclose(np.linalg.det(r[:3, :3].astype(np.float64)), 1.0, atol=1e-5)
+    # the projected origin of the instance grid's centre cell sits in front of the camera
+    proj = U.matrix_multiplication(U.perspective_projection(np.pi * 0.5, 16 / 9, 1.0, 1000.0), m)
+    clip = proj[3]
+    assert clip[3] > 0 and abs(clip[0]) < 1e-6 and abs(clip[1]) < 1e-6
+
+
+def test_save_png_round_trip(tmp_path):
+    import struct
+    import zlib
+    frame = np.zeros((5, 7, 4), np.float32)
+    frame[1:4, 2:5] = [0.5, 0.25, 0.0, 0.5]   # premultiplied: colour (1, 0.5, 0) at half opacity
+    path = tmp_path / "frame.png"
+    U.save_png(str(path), frame)
+    data = path.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h, depth, kind = struct.unpack(">IIBB", data[16:26])
+    assert (w, h, depth, kind) == (7, 5, 8, 6)
+    idat_len = struct.unpack(">I", data[33:37])[0]
+    raw = zlib.decompress(data[41:41 + idat_len])
+    rows = np.frombuffer(raw, np.uint8).reshape(5, 1 + 7 * 4)
+    assert (rows[:, 0] == 0).all()
+    px = rows[:, 1:].reshape(5, 7, 4)
+    assert tuple(px[2, 3]) == (255, 188, 0, 128) and tuple(px[0, 0]) == (0, 0, 0, 0)
+    texels = np.arange(5 * 7 * 4, dtype=np.uint8).reshape(5, 7, 4)
+    U.save_png(str(path), texels)
+    data = path.read_bytes()
+    idat_len = struct.unpack(">I", data[33:37])[0]
+    assert np.array_equal(np.frombuffer(zlib.decompress(data[41:41 + idat_len]), np.uint8).reshape(5, 29)[:, 1:].reshape(5, 7, 4), texels)
