@@ -3,7 +3,7 @@ import ctypes as C
 
 CR_MAX_DASH_INTERVALS = 4
 CR_DASH_PATTERN_CAPACITY = 8
-CR_MAX_STEPS_PER_INTERVAL = 256
+CR_MAX_STEPS_PER_INTERVAL = 4194304
 
 # enum cr_status — 1..5 are `enum Error` of the reference in declaration order (src/error.rs:5-16)
 CR_OK = 0

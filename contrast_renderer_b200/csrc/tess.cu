@@ -321,10 +321,13 @@ __device__ __forceinline__ void stroke_sample(Sink<true>& s, StrokeCtx& c, const
     emit_stroke_vertices(s, c, c.group, c.length, pt, tangent);
     previous_point = pt;
 }
+// interpolate_normal! has no limit (src/curve.rs:228-252); the device keeps one: 2^22 samples per inflection-free interval keep
+// every 32-bit count of a path far from wrapping. (Up to round 1 the limit was the 256-entry parameter buffer of the cubic.)
 __device__ __forceinline__ uint32_t clamp_steps(uint32_t steps, uint32_t& err) {
     if (steps > CR_MAX_STEPS_PER_INTERVAL) { err |= CR_DEVERR_STEPS; return CR_MAX_STEPS_PER_INTERVAL; }
     return steps;
 }
+#define CR_PARAM_BUFFER 256u   // cubic parameters of one interval that are sorted in local memory; longer intervals sort in the output array
 
 // Quadratic curve body: *_quadratic_uniform_tangent_angle (src/curve.rs:306-322,355-380) + emit_curve_stroke!.
 template <bool EMIT, int KIND>
@@ -392,7 +395,7 @@ __device__ void stroke_cubic(Sink<EMIT>& s, StrokeCtx& c, const Pt* pb, bool uta
     const bool cusp = cr::fabs_f(inf.disc) < CR_ERROR_MARGIN;
     float previous_split = 0.0f;
     Pt prev = start;
-    float params[EMIT ? CR_MAX_STEPS_PER_INTERVAL : 1];
+    float params[EMIT ? CR_PARAM_BUFFER : 1];
     (void)params;
     for (int iv = 0; iv <= n_split; ++iv) {
         float a = previous_split, b = 1.0f;
@@ -420,13 +423,32 @@ __device__ void stroke_cubic(Sink<EMIT>& s, StrokeCtx& c, const Pt* pb, bool uta
                 sp.p[4] = join(tr[3], tr[2]);
             }
             const cr::Complex pstep = cr::cpowf(range, 1.0f / (float)steps);
-            for (uint32_t i = 1; i < steps; ++i) {
+            auto parameter = [&](uint32_t i) -> float {
                 const cr::Complex ip = cr::cmul(pstart, cr::cpowi(pstep, i));
-                const float t = first_root_in_unit<KIND>(sp, mk_ln(0.0f, ip.re, ip.im));
-                const float mapped = a + (b - a) * t;
-                uint32_t j = np++;   // stable insertion sort (src/curve.rs:297)
-                while (j > 0 && params[j - 1] > mapped) { params[j] = params[j - 1]; --j; }
-                params[j] = mapped;
+                return a + (b - a) * first_root_in_unit<KIND>(sp, mk_ln(0.0f, ip.re, ip.im));
+            };
+            if (steps - 1u <= CR_PARAM_BUFFER) {
+                for (uint32_t i = 1; i < steps; ++i) {
+                    const float mapped = parameter(i);
+                    uint32_t j = np++;   // stable insertion sort (src/curve.rs:297)
+                    while (j > 0 && params[j - 1] > mapped) { params[j] = params[j - 1]; --j; }
+                    params[j] = mapped;
+                }
+            } else {
+                // More parameters than the local buffer holds: they are sorted (src/curve.rs:297, stable insertion sort — they come out
+                // nearly ordered) in GLOBAL memory, in the tail of the very vertex slots this interval is about to fill: its
+                // steps samples own 40 bytes each in the line-vertex array, the steps - 1 floats sit in the last bytes of that
+                // range, and sample i is read before its vertices are written; the write front (40 bytes per sample) never
+                // reaches a parameter that has not been consumed (36 np + 4 (i + 1) >= 36 i + 40 bytes for every i < np).
+                const uint32_t np_long = steps - 1u;
+                float* const gp = reinterpret_cast<float*>(s.out.vtx[CAT_LINE]) + (size_t)5 * (s.base.v[CAT_LINE] + s.n[CAT_LINE] + 2u * steps) - np_long;
+                for (uint32_t i = 1; i < steps; ++i) {
+                    const float mapped = parameter(i);
+                    uint32_t j = i - 1u;
+                    while (j > 0 && gp[j - 1] > mapped) { gp[j] = gp[j - 1]; --j; }
+                    gp[j] = mapped;
+                }
+                for (uint32_t i = 0; i < np_long; ++i) { const float t = gp[i]; stroke_sample<true>(s, c, pb, t, prev); }
             }
         }
         for (uint32_t i = 0; i < np; ++i) stroke_sample<true>(s, c, pb, params[i], prev);

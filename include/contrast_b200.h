@@ -82,7 +82,7 @@ typedef enum cr_color_format { CR_FORMAT_RGBA32F = 0, CR_FORMAT_RGBA8_UNORM = 1,
 
 #define CR_MAX_DASH_INTERVALS 4           /* src/path.rs:121 */
 #define CR_DASH_PATTERN_CAPACITY 8        /* struct capacity; > CR_MAX_DASH_INTERVALS yields CR_ERR_TOO_MANY_DASH_INTERVALS */
-#define CR_MAX_STEPS_PER_INTERVAL 256     /* device-side capacity for one interpolate_normal! run (src/curve.rs:228-252) */
+#define CR_MAX_STEPS_PER_INTERVAL 4194304 /* samples of one interpolate_normal! run (src/curve.rs:228-252): keeps the 32-bit vertex counts of a path from wrapping */
 
 /* ------------------------------------------------------------------------------------------------ path model */
 

@@ -262,11 +262,35 @@ def test_error_codes(cr, oracle):
     with pytest.raises(cr.TooManyNestedOpacityGroups):
         rp.restore_alpha_context(1)
     rp.submit()
-    # a curve with more tangent-angle steps than the device-side capacity is reported, not truncated silently
-    tight = stroke_path([("Q", [[1, 2], [2, 0]])], [0, 0], width=0.1, curve_approximation=CurveApproximation.UniformTangentAngle(0.001))
+    # a curve with more tangent-angle steps than the device admits (2^22 per interval) is reported, not truncated silently
+    tight = stroke_path([("Q", [[1, 2], [2, 0]])], [0, 0], width=0.1, curve_approximation=CurveApproximation.UniformTangentAngle(1e-7))
     with pytest.raises(cr.Error) as e:
         cr.Shape.from_paths(rnd, [DynamicStrokeOptions.Solid(Join.Miter, Cap.Butt, Cap.Butt)], PathSoA.from_paths([tight]))
     assert e.value.status == _abi.CR_ERR_CURVE_STEPS_CAPACITY
+    rnd.close()
+
+
+def test_fine_tangent_angle_steps_beyond_the_parameter_buffer(cr, oracle):
+    """UniformTangentAngle(0.001) puts thousands of samples into one inflection-free interval (src/curve.rs:228-303 has no limit):
+    quadratics stream their samples, cubics sort up to 256 parameters per interval in place and stream longer, ordered runs.
+    Every segment kind, an S cubic (two intervals) and a loop cubic, byte for byte against the oracle."""
+    w = 0.70710678
+    so = dict(width=0.2, offset=0.05, miter_clip=2.0, closed=False, curve_approximation=CurveApproximation.UniformTangentAngle(0.001))
+    paths = [
+        stroke_path([("Q", [[1, 2], [2, 0]])], [0, 0], **so),
+        stroke_path([("RQ", (w, [[1, 1], [0, 1]]))], [1, 0], **so),
+        stroke_path([("C", [[3, -1], [4, 2], [5, 0]])], [0, 0], **so),
+        stroke_path([("C", [[3, 2], [-1, 2], [2, 0]])], [0, 0], **so),
+        stroke_path([("RC", ([1, 0.6, 1.7, 1], [[0.5, 1.5], [2.5, 1.2], [3, 0]]))], [0, 0], **so),
+    ]
+    dso = [DynamicStrokeOptions.Solid(Join.Round, Cap.Round, Cap.Square)]
+    soa = PathSoA.from_paths(paths)
+    rnd = cr.Renderer()
+    shape = cr.Shape.from_paths(rnd, dso, soa)
+    ref = oracle.shape_from_paths(dso, soa)
+    assert ref.vertex_offsets[0] // 20 > 5 * 2 * 1000, "the scene is meant to exceed the 256-parameter buffer by far"
+    assert_shape_equal(oracle, shape, ref, "fine steps")
+    shape.close()
     rnd.close()
 
 
