@@ -112,7 +112,7 @@ int decode_device_error(uint32_t flags) {
 
 // ---------------------------------------------------------------------------------------------------- objects
 // Words of the renderer's pinned read-back area.
-enum { PIN_TESS = 0 /* 11 totals, err, max_proto, 5 type totals */, PIN_PASS = 24 /* PassCounters snapshot, 8 words */, PIN_MISC = 40 /* one 48-byte descriptor */, PIN_WORDS = 64 };
+enum { PIN_TESS = 0 /* 11 totals, err, max_proto, 5 type totals */, PIN_PASS = 24 /* PassCounters snapshot, 10 words */, PIN_MISC = 40 /* one 48-byte descriptor */, PIN_WORDS = 64 };
 
 struct cr_pass;
 struct cr_renderer {
@@ -134,7 +134,7 @@ struct cr_renderer {
     DevBuf color, stencil, alpha_layers, depth;
     // scratch shared by every from_paths / submit of this renderer
     DevBuf staging[2][10], counts, scan_scratch_tess, scan_scratch, shape_begin_dev, hull_scratch_a, hull_scratch_b;
-    DevBuf compact_dev, cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, tile_prims, radix_scratch, tile_begin,
+    DevBuf compact_dev, cmds_dev, batches_dev, cmd_cands, cand_tiles, records, big_list, pair_tile, pair_cand, pair_tile_alt, pair_cand_alt, tile_prims, clip_list, clip_attrs, radix_scratch, tile_begin,
         inst_transforms, inst_colors, pass_counters;
     uint32_t* pinned = nullptr;   // PIN_WORDS words of pinned read-back area
     cr_stats stats{};
@@ -152,6 +152,7 @@ struct cr_renderer {
     bool cmd_arena_busy = false;
     // Capacities the next pass is sized with (candidates, (tile, candidate) pairs): what the last pass needed plus slack. 0: unknown.
     uint32_t cand_cap = 0, pair_cap = 0, last_cands = 0, last_pairs = 0;
+    uint32_t clip_cap = 1024;         // triangles frustum clipping may produce in one pass (grows when a pass needs more)
     cr_pass* inflight = nullptr;      // the last submitted pass until its device-side sizes have been checked (settle)
     int deferred_status = CR_OK;      // an error found while settling, reported by the next entry point that can fail
     char deferred_message[256] = "";
@@ -622,7 +623,7 @@ static void renderer_free(cr_renderer* r) {
     cudaStream_t st = r->stream;
     DevBuf* all[] = {&r->color, &r->stencil, &r->alpha_layers, &r->depth, &r->exchange, &r->counts, &r->scan_scratch, &r->shape_begin_dev, &r->hull_scratch_a,
                      &r->hull_scratch_b, &r->scan_scratch_tess, &r->compact_dev, &r->cmds_dev, &r->batches_dev, &r->cmd_cands, &r->cand_tiles, &r->records, &r->big_list, &r->pair_tile, &r->pair_cand,
-                     &r->pair_tile_alt, &r->pair_cand_alt, &r->tile_prims, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->pass_counters};
+                     &r->pair_tile_alt, &r->pair_cand_alt, &r->tile_prims, &r->clip_list, &r->clip_attrs, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->pass_counters};
     for (DevBuf* d : all) d->release(st);
     for (auto& set : r->staging) for (auto& d : set) d.release(st);
     cudaStreamSynchronize(st);
@@ -1113,7 +1114,7 @@ static int clear_attachments(cr_pass* p) {
 // behind, nothing is read back before everything is enqueued; the kernels check the capacities on the device and the tile
 // kernel does not run when one did not suffice (settle() then re-submits). `sized` = true: the host waits for the candidate
 // and pair totals and sizes exactly (first pass of a renderer, tile-sharded targets, re-submission).
-static int enqueue_pass(cr_pass* p, bool sized) {
+static int enqueue_pass(cr_pass* p, bool sized, int attempt = 0) {
     cr_renderer* r = p->renderer;
     cudaStream_t st = r->stream;
     const CompactCommand* const cmds = p->arena ? r->cmd_arena : p->commands.data();
@@ -1158,20 +1159,31 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     sc.n_commands = n_cmds;
     sc.transforms = r->inst_transforms.as<float>();
     sc.colors = p->any_color ? r->inst_colors.as<float>() : nullptr;
+    const uint32_t clip_cap = r->clip_cap;
+    CR_TRY(r->clip_attrs.reserve(st, (size_t)clip_cap * sizeof(ClipAttr)));
+    sc.clip_attrs = r->clip_attrs.as<ClipAttr>();
     const RasterTarget tg = make_target(p);
     const uint32_t n_tiles = r->tiles_x * r->tiles_y;
 
     // ---- bin: count, scan, emit, sort by tile (stable => draw order survives inside every tile)
     CR_TRY(r->cand_tiles.reserve(st, (size_t)(cand_cap + 1) * 4));
-    CR_TRY(r->records.reserve(st, (size_t)std::max<uint32_t>(cand_cap, 1u) * sizeof(PrimRecord)));
+    CR_TRY(r->records.reserve(st, ((size_t)std::max<uint32_t>(cand_cap, 1u) + clip_cap) * sizeof(PrimRecord)));   // the fan triangles of frustum clipping live behind the candidates
+    CR_TRY(r->clip_list.reserve(st, (size_t)(cand_cap + 1) * 4));
     CR_TRY(reserve_scan_scratch(r, st, r->scan_scratch, cr_scan_scratch_words(cand_cap + 1, 1)));
     CR_TRY(r->big_list.reserve(st, (size_t)(cand_cap + 1) * 4));
-    CR_TRY(cr_raster_setup(st, sc, tg, cand_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), counters));
+    CR_TRY(cr_raster_setup(st, sc, tg, cand_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), r->clip_list.as<uint32_t>(),
+                           r->clip_attrs.as<ClipAttr>(), clip_cap, counters));
     if (sized) {
-        CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_PASS + 2], &counters->pair_total, 8, cudaMemcpyDeviceToHost, st));
+        CR_CUDA_TRY(cudaMemcpyAsync(&r->pinned[PIN_PASS], counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
         CR_CUDA_TRY(cudaStreamSynchronize(st));
-        unsigned long long pair_total = 0;
-        memcpy(&pair_total, &r->pinned[PIN_PASS + 2], 8);
+        PassCounters seen;
+        memcpy(&seen, &r->pinned[PIN_PASS], sizeof(seen));
+        if ((seen.flags & CR_PASS_OVERFLOW_CLIP) != 0u && attempt == 0) {   // more clipped triangles than the capacity: size it and run the vertex stage again
+            r->clip_cap = std::max<uint32_t>(r->clip_cap, seen.clip_total + seen.clip_total / 8 + 64);
+            if (r->order_world > 1) r->order_epoch -= 1;   // nothing of this attempt has used the epoch yet
+            return enqueue_pass(p, true, 1);
+        }
+        const unsigned long long pair_total = seen.pair_total;
         if (pair_total >= 0xFFFFFFFFull)
             return fail(CR_ERR_INVALID_ARGUMENT, "%llu (tile, primitive) pairs in one pass exceed 2^32; submit in several passes", pair_total);
         r->last_pairs = (uint32_t)pair_total;
@@ -1185,8 +1197,8 @@ static int enqueue_pass(cr_pass* p, bool sized) {
     CR_TRY(r->pair_cand_alt.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
     CR_TRY(reserve_scan_scratch(r, st, r->radix_scratch, cr_radix_scratch_words(pair_cap)));
     CR_TRY(r->tile_begin.reserve(st, (size_t)(n_tiles + 1) * 4));
-    CR_TRY(cr_raster_bin_emit(st, tg, cand_cap, pair_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), r->pair_tile.as<uint32_t>(),
-                              r->pair_cand.as<uint32_t>(), counters));
+    CR_TRY(cr_raster_bin_emit(st, tg, cand_cap, pair_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), r->clip_list.as<uint32_t>(),
+                              r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>(), counters));
     if (cand_cap == 0) {   // no candidates: bin_emit (which publishes the live pair count) did not run
         CR_CUDA_TRY(cudaMemsetAsync(&counters->n_pairs_live, 0, 4, st));
     }
@@ -1262,6 +1274,7 @@ int settle(cr_renderer* r) {
         if (pc.cand_total >= 0xFFFFFFFFull) status = fail(CR_ERR_INVALID_ARGUMENT, "%llu candidate primitives in one pass exceed 2^32; submit in several passes", pc.cand_total);
         else {
             r->cand_cap = std::max<uint32_t>(r->cand_cap, (uint32_t)pc.cand_total);
+            if (pc.flags & CR_PASS_OVERFLOW_CLIP) r->clip_cap = std::max<uint32_t>(r->clip_cap, pc.clip_total + pc.clip_total / 8 + 64);
             status = enqueue_pass(p, true);
             if (status == CR_OK) {
                 if (cudaEventSynchronize(r->ev_pass) != cudaSuccess) status = fail(CR_ERR_CUDA, "waiting for the re-submitted pass failed");

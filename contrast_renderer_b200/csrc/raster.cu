@@ -63,6 +63,8 @@ enum Pipe : uint32_t {
 #define META_FULL 2048u   // (tile-local) every pixel centre of the tile is inside the primitive
 #define META_RUN_START 8192u   // (tile-local) this primitive does not commute with its predecessor in the tile: it opens a run
 #define META_BIAS_SHIFT 16     // (tile-local) bit 16 + e: edge e is neither a top nor a left edge (bias -1)
+#define META_CLIPPED 16384u    // a fan triangle produced by frustum clipping: its corners' 1/w and attributes are in ClipAttr[v[0]]
+#define META_CLIP_PARENT 32768u   // (record of a clipped candidate, not VALID) X[0] = first fan triangle, X[1] = their number
 
 __device__ __forceinline__ const float* vertex_ptr(const DeviceBatch& b, uint32_t cat, uint32_t v) {
     switch (cat) {
@@ -165,61 +167,75 @@ __device__ __forceinline__ uint32_t find_command(const uint32_t* __restrict__ be
     return lo;
 }
 
-__device__ bool build_record(const RasterScene& sc, const RasterTarget& tg, uint32_t cand, const uint32_t* __restrict__ cmd_begin, PrimRecord& rec) {
-    rec.meta = 0;
-    const uint32_t ci = find_command(cmd_begin, sc.n_commands, cand);
-    const DeviceCommand& cmd = sc.commands[ci];
-    uint32_t rem = cand - cmd_begin[ci];
+// What a candidate number stands for: the command, the vertex category, the instance and the three vertices of its triangle.
+struct CandInfo { uint32_t ci, cat, instance, v[3]; bool odd; };
+__device__ bool candidate_info(const RasterScene& sc, uint32_t cand, const uint32_t* __restrict__ cmd_begin, CandInfo& c) {
+    c.ci = find_command(cmd_begin, sc.n_commands, cand);
+    const DeviceCommand& cmd = sc.commands[c.ci];
+    uint32_t rem = cand - cmd_begin[c.ci];
     uint32_t cat = 0, prev_end = 0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { const uint32_t e = cmd.cat_end[c]; if (rem >= e) { cat = c + 1; prev_end = e; } }
+    for (int k = 0; k < 8; ++k) { const uint32_t e = cmd.cat_end[k]; if (rem >= e) { cat = k + 1; prev_end = e; } }
     if (cat > 7) return false;
     rem -= prev_end;
     const uint32_t n = cmd.slots[cat];
     const uint32_t inst = rem / n, local = rem - inst * n;
     const DeviceBatch& b = sc.batches[cmd.batch];
-    uint32_t v[3];
-    bool odd = false;
+    c.odd = false;
     if (cat <= 2) {   // indexed triangle strips with primitive restart (src/renderer.rs:476)
         if (local + 2 >= n) return false;
         const uint32_t* idx = b.idx[cat] + cmd.ibase[cat] + local;
         const uint32_t i0 = idx[0], i1 = idx[1], i2 = idx[2];
         if (i0 == CR_RESTART || i1 == CR_RESTART || i2 == CR_RESTART) return false;
-        v[0] = cmd.vbase[cat] + (i0 >> 1); v[1] = cmd.vbase[cat] + (i1 >> 1); v[2] = cmd.vbase[cat] + (i2 >> 1);
-        odd = (i0 & 1u) != 0;
+        c.v[0] = cmd.vbase[cat] + (i0 >> 1); c.v[1] = cmd.vbase[cat] + (i1 >> 1); c.v[2] = cmd.vbase[cat] + (i2 >> 1);
+        c.odd = (i0 & 1u) != 0;
     } else if (cat <= 6) {   // triangle lists
-        v[0] = cmd.vbase[cat] + 3 * local; v[1] = v[0] + 1; v[2] = v[0] + 2;
+        c.v[0] = cmd.vbase[cat] + 3 * local; c.v[1] = c.v[0] + 1; c.v[2] = c.v[0] + 2;
     } else {   // non-indexed hull strip (src/renderer.rs:354)
-        v[0] = cmd.vbase[7] + local; v[1] = v[0] + 1; v[2] = v[0] + 2;
-        odd = (local & 1u) != 0;
+        c.v[0] = cmd.vbase[7] + local; c.v[1] = c.v[0] + 1; c.v[2] = c.v[0] + 2;
+        c.odd = (local & 1u) != 0;
     }
-    const uint32_t instance = cmd.instance_begin + inst;
-    const float* m = sc.transforms + 16 * (size_t)instance;
-    SnapVertex sv[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float* p = vertex_ptr(b, cat, v[i]);   // 20- and 24-byte vertices are only 4-byte aligned
-        sv[i] = snap_vertex(m, p[0], p[1], tg.width, tg.height);
-    }
-    if (!sv[0].ok || !sv[1].ok || !sv[2].ok) return false;
+    c.cat = cat;
+    c.instance = cmd.instance_begin + inst;
+    return true;
+}
+// Orientation, culling and the record of one snapped triangle. false: zero area or culled.
+__device__ __forceinline__ bool finish_record(const RasterTarget& tg, const DeviceCommand& cmd, const CandInfo& c, const SnapVertex* sv, PrimRecord& rec) {
     const long long area2 = (long long)(sv[1].X - sv[0].X) * (sv[2].Y - sv[0].Y) - (long long)(sv[2].X - sv[0].X) * (sv[1].Y - sv[0].Y);
     if (area2 == 0) return false;
-    const bool front = (area2 < 0) != odd;   // counter-clockwise in NDC (y up) = negative area in y-down pixels; odd strip triangles flip
+    const bool front = (area2 < 0) != c.odd;   // counter-clockwise in NDC (y up) = negative area in y-down pixels; odd strip triangles flip
     const bool swapped = area2 < 0;
     if (cmd.operation == CR_OP_COLOR) {   // cull_mode applies to the colour cover only (src/renderer.rs:743)
         if (tg.cull_mode == CR_CULL_BACK && !front) return false;
         if (tg.cull_mode == CR_CULL_FRONT && front) return false;
     }
-    const uint32_t pipe = cmd.operation == CR_OP_STENCIL ? cat : P_CLIP + (cmd.operation - CR_OP_CLIP);   // CLIP..RESTORE follow the enum order
+    const uint32_t pipe = cmd.operation == CR_OP_STENCIL ? c.cat : P_CLIP + (cmd.operation - CR_OP_CLIP);   // CLIP..RESTORE follow the enum order
     rec.X[0] = sv[0].X; rec.Y[0] = sv[0].Y;
     rec.X[1] = swapped ? sv[2].X : sv[1].X; rec.Y[1] = swapped ? sv[2].Y : sv[1].Y;
     rec.X[2] = swapped ? sv[1].X : sv[2].X; rec.Y[2] = swapped ? sv[1].Y : sv[2].Y;
-    rec.meta = pipe | (front ? META_FRONT : 0u) | (swapped ? META_SWAPPED : 0u) | META_VALID | (cat << 8);
-    rec.cmd = ci;
-    rec.instance = instance;
-    rec.v[0] = v[0]; rec.v[1] = v[1]; rec.v[2] = v[2];
+    rec.meta = pipe | (front ? META_FRONT : 0u) | (swapped ? META_SWAPPED : 0u) | META_VALID | (c.cat << 8);
+    rec.cmd = c.ci;
+    rec.instance = c.instance;
+    rec.v[0] = c.v[0]; rec.v[1] = c.v[1]; rec.v[2] = c.v[2];
     rec.ref = cmd.ref; rec.layers = cmd.layers; rec.batch = cmd.batch; rec._pad = 0;
     return true;
+}
+// 0: nothing to draw, 1: `rec` is the candidate's record, 2: a vertex cannot be snapped (eye plane / range): frustum clipping decides
+__device__ int build_record(const RasterScene& sc, const RasterTarget& tg, uint32_t cand, const uint32_t* __restrict__ cmd_begin, PrimRecord& rec) {
+    rec.meta = 0;
+    CandInfo c;
+    if (!candidate_info(sc, cand, cmd_begin, c)) return 0;
+    const DeviceCommand& cmd = sc.commands[c.ci];
+    const DeviceBatch& b = sc.batches[cmd.batch];
+    const float* m = sc.transforms + 16 * (size_t)c.instance;
+    SnapVertex sv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float* p = vertex_ptr(b, c.cat, c.v[i]);   // 20- and 24-byte vertices are only 4-byte aligned
+        sv[i] = snap_vertex(m, p[0], p[1], tg.width, tg.height);
+    }
+    if (!sv[0].ok || !sv[1].ok || !sv[2].ok) return 2;
+    return finish_record(tg, cmd, c, sv, rec) ? 1 : 0;
 }
 
 __device__ __forceinline__ void store_record(PrimRecord* dst, const PrimRecord& rec) {
@@ -368,6 +384,7 @@ __global__ void __launch_bounds__(1024) expand_scan_kernel(const CompactCommand*
         counters->covered = 0;
         counters->n_pairs_live = 0;
         counters->flags = 0;
+        counters->clip_total = 0;
     }
 }
 // More commands than that: one thread per command writes its count into cmd_cand_begin (scanned afterwards by cr_scan_exclusive).
@@ -394,7 +411,7 @@ __global__ void __launch_bounds__(256) expand_kernel(const CompactCommand* __res
 #define META_BIG 128u
 // big[0] = number of big candidates, big[1 ...] = their candidate numbers
 __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_kernel(RasterScene sc, RasterTarget tg, uint32_t cand_capacity, PrimRecord* __restrict__ records,
-                                                                   uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ big,
+                                                                   uint32_t* __restrict__ cand_tiles, uint32_t* __restrict__ big, uint32_t* __restrict__ clip_list,
                                                                    PassCounters* __restrict__ counters) {
     const uint32_t n = live_candidates(counters, cand_capacity);   // 0 when the capacity does not suffice: nothing is produced, the host re-submits
     if (blockIdx.x == 0 && threadIdx.x == 0 && n == 0 && counters->cand_total != 0ull) atomicOr(&counters->flags, CR_PASS_OVERFLOW_CANDS);
@@ -409,7 +426,9 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_ke
     uint32_t count = 0;
     if (cand < n) {
         PrimRecord rec;
-        if (build_record(sc, tg, cand, cmd_begin, rec)) {
+        const int built = build_record(sc, tg, cand, cmd_begin, rec);
+        if (built == 2) clip_list[1 + atomicAdd(clip_list, 1u)] = cand;   // clipped, counted and binned by clip_kernel
+        if (built == 1) {
             const Extent x = extent_of(rec.X, rec.Y, tg);
             if (x.empty) rec.meta = 0;
             else if ((x.tx1 - x.tx0 + 1) * (x.ty1 - x.ty0 + 1) <= BIG_TILE_BOX) count = walk_tiles_small<false>(rec.X, rec.Y, x, tg, cand, 0, nullptr, nullptr);
@@ -462,6 +481,147 @@ __global__ void __launch_bounds__(128) bin_big_kernel(RasterTarget tg, const Pri
     }
 }
 
+// ------------------------------------------------------------------------------------------ frustum clipping
+// (the rule is stated once, in words, in raster.h; oracle/raster.hpp implements the same words independently)
+struct ClipVertex { float x, y, z, w; float attr[4]; };
+__device__ __forceinline__ float clip_distance(const ClipVertex& v, int plane, float G) {
+    switch (plane) {
+        case 0: return v.w - CR_CLIP_W_MIN;
+        case 1: return G * v.w - v.x;
+        case 2: return G * v.w + v.x;
+        case 3: return G * v.w - v.y;
+        default: return G * v.w + v.y;
+    }
+}
+// The point where the edge from `in` (distance din >= 0) to `out` (distance dout < 0) meets the plane.
+__device__ __forceinline__ ClipVertex clip_intersection(const ClipVertex& in, const ClipVertex& out, float din, float dout) {
+    const float t = din / (din - dout);
+    ClipVertex r;
+    r.x = in.x + (out.x - in.x) * t; r.y = in.y + (out.y - in.y) * t; r.z = in.z + (out.z - in.z) * t; r.w = in.w + (out.w - in.w) * t;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.attr[k] = in.attr[k] + (out.attr[k] - in.attr[k]) * t;
+    return r;
+}
+// Sutherland-Hodgman over the five planes; poly holds n corners (capacity 9). Returns the number of corners left (0: nothing).
+__device__ int clip_polygon(ClipVertex* poly, int n, float G) {
+    ClipVertex tmp[9];
+    for (int plane = 0; plane < 5; ++plane) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const ClipVertex& cur = poly[i];
+            const ClipVertex& nxt = poly[i + 1 == n ? 0 : i + 1];
+            const float dc = clip_distance(cur, plane, G), dn = clip_distance(nxt, plane, G);
+            const bool cin = dc >= 0.0f, nin = dn >= 0.0f;
+            if (cin) tmp[m++] = cur;
+            if (cin != nin) tmp[m++] = cin ? clip_intersection(cur, nxt, dc, dn) : clip_intersection(nxt, cur, dn, dc);
+        }
+        n = m;
+        for (int i = 0; i < n; ++i) poly[i] = tmp[i];
+        if (n < 3) return 0;
+    }
+    return n;
+}
+// Viewport transform + snapping of a clip-space corner (same arithmetic as snap_vertex).
+__device__ __forceinline__ SnapVertex snap_clip_vertex(const ClipVertex& c, uint32_t W, uint32_t H) {
+    SnapVertex v;
+    v.ok = c.w > 0.0f;
+    const float invw = 1.0f / c.w;
+    const float fx = ((c.x * invw) * 0.5f + 0.5f) * (float)W;
+    const float fy = (0.5f - (c.y * invw) * 0.5f) * (float)H;
+    if (!(cr::fabs_f(fx) <= 2097152.0f) || !(cr::fabs_f(fy) <= 2097152.0f)) v.ok = false;
+    v.X = v.ok ? (int)cr::floor_f(fx * 256.0f + 0.5f) : 0;
+    v.Y = v.ok ? (int)cr::floor_f(fy * 256.0f + 0.5f) : 0;
+    return v;
+}
+
+// One thread per candidate of the clip list. EMIT == false: clips, writes the fan triangles' records (behind the candidates:
+// records[cand_capacity + k]) and corner attributes, counts their tiles into cand_tiles[cand] and leaves a parent record.
+// EMIT == true (after the scan): writes the fan triangles' (tile, record) pairs into the candidate's pair range.
+template <bool EMIT>
+__global__ void __launch_bounds__(128) clip_kernel(RasterScene sc, RasterTarget tg, uint32_t cand_capacity, uint32_t clip_capacity, PrimRecord* __restrict__ records,
+                                                   ClipAttr* __restrict__ clip_attrs, const uint32_t* __restrict__ clip_list, uint32_t* __restrict__ cand_tiles,
+                                                   uint32_t* __restrict__ pair_tile, uint32_t* __restrict__ pair_cand, PassCounters* __restrict__ counters,
+                                                   uint32_t pair_capacity) {
+    const uint32_t n_clip = min(clip_list[0], cand_capacity);
+    if (EMIT && (!pairs_fit(counters, pair_capacity) || (counters->flags & CR_PASS_OVERFLOW_CLIP) != 0u)) return;
+    const float G = cr_guard_band(tg.width, tg.height);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_clip; i += gridDim.x * blockDim.x) {
+        const uint32_t cand = clip_list[1 + i];
+        if (EMIT) {
+            const PrimRecord parent = load_record<false>(records + cand);
+            if (!(parent.meta & META_CLIP_PARENT)) continue;
+            uint32_t at = cand_tiles[cand];   // the exclusive scan by now
+            for (int j = 0; j < parent.X[1]; ++j) {
+                const uint32_t slot = cand_capacity + (uint32_t)parent.X[0] + (uint32_t)j;
+                const PrimRecord rec = load_record<false>(records + slot);
+                const Extent x = extent_of(rec.X, rec.Y, tg);
+                if (!x.empty) at += walk_tiles_small<true>(rec.X, rec.Y, x, tg, slot, at, pair_tile, pair_cand);
+            }
+            continue;
+        }
+        store_record(records + cand, PrimRecord{});   // whatever an earlier pass left there: not a parent unless the end of this iteration says so
+        CandInfo c;
+        if (!candidate_info(sc, cand, sc.cmd_cand_begin, c)) continue;
+        const DeviceCommand& cmd = sc.commands[c.ci];
+        const DeviceBatch& b = sc.batches[cmd.batch];
+        const float* m = sc.transforms + 16 * (size_t)c.instance;
+        const int n_attr = (int)((0x04332032u >> (4u * c.cat)) & 15u);   // attribute floats per category: 2,3,0,2,3,3,4,0
+        ClipVertex poly[9];
+        uint32_t flat_u = 0;
+        float flat_f = 0.0f;
+        for (int k = 0; k < 3; ++k) {
+            const float* p = vertex_ptr(b, c.cat, c.v[k]);
+            poly[k].x = (m[0] * p[0] + m[4] * p[1]) + m[12];
+            poly[k].y = (m[1] * p[0] + m[5] * p[1]) + m[13];
+            poly[k].z = clip_z(m, p[0], p[1]);
+            poly[k].w = clip_w(m, p[0], p[1]);
+            for (int a = 0; a < 4; ++a) poly[k].attr[a] = a < n_attr ? p[2 + a] : 0.0f;
+            if (k == 0 && c.cat <= 1) { flat_u = __float_as_uint(p[2 + n_attr]); flat_f = p[3]; }   // flat attributes: the first vertex of the ORIGINAL triangle
+        }
+        const int n = clip_polygon(poly, 3, G);
+        if (n < 3) continue;
+        PrimRecord sub[CR_CLIP_MAX_TRIANGLES];
+        ClipAttr att[CR_CLIP_MAX_TRIANGLES];
+        uint32_t n_sub = 0;
+        const bool depth_attr = tg.depth != nullptr && cmd.operation == CR_OP_COLOR;
+        for (int j = 1; j + 1 < n && n_sub < CR_CLIP_MAX_TRIANGLES; ++j) {
+            const ClipVertex* corner[3] = {&poly[0], &poly[j], &poly[j + 1]};
+            SnapVertex sv[3];
+            for (int k = 0; k < 3; ++k) sv[k] = snap_clip_vertex(*corner[k], tg.width, tg.height);
+            if (!sv[0].ok || !sv[1].ok || !sv[2].ok) continue;
+            PrimRecord rec;
+            if (!finish_record(tg, cmd, c, sv, rec)) continue;
+            rec.meta |= META_CLIPPED;
+            ClipAttr& a = att[n_sub];
+            for (int k = 0; k < 3; ++k) {
+                a.invw[k] = 1.0f / corner[k]->w;
+                for (int q = 0; q < 4; ++q) a.attr[k][q] = corner[k]->attr[q];
+                if (depth_attr) a.attr[k][0] = corner[k]->z / corner[k]->w;
+            }
+            if (c.cat <= 1) a.attr[1][3] = flat_f;
+            a.flat_u = flat_u;
+            sub[n_sub++] = rec;
+        }
+        if (n_sub == 0) continue;
+        const uint32_t base = atomicAdd(&counters->clip_total, n_sub);
+        if (base + n_sub > clip_capacity) { atomicOr(&counters->flags, CR_PASS_OVERFLOW_CLIP); continue; }
+        uint32_t tiles = 0;
+        for (uint32_t j = 0; j < n_sub; ++j) {
+            sub[j].v[0] = base + j;   // where its corners are
+            store_record(records + cand_capacity + base + j, sub[j]);
+            clip_attrs[base + j] = att[j];
+            const Extent x = extent_of(sub[j].X, sub[j].Y, tg);
+            if (!x.empty) tiles += walk_tiles_small<false>(sub[j].X, sub[j].Y, x, tg, 0u, 0u, nullptr, nullptr);
+        }
+        PrimRecord parent{};
+        parent.meta = META_CLIP_PARENT;
+        parent.X[0] = (int)base; parent.X[1] = (int)n_sub;
+        store_record(records + cand, parent);
+        cand_tiles[cand] = tiles;
+        if (tiles) atomicAdd(&counters->pair_total, (unsigned long long)tiles);
+    }
+}
+
 // ------------------------------------------------------------------------------ draw-order sharding: exchange
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -498,7 +658,7 @@ struct TilePrim {          // 128 bytes: one primitive set up for one tile (a re
     int A[3], B[3];         // per-pixel steps: +256 A per row, -256 B per column
     float invw[3];
     uint32_t meta;          // PrimRecord::meta + the tile-local flags; META_VALID cleared if nothing of it can land in this tile
-    float attr[3][4];       // attr[0][1] doubles as the flat float of stroke vertices, attr[0][3] holds their flat u32 (bits)
+    float attr[3][4];       // stroke vertices: attr[0][3] holds their flat u32 (bits), attr[1][3] their flat float
     uint32_t bbox;          // x0 | y0 << 8 | x1 << 16 | y1 << 24 in tile pixels
     uint32_t ref_batch;     // stencil reference (8 bits) | batch << 8
     uint32_t instance, layers;
@@ -563,7 +723,7 @@ __device__ __forceinline__ bool fragment_keep(const RasterScene& sc, const TileP
             const uint32_t flat_u = prim_flat_u(ps);
             const Descriptor& d = reinterpret_cast<const Descriptor*>(sc.batches[prim_batch(ps)].stroke)[flat_u & 65535u];
             if ((d.count_dashed_join & 4u) != 0u) return stroke_dashed(d, a[0], a[1]);
-            if ((flat_u & 65536u) != 0u) return cap_test(a[0], a[1] - ps.attr[0][1], d.caps >> 4u);
+            if ((flat_u & 65536u) != 0u) return cap_test(a[0], a[1] - ps.attr[1][3], d.caps >> 4u);
             if (a[1] < 0.0f) return cap_test(a[0], -a[1], d.caps);
             return true;
         }
@@ -699,11 +859,26 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
     ps.ref_batch = (rec.ref & 255u) | (rec.batch << 8);
     ps.instance = rec.instance;
     ps.layers = rec.layers;
-    if (pipe <= P_FILL_RC && pipe != P_FILL_SOLID) {   // pipelines with a fragment predicate need the vertex attributes
+    if (rec.meta & META_CLIPPED) {   // a fan triangle of frustum clipping: its corners carry interpolated 1 / w and attributes (and z / w)
+        const ClipAttr* ca = sc.clip_attrs + rec.v[0];
+        const bool swapped = (rec.meta & META_SWAPPED) != 0;
+        const float4* q = reinterpret_cast<const float4*>(ca);   // invw[3] attr[3][4] flat_u = 16 words
+        const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+        const float w16[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int src = i == 0 ? 0 : (swapped ? 3 - i : i);
+            ps.invw[i] = w16[src];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) ps.attr[i][a] = w16[3 + 4 * src + a];
+        }
+        if (cat <= 1) { ps.attr[0][3] = w16[15]; ps.attr[1][3] = w16[3 + 4 * 1 + 3]; }   // flat u32 (bits) and flat float, where no stroke predicate interpolates
+    } else if (pipe <= P_FILL_RC && pipe != P_FILL_SOLID) {   // pipelines with a fragment predicate need the vertex attributes
         const DeviceBatch& b = sc.batches[rec.batch];
         const float* m = sc.transforms + 16 * (size_t)rec.instance;
         const int n_attr = (int)((0x04332032u >> (4u * cat)) & 15u);   // attribute floats per category: 2,3,0,2,3,3,4,0
         const bool swapped = (rec.meta & META_SWAPPED) != 0;
+        float flat_f = 0.0f;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int src = i == 0 ? 0 : (swapped ? 3 - i : i);   // stored vertex order is (0, 2, 1) when swapped
@@ -711,12 +886,13 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
             ps.invw[i] = 1.0f / clip_w(m, p[0], p[1]);
 #pragma unroll
             for (int a = 0; a < 4; ++a) ps.attr[i][a] = a < n_attr ? p[2 + a] : 0.0f;
-            // flat attributes come from the first (provoking) vertex: the flat float of a stroke vertex IS attr[0][1]; its flat
-            // u32 goes into attr[0][3], which no stroke predicate interpolates (2 and 3 attributes)
-            if (i == 0 && cat <= 1) ps.attr[0][3] = p[2 + n_attr];
+            // flat attributes come from the first (provoking) vertex: the stroke vertices' flat u32 goes into attr[0][3], their
+            // flat float (the first vertex's second attribute) into attr[1][3] — no stroke predicate interpolates a fourth attribute
+            if (i == 0 && cat <= 1) { ps.attr[0][3] = p[2 + n_attr]; flat_f = p[3]; }
         }
+        if (cat <= 1) ps.attr[1][3] = flat_f;
     }
-    if (DEPTH && pipe == P_COLOR) {   // the depth test of the colour cover needs z / w of the three hull vertices (src/shaders.wgsl:72)
+    if (DEPTH && pipe == P_COLOR && !(rec.meta & META_CLIPPED)) {   // the depth test of the colour cover needs z / w of the three hull vertices (src/shaders.wgsl:72)
         const DeviceBatch& b = sc.batches[rec.batch];
         const float* m = sc.transforms + 16 * (size_t)rec.instance;
         const bool swapped = (rec.meta & META_SWAPPED) != 0;
@@ -1241,23 +1417,30 @@ int cr_raster_expand(cudaStream_t stream, const CompactCommand* compact, uint32_
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }
+#define CLIP_GRID 148
 int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t cand_capacity, PrimRecord* records, uint32_t* cand_tiles,
-                    uint32_t* big_list, PassCounters* counters) {
+                    uint32_t* big_list, uint32_t* clip_list, ClipAttr* clip_attrs, uint32_t clip_capacity, PassCounters* counters) {
     if (cand_capacity == 0) return CR_OK;
     CR_CUDA_TRY(cudaMemsetAsync(big_list, 0, 4, stream));
-    prim_setup_kernel<<<(cand_capacity + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(scene, target, cand_capacity, records, cand_tiles, big_list, counters);
+    CR_CUDA_TRY(cudaMemsetAsync(clip_list, 0, 4, stream));
+    prim_setup_kernel<<<(cand_capacity + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(scene, target, cand_capacity, records, cand_tiles, big_list, clip_list,
+                                                                                                        counters);
     bin_big_kernel<false><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, cand_tiles, nullptr, nullptr, counters, 0u);
-    g_cr_kernel_launches += 2;
+    clip_kernel<false><<<CLIP_GRID, 128, 0, stream>>>(scene, target, cand_capacity, clip_capacity, records, clip_attrs, clip_list, cand_tiles, nullptr, nullptr, counters, 0u);
+    g_cr_kernel_launches += 3;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }
 int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t cand_capacity, uint32_t pair_capacity, const PrimRecord* records,
-                       const uint32_t* cand_pair_begin, const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand, PassCounters* counters) {
+                       const uint32_t* cand_pair_begin, const uint32_t* big_list, const uint32_t* clip_list, uint32_t* pair_tile, uint32_t* pair_cand,
+                       PassCounters* counters) {
     if (cand_capacity == 0) return CR_OK;
     bin_emit_kernel<<<(cand_capacity + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(target, cand_capacity, pair_capacity, records, cand_pair_begin, pair_tile,
                                                                                                       pair_cand, counters);
     bin_big_kernel<true><<<BIG_GRID, 128, 0, stream>>>(target, records, big_list, const_cast<uint32_t*>(cand_pair_begin), pair_tile, pair_cand, counters, pair_capacity);
-    g_cr_kernel_launches += 2;
+    clip_kernel<true><<<CLIP_GRID, 128, 0, stream>>>(RasterScene{}, target, cand_capacity, 0u, const_cast<PrimRecord*>(records), nullptr, clip_list, const_cast<uint32_t*>(cand_pair_begin),
+                                                     pair_tile, pair_cand, counters, pair_capacity);
+    g_cr_kernel_launches += 3;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
 }

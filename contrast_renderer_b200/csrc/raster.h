@@ -36,13 +36,40 @@ static_assert(sizeof(CompactCommand) == 32, "CompactCommand layout");
 // it do nothing, the tile kernel does not run (the attachments stay untouched) and the host re-submits with larger buffers.
 #define CR_PASS_OVERFLOW_CANDS 1u
 #define CR_PASS_OVERFLOW_PAIRS 2u
+#define CR_PASS_OVERFLOW_CLIP 4u
 struct PassCounters {
     unsigned long long cand_total;    // candidates of the pass, 64-bit (the numbering itself is 32-bit)
     unsigned long long pair_total;    // (tile, candidate) pairs, 64-bit
     unsigned long long covered;       // samples that passed the stencil test of a colour cover
     uint32_t n_pairs_live;            // pair_total if it fits the pair capacity and 32 bits, else 0 (published by the bin-emit kernel)
     uint32_t flags;                   // CR_PASS_OVERFLOW_*
+    uint32_t clip_total;              // triangles produced by frustum clipping (they live behind the candidates in the record array)
+    uint32_t _pad;
 };
+static_assert(sizeof(PassCounters) == 40, "PassCounters is read back into 10 pinned words");
+
+// Frustum clipping (WebGPU clips primitives against the view volume; the reference's demo places instances in perspective,
+// examples/showcase/main.rs:163-201). A triangle with a vertex on or behind the eye plane (w <= 0) or further than 2^21 px from
+// the origin cannot be snapped; it is clipped in clip space (Sutherland-Hodgman, planes in this order: w >= CR_CLIP_W_MIN,
+// G w - x >= 0, G w + x >= 0, G w - y >= 0, G w + y >= 0 with the guard band G = cr_guard_band(width, height); an edge's
+// intersection point is always interpolated from its INSIDE end, so that two triangles sharing the edge get the same point),
+// the polygon is cut into a fan and every fan triangle takes the place of the original in the draw order. Depth (z) is not
+// clipped (as with WebGPU's unclipped-depth control). Attributes, w and z of the new vertices are interpolated linearly in
+// clip space; flat attributes stay those of the original first vertex.
+#define CR_CLIP_W_MIN 1.0e-6f
+#define CR_CLIP_MAX_TRIANGLES 6   // a triangle cut by five planes has at most 8 corners
+__host__ __device__ inline float cr_guard_band(uint32_t width, uint32_t height) {
+    const uint32_t m = width > height ? width : height;
+    const uint32_t g = 1048576u / (m ? m : 1u);
+    return (float)(g ? g : 1u);
+}
+// Per clipped triangle: what its three corners carry instead of vertex-array attributes (in fan order, before orientation).
+struct ClipAttr {
+    float invw[3];
+    float attr[3][4];   // interpolated attributes (strokes: [1][3] = flat float, see TilePrim); colour covers with a depth test: [i][0] = z / w
+    uint32_t flat_u;
+};
+static_assert(sizeof(ClipAttr) == 64, "ClipAttr layout");
 
 // The expanded form of a command (built on the device by cr_raster_expand from the batch's slice tables), so that the
 // vertex stage needs no further table walks. A "candidate" is one
@@ -126,6 +153,7 @@ struct RasterScene {
     uint32_t n_commands;
     const float* transforms;          // [n_instances][16]
     const float* colors;              // [n_instances][4] or null
+    const ClipAttr* clip_attrs;       // [clip capacity] corners of the triangles frustum clipping produced (PrimRecord::v[0] indexes it)
 };
 
 // Commands -> DeviceCommands + the exclusive scan of their candidate counts (cmd_cand_begin, n_commands + 1 words; one launch
@@ -136,11 +164,14 @@ int cr_raster_expand(cudaStream_t stream, const CompactCommand* compact, uint32_
 // Vertex stage + tile counting over the candidate CAPACITY: fills records and cand_tiles[0..cand_capacity) (zero beyond the
 // live count). big_list: cand_capacity + 1 words of scratch (candidates whose tile box is large are listed there and binned
 // one warp each). counters->pair_total receives the 64-bit number of (tile, candidate) pairs: the placing scan is 32-bit.
+// clip_list: cand_capacity + 1 words of scratch (candidates that need frustum clipping); their fan triangles go to
+// records[cand_capacity ...) / clip_attrs[0 ... clip_capacity).
 int cr_raster_setup(cudaStream_t stream, const RasterScene& scene, const RasterTarget& target, uint32_t cand_capacity, PrimRecord* records, uint32_t* cand_tiles,
-                    uint32_t* big_list, PassCounters* counters);
+                    uint32_t* big_list, uint32_t* clip_list, ClipAttr* clip_attrs, uint32_t clip_capacity, PassCounters* counters);
 // (tile, candidate) pairs of every valid record, at cand_pair_begin[candidate]; publishes counters->n_pairs_live / flags.
 int cr_raster_bin_emit(cudaStream_t stream, const RasterTarget& target, uint32_t cand_capacity, uint32_t pair_capacity, const PrimRecord* records,
-                       const uint32_t* cand_pair_begin, const uint32_t* big_list, uint32_t* pair_tile, uint32_t* pair_cand, PassCounters* counters);
+                       const uint32_t* cand_pair_begin, const uint32_t* big_list, const uint32_t* clip_list, uint32_t* pair_tile, uint32_t* pair_cand,
+                       PassCounters* counters);
 // Draw-order sharding: publishes which tiles this rank's slice touches (bitmap from tile_begin) to every rank, then the ready flag.
 int cr_raster_publish_touched_tiles(cudaStream_t stream, const RasterTarget& target, const uint32_t* tile_begin);
 // counters may be null (clear-only launch on an empty tile table).

@@ -4,8 +4,14 @@
 // src/shaders.wgsl. One sample at a time, one triangle at a time, in exact draw order.
 //
 // Rasterisation contract (shared, in words, with csrc/raster.cu — the code is written twice):
-//  * clip = col0*x + col1*y + col3 of the instance mat4 (src/shaders.wgsl:20-27,72); a primitive with any w <= 0 or a vertex
-//    further than 2^21 px from the origin is discarded (no frustum clipping).
+//  * clip = col0*x + col1*y + col3 of the instance mat4 (src/shaders.wgsl:20-27,72). A triangle with a vertex at w <= 0 or
+//    further than 2^21 px from the origin is CLIPPED in clip space (WebGPU clips primitives to the view volume): Sutherland-
+//    Hodgman against, in this order, w >= 1e-6, G w - x >= 0, G w + x >= 0, G w - y >= 0, G w + y >= 0 with the guard band
+//    G = float(2^20 / max(W, H)) (integer division, at least 1); the point where an edge meets a plane is interpolated from
+//    the edge's INSIDE end (in + (out - in) * (d_in / (d_in - d_out)), every component and attribute alike), so triangles
+//    sharing the edge agree on it; the polygon is cut into the fan (p0, pi, pi+1), each fan triangle is snapped and
+//    rasterised like any other, in the original's place; flat attributes stay those of the original first vertex. Depth is
+//    not clipped (unclipped-depth semantics).
 //  * depth (colour cover only, src/renderer.rs:743-745): z / w of each vertex, interpolated linearly in screen space with
 //    the unbiased edge values as weights, f32 attachment, viewport depth range [0, 1]; order stencil test -> depth test;
 //    stencil fail -> fail_op (Zero), depth fail -> depth_fail_op (Keep, src/renderer.rs:442), both pass -> pass_op (Zero),
@@ -64,6 +70,7 @@ struct RVertex {
     float attr[4];
     uint32_t flat_u;
     bool ok;
+    float clip[4];   // clip-space x, y, z, w (what frustum clipping works on)
 };
 
 struct DrawState {
@@ -86,10 +93,12 @@ inline RVertex transform_vertex(const float* m, const float pos[2], uint32_t W, 
     const float cx = (m[0] * x + m[4] * y) + m[12];
     const float cy = (m[1] * x + m[5] * y) + m[13];
     const float cw = (m[3] * x + m[7] * y) + m[15];
+    const float cz = (m[2] * x + m[6] * y) + m[14];
+    v.clip[0] = cx; v.clip[1] = cy; v.clip[2] = cz; v.clip[3] = cw;
     v.ok = cw > 0.0f;
     if (!v.ok) return v;
     v.invw = 1.0f / cw;
-    v.z = ((m[2] * x + m[6] * y) + m[14]) / cw;
+    v.z = cz / cw;
     const float fx = ((cx * v.invw) * 0.5f + 0.5f) * (float)W;
     const float fy = (0.5f - (cy * v.invw) * 0.5f) * (float)H;
     if (!(cr::fabs_f(fx) <= 2097152.0f) || !(cr::fabs_f(fy) <= 2097152.0f)) { v.ok = false; return v; }
@@ -252,10 +261,8 @@ inline void apply_sample(PipelineKind pipe, const DrawState& st, bool front, siz
 
 inline bool is_top_left(int64_t dx, int64_t dy) { return (dy == 0 && dx > 0) || dy < 0; }
 
-inline void rasterize_triangle(PipelineKind pipe, const DrawState& st, RVertex v0, RVertex v1, RVertex v2, bool odd) {
+inline void rasterize_snapped(PipelineKind pipe, const DrawState& st, RVertex v0, RVertex v1, RVertex v2, bool odd, uint32_t flat_u, float flat_f) {
     if (!v0.ok || !v1.ok || !v2.ok) return;
-    const uint32_t flat_u = v0.flat_u;
-    const float flat_f = v0.attr[1];
     int64_t area2 = (v1.X - v0.X) * (v2.Y - v0.Y) - (v2.X - v0.X) * (v1.Y - v0.Y);
     if (area2 == 0) return;
     const bool front = (area2 < 0) != odd;
@@ -306,6 +313,71 @@ inline void rasterize_triangle(PipelineKind pipe, const DrawState& st, RVertex v
                 }
                 apply_sample(pipe, st, front, sample_index, z);
             }
+}
+
+// ---- frustum clipping (see the contract at the top of this file)
+struct ClipV { float x, y, z, w; float attr[4]; };
+inline float clip_distance(const ClipV& v, int plane, float G) {
+    switch (plane) {
+        case 0: return v.w - 1.0e-6f;
+        case 1: return G * v.w - v.x;
+        case 2: return G * v.w + v.x;
+        case 3: return G * v.w - v.y;
+        default: return G * v.w + v.y;
+    }
+}
+inline ClipV clip_meet(const ClipV& in, const ClipV& out, float din, float dout) {
+    const float t = din / (din - dout);
+    ClipV r;
+    r.x = in.x + (out.x - in.x) * t;
+    r.y = in.y + (out.y - in.y) * t;
+    r.z = in.z + (out.z - in.z) * t;
+    r.w = in.w + (out.w - in.w) * t;
+    for (int k = 0; k < 4; ++k) r.attr[k] = in.attr[k] + (out.attr[k] - in.attr[k]) * t;
+    return r;
+}
+inline RVertex snap_clipped(const ClipV& c, uint32_t W, uint32_t H) {
+    RVertex v{};
+    v.clip[0] = c.x; v.clip[1] = c.y; v.clip[2] = c.z; v.clip[3] = c.w;
+    for (int k = 0; k < 4; ++k) v.attr[k] = c.attr[k];
+    v.ok = c.w > 0.0f;
+    if (!v.ok) return v;
+    v.invw = 1.0f / c.w;
+    v.z = c.z / c.w;
+    const float fx = ((c.x * v.invw) * 0.5f + 0.5f) * (float)W;
+    const float fy = (0.5f - (c.y * v.invw) * 0.5f) * (float)H;
+    if (!(cr::fabs_f(fx) <= 2097152.0f) || !(cr::fabs_f(fy) <= 2097152.0f)) { v.ok = false; return v; }
+    v.X = (int64_t)cr::floor_f(fx * 256.0f + 0.5f);
+    v.Y = (int64_t)cr::floor_f(fy * 256.0f + 0.5f);
+    return v;
+}
+inline void rasterize_triangle(PipelineKind pipe, const DrawState& st, const RVertex& v0, const RVertex& v1, const RVertex& v2, bool odd) {
+    const uint32_t flat_u = v0.flat_u;
+    const float flat_f = v0.attr[1];
+    if (v0.ok && v1.ok && v2.ok) { rasterize_snapped(pipe, st, v0, v1, v2, odd, flat_u, flat_f); return; }
+    const uint32_t W = st.fb->width, H = st.fb->height;
+    const uint32_t g = 1048576u / std::max(W, H);
+    const float G = (float)(g ? g : 1u);
+    std::vector<ClipV> poly, next;
+    for (const RVertex* v : {&v0, &v1, &v2}) {
+        ClipV c{v->clip[0], v->clip[1], v->clip[2], v->clip[3], {v->attr[0], v->attr[1], v->attr[2], v->attr[3]}};
+        poly.push_back(c);
+    }
+    for (int plane = 0; plane < 5; ++plane) {
+        next.clear();
+        for (size_t i = 0; i < poly.size(); ++i) {
+            const ClipV& cur = poly[i];
+            const ClipV& nxt = poly[(i + 1) % poly.size()];
+            const float dc = clip_distance(cur, plane, G), dn = clip_distance(nxt, plane, G);
+            const bool cin = dc >= 0.0f, nin = dn >= 0.0f;
+            if (cin) next.push_back(cur);
+            if (cin != nin) next.push_back(cin ? clip_meet(cur, nxt, dc, dn) : clip_meet(nxt, cur, dn, dc));
+        }
+        poly.swap(next);
+        if (poly.size() < 3) return;
+    }
+    for (size_t j = 1; j + 1 < poly.size(); ++j)
+        rasterize_snapped(pipe, st, snap_clipped(poly[0], W, H), snap_clipped(poly[j], W, H), snap_clipped(poly[j + 1], W, H), odd, flat_u, flat_f);
 }
 
 struct VertexFormat { size_t stride; int n_attr; bool has_u; };

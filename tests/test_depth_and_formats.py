@@ -187,3 +187,98 @@ def test_unorm8_config4_matches_oracle(cr, oracle, fmt, samples):
     assert np.array_equal(rnd.read_color().view(np.uint32), again.view(np.uint32))
     batch.close()
     rnd.close()
+
+
+# ------------------------------------------------------------------------------------------------ frustum clipping
+def eye_crossing_transforms(base_columns, n=5):
+    """Instance matrices whose projective row makes w change sign inside the shapes (tilted planes that pass the eye), a steep
+    one that throws vertices far outside the 2^21-pixel range, and an ordinary one."""
+    base = np.asarray(base_columns, np.float64).reshape(4, 4).T
+    mats = []
+    for k in range(n):
+        persp = np.eye(4)
+        persp[3, 0] = (-0.9 - 0.35 * k) * (1 if k % 2 == 0 else -1)     # w = 1 + a x_ndc + b y_ndc: zero inside the frame
+        persp[3, 1] = 0.25 * k - 0.4
+        persp[2, :] = 0.5 * persp[3, :] + np.array([0.05, -0.03, 0.0, 0.0])    # z / w = 0.5 + a term that varies over the shape (depth test)
+        mats.append((persp @ base).T.reshape(16))
+    far = np.eye(4)
+    far[3, 0], far[3, 3] = 1.0, 1.0e-6 + 1.0                                 # nearly singular: some vertices land ~1e6 NDC units away
+    far[3, 0] = -0.999999
+    mats.append((far @ base).T.reshape(16))
+    mats.append(base.T.reshape(16))
+    return np.asarray(mats, np.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("samples", [1, 4], ids=["1x", "msaa4"])
+def test_frustum_clipped_instances_match_oracle(cr, oracle, samples):
+    """Triangles with corners behind the eye plane or out of snapping range are clipped (not dropped), identically on both sides:
+    fills of every segment kind (interpolated implicit-curve attributes at the new corners), covers with a depth test (z / w at the
+    new corners), culling decided per fan triangle, 1x and 4x."""
+    from contrast_renderer_b200 import scenes
+    scene = scenes.mixed_fills(10, extent=(320, 240), size=(60.0, 160.0), rational=True, paths_per_shape=5, seed=21)
+    transforms = eye_crossing_transforms(scene.transforms()[0])
+    colors = np.random.default_rng(5).uniform(0.2, 1.0, (len(transforms), 4)).astype(np.float32)
+    colors[:, 3] = [1.0, 0.6, 1.0, 0.8, 1.0, 0.7, 1.0][:len(transforms)]
+    cmds = []
+    for s in range(scene.n_shapes):
+        for i in range(len(transforms)):
+            cmds += [(s, i, i + 1, 0), (s, i, i + 1, 3)]
+    cull = 1   # CullMode.Front: these matrices mirror the shapes, their hulls face backwards
+    for cfg in (Configuration(msaa_sample_count=samples),
+                Configuration(msaa_sample_count=samples, depth_compare=CompareFunction.LessEqual, depth_write_enabled=True, cull_mode=cull)):
+        rnd = cr.Renderer(cfg)
+        rnd.resize_internal_buffers(scene.width, scene.height)
+        batch = cr.ShapeBatch(rnd, scene.dynamic_stroke_options, scene.paths, scene.shape_path_begin)
+        rp = rnd.begin_render_pass()
+        rp.set_instances(transforms, colors)
+        rp.render_batch(batch, np.asarray(cmds, np.uint32))
+        rp.submit()
+        color, stencil, stats = rnd.read_color(), rnd.read_stencil(), rnd.stats()
+        refs = [oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
+                for i in range(scene.n_shapes)]
+        depth = np.ones((scene.height, scene.width, samples), np.float32) if cfg.has_depth else None
+        ocmds = [(c[0], c[1], c[2], c[3], 0, 0, 0) for c in cmds]
+        ref_color, ref_stencil, _, ref_covered = oracle.render(cfg.to_c(), scene.width, scene.height, refs, ocmds, transforms, colors, depth=depth, threads=4)
+        assert ref_covered > 20000, "the clipped instances must actually draw (and survive culling / the depth test)"
+        assert np.array_equal(stencil, ref_stencil), f"stencil differs at {np.argwhere(stencil != ref_stencil)[:5]}"
+        assert np.array_equal(color.view(np.uint32), ref_color.view(np.uint32))
+        assert int(stats.covered_samples) == ref_covered
+        if cfg.has_depth:
+            assert np.array_equal(rnd.read_depth().view(np.uint32), depth.view(np.uint32))
+        batch.close()
+        rnd.close()
+
+
+@pytest.mark.gpu
+def test_frustum_clipped_strokes_and_capacity_growth(cr, oracle):
+    """Stroke triangles keep their FLAT attributes (path index / cap flags of the original first vertex) through clipping, dashes and
+    caps included; the scene clips far more triangles than the renderer's initial clip capacity (1024), so the pass is re-sized
+    and re-submitted, twice in a row with the same result (the second pass runs optimistically with the grown capacity)."""
+    from contrast_renderer_b200 import scenes
+    scene = scenes.dashed_rational_strokes(160, paths_per_shape=20, extent=(320, 240))
+    transforms = eye_crossing_transforms(scene.transforms()[0], n=3)
+    colors = np.random.default_rng(6).uniform(0.2, 1.0, (len(transforms), 4)).astype(np.float32)
+    cmds = []
+    for s in range(scene.n_shapes):
+        cmds += [(s, 0, len(transforms), 0), (s, 0, len(transforms), 3)]
+    cfg = Configuration()
+    rnd = cr.Renderer(cfg)
+    rnd.resize_internal_buffers(scene.width, scene.height)
+    batch = cr.ShapeBatch(rnd, scene.dynamic_stroke_options, scene.paths, scene.shape_path_begin)
+    refs = [oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
+            for i in range(scene.n_shapes)]
+    ocmds = [(c[0], c[1], c[2], c[3], 0, 0, 0) for c in cmds]
+    ref_color, ref_stencil, _, ref_covered = oracle.render(cfg.to_c(), scene.width, scene.height, refs, ocmds, transforms, colors, threads=4)
+    assert ref_covered > 5000
+    for _ in range(2):
+        rp = rnd.begin_render_pass()
+        rp.set_instances(transforms, colors)
+        rp.render_batch(batch, np.asarray(cmds, np.uint32))
+        rp.submit()
+        color, stencil = rnd.read_color(), rnd.read_stencil()
+        assert np.array_equal(stencil, ref_stencil), f"stencil differs at {np.argwhere(stencil != ref_stencil)[:5]}"
+        assert np.array_equal(color.view(np.uint32), ref_color.view(np.uint32))
+        assert int(rnd.stats().covered_samples) == ref_covered
+    batch.close()
+    rnd.close()

@@ -506,6 +506,49 @@ def test_perspective_correct_attribute_interpolation(oracle):
     assert int((((stencil[..., 0] != 0) != inside) & far).sum()) <= 2
 
 
+def test_frustum_clipping_keeps_exactly_the_part_in_front_of_the_eye(oracle):
+    """A projective instance matrix whose w changes sign INSIDE the shape (the plane of the shape crosses the eye plane, as with
+    the demo's perspective camera, examples/showcase/main.rs:163-201): WebGPU clips the primitives, so exactly the points of the
+    shape with w > 0 are drawn. Every pixel centre is mapped back to model space; it must be covered iff that point lies in
+    the shape AND has w > 0 (a back-projected point with w < 0 is the 'ghost' image behind the eye and must stay empty)."""
+    w, h = 240, 200
+    path = Path([1.0, 1.0])
+    path.push_integral_quadratic_curve([[4.0, -1.5], [7.0, 1.5]])
+    path.push_line([9.0, 3.0])
+    path.push_rational_quadratic_curve(RationalQuadraticCurveSegment(1.8, [[8.5, 5.5], [2.0, 6.0]]))
+    soa = PathSoA.from_paths([path])
+    shape = oracle.shape_from_paths([], soa)
+    m = np.zeros(16, np.float32)
+    # w = 1 - 0.16 x + 0.01 y is zero near x = 6.4 (the shape spans x in [1, 9]); clip x = -0.0965 (x - 5.35) puts the visible
+    # part on the left of the frame (running off to -infinity as w -> 0+) and the ghost of the part behind the eye on the right
+    m[0], m[5], m[10], m[12], m[13], m[15] = -0.0965, -0.05, 1.0, 0.516, 0.17, 1.0
+    m[3], m[7] = -0.16, 0.01
+    m[4], m[1] = 0.004, -0.003
+    _, stencil, _, _ = oracle.render(Configuration().to_c(), w, h, [shape], [(0, 0, 1, 0, 0, 0, 0)], m.reshape(1, 16), None)
+    ys, xs = np.mgrid[0:h, 0:w]
+    nx, ny = 2.0 * (xs + 0.5) / w - 1.0, 1.0 - 2.0 * (ys + 0.5) / h
+    md = m.astype(np.float64)
+    a11, a12, b1 = md[0] - nx * md[3], md[4] - nx * md[7], nx * md[15] - md[12]
+    a21, a22, b2 = md[1] - ny * md[3], md[5] - ny * md[7], ny * md[15] - md[13]
+    det = a11 * a22 - a12 * a21
+    mx, my = (b1 * a22 - a12 * b2) / det, (a11 * b2 - b1 * a21) / det
+    wc = md[3] * mx + md[7] * my + md[15]
+    poly = flatten(soa, 0, samples=400)
+    total = np.zeros((h, w))
+    for (ax, ay), (bx, by) in zip(poly, np.roll(poly, -1, axis=0)):
+        ux, uy, vx, vy = ax - mx, ay - my, bx - mx, by - my
+        total += np.arctan2(ux * vy - uy * vx, ux * vx + uy * vy)
+    inside = (np.rint(total / (2 * np.pi)).astype(np.int64) != 0) & (wc > 0)
+    dist = np.min(np.hypot(poly[:, 0][None, None] - mx[..., None], poly[:, 1][None, None] - my[..., None]), -1)
+    px_model = np.abs(wc) / 0.05 * 2.0 / h                                     # ~ one pixel in model units where the pixel looks at
+    far = (dist > 3.0 * px_model) & (np.abs(wc) > 1e-3)
+    covered = stencil[..., 0] != 0
+    ghost = (np.rint(total / (2 * np.pi)).astype(np.int64) != 0) & (wc < 0) & far
+    assert inside.sum() > 3000 and ghost.sum() > 200, "the scene must show both a visible part and a ghost region"
+    assert int((covered & ghost).sum()) == 0, "nothing behind the eye may be drawn"
+    assert int(((covered != inside) & far).sum()) <= 2
+
+
 def test_andrew_hull_invariants(oracle):
     """§4 invariant 7: convex, clockwise (y up), no three collinear points within 1e-4, and it contains every input point."""
     rng = np.random.default_rng(2)
