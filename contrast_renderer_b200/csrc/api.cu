@@ -152,6 +152,7 @@ struct cr_renderer {
     bool cmd_arena_busy = false;
     // Capacities the next pass is sized with (candidates, (tile, candidate) pairs): what the last pass needed plus slack. 0: unknown.
     uint32_t cand_cap = 0, pair_cap = 0, last_cands = 0, last_pairs = 0;
+    uint32_t radix_layout_cap = 0xFFFFFFFFu;   // pair capacity the radix scratch is laid out (and zeroed) for
     uint32_t clip_cap = 1024;         // triangles frustum clipping may produce in one pass (grows when a pass needs more)
     cr_pass* inflight = nullptr;      // the last submitted pass until its device-side sizes have been checked (settle)
     int deferred_status = CR_OK;      // an error found while settling, reported by the next entry point that can fail
@@ -1196,6 +1197,13 @@ static int enqueue_pass(cr_pass* p, bool sized, int attempt = 0) {
     CR_TRY(r->pair_tile_alt.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
     CR_TRY(r->pair_cand_alt.reserve(st, (size_t)std::max<uint32_t>(pair_cap, 1u) * 4));
     CR_TRY(reserve_scan_scratch(r, st, r->radix_scratch, cr_radix_scratch_words(pair_cap)));
+    if (r->radix_layout_cap != pair_cap) {
+        // The sort keeps its histograms in front of the scan's tickets and status words, at an offset that depends on the pair
+        // capacity: with another capacity the tickets would lie where histogram values were (a scan that finds a non-zero ticket
+        // never ends). Zero the scratch whenever the layout moves.
+        CR_TRY(cr_scan_prepare(st, r->radix_scratch.as<uint32_t>(), r->radix_scratch.cap / 4));
+        r->radix_layout_cap = pair_cap;
+    }
     CR_TRY(r->tile_begin.reserve(st, (size_t)(n_tiles + 1) * 4));
     CR_TRY(cr_raster_bin_emit(st, tg, cand_cap, pair_cap, r->records.as<PrimRecord>(), r->cand_tiles.as<uint32_t>(), r->big_list.as<uint32_t>(), r->clip_list.as<uint32_t>(),
                               r->pair_tile.as<uint32_t>(), r->pair_cand.as<uint32_t>(), counters));

@@ -191,3 +191,28 @@ def test_frame_pipelining_renders_the_same_frames(cr, oracle):
     assert np.array_equal(rnd.read_stencil(), ref_stencil) and np.array_equal(rnd.read_color().view(np.uint32), ref_color.view(np.uint32))
     batch.close()
     rnd.close()
+
+
+@pytest.mark.timeout(120)
+def test_a_smaller_pass_after_resize_reuses_the_sort_scratch(cr, oracle):
+    """One renderer, a large pass, then resize_internal_buffers and a much smaller pass (what __graft_entry__.smoke() does): the
+    pair capacity SHRINKS, so the radix sort lays its histograms and the scan's ticket counters out differently inside the same
+    scratch allocation. (A ticket counter found where histogram values used to be made the look-back scan wait for ever.)"""
+    rnd = cr.Renderer()
+    for scene in (scenes.mixed_fills(64, extent=(256, 192), rational=True), scenes.closed_cubic_strokes(24, extent=(256, 192)),
+                  scenes.mixed_fills(300, extent=(512, 384), rational=True, seed=9), scenes.closed_cubic_strokes(6, extent=(128, 96))):
+        rnd.resize_internal_buffers(scene.width, scene.height)
+        batch = cr.ShapeBatch(rnd, scene.dynamic_stroke_options, scene.paths, scene.shape_path_begin)
+        cmds = scenes.stencil_cover_commands(scene.n_shapes)
+        rp = rnd.begin_render_pass()
+        rp.set_instances(scene.transforms(), scene.colors)
+        rp.render_batch(batch, cmds)
+        rp.submit()
+        color, stencil = rnd.read_color(), rnd.read_stencil()
+        refs = [oracle.shape_from_paths(scene.dynamic_stroke_options, scene.paths, int(scene.shape_path_begin[i]), int(scene.shape_path_begin[i + 1]))
+                for i in range(scene.n_shapes)]
+        ocmds = [(int(c[0]), int(c[1]), int(c[2]), int(c[3]), 0, 0, 0) for c in cmds]
+        ref_color, ref_stencil, _, _ = oracle.render(rnd.config.to_c(), scene.width, scene.height, refs, ocmds, scene.transforms(), scene.colors, threads=4)
+        assert np.array_equal(stencil, ref_stencil) and np.array_equal(color.view(np.uint32), ref_color.view(np.uint32))
+        batch.close()
+    rnd.close()

@@ -13,9 +13,9 @@ import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEEP = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
-    "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size",
-    "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__average_warp_latency_issue_stalled_barrier.ratio",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum", "sm__inst_executed.sum.per_cycle_elapsed", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
@@ -78,7 +78,7 @@ def main():
             w.writeheader()
             w.writerows(summary)
     for line in summary:
-        print(f"{line['kernel']:28s} {line['duration_us'] or 0:9.1f} us  dram {((line['dram_bytes'] or 0) / 1e6):9.2f} MB  issue {line.get('smsp__issue_active.avg.pct')}")
+        print(f"{line['kernel']:28s} {line['duration_us'] or 0:9.1f} us  dram {((line['dram_bytes'] or 0) / 1e6):9.2f} MB  issue {line.get('sm__issue_active.avg.pct_of_peak_sustained_elapsed')} %  barrier stall {line.get('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio')}")
 
 
 if __name__ == "__main__":
