@@ -574,7 +574,9 @@ def main():
         rooflines = [roofline_of("hull_chain_kernel", chain_alg, k_ms["hull_chain"], "8 B x proto-hull points + 8 B x hull vertices (latency-bound sequential stack machines)"),
                      roofline_of("tess_count+scan+emit", tess_alg, tess_emit_ms, "B_in + B_out of SURVEY 8d (path input + packed vertex / index output)")]
         if not work.tess_only:
-            rooflines.append(roofline_of("raster_tiles_kernel", raster_alg, k_ms["raster"], "vertex+index bytes + 80 B x instances + W x H x (1 B stencil + 16 B rgba32f)"))
+            # timed together: tile_prims_kernel (per-pair set-up, writes the tile-ordered stream) and K3 (bulk-loads it and rasterises)
+            rooflines.append(roofline_of("raster_tiles_kernel+tile_prims_kernel", raster_alg, k_ms["raster"],
+                                         "vertex+index bytes + 80 B x instances + W x H x (1 B stencil + 16 B rgba32f)"))
         rooflines.sort(key=lambda r: -r["kernel_ms"])
         cfg = work.config_dict()
         cfg.update({"sharding": (("ONE render target tile-sharded over the ranks (16x16 tiles, owner (tx + ty) % N), finished tiles stored into every rank's attachments over NVLink"
