@@ -91,3 +91,19 @@ void cr_set_error_message(const char* fmt, ...);
             return CR_ERR_CUDA;                                                                              \
         }                                                                                                    \
     } while (0)
+
+// Last index i of a non-decreasing array with arr[i] <= key (arr[0] <= key), found by the whole warp: 32 probes per round,
+// so a table of a million entries takes 4 dependent loads instead of 20.
+__device__ __forceinline__ uint32_t warp_search_last_le(const uint32_t* __restrict__ arr, uint32_t n, uint32_t key, uint32_t lane) {
+    uint32_t lo = 0, len = n;
+    while (len > 1u) {
+        const uint32_t step = (len + 31u) / 32u, pos = lo + lane * step;
+        const bool le = pos < lo + len && arr[pos] <= key;
+        const uint32_t hit = __ballot_sync(0xffffffffu, le);          // monotone: lanes 0 .. j
+        const uint32_t j = 31u - (uint32_t)__clz((int)(hit | 1u));
+        const uint32_t end = lo + len;
+        lo += j * step;
+        len = min(step, end - lo);
+    }
+    return lo;
+}

@@ -169,8 +169,11 @@ __device__ __forceinline__ uint32_t find_command(const uint32_t* __restrict__ be
 
 // What a candidate number stands for: the command, the vertex category, the instance and the three vertices of its triangle.
 struct CandInfo { uint32_t ci, cat, instance, v[3]; bool odd; };
-__device__ bool candidate_info(const RasterScene& sc, uint32_t cand, const uint32_t* __restrict__ cmd_begin, CandInfo& c) {
-    c.ci = find_command(cmd_begin, sc.n_commands, cand);
+// `hint`: a command at or before the candidate's (0xFFFFFFFF: none, binary search); walking forwards from it is one or two steps
+// for the consecutive candidates of a CTA.
+__device__ bool candidate_info(const RasterScene& sc, uint32_t cand, const uint32_t* __restrict__ cmd_begin, CandInfo& c, uint32_t hint = 0xFFFFFFFFu) {
+    if (hint == 0xFFFFFFFFu) c.ci = find_command(cmd_begin, sc.n_commands, cand);
+    else { c.ci = hint; while (c.ci + 1u < sc.n_commands && cmd_begin[c.ci + 1u] <= cand) ++c.ci; }
     const DeviceCommand& cmd = sc.commands[c.ci];
     uint32_t rem = cand - cmd_begin[c.ci];
     uint32_t cat = 0, prev_end = 0;
@@ -221,10 +224,10 @@ __device__ __forceinline__ bool finish_record(const RasterTarget& tg, const Devi
     return true;
 }
 // 0: nothing to draw, 1: `rec` is the candidate's record, 2: a vertex cannot be snapped (eye plane / range): frustum clipping decides
-__device__ int build_record(const RasterScene& sc, const RasterTarget& tg, uint32_t cand, const uint32_t* __restrict__ cmd_begin, PrimRecord& rec) {
+__device__ int build_record(const RasterScene& sc, const RasterTarget& tg, uint32_t cand, const uint32_t* __restrict__ cmd_begin, PrimRecord& rec, uint32_t hint) {
     rec.meta = 0;
     CandInfo c;
-    if (!candidate_info(sc, cand, cmd_begin, c)) return 0;
+    if (!candidate_info(sc, cand, cmd_begin, c, hint)) return 0;
     const DeviceCommand& cmd = sc.commands[c.ci];
     const DeviceBatch& b = sc.batches[cmd.batch];
     const float* m = sc.transforms + 16 * (size_t)c.instance;
@@ -415,18 +418,20 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_ke
                                                                    PassCounters* __restrict__ counters) {
     const uint32_t n = live_candidates(counters, cand_capacity);   // 0 when the capacity does not suffice: nothing is produced, the host re-submits
     if (blockIdx.x == 0 && threadIdx.x == 0 && n == 0 && counters->cand_total != 0ull) atomicOr(&counters->flags, CR_PASS_OVERFLOW_CANDS);
-    __shared__ uint32_t sh_begin[SETUP_CMD_CACHE + 1];
+    // the command of the CTA's first candidate, found once by a warp-wide 32-way search; every thread walks forwards from it
+    // (a CTA's 256 consecutive candidates lie in one or two commands unless the commands are tiny)
+    __shared__ uint32_t sh_first_command;
     const uint32_t* cmd_begin = sc.cmd_cand_begin;
-    if (sc.n_commands <= SETUP_CMD_CACHE) {
-        for (uint32_t i = threadIdx.x; i <= sc.n_commands; i += blockDim.x) sh_begin[i] = sc.cmd_cand_begin[i];
-        __syncthreads();
-        cmd_begin = sh_begin;
+    if (threadIdx.x < 32u) {
+        const uint32_t first = warp_search_last_le(cmd_begin, sc.n_commands, min(blockIdx.x * blockDim.x, n ? n - 1u : 0u), threadIdx.x);
+        if (threadIdx.x == 0) sh_first_command = first;
     }
+    __syncthreads();
     const uint32_t cand = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t count = 0;
     if (cand < n) {
         PrimRecord rec;
-        const int built = build_record(sc, tg, cand, cmd_begin, rec);
+        const int built = build_record(sc, tg, cand, cmd_begin, rec, sh_first_command);
         if (built == 2) clip_list[1 + atomicAdd(clip_list, 1u)] = cand;   // clipped, counted and binned by clip_kernel
         if (built == 1) {
             const Extent x = extent_of(rec.X, rec.Y, tg);

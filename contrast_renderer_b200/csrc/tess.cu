@@ -961,21 +961,6 @@ __device__ __forceinline__ void store_proto(float2* __restrict__ proto, uint32_t
 __device__ __forceinline__ uint32_t fan_to_strip_slot(uint32_t j, uint32_t total) { return (j < (total + 1) / 2) ? 2 * j : 2 * (total - 1 - j) + 1; }   // src/vertex.rs:28-35
 
 #define FS_THREADS 256
-// Last index i of a non-decreasing array with arr[i] <= key (arr[0] <= key), found by the whole warp: 32 probes per round,
-// so a table of a million entries takes 4 dependent loads instead of 20.
-__device__ __forceinline__ uint32_t warp_search_last_le(const uint32_t* __restrict__ arr, uint32_t n, uint32_t key, uint32_t lane) {
-    uint32_t lo = 0, len = n;
-    while (len > 1u) {
-        const uint32_t step = (len + 31u) / 32u, pos = lo + lane * step;
-        const bool le = pos < lo + len && arr[pos] <= key;
-        const uint32_t hit = __ballot_sync(0xffffffffu, le);          // monotone: lanes 0 .. j
-        const uint32_t j = 31u - (uint32_t)__clz((int)(hit | 1u));
-        const uint32_t end = lo + len;
-        lo += j * step;
-        len = min(step, end - lo);
-    }
-    return lo;
-}
 // Everything a segment thread needs to know about its path, loaded once per CTA into shared memory (a CTA's 256 consecutive
 // segments belong to a handful of consecutive paths).
 struct FillPathInfo {
