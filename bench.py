@@ -527,15 +527,40 @@ def main():
         def read_frame():
             rnd8.read_color_texels(frame.data_ptr(), frame.numel())
 
+        # pipelined: the frame of step N is snapshot behind its pass and copied to the host (three pinned frames rotate) while the
+        # next steps are rendered; the host waits for frame N - 2 every step and for the last frames before the timed region ends
+        frames = [frame, torch.empty_like(frame).pin_memory(), torch.empty_like(frame).pin_memory()]
+        tickets = []
+
+        def read_frame_async():
+            if len(tickets) == 3:
+                rnd8.wait_readback(tickets.pop(0))
+            k = read_frame_async.count = getattr(read_frame_async, "count", 0) + 1
+            tickets.append(rnd8.read_color_texels_async(frames[k % 3].data_ptr(), frame.numel()))
+
+        def drain_frames():
+            while tickets:
+                rnd8.wait_readback(tickets.pop(0))
+
         torch.cuda.set_stream(stream8)
-        for _ in range(3):
-            step(rnd8, False, in_order=True)
-            read_frame()
-        ms_frame = timed(rnd8, stream8, args.steps, False, per_step=read_frame, in_order=True)
+        pipelined_frames = software_pipelined
+        for _ in range(8 if pipelined_frames else 3):
+            step(rnd8, False, in_order=not pipelined_frames)
+            read_frame_async() if pipelined_frames else read_frame()
+        flush(rnd8)
+        drain_frames()
+        if pipelined_frames:
+            ms_frame = timed(rnd8, stream8, args.steps, False, per_step=read_frame_async, finish=lambda: (read_frame_async(), drain_frames()))
+        else:
+            ms_frame = timed(rnd8, stream8, args.steps, False, per_step=read_frame, in_order=True)
         torch.cuda.set_stream(stream)
         frame_line = {"value": None, "unit": "paths/s", "ms_per_step": ms_frame / args.steps, "h2d_bytes_per_step": int(h2d_bytes),
-                      "d2h_bytes_per_step": int(frame.numel()), "color_format": "rgba8unorm"}
-        state.pop((rnd8, 0)).close()
+                      "d2h_bytes_per_step": int(frame.numel()), "color_format": "rgba8unorm",
+                      "frame_read": ("every step's RGBA8 frame is snapshot behind its pass and copied to pinned host memory on its own stream while the next "
+                                     "steps run; the host waits for each frame two steps later and for the last ones before the timed region ends")
+                                    if pipelined_frames else "the host waits for every step's frame before it starts the next step"}
+        for key in [k for k in state if k[0] is rnd8]:
+            state.pop(key).close()
         rnd8.close()
 
     total_paths, total_covered = work.paths_per_step, covered

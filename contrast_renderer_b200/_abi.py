@@ -85,7 +85,7 @@ EXPORTED_SYMBOLS = (
     "cr_renderer_synchronize", "cr_renderer_set_pipelining", "cr_shape_from_paths", "cr_shape_destroy", "cr_shape_batch_from_paths", "cr_shape_batch_destroy",
     "cr_shape_batch_size", "cr_shape_batch_get", "cr_shape_set_dynamic_stroke_options", "cr_shape_batch_set_dynamic_stroke_options",
     "cr_shape_get_layout", "cr_shape_read_vertex_buffer", "cr_shape_read_index_buffer", "cr_shape_read_stroke_buffer",
-    "cr_pass_begin", "cr_pass_begin_depth", "cr_renderer_read_depth", "cr_renderer_read_color_texels", "cr_pass_set_instances", "cr_pass_set_clip_depth", "cr_pass_save_alpha_context",
+    "cr_pass_begin", "cr_pass_begin_depth", "cr_renderer_read_depth", "cr_renderer_read_color_texels", "cr_renderer_read_color_texels_async", "cr_renderer_wait_readback", "cr_pass_set_instances", "cr_pass_set_clip_depth", "cr_pass_save_alpha_context",
     "cr_pass_restore_alpha_context", "cr_shape_render", "cr_pass_render_batch", "cr_pass_render_script", "cr_pass_submit", "cr_pass_abort", "cr_renderer_read_color",
     "cr_renderer_read_stencil", "cr_renderer_read_alpha_layer", "cr_renderer_get_attachments", "cr_renderer_get_stats", "cr_renderer_get_settled_pass_stats",
     "cr_renderer_enable_timing", "cr_renderer_set_tile_sharding", "cr_renderer_set_order_sharding", "cr_renderer_export_exchange", "cr_renderer_import_peer_exchange", "cr_renderer_export_attachments", "cr_renderer_import_peer_attachments",

@@ -152,6 +152,12 @@ struct cr_renderer {
     bool cmd_arena_busy = false;
     // Capacities the next pass is sized with (candidates, (tile, candidate) pairs): what the last pass needed plus slack. 0: unknown.
     uint32_t cand_cap = 0, pair_cap = 0, last_cands = 0, last_pairs = 0;
+    // asynchronous frame read-back (cr_renderer_read_color_texels_async): the attachment is snapshot on the renderer's stream behind the
+    // pass (device-to-device, a few microseconds) and copied to the host on a stream of its own while the next frame is rendered
+    struct Readback { void* dst = nullptr; size_t bytes = 0; uint64_t ticket = 0, pass_serial = 0; bool pending = false; cudaEvent_t snapshot = nullptr, done = nullptr; DevBuf buf; };
+    Readback readback[4];
+    cudaStream_t out = nullptr;
+    uint64_t readback_tickets = 0, pass_serial = 0, inflight_serial = 0;
     uint32_t radix_layout_cap = 0xFFFFFFFFu;   // pair capacity the radix scratch is laid out (and zeroed) for
     uint32_t clip_cap = 1024;         // triangles frustum clipping may produce in one pass (grows when a pass needs more)
     cr_pass* inflight = nullptr;      // the last submitted pass until its device-side sizes have been checked (settle)
@@ -627,6 +633,8 @@ static void renderer_free(cr_renderer* r) {
                      &r->pair_tile_alt, &r->pair_cand_alt, &r->tile_prims, &r->clip_list, &r->clip_attrs, &r->radix_scratch, &r->tile_begin, &r->inst_transforms, &r->inst_colors, &r->pass_counters};
     for (DevBuf* d : all) d->release(st);
     for (auto& set : r->staging) for (auto& d : set) d.release(st);
+    if (r->out) cudaStreamSynchronize(r->out);
+    for (auto& rb : r->readback) { rb.buf.release(st); if (rb.snapshot) cudaEventDestroy(rb.snapshot); if (rb.done) cudaEventDestroy(rb.done); }
     cudaStreamSynchronize(st);
     for (auto& e : r->ev) if (e) cudaEventDestroy(e);
     if (r->pinned) cudaFreeHost(r->pinned);
@@ -635,7 +643,7 @@ static void renderer_free(cr_renderer* r) {
     if (r->ev_pass) cudaEventDestroy(r->ev_pass);
     if (r->ev_update) cudaEventDestroy(r->ev_update);
     for (cudaEvent_t e : {r->staging_free[0], r->staging_free[1], r->ev_copied, r->ev_emitted, r->ev_hull_idle}) if (e) cudaEventDestroy(e);
-    for (cudaStream_t q : {r->tess, r->copy, r->hull}) if (q) cudaStreamDestroy(q);
+    for (cudaStream_t q : {r->tess, r->copy, r->hull, r->out}) if (q) cudaStreamDestroy(q);
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
     delete r;
 }
@@ -669,6 +677,8 @@ int cr_renderer_resize(cr_renderer* r, uint32_t width, uint32_t height) {
     if (width == 0 || height == 0 || width > 32768 || height > 32768) return fail(CR_ERR_INVALID_ARGUMENT, "bad extent %ux%u", width, height);
     CR_GUARD(r);
     CR_TRY(settle(r));
+    if (r->out) CR_CUDA_TRY(cudaStreamSynchronize(r->out));   // read-backs of the old extent
+    for (auto& rb : r->readback) rb.pending = false;
     r->cand_cap = r->pair_cap = 0;   // sized for another extent
     const size_t samples = (size_t)width * height * r->config.msaa_sample_count;
     if (r->order_world > 1) return fail(CR_ERR_INVALID_ARGUMENT, "resize of an order-sharded target: call cr_renderer_set_order_sharding(r, 1, 0) first");
@@ -1288,6 +1298,14 @@ int settle(cr_renderer* r) {
                 if (cudaEventSynchronize(r->ev_pass) != cudaSuccess) status = fail(CR_ERR_CUDA, "waiting for the re-submitted pass failed");
                 memcpy(&pc, &r->pinned[PIN_PASS], sizeof(pc));
             }
+            // an asynchronous read-back taken behind the first (skipped) attempt holds the frame as it was before the pass: take it again
+            for (auto& rb : r->readback) {
+                if (!rb.pending || rb.pass_serial != r->inflight_serial || status != CR_OK) continue;
+                cudaStreamSynchronize(r->out);
+                if (cudaMemcpyAsync(rb.dst, r->color.p, rb.bytes, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess || cudaStreamSynchronize(r->stream) != cudaSuccess)
+                    status = fail(CR_ERR_CUDA, "repeating the frame read-back failed");
+                cudaEventRecord(rb.done, r->stream);
+            }
         }
     }
     if (status == CR_OK) {
@@ -1324,7 +1342,7 @@ int cr_pass_submit(cr_pass* p) {
             keep = st == CR_OK && n_cmds != 0;
         }
     }
-    if (keep) { r->inflight = p; return CR_OK; }   // its commands, batches and instance copies stay until settle()
+    if (keep) { r->inflight = p; r->inflight_serial = ++r->pass_serial; return CR_OK; }   // its commands, batches and instance copies stay until settle()
     pass_free(p);
     renderer_release_child(r);
     return st;
@@ -1367,6 +1385,46 @@ int cr_renderer_read_color(cr_renderer* r, float* dst, size_t capacity_bytes) {
 int cr_renderer_read_color_texels(cr_renderer* r, void* dst, size_t capacity_bytes) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
     return read_back(r, r->color.p, (size_t)r->width * r->height * r->config.msaa_sample_count * color_texel_bytes(r), dst, capacity_bytes);
+}
+// The frame of the pass submitted last, without stopping the pipeline: snapshot behind the pass, host copy on its own stream.
+int cr_renderer_read_color_texels_async(cr_renderer* r, void* dst, size_t capacity_bytes, uint64_t* ticket) {
+    if (!r || !dst || !ticket) return fail(CR_ERR_INVALID_ARGUMENT, "null argument");
+    if (r->width == 0) return fail(CR_ERR_NOT_RESIZED, "cr_renderer_resize has not been called");
+    const size_t bytes = (size_t)r->width * r->height * r->config.msaa_sample_count * color_texel_bytes(r);
+    if (capacity_bytes < bytes) return fail(CR_ERR_INVALID_ARGUMENT, "capacity %zu < %zu", capacity_bytes, bytes);
+    CR_GUARD(r);
+    if (!r->out) CR_CUDA_TRY(cudaStreamCreateWithFlags(&r->out, cudaStreamNonBlocking));
+    cr_renderer::Readback& rb = r->readback[r->readback_tickets & 3u];
+    if (rb.pending) {   // four read-backs are in flight at most: the older one of this slot finishes first
+        CR_CUDA_TRY(cudaEventSynchronize(rb.done));
+        rb.pending = false;
+    }
+    if (!rb.snapshot) { CR_CUDA_TRY(cudaEventCreateWithFlags(&rb.snapshot, cudaEventDisableTiming)); CR_CUDA_TRY(cudaEventCreateWithFlags(&rb.done, cudaEventDisableTiming)); }
+    CR_TRY(rb.buf.reserve(r->stream, bytes));
+    CR_CUDA_TRY(cudaMemcpyAsync(rb.buf.p, r->color.p, bytes, cudaMemcpyDeviceToDevice, r->stream));
+    CR_CUDA_TRY(cudaEventRecord(rb.snapshot, r->stream));
+    CR_CUDA_TRY(cudaStreamWaitEvent(r->out, rb.snapshot, 0));
+    CR_CUDA_TRY(cudaMemcpyAsync(dst, rb.buf.p, bytes, cudaMemcpyDeviceToHost, r->out));
+    CR_CUDA_TRY(cudaEventRecord(rb.done, r->out));
+    rb.dst = dst; rb.bytes = bytes; rb.pending = true;
+    rb.pass_serial = r->inflight ? r->inflight_serial : 0;   // 0: no pass in flight, nothing can be re-submitted under it
+    rb.ticket = ++r->readback_tickets;
+    *ticket = rb.ticket;
+    return CR_OK;
+}
+// Waits until the read-back `ticket` has arrived in its destination. The pass it belongs to is settled first: if that pass had to
+// be re-submitted (a capacity did not suffice), the frame is read again.
+int cr_renderer_wait_readback(cr_renderer* r, uint64_t ticket) {
+    if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");
+    CR_GUARD(r);
+    for (auto& rb : r->readback) {
+        if (!rb.pending || rb.ticket != ticket) continue;
+        if (r->inflight && rb.pass_serial == r->inflight_serial) { CR_TRY(settle(r)); CR_TRY(take_deferred(r)); }
+        CR_CUDA_TRY(cudaEventSynchronize(rb.done));
+        rb.pending = false;
+        return CR_OK;
+    }
+    return CR_OK;   // already waited for (or replaced by a newer read-back of its slot, which waited for it)
 }
 int cr_renderer_read_depth(cr_renderer* r, float* dst, size_t capacity_bytes) {
     if (!r) return fail(CR_ERR_INVALID_ARGUMENT, "null renderer");

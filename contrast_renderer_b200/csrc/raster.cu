@@ -39,6 +39,9 @@ static_assert(RCHUNK == 64, "K3 scans a run's row counts two primitives per lane
 #ifndef K3_MIN_BLOCKS_MSAA
 #define K3_MIN_BLOCKS_MSAA 3
 #endif
+#ifndef K3_MIN_BLOCKS_U8
+#define K3_MIN_BLOCKS_U8 5   // 1x, 8-bit colour: the unorm conversions cost a few registers more
+#endif
 #define PIXEL_RUN_MAX 12u     // runs of at most this many primitives execute in pixel mode (see K3)
 #define ROW_SWEEP_MAX 32u     // stencil runs up to this length use the fixed 16 x 16 (primitive, row) grid, longer ones compact their rows (measured: text 8 % slower, dashed strokes 21 % faster with compaction everywhere)
 #define BIG_TILE_BOX 8        // candidates touching more tiles than this are binned by the whole warp
@@ -1010,7 +1013,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 }
 
 template <int S, bool DEPTH, bool U8>   // samples per pixel; depth test / write on the colour cover; 8-bit unorm colour + R8 alpha layers
-__global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH && !U8) ? K3_MIN_BLOCKS : K3_MIN_BLOCKS_MSAA) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const TilePrim* __restrict__ prims,
+__global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH) ? (U8 ? K3_MIN_BLOCKS_U8 : K3_MIN_BLOCKS) : K3_MIN_BLOCKS_MSAA) raster_tiles_kernel(RasterScene sc, RasterTarget tg, const TilePrim* __restrict__ prims,
                                                                                          const uint32_t* __restrict__ tile_begin,
                                                                                          PassCounters* __restrict__ counters) {
     __shared__ __align__(128) TilePrim sh_buf[2][RCHUNK];   // the tile's primitive stream, RCHUNK at a time: chunk c + 1 streams in (bulk copy) while chunk c is rasterised

@@ -74,6 +74,8 @@ def lib():
             "cr_renderer_get_attachments": [vp, C.POINTER(vp), C.POINTER(vp)],
             "cr_renderer_get_stats": [vp, C.POINTER(_abi.StatsC)],
             "cr_renderer_get_settled_pass_stats": [vp, C.POINTER(_abi.StatsC)],
+            "cr_renderer_read_color_texels_async": [vp, vp, C.c_size_t, C.POINTER(C.c_uint64)],
+            "cr_renderer_wait_readback": [vp, C.c_uint64],
             "cr_renderer_enable_timing": [vp, u32],
             "cr_renderer_set_tile_sharding": [vp, u32, u32],
             "cr_renderer_set_order_sharding": [vp, u32, u32],
@@ -309,6 +311,16 @@ class Renderer:
     def read_color_texels(self, dst_address: int, capacity_bytes: int) -> None:
         """The colour attachment as stored (16 B per sample, or one unorm8 texel), into caller memory (pinned for PCIe speed)."""
         _check(lib().cr_renderer_read_color_texels(self._h, dst_address, capacity_bytes))
+
+    def read_color_texels_async(self, dst_address: int, capacity_bytes: int) -> int:
+        """Starts the read-back of the frame of the pass submitted last (snapshot behind the pass, host copy on its own stream) and
+        returns a ticket for `wait_readback`; the pipeline keeps running."""
+        ticket = C.c_uint64(0)
+        _check(lib().cr_renderer_read_color_texels_async(self._h, dst_address, capacity_bytes, C.byref(ticket)))
+        return int(ticket.value)
+
+    def wait_readback(self, ticket: int) -> None:
+        _check(lib().cr_renderer_wait_readback(self._h, ticket))
 
     def read_depth(self) -> np.ndarray:
         out = np.empty((self.height, self.width, self.config.msaa_sample_count), np.float32)

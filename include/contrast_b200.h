@@ -293,6 +293,12 @@ int cr_renderer_read_color(cr_renderer* renderer, float* dst, size_t capacity_by
 /* The colour attachment as stored: 16 bytes per sample (RGBA32F) or one packed unorm8 texel per sample (RGBA8 / BGRA8). This
  * is the frame a presenter consumes; `dst` should be pinned host memory for the copy to run at PCIe speed. */
 int cr_renderer_read_color_texels(cr_renderer* renderer, void* dst, size_t capacity_bytes);
+/* The same frame without stopping the pipeline (wgpu: copy_texture_to_buffer + map_async): the attachment is snapshot on the
+ * renderer's stream behind the pass submitted last and copied to `dst` (pinned host memory, untouched until waited for) on a
+ * stream of its own while the next frames are rendered. At most four read-backs are in flight; a fifth waits for the oldest.
+ * cr_renderer_wait_readback returns when `ticket`'s bytes have arrived (and are the frame of a pass that was not skipped). */
+int cr_renderer_read_color_texels_async(cr_renderer* renderer, void* dst, size_t capacity_bytes, uint64_t* ticket);
+int cr_renderer_wait_readback(cr_renderer* renderer, uint64_t ticket);
 int cr_renderer_read_stencil(cr_renderer* renderer, uint8_t* dst, size_t capacity_bytes);
 int cr_renderer_read_alpha_layer(cr_renderer* renderer, uint32_t layer, float* dst, size_t capacity_bytes);
 /* depth: [height][width][samples] f32; CR_ERR_INVALID_ARGUMENT if the configuration has no depth attachment. */

@@ -216,3 +216,38 @@ def test_a_smaller_pass_after_resize_reuses_the_sort_scratch(cr, oracle):
         assert np.array_equal(stencil, ref_stencil) and np.array_equal(color.view(np.uint32), ref_color.view(np.uint32))
         batch.close()
     rnd.close()
+
+
+@pytest.mark.timeout(120)
+def test_asynchronous_frame_readback(cr, oracle):
+    """cr_renderer_read_color_texels_async: the frame of the pass submitted last arrives in caller memory while later passes run —
+    also when that pass turns out to be undersized and is re-submitted (the snapshot taken behind the skipped attempt is replaced),
+    with two read-backs in flight, and with the frame of an EARLIER pass waited for after a later pass has been submitted."""
+    small = scenes.mixed_fills(12, extent=(512, 384), size=(10.0, 40.0), seed=5)
+    large = scenes.mixed_fills(500, extent=(512, 384), size=(10.0, 120.0), rational=True, seed=6)
+    rnd = cr.Renderer(cr.Configuration(color_format=cr.ColorFormat.Rgba8Unorm))
+    rnd.resize_internal_buffers(512, 384)
+    want = {}
+    for name, scene in (("small", small), ("large", large)):
+        b = _render_scene(cr, rnd, scene)
+        frame = np.empty((384, 512), np.uint32)
+        rnd.read_color_texels(frame.ctypes.data, frame.nbytes)
+        want[name] = frame
+        b.close()
+    assert not np.array_equal(want["small"], want["large"])
+    rnd.close()
+    rnd = cr.Renderer(cr.Configuration(color_format=cr.ColorFormat.Rgba8Unorm))
+    rnd.resize_internal_buffers(512, 384)
+    got = [np.zeros((384, 512), np.uint32) for _ in range(4)]
+    batches, tickets = [], []
+    for k, scene in enumerate((small, large, small, large)):   # the large pass after a small one exceeds the capacities: re-submission
+        batches.append(_render_scene(cr, rnd, scene))
+        tickets.append(rnd.read_color_texels_async(got[k].ctypes.data, got[k].nbytes))
+        if k >= 1:
+            rnd.wait_readback(tickets[k - 1])                   # the frame before: its pass has been settled by this submit
+            assert np.array_equal(got[k - 1], want["small" if (k - 1) % 2 == 0 else "large"]), f"frame {k - 1}"
+    rnd.wait_readback(tickets[-1])
+    assert np.array_equal(got[3], want["large"])
+    for b in batches:
+        b.close()
+    rnd.close()
