@@ -66,6 +66,7 @@ enum Pipe : uint32_t {
 #define META_FULL 2048u   // (tile-local) every pixel centre of the tile is inside the primitive
 #define META_RUN_START 8192u   // (tile-local) this primitive does not commute with its predecessor in the tile: it opens a run
 #define META_BIAS_SHIFT 16     // (tile-local) bit 16 + e: edge e is neither a top nor a left edge (bias -1)
+#define META_KIND_SHIFT 19     // (tile-local) bits 19-20: run kind of the primitive's pipeline (0 stroke stencil, 1 fill stencil, 2 cover)
 #define META_CLIPPED 16384u    // a fan triangle produced by frustum clipping: its corners' 1/w and attributes are in ClipAttr[v[0]]
 #define META_CLIP_PARENT 32768u   // (record of a clipped candidate, not VALID) X[0] = first fan triangle, X[1] = their number
 
@@ -667,11 +668,15 @@ struct TilePrim {          // 128 bytes: one primitive set up for one tile (a re
     float invw[3];
     uint32_t meta;          // PrimRecord::meta + the tile-local flags; META_VALID cleared if nothing of it can land in this tile
     float attr[3][4];       // stroke vertices: attr[0][3] holds their flat u32 (bits), attr[1][3] their flat float
-    uint32_t bbox;          // x0 | y0 << 8 | x1 << 16 | y1 << 24 in tile pixels
+    uint32_t box_mask;      // the bounding box clipped to the tile as bit masks: bits x0..x1 | (bits y0..y1) << 16 — "is my pixel in the box" is one AND + compare
     uint32_t ref_batch;     // stencil reference (8 bits) | batch << 8
     uint32_t instance, layers;
 };
 static_assert(sizeof(TilePrim) == 128, "TilePrim streams are moved with 16-byte bulk copies");
+__device__ __forceinline__ int box_x0(uint32_t m) { return __ffs((int)(m & 0xFFFFu)) - 1; }
+__device__ __forceinline__ int box_x1(uint32_t m) { return 31 - __clz((int)(m & 0xFFFFu)); }
+__device__ __forceinline__ int box_y0(uint32_t m) { return __ffs((int)(m >> 16)) - 1; }
+__device__ __forceinline__ int box_y1(uint32_t m) { return 31 - __clz((int)(m >> 16)); }
 __device__ __forceinline__ int prim_bias(uint32_t meta, int e) { return -(int)((meta >> (META_BIAS_SHIFT + e)) & 1u); }   // top-left bias of edge e: 0 or -1
 __device__ __forceinline__ uint32_t prim_ref(const TilePrim& ps) { return ps.ref_batch & 255u; }
 __device__ __forceinline__ uint32_t prim_batch(const TilePrim& ps) { return ps.ref_batch >> 8; }
@@ -827,8 +832,9 @@ __device__ __forceinline__ bool tile_bbox(const RasterTarget& tg, const PrimReco
     const int slo = S == 1 ? 128 : 32, shi = S == 1 ? 128 : 224;   // sample offsets inside a pixel span [slo, shi]
     const int x0 = max(0, ((minX - shi + 255) >> 8) - tile_px), x1 = min(min(CR_TILE - 1, (int)tg.width - 1 - tile_px), ((maxX - slo) >> 8) - tile_px);
     const int y0 = max(0, ((minY - shi + 255) >> 8) - tile_py), y1 = min(min(CR_TILE - 1, (int)tg.height - 1 - tile_py), ((maxY - slo) >> 8) - tile_py);
-    bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
-    return x0 <= x1 && y0 <= y1;
+    if (x0 > x1 || y0 > y1) { bbox = 0; return false; }
+    bbox = (((2u << x1) - 1u) & ~((1u << x0) - 1u)) | ((((2u << y1) - 1u) & ~((1u << y0) - 1u)) << 16);   // TilePrim::box_mask
+    return true;
 }
 
 // Set one primitive up for one tile (one thread per (tile, primitive) pair). The edge functions are evaluated at the
@@ -836,7 +842,7 @@ __device__ __forceinline__ bool tile_bbox(const RasterTarget& tg, const PrimReco
 template <int S, bool DEPTH>
 __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, const PrimRecord& rec, int tile_px, int tile_py, TilePrim& ps) {
     ps.meta = 0;
-    ps.bbox = 0; ps.ref_batch = 0; ps.instance = 0; ps.layers = 0;
+    ps.box_mask = 0; ps.ref_batch = 0; ps.instance = 0; ps.layers = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         ps.e0[i] = 0; ps.A[i] = 0; ps.B[i] = 0; ps.invw[i] = 0.0f;
@@ -856,7 +862,7 @@ __device__ void stage_primitive(const RasterScene& sc, const RasterTarget& tg, c
         if (t.bias[e]) bias_bits |= 1u << (META_BIAS_SHIFT + e);
         ps.e0[e] = (long long)t.A[e] * (PY - rec.Y[e]) - (long long)t.B[e] * (PX - rec.X[e]) + t.bias[e];
     }
-    ps.bbox = bbox;
+    ps.box_mask = bbox;
     bool full = true;   // minimum of every edge function over all sample positions of the tile is still inside
     const int far = (CR_TILE - 1) * 256 + (S == 1 ? 0 : 224), near = S == 1 ? 0 : 32;   // sample offsets from the evaluation origin
 #pragma unroll
@@ -972,6 +978,7 @@ __global__ void __launch_bounds__(256) tile_prims_kernel(RasterScene sc, RasterT
         else boundary = qv;   // a valid primitive after a staged-out one conservatively opens a run
     }
     if (boundary) ps.meta |= META_RUN_START;
+    if (ps.meta & META_VALID) ps.meta |= run_kind(ps.meta & 15u) << META_KIND_SHIFT;
     // The warp's 32 records leave through shared memory so that every store instruction writes 512 contiguous bytes (a record
     // per thread would be 16 bytes every 128). Chunk k of lane l sits at slot 8 l + (k ^ (l & 7)): conflict free both ways.
     uint4 q[8];
@@ -981,7 +988,7 @@ __global__ void __launch_bounds__(256) tile_prims_kernel(RasterScene sc, RasterT
     q[3] = make_uint4(__float_as_uint(ps.invw[0]), __float_as_uint(ps.invw[1]), __float_as_uint(ps.invw[2]), ps.meta);
 #pragma unroll
     for (int k = 0; k < 3; ++k) q[4 + k] = make_uint4(__float_as_uint(ps.attr[k][0]), __float_as_uint(ps.attr[k][1]), __float_as_uint(ps.attr[k][2]), __float_as_uint(ps.attr[k][3]));
-    q[7] = make_uint4(ps.bbox, ps.ref_batch, ps.instance, ps.layers);
+    q[7] = make_uint4(ps.box_mask, ps.ref_batch, ps.instance, ps.layers);
     uint4* const mine = sh_out[threadIdx.x >> 5];
 #pragma unroll
     for (int k = 0; k < 8; ++k) mine[8u * lane + ((uint32_t)k ^ (lane & 7u))] = q[k];
@@ -1185,9 +1192,9 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH) ? (U8 ? 
     };
     // PIXEL MODE for short runs: every thread walks the run's primitives for its own pixel — no shared accumulator, no
     // barrier, all 256 threads busy however few primitives the run has.
+    const uint32_t my_box_bits = (1u << lx) | (1u << (16 + ly));
     auto pixel_in_box = [&](const TilePrim& ps) -> bool {
-        const uint32_t bbox = ps.bbox;
-        return lx >= (int)(bbox & 255u) && lx <= (int)((bbox >> 16) & 255u) && ly >= (int)((bbox >> 8) & 255u) && ly <= (int)(bbox >> 24);
+        return (ps.box_mask & my_box_bits) == my_box_bits;
     };
 
     if (n_chunks != 0u) __syncthreads();   // the mbarriers are initialised before anybody waits on them
@@ -1207,14 +1214,18 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH) ? (U8 ? 
             const uint32_t k = (uint32_t)w * 32u + lane;
             starts |= (unsigned long long)__ballot_sync(0xffffffffu, k < n && (sh[k].meta & META_RUN_START) != 0u) << (32 * w);
         }
-        while (starts != 0ull) {
-            const uint32_t a = (uint32_t)__ffsll((long long)starts) - 1u;
-            starts &= starts - 1ull;
+        starts &= ~1ull;   // the first run starts at 0; every later run starts where its predecessor ends (one find-first-set per run)
+        uint32_t next_a = 0;
+        for (bool more = true; more;) {
+            const uint32_t a = next_a;
             const uint32_t b = starts != 0ull ? (uint32_t)__ffsll((long long)starts) - 1u : n;
+            more = starts != 0ull;
+            starts &= starts - 1ull;
+            next_a = b;
             uint32_t first = a;   // a run that starts with staged-out primitives (first of the tile / of the chunk) has nothing else
             while (first < b && !(sh[first].meta & META_VALID)) ++first;
             if (first == b) continue;
-            const uint32_t kind = run_kind(sh[first].meta & 15u);
+            const uint32_t kind = (sh[first].meta >> META_KIND_SHIFT) & 3u;   // run_kind of its pipeline, set by tile_prims_kernel
             apply_pending();
             if (kind < 2u && b - a <= tg.pixel_run_max) {
                 // short stencil run, pixel mode: the run's net effect on this pixel's samples, applied at once
@@ -1258,8 +1269,8 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH) ? (U8 ? 
                         const uint32_t k = a + (uint32_t)half * 32u + lane;
                         h[half] = 0;
                         if (k < b) {
-                            const uint32_t meta = sh[k].meta, bbox = sh[k].bbox;
-                            if (meta & META_VALID) h[half] = (bbox >> 24) - ((bbox >> 8) & 255u) + 1u;
+                            const uint32_t meta = sh[k].meta, box = sh[k].box_mask;
+                            if (meta & META_VALID) h[half] = (uint32_t)__popc(box >> 16);
                         }
                     }
                     uint32_t s0 = h[0], s1 = h[1];
@@ -1289,11 +1300,11 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH) ? (U8 ? 
                         if (k >= b) continue;
                     }
                     const TilePrim& ps = sh[k];
-                    const uint32_t meta = ps.meta, bbox = ps.bbox;
+                    const uint32_t meta = ps.meta, box = ps.box_mask;
                     if (!(meta & META_VALID)) continue;
-                    const int y = (int)((bbox >> 8) & 255u) + (int)row;
-                    if (y > (int)(bbox >> 24)) continue;
-                    const int x0 = (int)(bbox & 255u), x1 = (int)((bbox >> 16) & 255u);
+                    const int y = box_y0(box) + (int)row;
+                    if (y > box_y1(box)) continue;
+                    const int x0 = box_x0(box), x1 = box_x1(box);
                     const uint32_t pipe = meta & 15u;
                     const int delta = kind == 0u ? 1 : ((meta & META_FRONT) ? 1 : -1);
                     if (meta & META_E32) stencil_row<S, int>(sc, ps, pipe, kind, delta, y, x0, x1, out);
@@ -1326,10 +1337,10 @@ __global__ void __launch_bounds__(CR_TILE * CR_TILE, (S == 1 && !DEPTH) ? (U8 ? 
                         if (k < b) {
                             const TilePrim& ps = sh[k];
                             const uint32_t meta = ps.meta;
-                            const uint32_t bbox = ps.bbox;
+                            const uint32_t box = ps.box_mask;
                             const int y = (int)(threadIdx.x & 15u);
-                            if ((meta & META_VALID) && y >= (int)((bbox >> 8) & 255u) && y <= (int)(bbox >> 24)) {
-                                const int x0 = (int)(bbox & 255u), x1 = (int)((bbox >> 16) & 255u);
+                            if ((meta & META_VALID) && ((box >> (16 + y)) & 1u) != 0u) {
+                                const int x0 = box_x0(box), x1 = box_x1(box);
                                 if (meta & META_FULL) mask = (x1 * S + S >= 64 ? ~0ull : ((1ull << (x1 * S + S)) - 1ull)) & ~((1ull << (x0 * S)) - 1ull);
                                 else mask = (meta & META_E32) ? cover_row_mask<S, int>(ps, y, x0, x1) : cover_row_mask<S, long long>(ps, y, x0, x1);
                             }
