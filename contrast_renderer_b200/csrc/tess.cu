@@ -1383,68 +1383,86 @@ struct HullLine { float l0, l1, l2; };
 __device__ __forceinline__ HullLine hull_line(float2 a, float2 b) { return {a.y * b.x - a.x * b.y, b.y - a.y, a.x - b.x}; }   // == join(a, b), unit weights
 __device__ __forceinline__ float hull_side(const HullLine& l, float2 p) { return (l.l0 + p.x * l.l1) + p.y * l.l2; }           // == (a v b) v p
 
-#define HULL_STACK 1024     // shared-memory chain stacks; deeper chains are redone with global stacks
+#define HULL_STACK 512      // shared-memory chain stacks; deeper chains are redone with global stacks
 #define CHAIN_WINDOW 128    // points per prefetch window
-#define CHAIN_SHAPES 2      // shapes per CTA: four chain warps, one per SM sub-partition
-#define CHAIN_THREADS (64 * CHAIN_SHAPES)
+#ifndef CHAIN_LANES
+#define CHAIN_LANES 2       // chains per warp, one per lane: lower and upper chain of CHAIN_LANES / 2 shapes. Measured on the text scene (kernel alone /
+                            // pipelined step): 1 lane 0.492 / 1.109 ms, 2 lanes 0.532 / 0.987 ms, 4 lanes 0.604 / 1.016 ms, 8 lanes 0.741 / 1.041 ms
+#endif
+#define CHAIN_THREADS 128
+#define CHAINS_PER_CTA (CHAIN_LANES * CHAIN_THREADS / 32)
+#define CHAIN_SHAPES (CHAINS_PER_CTA / 2)
+#define STACK_STRIDE (HULL_STACK + 1)      // + 1: the chains of a warp walk their stacks and windows at similar depths — keep them in different banks
+#define WINDOW_STRIDE (CHAIN_WINDOW + 1)
+// The chains are sequential stack machines (the pop test has a tolerance, so the result depends on every transient stack
+// state): one LANE per chain. A lone lane per warp, as in round 1, left 31 of 32 lanes of every issued instruction idle — 1250
+// chains took 46 % of the GPU's issue slots for half a millisecond, which is what the frames overlapping this kernel paid for.
+// With CHAIN_LANES chains per warp the same instruction stream serves several chains (the common keep / replace-the-top
+// outcomes are branch free; lanes that must pop deeper make the others wait), the remaining lanes stream the sorted points
+// of all the warp's chains into double-buffered windows (cp.async).
 __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2* __restrict__ sorted, float2* __restrict__ scratch_a, float2* __restrict__ scratch_b,
                                                                    const uint32_t* __restrict__ proto_begin, uint32_t n_shapes,
                                                                    float2* __restrict__ hull_out, uint32_t* __restrict__ hull_count, const uint32_t* __restrict__ err) {
     if (*reinterpret_cast<volatile const uint32_t*>(err) & CR_DEVERR_FATAL_MASK) return;   // nothing was emitted
-    __shared__ float2 window[2 * CHAIN_SHAPES][2][CHAIN_WINDOW];
-    __shared__ float2 stacks[2 * CHAIN_SHAPES][HULL_STACK];
-    __shared__ uint32_t sh_len[2 * CHAIN_SHAPES];
+    extern __shared__ float2 sh_chain[];
+    float2* const stacks = sh_chain;                                         // [CHAINS_PER_CTA][STACK_STRIDE]
+    float2* const windows = sh_chain + CHAINS_PER_CTA * STACK_STRIDE;        // [CHAINS_PER_CTA][2][WINDOW_STRIDE]
+    __shared__ uint32_t sh_len[CHAINS_PER_CTA];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t slot = warp >> 1, tid = threadIdx.x & 63u;   // the CTA's slot-th shape is handled by 64 threads
-    const uint32_t s = blockIdx.x * CHAIN_SHAPES + slot;
-    if (s >= n_shapes) return;
-    const uint32_t begin = proto_begin[s], n = proto_begin[s + 1] - begin;
-    float2* out = hull_out + begin;
-    const float2* pts = sorted + begin;
-    if (n < 3) {  // returned as-is (src/convex_hull.rs:9-11); fan->strip of <= 2 points is the identity
-        if (tid < n) out[tid] = pts[tid];
-        if (tid == 0) hull_count[s] = n;
-        return;
-    }
-    const bool descending = (warp & 1u) != 0;   // even warp: lower chain (ascending points), odd warp: upper chain (descending)
-    // logical point k of this chain
-    auto fetch = [&](uint32_t w) {       // stream window w (points w * CHAIN_WINDOW ...) into window[warp][w & 1]
-        const uint32_t base = w * CHAIN_WINDOW;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&window[warp][w & 1u][0]);
+    // the chain this lane describes (lanes >= CHAIN_LANES describe chain lane % CHAIN_LANES again: every lane helps prefetching)
+    const uint32_t c_own = lane % CHAIN_LANES, chain_own = warp * CHAIN_LANES + c_own;
+    const uint32_t s_own = blockIdx.x * CHAIN_SHAPES + (chain_own >> 1);
+    uint32_t begin_own = 0, n_own = 0;
+    if (s_own < n_shapes) { begin_own = proto_begin[s_own]; n_own = proto_begin[s_own + 1] - begin_own; }
+    const bool descending = (c_own & 1u) != 0;   // even chain: lower (ascending points), odd chain: upper (descending)
+    const bool runs = lane < CHAIN_LANES && n_own >= 3u;   // this lane executes a machine
+    uint32_t n_max = 0;
 #pragma unroll
-        for (uint32_t i = 0; i < CHAIN_WINDOW / 32; ++i) {
-            const uint32_t k = base + lane + 32u * i;
-            if (k < n) {
-                const float2* src = pts + (descending ? n - 1u - k : k);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (lane + 32u * i) * 8u), "l"(src) : "memory");
+    for (uint32_t c = 0; c < CHAIN_LANES; ++c) n_max = max(n_max, __shfl_sync(0xffffffffu, n_own >= 3u ? n_own : 0u, c));
+    auto fetch = [&](uint32_t w) {       // stream window w of every chain of this warp into its buffer w & 1
+        const uint32_t base = w * CHAIN_WINDOW;
+#pragma unroll
+        for (uint32_t c = 0; c < CHAIN_LANES; ++c) {
+            const uint32_t n_c = __shfl_sync(0xffffffffu, n_own, c), begin_c = __shfl_sync(0xffffffffu, begin_own, c);
+            if (n_c < 3u) continue;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(windows + ((size_t)(warp * CHAIN_LANES + c) * 2u + (w & 1u)) * WINDOW_STRIDE);
+#pragma unroll
+            for (uint32_t i = 0; i < CHAIN_WINDOW / 32; ++i) {
+                const uint32_t k = base + lane + 32u * i;
+                if (k < n_c) {
+                    const float2* src = sorted + begin_c + ((c & 1u) ? n_c - 1u - k : k);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (lane + 32u * i) * 8u), "l"(src) : "memory");
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    fetch(0);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    const uint32_t stack0 = (uint32_t)__cvta_generic_to_shared(&stacks[warp][0]);
+    if (n_max != 0u) {
+        fetch(0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    const uint32_t stack0 = (uint32_t)__cvta_generic_to_shared(stacks + (size_t)chain_own * STACK_STRIDE);
+    const uint32_t window0 = (uint32_t)__cvta_generic_to_shared(windows + (size_t)chain_own * 2u * WINDOW_STRIDE);
     const uint32_t floor2 = stack0 + 16;                 // top == floor2  <=>  two entries
     const uint32_t limit = stack0 + HULL_STACK * 8;      // pushing at `limit` would overflow
     uint32_t top = floor2;                               // address one past the top entry
     float2 a = make_float2(0.f, 0.f), b = a, c = a;
     HullLine lab = {0.f, 0.f, 0.f}, lca = lab;
     bool overflow = false;
-    if (lane == 0) {
-        const uint32_t w0 = (uint32_t)__cvta_generic_to_shared(&window[warp][0][0]);
-        a = lds_f2(w0); b = lds_f2(w0 + 8);
+    if (runs) {
+        a = lds_f2(window0); b = lds_f2(window0 + 8);
         sts_f2(stack0, a); sts_f2(stack0 + 8, b);
         c = a; lab = hull_line(a, b); lca = lab;         // c, lca are meaningful only while the stack holds >= 3 entries
     }
-    const uint32_t n_windows = (n + CHAIN_WINDOW - 1) / CHAIN_WINDOW;
+    const uint32_t n_windows = (n_max + CHAIN_WINDOW - 1) / CHAIN_WINDOW;
     for (uint32_t w = 0; w < n_windows; ++w) {
         if (w + 1 < n_windows) fetch(w + 1);
         // The stack grows by at most one entry per point: one capacity check per window keeps it out of the loop.
-        if (lane == 0 && !overflow && top + CHAIN_WINDOW * 8u > limit) overflow = true;
-        if (lane == 0 && !overflow) {
-            uint32_t src = (uint32_t)__cvta_generic_to_shared(&window[warp][w & 1u][0]);
-            const uint32_t k0 = w == 0 ? 2u : 0u, k1 = min((uint32_t)CHAIN_WINDOW, n - w * CHAIN_WINDOW);
+        if (runs && !overflow && top + CHAIN_WINDOW * 8u > limit) overflow = true;
+        if (runs && !overflow && w * CHAIN_WINDOW < n_own) {
+            uint32_t src = window0 + (w & 1u) * (WINDOW_STRIDE * 8u);
+            const uint32_t k0 = w == 0 ? 2u : 0u, k1 = min((uint32_t)CHAIN_WINDOW, n_own - w * CHAIN_WINDOW);
             src += k0 * 8u;
             float2 pn = lds_f2(src);
             for (uint32_t k = k0; k < k1; ++k) {
@@ -1484,22 +1502,37 @@ __global__ void __launch_bounds__(CHAIN_THREADS) hull_chain_kernel(const float2*
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
     }
-    if (lane == 0) {
-        uint32_t len = (top - stack0) >> 3;
-        if (overflow) len = descending ? hull_chain<-1>(pts, n, scratch_b + begin, n) : hull_chain<1>(pts, n, scratch_a + begin, n);
-        sh_len[warp] = len | (overflow ? 0x80000000u : 0u);
+    if (lane < CHAIN_LANES) {
+        uint32_t len = n_own;   // n < 3: returned as-is (src/convex_hull.rs:9-11)
+        if (runs) {
+            len = (top - stack0) >> 3;
+            if (overflow) len = descending ? hull_chain<-1>(sorted + begin_own, n_own, scratch_b + begin_own, n_own) : hull_chain<1>(sorted + begin_own, n_own, scratch_a + begin_own, n_own);
+        }
+        sh_len[chain_own] = len | (overflow ? 0x80000000u : 0u);
     }
-    asm volatile("bar.sync %0, 64;" ::"r"(1u + slot) : "memory");   // the two chain warps of this shape
-    const uint32_t len_a = sh_len[2 * slot], len_b = sh_len[2 * slot + 1];
-    const float2* sa = (len_a >> 31) ? scratch_a + begin : &stacks[2 * slot][0];
-    const float2* sb = (len_b >> 31) ? scratch_b + begin : &stacks[2 * slot + 1][0];
-    const uint32_t la = (len_a & 0x7fffffffu) - 1, lb = (len_b & 0x7fffffffu) - 1, total = la + lb;   // hull.pop() after each chain
-    // triangle_fan_to_strip(andrew(..)) (src/renderer.rs:197, src/vertex.rs:28-35)
-    for (uint32_t i = tid; i < total; i += 64u) {
-        const uint32_t src = (i & 1u) == 0 ? (i >> 1) : total - 1 - (i >> 1);
-        out[i] = src < la ? sa[src] : sb[src - la];
+    __syncwarp();
+    // triangle_fan_to_strip(andrew(..)) (src/renderer.rs:197, src/vertex.rs:28-35): the whole warp writes the hulls of its shapes
+#pragma unroll 1
+    for (uint32_t j = 0; j < CHAIN_LANES / 2; ++j) {
+        const uint32_t chain = warp * CHAIN_LANES + 2u * j, s = blockIdx.x * CHAIN_SHAPES + (chain >> 1);
+        if (s >= n_shapes) break;
+        const uint32_t begin = __shfl_sync(0xffffffffu, begin_own, 2u * j), n = __shfl_sync(0xffffffffu, n_own, 2u * j);
+        float2* out = hull_out + begin;
+        if (n < 3u) {   // fan->strip of <= 2 points is the identity
+            if (lane < n) out[lane] = sorted[begin + lane];
+            if (lane == 0) hull_count[s] = n;
+            continue;
+        }
+        const uint32_t len_a = sh_len[chain], len_b = sh_len[chain + 1];
+        const float2* sa = (len_a >> 31) ? scratch_a + begin : stacks + (size_t)chain * STACK_STRIDE;
+        const float2* sb = (len_b >> 31) ? scratch_b + begin : stacks + (size_t)(chain + 1) * STACK_STRIDE;
+        const uint32_t la = (len_a & 0x7fffffffu) - 1, lb = (len_b & 0x7fffffffu) - 1, total = la + lb;   // hull.pop() after each chain
+        for (uint32_t i = lane; i < total; i += 32u) {
+            const uint32_t src = (i & 1u) == 0 ? (i >> 1) : total - 1 - (i >> 1);
+            out[i] = src < la ? sa[src] : sb[src - la];
+        }
+        if (lane == 0) hull_count[s] = total;
     }
-    if (tid == 0) hull_count[s] = total;
 }
 
 }  // namespace
@@ -1554,7 +1587,9 @@ int cr_tess_hull(cudaStream_t stream, float2* proto, float2* scratch_a, float2* 
     const uint32_t threads = std::min<uint32_t>(512u, std::max<uint32_t>(64u, cap / 16u));   // one 16-element register tile per thread
     hull_sort_kernel<<<n_shapes, threads, (size_t)SORT_SLOT(cap) * sizeof(float2), stream>>>(proto, proto_begin, cap, err_flag);
     if (after_sort) CR_CUDA_TRY(cudaEventRecord(after_sort, stream));
-    hull_chain_kernel<<<(n_shapes + CHAIN_SHAPES - 1) / CHAIN_SHAPES, CHAIN_THREADS, 0, stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out, hull_count, err_flag);
+    const size_t chain_smem = ((size_t)CHAINS_PER_CTA * STACK_STRIDE + (size_t)CHAINS_PER_CTA * 2 * WINDOW_STRIDE) * sizeof(float2);
+    CR_CUDA_TRY(cudaFuncSetAttribute(hull_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem));   // per device: set on every call
+    hull_chain_kernel<<<(n_shapes + CHAIN_SHAPES - 1) / CHAIN_SHAPES, CHAIN_THREADS, chain_smem, stream>>>(proto, scratch_a, scratch_b, proto_begin, n_shapes, hull_out, hull_count, err_flag);
     g_cr_kernel_launches += 2;
     CR_CUDA_TRY(cudaGetLastError());
     return CR_OK;
