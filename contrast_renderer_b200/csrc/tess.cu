@@ -946,8 +946,8 @@ __global__ void __launch_bounds__(128) tess_emit_kernel(DevicePaths P, const uin
 // earlier segments of its type), its proto-hull points behind 1 + lines + 2 x quadratics before it; the point it starts from is
 // the end point of segment i - 1. So filled paths without cubic segments ("simple" paths: the Loop-Blinn builder emits a
 // data-dependent number of vertices) are tessellated with one thread per segment: coalesced reads of the type stream and the
-// per-type segment arrays, ranks by warp ballots (plus one cooperative count for a path that began before the warp), and every
-// thread writes at its final address. The count pass, the scan and the layout are those of the per-path kernels; paths that are
+// per-type segment arrays, ranks by warp ballots (plus one cooperative count for a path that began before the warp), path
+// records shared inside the warp by shuffles, and every thread writes at its final address. The count pass, the scan and the layout are those of the per-path kernels; paths that are
 // stroked or hold cubics stay with tess_emit_kernel (which skips the simple ones when this kernel runs).
 __device__ __forceinline__ uint32_t shape_of_path(const uint32_t* __restrict__ shape_path_begin, uint32_t n_shapes, uint32_t p) {
     uint32_t lo = 0, hi = n_shapes;   // last s with shape_path_begin[s] <= p
@@ -991,8 +991,6 @@ __device__ __forceinline__ FillPathInfo load_fill_path_info(const DevicePaths& P
 __global__ void __launch_bounds__(FS_THREADS) fill_segments_kernel(DevicePaths P, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ shape_path_begin,
                                                                    uint32_t n_shapes, TessOutput out, uint32_t* __restrict__ err, uint32_t all_simple) {
     if (*reinterpret_cast<volatile const uint32_t*>(err) & CR_DEVERR_FATAL_MASK) return;   // the count pass rejected the input (uniform): write nothing
-    __shared__ FillPathInfo sh_info[FS_THREADS];
-    __shared__ uint32_t sh_range[2];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
     const uint32_t seg_threads = (P.n_segments + FS_THREADS - 1u) / FS_THREADS * FS_THREADS;   // whole CTAs of segment threads, then one thread per path for its start point
     uint32_t e = 0;
@@ -1012,48 +1010,56 @@ __global__ void __launch_bounds__(FS_THREADS) fill_segments_kernel(DevicePaths P
         if (e) atomicOr(err, e);
         return;
     }
-    // ---- the CTA's paths: the first one (and its shape) by a warp-wide search, then everything about the next FS_THREADS paths into
-    // shared memory in one round of independent loads; the ones that begin beyond the CTA's last segment are not used
-    const uint32_t g = tid, g0 = blockIdx.x * FS_THREADS, g_last = min(g0 + FS_THREADS, P.n_segments) - 1u;
-    if (threadIdx.x < 32u) {
-        const uint32_t pf = warp_search_last_le(P.segment_begin, P.n_paths, g0, lane);   // segment_begin[n_paths] = n_segments > g0; empty paths share a value: the last one owns the segment
-        const uint32_t sf = warp_search_last_le(shape_path_begin, n_shapes, pf, lane);
-        if (lane == 0) { sh_range[0] = pf; sh_range[1] = sf; }
-    }
-    __syncthreads();
-    const uint32_t p_first = sh_range[0];
-    uint32_t mine_needed = 0;
-    if (p_first + threadIdx.x < P.n_paths) {
-        const FillPathInfo f = load_fill_path_info(P, offsets, shape_path_begin, n_shapes, p_first + threadIdx.x, all_simple != 0u, sh_range[1]);
-        sh_info[threadIdx.x] = f;
-        mine_needed = f.sb <= g_last ? 1u : 0u;
-    }
-    const uint32_t n_local = (uint32_t)__syncthreads_count((int)mine_needed);   // paths with sb <= g_last form a prefix (sb is non-decreasing)
-    const bool cached = n_local < FS_THREADS || p_first + FS_THREADS >= P.n_paths;   // else the CTA's last segment may belong to a path beyond the cached ones (runs of EMPTY paths)
+    // ---- the warp's paths: the first one (and its shape) by a warp-wide search, then lane j loads everything about path first + j in
+    // one round of independent loads; the paths that begin at or before the warp's last segment form a prefix of the lanes, and a
+    // segment finds its path among them by a five-step search over the lanes (shuffles). No shared memory, no CTA barrier: the
+    // warps of a CTA do not wait for each other's dependent loads.
+    const uint32_t g = tid, g_warp = g - lane;
+    if (g_warp >= P.n_segments) return;
+    const uint32_t g_warp_last = min(g_warp + 32u, P.n_segments) - 1u;
+    const uint32_t p_first = warp_search_last_le(P.segment_begin, P.n_paths, g_warp, lane);   // segment_begin[n_paths] = n_segments > g: empty paths share a value, the last one owns the segment
+    const uint32_t s_first = warp_search_last_le(shape_path_begin, n_shapes, p_first, lane);
+    FillPathInfo mine{};
+    mine.sb = 0xFFFFFFFFu;
+    if (p_first + lane < P.n_paths) mine = load_fill_path_info(P, offsets, shape_path_begin, n_shapes, p_first + lane, all_simple != 0u, s_first);
+    const uint32_t n_local = (uint32_t)__popc(__ballot_sync(0xffffffffu, mine.sb <= g_warp_last));   // sb is non-decreasing: a prefix of the lanes
+    const bool cached = n_local < 32u || p_first + 32u >= P.n_paths;   // else the warp's last segments may belong to paths beyond the loaded ones (runs of EMPTY paths)
     const bool live = g < P.n_segments;
     uint32_t p = 0xFFFFFFFFu, type = 255u;
     FillPathInfo f{};
+    {
+        uint32_t lo = 0;   // last loaded path with sb <= g
+#pragma unroll
+        for (uint32_t step = 16u; step != 0u; step >>= 1) {
+            const uint32_t cand = lo + step;
+            const uint32_t sb_cand = __shfl_sync(0xffffffffu, mine.sb, cand & 31u);
+            if (cand < n_local && sb_cand <= g) lo = cand;
+        }
+        f.sb = __shfl_sync(0xffffffffu, mine.sb, lo);
+        f.solid = __shfl_sync(0xffffffffu, mine.solid, lo); f.proto = __shfl_sync(0xffffffffu, mine.proto, lo);
+        f.iq = __shfl_sync(0xffffffffu, mine.iq, lo); f.rq = __shfl_sync(0xffffffffu, mine.rq, lo);
+        f.solid_idx = __shfl_sync(0xffffffffu, mine.solid_idx, lo);
+        f.tb0 = __shfl_sync(0xffffffffu, mine.tb0, lo); f.tb1 = __shfl_sync(0xffffffffu, mine.tb1, lo); f.tb3 = __shfl_sync(0xffffffffu, mine.tb3, lo);
+        f.te0 = __shfl_sync(0xffffffffu, mine.te0, lo); f.te1 = __shfl_sync(0xffffffffu, mine.te1, lo); f.te3 = __shfl_sync(0xffffffffu, mine.te3, lo);
+        f.rel = __shfl_sync(0xffffffffu, mine.rel, lo); f.total_simple = __shfl_sync(0xffffffffu, mine.total_simple, lo);
+        p = p_first + lo;
+    }
     if (live) {
-        if (cached) {
-            uint32_t lo = 0, hi = n_local;   // last local path with sb <= g
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_info[mid].sb <= g) lo = mid; else hi = mid; }
-            p = p_first + lo;
-            f = sh_info[lo];
-        } else {
+        if (!cached) {
             uint32_t lo = 0, hi = P.n_paths;
             while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.segment_begin[mid] <= g) lo = mid; else hi = mid; }
             p = lo;
             f = load_fill_path_info(P, offsets, shape_path_begin, n_shapes, p, all_simple != 0u, shape_of_path(shape_path_begin, n_shapes, p));
         }
         type = P.segment_types[g];
-    }
+    } else p = 0xFFFFFFFFu;
     // ranks: how many segments of each type precede this one in its path. Inside the warp by ballots ...
     const uint32_t same = __match_any_sync(0xffffffffu, p) & ((1u << lane) - 1u);
     const uint32_t b0 = __ballot_sync(0xffffffffu, type == CR_SEG_LINE), b1 = __ballot_sync(0xffffffffu, type == CR_SEG_INTEGRAL_QUADRATIC),
                    b3 = __ballot_sync(0xffffffffu, type == CR_SEG_RATIONAL_QUADRATIC);
     uint32_t r0 = __popc(b0 & same), r1 = __popc(b1 & same), r3 = __popc(b3 & same);
     // ... and, for the one path that began before this warp's first segment, by a cooperative count over [its begin, the warp's first segment)
-    const uint32_t g_warp = g - lane, p_lane0 = __shfl_sync(0xffffffffu, p, 0), sb_lane0 = __shfl_sync(0xffffffffu, f.sb, 0);
+    const uint32_t p_lane0 = __shfl_sync(0xffffffffu, p, 0), sb_lane0 = __shfl_sync(0xffffffffu, f.sb, 0);
     if (p_lane0 != 0xFFFFFFFFu && sb_lane0 < g_warp) {
         uint32_t c0 = 0, c1 = 0, c3 = 0;
         for (uint32_t k = sb_lane0 + lane; k < g_warp; k += 32u) {
