@@ -627,6 +627,8 @@ def main():
             "gpu_launches": launches,
             "kernel_ms_per_step": k_ms,
             "kernel_ms_sum_over_step": (k_ms["tess"] + k_ms["bin"] + k_ms["raster"]) / (ms_dev / args.steps) if ms_dev > 0 else None,
+            "kernel_ms_note": ("kernel_ms_per_step is measured with one step at a time (CUDA events inside the library); with frame pipelining the stages of "
+                               "consecutive steps overlap, so their sum exceeds ms_per_step"),
             "roofline": rooflines[0],
             "roofline_other": rooflines[1:],
             "stages": {"tessellation": {"ms": k_ms["tess"], "algorithmic_bytes": tess_alg, "achieved_gbs": tess_alg / (k_ms["tess"] * 1e-3) / 1e9 if k_ms["tess"] else 0.0},

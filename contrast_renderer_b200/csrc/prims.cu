@@ -57,11 +57,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(uint32_t* _
     const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t sum = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15u) == 0;   // a thread's 16 items are 64 bytes: four 128-bit accesses when the row allows
+    if (aligned && base + SCAN_ITEMS < n_plus_1) {
+        const uint4* src = reinterpret_cast<const uint4*>(row + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const uint32_t i = base + k;
-        v[k] = (i + 1 < n_plus_1) ? row[i] : 0u;   // slot n is not an input
-        sum += v[k];
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+            const uint4 t = src[q];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) sum += v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const uint32_t i = base + k;
+            v[k] = (i + 1 < n_plus_1) ? row[i] : 0u;   // slot n is not an input
+            sum += v[k];
+        }
     }
     // block exclusive scan of the per-thread sums
     uint32_t incl = sum;
@@ -104,11 +116,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(uint32_t* _
     }
     __syncthreads();
     uint32_t running = sh_prefix + thread_excl;
+    if (aligned && base + SCAN_ITEMS <= n_plus_1) {
+        uint4* dst = reinterpret_cast<uint4*>(row + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const uint32_t i = base + k;
-        if (i < n_plus_1) row[i] = running;
-        running += v[k];
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+            uint4 t;
+            t.x = running; running += v[4 * q];
+            t.y = running; running += v[4 * q + 1];
+            t.z = running; running += v[4 * q + 2];
+            t.w = running; running += v[4 * q + 3];
+            dst[q] = t;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const uint32_t i = base + k;
+            if (i < n_plus_1) row[i] = running;
+            running += v[k];
+        }
     }
 }
 
