@@ -3,26 +3,32 @@
 // Replaces the wgpu render pass of the reference: Shape::render draw recording (src/renderer.rs:267-355), the 13
 // pipeline stencil / blend states (src/renderer.rs:565-861) and every entry point of src/shaders.wgsl.
 //
-// Data flow (all in HBM, one 4-byte read-back of the pair count):
-//   commands -> candidates (one per index slot / list triangle / hull-strip triangle, numbered in exact draw order)
-//   --prim_setup--> 64-byte PrimRecords (vertex stage done once) + tiles touched per candidate --scan-->
-//   --bin_emit--> (tile, candidate) pairs --stable radix sort by tile--> per-tile ranges in draw order --K3--> framebuffer.
+// Data flow (all in HBM; nothing is read back before the pass has been enqueued — the host sizes everything from capacities and
+// the kernels check them on the device, api.cu "optimistic submit"):
+//   compact commands --expand--> commands + candidate numbering (one candidate per index slot / list triangle / hull-strip
+//   triangle, in exact draw order) --prim_setup--> 64-byte PrimRecords (vertex stage done once) + tiles touched per candidate
+//   (candidates with a big tile box: bin_big, one warp each; candidates that cross the eye plane: clip_kernel, fan triangles
+//   behind the candidates) --scan--> --bin_emit--> (tile, candidate) pairs --stable radix sort by tile--> per-tile ranges in
+//   draw order --tile_prims--> the tile-ordered 128-byte TilePrim stream (every pair set up for its tile once) --K3--> framebuffer.
 //
-// K3: one CTA per 16x16 tile. The pixel's stencil byte and RGBA colour live in the REGISTERS of "its" thread for the whole
-// pass, so the tile is read once and written once (128-bit accesses) and overdraw costs no HBM traffic. The tile's
-// primitives are walked in draw order in chunks; inside a chunk, maximal runs of primitives whose stencil effect
-// commutes are executed in parallel over (primitive, pixel row) pairs into a shared-memory accumulator:
+// K3: one CTA per 16x16 tile. The pixel's stencil byte, RGBA colour (and depth) live in the REGISTERS of "its" thread for the
+// whole pass, so the tile is read once and written once (128-bit accesses) and overdraw costs no HBM traffic. The tile's
+// primitives arrive as one contiguous stream, 64 at a time, by bulk asynchronous copies (cp.async.bulk + mbarrier) into two
+// shared-memory buffers — the next chunk is in flight while this one is rasterised. Inside a chunk, maximal runs of primitives
+// whose stencil effect commutes are executed in parallel into a shared-memory accumulator:
 //   * fill stencil (src/renderer.rs:577-582): the test only looks at the clip bits, the op is +-1 mod 2^winding_bits
 //     => the run's net effect on a pixel is the signed count of covering front/back faces;
 //   * stroke stencil (src/renderer.rs:571-576): passes only while the winding bits are still equal to the reference
 //     (zero), then sets them to one => the run's net effect is "any primitive covers".
-// Cover operations (colour, clip, alpha contexts) are order dependent and run one thread per pixel.
 // Runs of at most PIXEL_RUN_MAX primitives (the usual hull cover, small fans) skip the shared accumulator altogether: every
-// thread walks the run's primitives for its own pixel (no barrier, all threads busy). Edge functions are evaluated in 32-bit
-// integers whenever every value over the tile fits (exact), else in 64-bit. The pass's LoadOp::Clear is fused: cleared tiles
-// start from zero instead of being loaded and every tile is written (empty ones too), so the target is neither memset nor
-// read. With a tile-sharded target (several GPUs, one frame) a CTA only processes tiles its rank owns and stores the
-// finished tile into every rank's attachments (peer-mapped, P2P over NVLink).
+// thread walks the run's primitives for its own pixel (no barrier, all threads busy); runs up to ROW_SWEEP_MAX lay (primitive,
+// row) items out on a 16 x 16 grid; longer runs compact their rows with a per-warp prefix sum. Cover operations (colour, clip,
+// alpha contexts) are order dependent and run one thread per pixel. Edge functions are evaluated in 32-bit integers whenever
+// every value over the tile fits (exact), else in 64-bit. The pass's LoadOp::Clear is fused: cleared tiles start from zero
+// instead of being loaded and every tile is written (empty ones too), so the target is neither memset nor read.
+// One target on several GPUs: with tile sharding a CTA only processes tiles its rank owns and stores the finished tile into
+// every rank's attachments (peer-mapped, P2P over NVLink); with draw-order sharding it waits for its predecessor's tile state
+// and hands the tile to its successor (see RasterTarget in raster.h).
 //
 // Rasterisation contract: see the header comment of oracle/raster.hpp (written independently, same rules).
 #include "device_common.cuh"
@@ -414,7 +420,6 @@ __global__ void __launch_bounds__(256) expand_kernel(const CompactCommand* __res
 #ifndef SETUP_MIN_BLOCKS
 #define SETUP_MIN_BLOCKS 6   // 40 registers: bin stage 0.295 -> 0.283 ms on the text scene
 #endif
-#define SETUP_CMD_CACHE 2048
 #define META_BIG 128u
 // big[0] = number of big candidates, big[1 ...] = their candidate numbers
 __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) prim_setup_kernel(RasterScene sc, RasterTarget tg, uint32_t cand_capacity, PrimRecord* __restrict__ records,

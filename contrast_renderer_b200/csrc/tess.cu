@@ -4,11 +4,14 @@
 // Replaces, on the device: src/curve.rs (all), src/stroke.rs (all), src/fill.rs (all), src/convex_hull.rs,
 // src/vertex.rs and the buffer concatenation of Shape::from_paths (src/renderer.rs:184-209).
 //
-// Structure: one thread walks one Path exactly like StrokeBuilder::add_path / FillBuilder::add_path do (the
-// sequential state — arc length, previous tangent, strip cuts, the five per-type cursors — lives in registers),
-// first with a counting sink, then, after an exclusive scan over paths, with an emitting sink that writes
-// every vertex / index / proto-hull point to its final address. The per-sample root solving of
-// interpolate_normal! (src/curve.rs:228-252) only runs in the emit pass.
+// Structure: a counting pass (one thread per Path, with a counting sink), an exclusive scan over paths, then the emit pass that
+// writes every vertex / index / proto-hull point to its final address:
+//   * filled paths without cubic segments: fill_segments_kernel, one thread per SEGMENT (the fill builder's only running state
+//     are counts, which warp ballots provide);
+//   * stroked paths and fills with cubics: tess_emit_kernel, one thread walks one Path exactly like StrokeBuilder::add_path /
+//     FillBuilder::add_path do (the sequential state — arc length, previous tangent, strip cuts, the five per-type cursors —
+//     lives in registers). The per-sample root solving of interpolate_normal! (src/curve.rs:228-252) only runs in the emit pass.
+// Then, per Shape, convex_hull::andrew: a shared-memory bitonic sort and the two monotone chains (one lane per chain).
 //
 // Output layout in HBM: one array per vertex category for the WHOLE batch (all shapes), categories in
 // concat_buffers! order; a shape's slice of category c is [cat_begin[c][s], cat_begin[c][s+1]). Index buffers are
