@@ -576,3 +576,42 @@ def tiger_like(n_instances: int = 1000, seed: int = SEED0 + 4, extent: Tuple[int
     script[:, :, 3] = g[None, :, 1]
     script[:, :, 4:7] = g[None, :, 2:5]
     return ScriptedScene(soa, begin, [], extent[0], extent[1], np.ascontiguousarray(transforms), colors, script.reshape(-1, 7), "tiger_like", 2)
+
+
+# ------------------------------------------------------------------------------------------------------ the reference's showcase
+def showcase(extent: Tuple[int, int] = (640, 360), view_angles: Tuple[float, float] = (0.0, 0.0), view_distance: float = 5.0):
+    """The scene of examples/showcase/main.rs, built with the host mirrors of the reference's own helpers: ONE Shape — the
+    string "Hello World" through the text front-end (every glyph path reversed, main.rs:81-83) inside a rounded rectangle that
+    is stroked with a dashed miter line (main.rs:58-92) — drawn 46 times: instance 0 with the camera's projection, a 5 x 9 grid
+    of copies placed in 3D behind it (main.rs:163-201); the camera is `Translator(1, 0, 0, -view_distance / 2) * view_rotation`
+    with `view_rotation = rotate_around_axis(a, y) * rotate_around_axis(b, x)` (main.rs:258-259). The demo renders it with
+    4x MSAA, depth LessEqual + depth write, back-face culling (main.rs:28-52) and Stencil + Color per instance (main.rs:236-250).
+    Returns (paths, shape_path_begin, dynamic_stroke_options, transforms [46, 16], colors [46, 4])."""
+    import os
+    from . import utils as U
+    from .path import Cap, CurveApproximation, DashInterval, DynamicStrokeOptions, Join, Path, PathSoA, StrokeOptions
+    from .text import Alignment, FixtureFace, Layout, Orientation, paths_of_text
+    fixture = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "opensans_ascii.npz")
+    face = FixtureFace(dict(np.load(fixture)))
+    paths = paths_of_text(face, Layout(2.7, Orientation.LeftToRight, Alignment.Center, Alignment.Center), "Hello World")
+    for p in paths:
+        p.reverse()
+    frame = Path.from_rounded_rect([0.0, 0.0], [5.8, 1.3], 0.5)
+    frame.stroke_options = StrokeOptions(width=0.1, offset=0.0, miter_clip=1.0, closed=True, dynamic_stroke_options_group=0,
+                                         curve_approximation=CurveApproximation.UniformTangentAngle(0.1))
+    paths.insert(0, frame)
+    dso = [DynamicStrokeOptions.Dashed(Join.Miter, [DashInterval(3.0, 4.0, Cap.Butt, Cap.Butt)], 0.0)]
+    rotation = U.motor3d_product(U.rotor3d_to_motor3d(U.rotate_around_axis(view_angles[0], [0.0, 1.0, 0.0])),
+                                 U.rotor3d_to_motor3d(U.rotate_around_axis(view_angles[1], [1.0, 0.0, 0.0])))
+    camera = U.motor3d_product(U.translator3d(0.0, 0.0, -0.5 * view_distance), rotation)
+    projection = U.matrix_multiplication(U.perspective_projection(np.pi * 0.5, extent[0] / extent[1], 1.0, 1000.0), U.motor3d_to_mat4(camera))
+    rows, columns = 9, 5
+    transforms, colors = [projection], [[1.0, 1.0, 1.0, 1.0]]
+    for y in range(rows):
+        for x in range(columns):
+            place = U.translator3d((x + 0.5 - columns * 0.5) * 7.0, (y + 0.5 - rows * 0.5) * 3.0, -5.0)
+            transforms.append(U.matrix_multiplication(projection, U.motor3d_to_mat4(place)))
+            red, green = x / columns, y / rows
+            colors.append([red, green, 1.0 - red - green, 1.0])
+    soa = PathSoA.from_paths(paths)
+    return (soa, np.array([0, soa.n_paths], np.uint32), dso, np.asarray(transforms, np.float32).reshape(-1, 16), np.asarray(colors, np.float32))
