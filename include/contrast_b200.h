@@ -251,7 +251,12 @@ int cr_pass_set_clip_depth(cr_pass* pass, uint32_t clip_depth);
 int cr_pass_save_alpha_context(cr_pass* pass, uint32_t alpha_layer);
 /* Renderer::restore_alpha_context, src/renderer.rs:979: selects the layer the next RESTORE_ALPHA_CONTEXT reads. */
 int cr_pass_restore_alpha_context(cr_pass* pass, uint32_t alpha_layer);
-/* Shape::render, src/renderer.rs:267. Records; nothing runs until cr_pass_submit. */
+/* Shape::render, src/renderer.rs:267. Records; nothing runs until cr_pass_submit.
+ * Rasterisation follows the WebGPU rules the reference relies on (restated in oracle/raster.hpp): clip = M (x, y, 0, 1)
+ * (src/shaders.wgsl:72), 1/256-pixel snapping, top-left fill rule, perspective-correct per-sample attributes, the standard 4x
+ * sample pattern. Primitives with a corner on or behind the eye plane (w <= 0), or further than 2^21 pixels away, are CLIPPED
+ * in clip space (eye plane + guard band) like a GPU clips them, not dropped; depth is not clipped against the near / far planes
+ * (unclipped-depth semantics), the depth test of the colour cover compares z / w against the f32 depth attachment. */
 int cr_shape_render(cr_pass* pass, cr_shape* shape, uint32_t instance_begin, uint32_t instance_end,
                     uint32_t render_operation);
 
